@@ -1,0 +1,183 @@
+/*
+ * matcha_b200 — C ABI of the B200-native Hyper-SAGNN hyperedge-scoring hot path.
+ *
+ * This is the drop-in boundary.  The reference (ma-compbio/MATCHA) is pure Python/PyTorch and has no
+ * FFI of its own; each entry point below names the reference function whose device work it replaces
+ * (paths relative to the reference's Code/ directory).  A maintainer binds it with ctypes (see
+ * INTEGRATION.md); our own host mirror lives in matcha_b200/Modules.py.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a CUDA device pointer allocated by the CALLER; the library never
+ *     allocates or frees device memory and keeps no global state besides lazily set function attributes;
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*) and is
+ *     stream-ordered; nothing synchronises the device;
+ *   - matrices are row-major fp32 unless stated; node ids are int64, 0 = padding, 1..N real bins;
+ *   - return value 0 = success, negative = error (message via matcha_last_error()); nothing throws
+ *     or calls exit().
+ */
+#ifndef MATCHA_B200_H
+#define MATCHA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MATCHA_OK 0
+#define MATCHA_ERR_ARG (-1)
+#define MATCHA_ERR_CUDA (-2)
+#define MATCHA_ERR_UNSUPPORTED (-3)
+
+#define MATCHA_MAX_CHROM 64
+#define MATCHA_MAX_WIDTH 8 /* hyperedge width L (reference uses 2..5, config.JSON:14) */
+
+const char* matcha_last_error(void);
+int matcha_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Model description: where every live tensor of Modules.Classifier sits.
+ * `params` / `grads` are flat fp32 device buffers with IDENTICAL layout; off_* are element offsets.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct matcha_model_desc {
+  int32_t d;        /* embed_dim (main.py:517); 64 supported */
+  int32_t n_head;   /* 8 (main.py:616) */
+  int32_t n_chrom;  /* C */
+  int32_t attr_dim; /* C + 1 (main.py:497-512) */
+  int64_t n_nodes;  /* N */
+  float* params;    /* dev */
+  float* grads;     /* dev (may be NULL for inference-only use) */
+
+  /* Classifier.attribute_nn, Classifier.next_w (Modules.py:242-249) */
+  int64_t off_attr_w, off_attr_b, off_next_w, off_next_b;
+  /* encode1.mul_head_attn: layer_norm1/2/3, w_qs/w_ks/w_vs, fc1 (Modules.py:481-500) */
+  int64_t off_lnq_g, off_lnq_b, off_lnk_g, off_lnk_b, off_lnv_g, off_lnv_b;
+  int64_t off_wq, off_wk, off_wv, off_fc1_w, off_fc1_b;
+  /* encode1.pff_n1: PWF_Conv0/1, layer_norm (Modules.py:604-605) */
+  int64_t off_pff_w0, off_pff_b0, off_pff_w1, off_pff_b1, off_pff_g, off_pff_b;
+  /* Classifier.layer_norm1/2, pff_classifier.PWF_Conv0 (Modules.py:218,240-241) */
+  int64_t off_ln1_g, off_ln1_b, off_ln2_g, off_ln2_b, off_cls_w, off_cls_b;
+
+  /* per chromosome c (Modules.py:163-171): ids [chrom_start[c], chrom_end[c]) , n_c = end - start */
+  int64_t chrom_start[MATCHA_MAX_CHROM];
+  int64_t chrom_end[MATCHA_MAX_CHROM];
+  int64_t off_w0[MATCHA_MAX_CHROM];  /* 'tied weight_0' [d, n_c]  */
+  int64_t off_w1[MATCHA_MAX_CHROM];  /* 'tied weight_1' [d, d]    */
+  int64_t off_rw[MATCHA_MAX_CHROM];  /* Embedding_recon{c}.FF_Linear0.weight [n_c, d] */
+  int64_t off_rb[MATCHA_MAX_CHROM];  /* Embedding_recon{c}.FF_Linear0.bias   [n_c]    */
+  const float* feat[MATCHA_MAX_CHROM]; /* dev: SparseEmbedding.embedding, dense [n_c, feat_ld[c]] (Modules.py:48-52) */
+  int64_t feat_ld[MATCHA_MAX_CHROM];
+  /* optional CSR form of the same feature rows (Modules.py:58-65, sparse=True); used when feat[c]==NULL */
+  const int64_t* feat_indptr[MATCHA_MAX_CHROM];  /* dev [n_c + 1] */
+  const int32_t* feat_indices[MATCHA_MAX_CHROM]; /* dev */
+  const float* feat_values[MATCHA_MAX_CHROM];    /* dev */
+
+  const float* attr_table; /* dev [N+1, attr_dim]: attribute_dict_embedding.weight (frozen, Modules.py:245-247) */
+  const float* inter;      /* dev [N, inter_ld] z-scored inter matrix (Modules.py:147-154) or NULL */
+  int64_t inter_ld;
+
+  /* effective ("derived") weights written by matcha_prepare: dev buffers of matcha_derived_elems() floats */
+  float* derived;
+  float* derived_grad;
+
+  float p_feature, p_attn, p_pff; /* dropout probabilities (Modules.py:174,226-227) */
+} matcha_model_desc;
+
+int64_t matcha_derived_elems(const matcha_model_desc* m);
+/* bytes of scratch needed for a batch of B hyperedges of padded width L (training=1 keeps activations) */
+int64_t matcha_workspace_bytes(const matcha_model_desc* m, int64_t B, int32_t L, int32_t training);
+
+/* Fold LayerNorm affine / temperature / fc1 into the effective projection weights.  Call after every
+ * parameter update and before forward.  Replaces nothing in the reference (a B200-side re-association
+ * of Modules.py:519-529,572); exact in real arithmetic. */
+int matcha_prepare(const matcha_model_desc* m, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Classifier.forward(x, return_recon=True)  — Modules.py:278-318 (and everything it calls).
+ *   x          dev int64 [B, L]
+ *   logits     dev fp32  [B]      raw logits (callers apply sigmoid: main.py:58)
+ *   recon      dev fp32  [1]      reconstruction loss for chromosome `random_chrom` (Modules.py:192-199);
+ *                                 random_chrom < 0 skips it and writes 0
+ *   training   0 = eval (no dropout), 1 = train (dropout from the counter RNG keyed by `seed`)
+ *   workspace  dev, matcha_workspace_bytes() bytes; after a training forward it holds the tape that
+ *              matcha_backward consumes
+ * --------------------------------------------------------------------------------------------- */
+int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int32_t L, int32_t training,
+                   uint64_t seed, int32_t random_chrom, float* logits, float* recon, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/* loss = alpha * BCEWithLogits(logits, y, weight=w).mean() + beta * recon   (main.py:56,166)
+ * writes loss_out (dev fp32 [3]) = {bce, recon, loss} and dlogit (dev fp32 [B]) = d loss / d logits.
+ * recon may be NULL (treated as 0). */
+int matcha_bce_loss(const float* logits, const float* y, const float* w, int64_t B, float alpha, float beta,
+                    const float* recon, float* dlogit, float* loss_out, void* stream);
+
+/* Backward pass of everything matcha_forward(training=1) did, given d loss / d logits (dev fp32 [B]) and
+ * the scalar d loss / d recon (`beta`, 0 skips the reconstruction head).  Uses the tape left in
+ * `workspace` by the forward call with the same (x, B, L, seed, random_chrom).  Gradients are
+ * ACCUMULATED into m->grads (zero the buffer first).
+ * active (dev int32 [2 * n_chrom], optional): per-chromosome flags "encoder c received a gradient" and
+ * "recon head c received a gradient" -- the tensors torch would have given a non-None .grad. */
+int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int32_t L, uint64_t seed,
+                    int32_t random_chrom, const float* dlogit, float beta, int32_t* active, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
+/* Classifier.get_node_embeddings in eval mode (Modules.py:252-259; rows of embeddings.npy, main.py:462-476)
+ * ids dev int64 [T] -> out dev fp32 [T, d]; workspace as for matcha_forward with B = T, L = 1. */
+int matcha_node_embeddings(const matcha_model_desc* m, const int64_t* ids, int64_t T, float* out,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* torch.optim.AdamW step on a flat range (main.py:630,671).  seg_* (dev, optional) describe
+ * conditionally-active segments: element range [seg_begin[s], seg_end[s]) is updated only when
+ * active[seg_flag[s]] != 0; step counts are per segment (seg_step, dev int32, incremented here).
+ * Elements outside every segment but inside [0, n_always) are always updated with step `step`. */
+int matcha_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n_always,
+                 int32_t step, int32_t n_seg, const int64_t* seg_begin, const int64_t* seg_end,
+                 const int32_t* seg_flag, int32_t* seg_step, const int32_t* active, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Positive k-mer hash set + negative sampler — main.py:361-459 (generate_negative), :345-346
+ * (neighbor_check), utils.py:75-97 (build_hash; exact set instead of a Bloom filter).
+ * Table: `capacity` (power of two) slots of 16 bytes PLUS one trailing status slot, i.e.
+ * (capacity + 1) * 16 bytes, caller-allocated and zero-filled; load factor must stay <= 0.5.
+ * Keys pack up to 6 ids of 21 bits (ids < 2^21).  chrom_start / chrom_end are HOST arrays.
+ * --------------------------------------------------------------------------------------------- */
+int matcha_hashset_insert(void* table, int64_t capacity, const int64_t* kmers, int64_t n, int32_t width,
+                          void* stream);
+int matcha_hashset_contains(const void* table, int64_t capacity, const int64_t* kmers, int64_t n,
+                            int32_t width, uint8_t* out, void* stream);
+/* pos dev int64 [P, L] (rows sorted ascending, zero padded) -> neg dev int64 [P * neg_num, L];
+ * valid dev uint8 [P * neg_num] = 0 where max_rounds candidate rounds were exhausted (row = the positive). */
+int matcha_neg_sample(const void* table, int64_t capacity, const int64_t* pos, int64_t P, int32_t L,
+                      int32_t neg_num, const int64_t* chrom_start, const int64_t* chrom_end, int32_t n_chrom,
+                      int32_t min_dis, uint64_t seed, uint64_t step, int32_t max_rounds, int64_t* neg,
+                      uint8_t* valid, int32_t* rounds_used, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Streaming scorers — denoise_contact.py:67-88 (generate_pair_wise + predict), predict_multiway.py:74-87.
+ * Pair path: per-node tables D, S [N+1, d] (k = 2 closed form, exact because with two tokens the
+ * diagonal-masked attention weight is 1) then logits for the row-major upper-triangular pair range.
+ * --------------------------------------------------------------------------------------------- */
+int matcha_pair_tables(const matcha_model_desc* m, float* D, float* S, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+/* pairs (i, j), lo <= i <= j - min_dis, j < hi  enumerated as generate_pair_wise does; writes
+ * out[p] for global pair indices p in [p_begin, p_end) (sigmoid applied when apply_sigmoid != 0). */
+int matcha_pair_score_range(const float* D, const float* S, const float* cls_w, const float* cls_b, int32_t d,
+                            int64_t lo, int64_t hi, int32_t min_dis, int64_t p_begin, int64_t p_end,
+                            int32_t apply_sigmoid, float* out, void* stream);
+int64_t matcha_pair_count(int64_t lo, int64_t hi, int32_t min_dis);
+
+/* ---------------------------------------------------------------------------------------------
+ * Building blocks exposed for tests (dense fp32 contractions used by the passes above).
+ *   form 0: C[M,N]  = A[M,K] . B[N,K]^T (+bias)      form 1: C[M,N] = A[M,K] . B[K,N]
+ *   form 2: C[M,N] += A[K,M]^T . B[K,N]
+ * impl 0 = SIMT fp32, 1 = tcgen05 (bf16x3 split, fp32 accumulate in TMEM)
+ * --------------------------------------------------------------------------------------------- */
+int matcha_gemm(int32_t form, int32_t impl, const float* A, const float* B, float* C, const float* bias,
+                int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATCHA_B200_H */

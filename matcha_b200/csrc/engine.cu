@@ -1,0 +1,623 @@
+// Host-side sequencing of the Hyper-SAGNN hot path behind the C ABI (include/matcha_b200.h):
+// parameter preparation, forward, backward, AdamW.  Every dense product is a GemmDesc handed to
+// the contraction kernels; everything else is a row-wise kernel from rowwise.cu.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "rowwise.cuh"
+
+namespace matcha {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return MATCHA_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return MATCHA_ERR_CUDA;
+}
+
+static int g_gemm_impl = -1;  // -1 = read MATCHA_GEMM_IMPL on first use; 0 = SIMT only; 1 = tcgen05 where eligible
+static int gemm_impl() {
+  if (g_gemm_impl < 0) {
+    const char* e = getenv("MATCHA_GEMM_IMPL");
+    g_gemm_impl = (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 1 : 0);
+  }
+  return g_gemm_impl;
+}
+static int run_gemm(const GemmDesc& d, cudaStream_t s) {
+  if (gemm_impl() == 1) {
+    bool handled = false;
+    int rc = launch_gemm_tc(d, s, &handled);
+    if (rc) return rc;
+    if (handled) return MATCHA_OK;
+  }
+  return launch_gemm_simt(d, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// derived-parameter layout
+// ------------------------------------------------------------------------------------------
+struct DerivedLayout {
+  int64_t wqkg, bqkg, bdyn, tables, total;  // float offsets
+};
+static __host__ __device__ DerivedLayout derived_layout() {
+  DerivedLayout l;
+  l.wqkg = 0;
+  l.bqkg = l.wqkg + (int64_t)kQKG * kD;
+  l.bdyn = l.bqkg + kQKG;
+  l.tables = l.bdyn + kD;
+  l.tables = (l.tables + 63) / 64 * 64;
+  const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
+  l.total = l.tables + 4 * table_floats;
+  return l;
+}
+enum { TAB_ENC0 = 0, TAB_ENC1 = 1, TAB_GW1 = 2, TAB_GW0 = 3 };
+static __host__ __device__ const GemmGroup* table_ptr(const float* derived, int which) {
+  const DerivedLayout l = derived_layout();
+  const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
+  return reinterpret_cast<const GemmGroup*>(derived + l.tables + which * table_floats);
+}
+
+// ------------------------------------------------------------------------------------------
+// parameter preparation kernels
+//   Q = LN_q(X) Wq^T / sqrt(d) = xhat (Wq diag(g_q) / sqrt(d))^T + Wq b_q / sqrt(d)
+//   K = xhat (Wk diag(g_k))^T                      (+ Wk b_k, constant over keys -> softmax-invariant, dropped)
+//   G_h = xhat (fc1_h Wv_h diag(g_v))^T            (fc1 folded into the value projection, per head)
+//   b_dyn = fc1.bias + sum_h fc1_h Wv_h b_v        (softmax rows sum to 1)
+// ------------------------------------------------------------------------------------------
+__global__ void prep_qk_kernel(const matcha_model_desc m) {
+  const DerivedLayout l = derived_layout();
+  const float* P = m.params;
+  float* W = m.derived + l.wqkg;
+  float* bq = m.derived + l.bqkg;
+  const float inv = rsqrtf((float)kD);
+  const int r = blockIdx.x;  // 0 .. 2*512-1
+  const int c = threadIdx.x; // 0 .. 63
+  if (r < kH * kD) {
+    const float w = P[m.off_wq + (int64_t)r * kD + c];
+    W[(int64_t)r * kD + c] = w * P[m.off_lnq_g + c] * inv;
+    float part = w * P[m.off_lnq_b + c] * inv;
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __shared__ float s2[2];
+    if ((c & 31) == 0) s2[c >> 5] = part;
+    __syncthreads();
+    if (c == 0) bq[r] = s2[0] + s2[1];
+  } else {
+    const int rk = r - kH * kD;
+    W[(int64_t)r * kD + c] = P[m.off_wk + (int64_t)rk * kD + c] * P[m.off_lnk_g + c];
+    if (c == 0) bq[r] = 0.f;
+  }
+}
+__global__ void prep_g_kernel(const matcha_model_desc m) {
+  // block = (head h), 64x64 output tile Wg_h[o][c] = sum_mm fc1[o][h*64+mm] * Wv[h*64+mm][c] * g_v[c]
+  const DerivedLayout l = derived_layout();
+  const float* P = m.params;
+  __shared__ float sF[kD][kD + 1];   // fc1_h[o][mm]
+  __shared__ float sV[kD][kD + 1];   // Wv_h[mm][c]
+  __shared__ float sVb[kD];          // (Wv_h b_v)[mm]
+  const int h = blockIdx.x, tid = threadIdx.x;  // 256 threads
+  for (int i = tid; i < kD * kD; i += blockDim.x) {
+    const int a = i / kD, b = i % kD;
+    sF[a][b] = P[m.off_fc1_w + (int64_t)a * (kH * kD) + h * kD + b];
+    sV[a][b] = P[m.off_wv + (int64_t)(h * kD + a) * kD + b];
+  }
+  __syncthreads();
+  if (tid < kD) {
+    float s = 0.f;
+    for (int c = 0; c < kD; ++c) s = fmaf(sV[tid][c], P[m.off_lnv_b + c], s);
+    sVb[tid] = s;
+  }
+  __syncthreads();
+  float* W = m.derived + l.wqkg + (int64_t)(2 * kH * kD + h * kD) * kD;
+  for (int i = tid; i < kD * kD; i += blockDim.x) {
+    const int o = i / kD, c = i % kD;
+    float s = 0.f;
+#pragma unroll 8
+    for (int mm = 0; mm < kD; ++mm) s = fmaf(sF[o][mm], sV[mm][c], s);
+    W[(int64_t)o * kD + c] = s * P[m.off_lnv_g + c];
+  }
+  if (tid < kD) {
+    m.derived[l.bqkg + 2 * kH * kD + h * kD + tid] = 0.f;
+    float s = 0.f;
+    for (int mm = 0; mm < kD; ++mm) s = fmaf(sF[tid][mm], sVb[mm], s);
+    if (h == 0) s += P[m.off_fc1_b + tid];
+    atomicAdd(m.derived + l.bdyn + tid, s);
+  }
+}
+__global__ void prep_tables_kernel(const matcha_model_desc m) {
+  const int c = threadIdx.x;
+  if (c >= m.n_chrom) return;
+  GemmGroup* t0 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_ENC0));
+  GemmGroup* t1 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_ENC1));
+  GemmGroup* t2 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_GW1));
+  GemmGroup* t3 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_GW0));
+  const int32_t n_c = (int32_t)(m.chrom_end[c] - m.chrom_start[c]);
+  GemmGroup g;
+  g.pad = 0;
+  // enc0: H0 = tanh(drop(F_c[id - start]) W0_c^T)
+  g.A = m.feat[c]; g.lda = m.feat_ld[c]; g.a_id_off = m.chrom_start[c];
+  g.B = m.params + m.off_w0[c]; g.ldb = n_c; g.C = nullptr; g.ldc = 0; g.dim = n_c;
+  t0[c] = g;
+  // enc1: E = H0 W1_c^T   (and, read as [K, N], dH0 = dE W1_c)
+  g.A = nullptr; g.lda = 0; g.a_id_off = 0; g.B = m.params + m.off_w1[c]; g.ldb = kD; g.dim = kD;
+  t1[c] = g;
+  if (m.grads) {
+    // dW1_c += dE^T H0
+    g.A = nullptr; g.B = nullptr; g.ldb = 0; g.C = m.grads + m.off_w1[c]; g.ldc = kD; g.dim = kD;
+    t2[c] = g;
+    // dW0_c += dH0pre^T drop(F_c[id - start])
+    g.B = m.feat[c]; g.ldb = m.feat_ld[c]; g.a_id_off = m.chrom_start[c];
+    g.C = m.grads + m.off_w0[c]; g.ldc = n_c; g.dim = n_c;
+    t3[c] = g;
+  }
+}
+
+// derived-parameter gradients -> gradients of the reference's own parameters
+__global__ void prep_bwd_qk_kernel(const matcha_model_desc m) {
+  const DerivedLayout l = derived_layout();
+  const float* P = m.params; float* G = m.grads;
+  const float* dW = m.derived_grad + l.wqkg;
+  const float* dbq = m.derived_grad + l.bqkg;
+  const float inv = rsqrtf((float)kD);
+  // one block per column c (64 blocks), threads stride over the 512 rows
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const float gq = P[m.off_lnq_g + c], bq = P[m.off_lnq_b + c], gk = P[m.off_lnk_g + c];
+  float a_gq = 0.f, a_bq = 0.f, a_gk = 0.f;
+  for (int r = tid; r < kH * kD; r += blockDim.x) {
+    const float wq = P[m.off_wq + (int64_t)r * kD + c], dwq = dW[(int64_t)r * kD + c], dcq = dbq[r];
+    atomicAdd(&G[m.off_wq + (int64_t)r * kD + c], (dwq * gq + dcq * bq) * inv);
+    a_gq = fmaf(dwq, wq * inv, a_gq);
+    a_bq = fmaf(dcq, wq * inv, a_bq);
+    const float wk = P[m.off_wk + (int64_t)r * kD + c], dwk = dW[(int64_t)(kH * kD + r) * kD + c];
+    atomicAdd(&G[m.off_wk + (int64_t)r * kD + c], dwk * gk);
+    a_gk = fmaf(dwk, wk, a_gk);
+  }
+  __shared__ float red[3][32];
+  for (int o = 16; o > 0; o >>= 1) {
+    a_gq += __shfl_xor_sync(0xffffffffu, a_gq, o);
+    a_bq += __shfl_xor_sync(0xffffffffu, a_bq, o);
+    a_gk += __shfl_xor_sync(0xffffffffu, a_gk, o);
+  }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = a_gq; red[1][tid >> 5] = a_bq; red[2][tid >> 5] = a_gk; }
+  __syncthreads();
+  if (tid == 0) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += red[0][i]; s1 += red[1][i]; s2 += red[2][i]; }
+    atomicAdd(&G[m.off_lnq_g + c], s0);
+    atomicAdd(&G[m.off_lnq_b + c], s1);
+    atomicAdd(&G[m.off_lnk_g + c], s2);   // layer_norm2.bias (key side): exactly zero gradient
+  }
+}
+__global__ void prep_bwd_g_kernel(const matcha_model_desc m) {
+  const DerivedLayout l = derived_layout();
+  const float* P = m.params; float* G = m.grads;
+  __shared__ float sF[kD][kD + 1];    // fc1_h[o][mm]
+  __shared__ float sV[kD][kD + 1];    // Wv_h[mm][c]
+  __shared__ float sdb[kD], svb[kD], sfb[kD];  // db_dyn[o], (fc1_h^T db_dyn)[mm], (Wv_h b_v)[mm]
+  const int h = blockIdx.x, tid = threadIdx.x;
+  const float* dWg = m.derived_grad + l.wqkg + (int64_t)(2 * kH * kD + h * kD) * kD;
+  for (int i = tid; i < kD * kD; i += blockDim.x) {
+    const int a = i / kD, b = i % kD;
+    sF[a][b] = P[m.off_fc1_w + (int64_t)a * (kH * kD) + h * kD + b];
+    sV[a][b] = P[m.off_wv + (int64_t)(h * kD + a) * kD + b];
+
+  }
+  if (tid < kD) sdb[tid] = m.derived_grad[l.bdyn + tid];
+  __syncthreads();
+  if (tid < kD) {
+    float s = 0.f, s2 = 0.f;
+    for (int o = 0; o < kD; ++o) s = fmaf(sF[o][tid], sdb[o], s);
+    for (int c = 0; c < kD; ++c) s2 = fmaf(sV[tid][c], P[m.off_lnv_b + c], s2);
+    svb[tid] = s; sfb[tid] = s2;
+    if (h == 0) atomicAdd(&G[m.off_fc1_b + tid], sdb[tid]);
+  }
+  __syncthreads();
+  for (int i = tid; i < kD * kD; i += blockDim.x) {
+    const int a = i / kD, b = i % kD;
+    // M_h[mm = a][c = b] = sum_o fc1_h[o][mm] dWg_h[o][c]
+    float mh = 0.f;
+#pragma unroll 8
+    for (int o = 0; o < kD; ++o) mh = fmaf(sF[o][a], __ldg(dWg + o * kD + b), mh);
+    const float gv = P[m.off_lnv_g + b], bv = P[m.off_lnv_b + b];
+    atomicAdd(&G[m.off_wv + (int64_t)(h * kD + a) * kD + b], mh * gv + svb[a] * bv);
+    atomicAdd(&G[m.off_lnv_g + b], mh * sV[a][b]);
+    atomicAdd(&G[m.off_lnv_b + b], svb[a] * sV[a][b]);
+    // dfc1[o = a][h*64 + mm = b] = sum_c dWg_h[o][c] Wv_h[mm][c] g_v[c] + db_dyn[o] (Wv_h b_v)[mm]
+    float df = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < kD; ++c) df = fmaf(__ldg(dWg + a * kD + c) * P[m.off_lnv_g + c], sV[b][c], df);
+    atomicAdd(&G[m.off_fc1_w + (int64_t)a * (kH * kD) + h * kD + b], df + sdb[a] * sfb[b]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace carving (identical on the sizing and the execution path)
+// ------------------------------------------------------------------------------------------
+struct Workspace {
+  int32_t *counts, *group_off, *cursor, *perm;
+  float *H0, *E, *V0, *X, *xhat, *rstd, *QKG, *U, *H1d, *H2, *pred, *recon;
+  float *dlogit, *dH2, *dXs, *dH1pre, *dU, *dQKG, *dxhat, *dP, *dV0, *dtE, *dE, *dH0pre;
+  int64_t pred_ld;
+  int64_t bytes;
+};
+static int64_t max_chrom_len(const matcha_model_desc* m) {
+  int64_t mx = 0;
+  for (int c = 0; c < m->n_chrom; ++c) mx = mx > (m->chrom_end[c] - m->chrom_start[c]) ? mx : (m->chrom_end[c] - m->chrom_start[c]);
+  return mx;
+}
+static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int training, void* base) {
+  Workspace w;
+  memset(&w, 0, sizeof(w));
+  const int64_t T = B * L;
+  char* p = reinterpret_cast<char*>(base);
+  int64_t off = 0;
+  auto take = [&](int64_t nbytes) -> void* {
+    void* r = p ? (void*)(p + off) : nullptr;
+    off += (nbytes + 255) / 256 * 256;
+    return r;
+  };
+  w.counts = (int32_t*)take(sizeof(int32_t) * (MATCHA_MAX_CHROM + 2));
+  w.group_off = (int32_t*)take(sizeof(int32_t) * (MATCHA_MAX_CHROM + 2));
+  w.cursor = (int32_t*)take(sizeof(int32_t) * (MATCHA_MAX_CHROM + 2));
+  w.perm = (int32_t*)take(sizeof(int32_t) * (T + 1));
+  w.recon = (float*)take(sizeof(float) * 4);
+  const int64_t row = sizeof(float) * T * kD;
+  w.H0 = (float*)take(row); w.E = (float*)take(row); w.V0 = (float*)take(row); w.X = (float*)take(row);
+  w.xhat = (float*)take(row); w.rstd = (float*)take(sizeof(float) * (T + 1));
+  w.QKG = (float*)take(sizeof(float) * T * kQKG);
+  w.U = (float*)take(row); w.H1d = (float*)take(row); w.H2 = (float*)take(row);
+  w.pred_ld = m->inter ? (max_chrom_len(m) + 3) / 4 * 4 : 0;
+  w.pred = (float*)take(sizeof(float) * T * (w.pred_ld > 0 ? w.pred_ld : 1));
+  if (training) {
+    w.dlogit = (float*)take(sizeof(float) * (B + 1));
+    w.dH2 = (float*)take(row); w.dXs = (float*)take(row); w.dH1pre = (float*)take(row); w.dU = (float*)take(row);
+    w.dQKG = (float*)take(sizeof(float) * T * kQKG);
+    w.dxhat = (float*)take(row); w.dP = (float*)take(row); w.dV0 = (float*)take(row); w.dtE = (float*)take(row);
+    w.dE = (float*)take(row); w.dH0pre = (float*)take(row);
+  }
+  w.bytes = off;
+  return w;
+}
+
+static int validate(const matcha_model_desc* m) {
+  MATCHA_REQUIRE(m != nullptr, "model descriptor is NULL");
+  if (m->d != kD || m->n_head != kH) {
+    set_error("this build supports embed_dim=%d n_head=%d (got %d, %d)", kD, kH, m->d, m->n_head);
+    return MATCHA_ERR_UNSUPPORTED;
+  }
+  MATCHA_REQUIRE(m->n_chrom >= 1 && m->n_chrom <= MATCHA_MAX_CHROM, "n_chrom=%d out of range", m->n_chrom);
+  MATCHA_REQUIRE(m->params && m->derived, "params / derived buffers missing");
+  MATCHA_REQUIRE(m->attr_dim >= 1 && m->attr_table, "attribute table missing");
+  for (int c = 0; c < m->n_chrom; ++c) {
+    if (!m->feat[c]) {
+      set_error("chromosome %d: dense feature rows missing (CSR-only features are not wired into this entry point)", c);
+      return MATCHA_ERR_UNSUPPORTED;
+    }
+  }
+  return MATCHA_OK;
+}
+
+static GemmDesc gemm_base(int form, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                          int64_t ldb, float* C, int64_t ldc) {
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.form = form; d.M = M; d.N = N; d.K = K; d.A = A; d.lda = lda; d.B = B; d.ldb = ldb; d.C = C; d.ldc = ldc;
+  d.out_scale = 1.f;
+  return d;
+}
+
+static ChromMeta chrom_meta(const matcha_model_desc* m) {
+  ChromMeta cm;
+  cm.n = m->n_chrom;
+  for (int c = 0; c < m->n_chrom; ++c) { cm.start[c] = m->chrom_start[c]; cm.end[c] = m->chrom_end[c]; }
+  return cm;
+}
+
+// encoder: bucket tokens, two grouped contractions.  Outputs H0, E (zero rows for pads)
+static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, int training, uint64_t seed,
+                       const Workspace& w, float* E_out, cudaStream_t s) {
+  int rc;
+  if ((rc = launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(w.H0, 0, sizeof(float) * T * kD, s), "memset H0"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * kD, s), "memset E"))) return rc;
+  GemmDesc d = gemm_base(FORM_NT, 0, kD, 0, nullptr, 0, nullptr, 0, w.H0, kD);
+  d.perm = w.perm; d.a_ids = x; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, TAB_ENC0);
+  d.group_off = w.group_off; d.total_rows = T; d.epi_act = 1;
+  if (training && m->p_feature > 0.f) { d.drop_on = 1; d.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
+  if ((rc = run_gemm(d, s))) return rc;
+  GemmDesc e = gemm_base(FORM_NT, 0, kD, kD, w.H0, kD, nullptr, 0, E_out, kD);
+  e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, TAB_ENC1);
+  e.group_off = w.group_off; e.total_rows = T;
+  return run_gemm(e, s);
+}
+
+// X = tanh(next_w(E + attribute_nn(attr[id]))), xhat, rstd, QKG
+static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, const Workspace& w, cudaStream_t s) {
+  int rc;
+  const float* P = m->params;
+  const DerivedLayout l = derived_layout();
+  GemmDesc a = gemm_base(FORM_NT, T, kD, m->attr_dim, m->attr_table, m->attr_dim, P + m->off_attr_w, m->attr_dim, w.V0, kD);
+  a.a_ids = x; a.bias = P + m->off_attr_b; a.addend = w.E; a.ld_add = kD;
+  if ((rc = run_gemm(a, s))) return rc;
+  GemmDesc b = gemm_base(FORM_NT, T, kD, kD, w.V0, kD, P + m->off_next_w, kD, w.X, kD);
+  b.bias = P + m->off_next_b; b.epi_act = 1;
+  if ((rc = run_gemm(b, s))) return rc;
+  if ((rc = launch_ln_fwd(w.X, w.xhat, w.rstd, T, s))) return rc;
+  GemmDesc q = gemm_base(FORM_NT, T, kQKG, kD, w.xhat, kD, m->derived + l.wqkg, kD, w.QKG, kQKG);
+  q.bias = m->derived + l.bqkg;
+  return run_gemm(q, s);
+}
+
+// pff_n1 (two 1x1 convolutions with residual), input U, output H2 (pre-LayerNorm)
+static int run_pff(const matcha_model_desc* m, int64_t T, int training, uint64_t seed, const Workspace& w, cudaStream_t s) {
+  int rc;
+  const float* P = m->params;
+  GemmDesc a = gemm_base(FORM_NT, T, kD, kD, w.U, kD, P + m->off_pff_w0, kD, w.H1d, kD);
+  a.bias = P + m->off_pff_b0; a.epi_act = 1;
+  if (training && m->p_pff > 0.f) { a.epi_drop = 1; a.edrop = make_drop(seed, SITE_PFF, m->p_pff, true); }
+  if ((rc = run_gemm(a, s))) return rc;
+  GemmDesc b = gemm_base(FORM_NT, T, kD, kD, w.H1d, kD, P + m->off_pff_w1, kD, w.H2, kD);
+  b.bias = P + m->off_pff_b1; b.addend = w.U; b.ld_add = kD;
+  return run_gemm(b, s);
+}
+
+static ScoreParams score_params(const matcha_model_desc* m) {
+  const float* P = m->params;
+  ScoreParams p;
+  p.pff_g = P + m->off_pff_g; p.pff_b = P + m->off_pff_b; p.ln1_g = P + m->off_ln1_g; p.ln1_b = P + m->off_ln1_b;
+  p.ln2_g = P + m->off_ln2_g; p.ln2_b = P + m->off_ln2_b; p.cls_w = P + m->off_cls_w; p.cls_b = P + m->off_cls_b;
+  return p;
+}
+
+}  // namespace matcha
+
+using namespace matcha;
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* matcha_last_error(void) { return g_err; }
+int matcha_version(void) { return 100; }
+
+int64_t matcha_derived_elems(const matcha_model_desc* m) {
+  (void)m;
+  return derived_layout().total;
+}
+
+int64_t matcha_workspace_bytes(const matcha_model_desc* m, int64_t B, int32_t L, int32_t training) {
+  if (!m || B < 0 || L < 1) return -1;
+  return carve(m, B, L, training, nullptr).bytes + 256;
+}
+
+int matcha_prepare(const matcha_model_desc* m, void* stream) {
+  int rc = validate(m);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const DerivedLayout l = derived_layout();
+  if ((rc = check_cuda(cudaMemsetAsync(m->derived + l.bdyn, 0, sizeof(float) * kD, s), "memset b_dyn"))) return rc;
+  prep_qk_kernel<<<2 * kH * kD, kD, 0, s>>>(*m);
+  MATCHA_CHECK_LAUNCH("prep_qk");
+  prep_g_kernel<<<kH, 256, 0, s>>>(*m);
+  MATCHA_CHECK_LAUNCH("prep_g");
+  prep_tables_kernel<<<1, MATCHA_MAX_CHROM, 0, s>>>(*m);
+  MATCHA_CHECK_LAUNCH("prep_tables");
+  return MATCHA_OK;
+}
+
+int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int32_t L, int32_t training,
+                   uint64_t seed, int32_t random_chrom, float* logits, float* recon, void* workspace,
+                   int64_t workspace_bytes, void* stream) {
+  int rc = validate(m);
+  if (rc) return rc;
+  MATCHA_REQUIRE(x && logits && workspace, "matcha_forward: NULL argument");
+  MATCHA_REQUIRE(L >= 2 && L <= 6, "matcha_forward: padded width L=%d unsupported (2..6)", L);
+  MATCHA_REQUIRE(random_chrom < m->n_chrom, "random_chrom=%d out of range", random_chrom);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B == 0) return MATCHA_OK;
+  uintptr_t base = ((uintptr_t)workspace + 255) / 256 * 256;
+  Workspace w = carve(m, B, L, training, (void*)base);
+  MATCHA_REQUIRE((int64_t)(base - (uintptr_t)workspace) + w.bytes <= workspace_bytes,
+                 "workspace too small: need %lld bytes", (long long)(w.bytes + 256));
+  const int64_t T = B * L;
+  const DerivedLayout l = derived_layout();
+
+  if ((rc = run_encoder(m, x, T, training, seed, w, w.E, s))) return rc;
+  {
+    if ((rc = check_cuda(cudaMemsetAsync(w.recon, 0, sizeof(float), s), "memset recon"))) return rc;
+    if (random_chrom >= 0 && m->inter) {
+      const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom];
+      GemmDesc p = gemm_base(FORM_NT, T, re - rs, kD, w.E, kD, m->params + m->off_rw[random_chrom], kD, w.pred, w.pred_ld);
+      p.a_act = 1; p.bias = m->params + m->off_rb[random_chrom];
+      if ((rc = run_gemm(p, s))) return rc;
+      if ((rc = launch_recon_diff(w.pred, w.pred_ld, x, T, m->inter, m->inter_ld, rs, re, w.counts, random_chrom,
+                                  m->n_chrom, w.recon, s))) return rc;
+    }
+    if (recon && (rc = check_cuda(cudaMemcpyAsync(recon, w.recon, sizeof(float), cudaMemcpyDeviceToDevice, s), "copy recon")))
+      return rc;
+  }
+  if ((rc = run_mix_qkg(m, x, T, w, s))) return rc;
+  DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, training != 0);
+  if ((rc = launch_attn_fwd(w.QKG, x, m->derived + l.bdyn, w.U, B, L, dattn, s))) return rc;
+  if ((rc = run_pff(m, T, training, seed, w, s))) return rc;
+  return launch_score_fwd(w.H2, w.xhat, x, score_params(m), logits, B, L, s);
+}
+
+int matcha_bce_loss(const float* logits, const float* y, const float* wgt, int64_t B, float alpha, float beta,
+                    const float* recon, float* dlogit, float* loss_out, void* stream) {
+  MATCHA_REQUIRE(logits && y && wgt && dlogit && loss_out && B > 0, "matcha_bce_loss: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = check_cuda(cudaMemsetAsync(loss_out, 0, 3 * sizeof(float), s), "memset loss"))) return rc;
+  if ((rc = launch_bce(logits, y, wgt, alpha, dlogit, loss_out, B, s))) return rc;
+  return launch_finalize_loss(loss_out, recon, alpha, beta, s);
+}
+
+int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int32_t L, uint64_t seed,
+                    int32_t random_chrom, const float* dlogit, float beta, int32_t* active, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
+  int rc = validate(m);
+  if (rc) return rc;
+  MATCHA_REQUIRE(m->grads && m->derived_grad, "matcha_backward: grads / derived_grad buffers missing");
+  MATCHA_REQUIRE(x && dlogit && workspace, "matcha_backward: NULL argument");
+  MATCHA_REQUIRE(L >= 2 && L <= 6, "matcha_backward: padded width L=%d unsupported (2..6)", L);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B == 0) return MATCHA_OK;
+  uintptr_t base = ((uintptr_t)workspace + 255) / 256 * 256;
+  Workspace w = carve(m, B, L, 1, (void*)base);
+  MATCHA_REQUIRE((int64_t)(base - (uintptr_t)workspace) + w.bytes <= workspace_bytes,
+                 "workspace too small: need %lld bytes", (long long)(w.bytes + 256));
+  const int64_t T = B * L;
+  const DerivedLayout l = derived_layout();
+  const float* P = m->params;
+  float* G = m->grads;
+  float* DG = m->derived_grad;
+  const bool recon_on = random_chrom >= 0 && m->inter && beta != 0.f;
+
+  if ((rc = check_cuda(cudaMemsetAsync(DG, 0, sizeof(float) * l.tables, s), "memset derived_grad"))) return rc;
+
+  // scorer + pff LayerNorm backward
+  ScoreGrads sg;
+  sg.pff_g = G + m->off_pff_g; sg.pff_b = G + m->off_pff_b; sg.ln1_g = G + m->off_ln1_g; sg.ln1_b = G + m->off_ln1_b;
+  sg.ln2_g = G + m->off_ln2_g; sg.ln2_b = G + m->off_ln2_b; sg.cls_w = G + m->off_cls_w; sg.cls_b = G + m->off_cls_b;
+  if ((rc = launch_score_bwd(w.H2, w.xhat, w.rstd, x, score_params(m), dlogit, w.dH2, w.dXs, sg, B, L, s))) return rc;
+
+  // pff_n1 backward
+  DropCfg dpff = make_drop(seed, SITE_PFF, m->p_pff, true);
+  {
+    GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dH2, kD, w.H1d, kD, G + m->off_pff_w1, kD);
+    d.colsum = G + m->off_pff_b1; d.colsum_n = kD;
+    if ((rc = run_gemm(d, s))) return rc;
+    GemmDesc e = gemm_base(FORM_NN, T, kD, kD, w.dH2, kD, P + m->off_pff_w1, kD, w.dH1pre, kD);
+    e.epi_act = 2; e.aux = w.H1d; e.ld_aux = kD;
+    if (m->p_pff > 0.f) { e.epi_drop = 1; e.edrop = dpff; }
+    if ((rc = run_gemm(e, s))) return rc;
+    GemmDesc f = gemm_base(FORM_TN, kD, kD, T, w.dH1pre, kD, w.U, kD, G + m->off_pff_w0, kD);
+    f.colsum = G + m->off_pff_b0; f.colsum_n = kD;
+    if ((rc = run_gemm(f, s))) return rc;
+    GemmDesc g = gemm_base(FORM_NN, T, kD, kD, w.dH1pre, kD, P + m->off_pff_w0, kD, w.dU, kD);
+    g.addend = w.dH2; g.ld_add = kD;
+    if ((rc = run_gemm(g, s))) return rc;
+  }
+  // attention backward
+  DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, true);
+  if ((rc = launch_attn_bwd(w.QKG, w.dU, x, w.dQKG, DG + l.bdyn, B, L, dattn, s))) return rc;
+  {
+    GemmDesc d = gemm_base(FORM_TN, kQKG, kD, T, w.dQKG, kQKG, w.xhat, kD, DG + l.wqkg, kD);
+    d.colsum = DG + l.bqkg; d.colsum_n = kH * kD;
+    if ((rc = run_gemm(d, s))) return rc;
+    GemmDesc e = gemm_base(FORM_NN, T, kD, kQKG, w.dQKG, kQKG, m->derived + l.wqkg, kD, w.dxhat, kD);
+    if ((rc = run_gemm(e, s))) return rc;
+  }
+  if ((rc = launch_ln_tanh_bwd(w.dxhat, w.dXs, w.xhat, w.rstd, w.X, w.dP, T, s))) return rc;
+  {
+    GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dP, kD, w.V0, kD, G + m->off_next_w, kD);
+    d.colsum = G + m->off_next_b; d.colsum_n = kD;
+    if ((rc = run_gemm(d, s))) return rc;
+    GemmDesc e = gemm_base(FORM_NN, T, kD, kD, w.dP, kD, P + m->off_next_w, kD, w.dV0, kD);
+    if ((rc = run_gemm(e, s))) return rc;
+    GemmDesc f = gemm_base(FORM_TN, kD, m->attr_dim, T, w.dV0, kD, m->attr_table, m->attr_dim, G + m->off_attr_w, m->attr_dim);
+    f.b_ids = x; f.colsum = G + m->off_attr_b; f.colsum_n = kD;
+    if ((rc = run_gemm(f, s))) return rc;
+  }
+  // reconstruction head backward (gdiff was left in w.pred by the forward pass, without the beta factor)
+  const float* dtE = nullptr;
+  if (recon_on) {
+    const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom], nr = re - rs;
+    GemmDesc d = gemm_base(FORM_TN, nr, kD, T, w.pred, w.pred_ld, w.E, kD, G + m->off_rw[random_chrom], kD);
+    d.b_act = 1; d.out_scale = beta; d.colsum = G + m->off_rb[random_chrom]; d.colsum_n = nr;
+    if ((rc = run_gemm(d, s))) return rc;
+    GemmDesc e = gemm_base(FORM_NN, T, kD, nr, w.pred, w.pred_ld, P + m->off_rw[random_chrom], kD, w.dtE, kD);
+    if ((rc = run_gemm(e, s))) return rc;
+    dtE = w.dtE;
+  }
+  if ((rc = launch_enc_combine_bwd(w.dV0, dtE, w.E, beta, w.dE, T * kD, s))) return rc;
+  // encoder backward (grouped by chromosome; token lists from the forward pass are still in the workspace)
+  {
+    GemmDesc d = gemm_base(FORM_TN, kD, kD, 0, w.dE, kD, w.H0, kD, nullptr, kD);
+    d.perm = w.perm; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, TAB_GW1); d.group_off = w.group_off;
+    d.total_rows = T; d.max_group_dim = kD;
+    if ((rc = run_gemm(d, s))) return rc;
+    GemmDesc e = gemm_base(FORM_NN, 0, kD, kD, w.dE, kD, nullptr, 0, w.dH0pre, kD);
+    e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, TAB_ENC1); e.group_off = w.group_off;
+    e.total_rows = T; e.epi_act = 2; e.aux = w.H0; e.ld_aux = kD;
+    if ((rc = run_gemm(e, s))) return rc;
+    GemmDesc f = gemm_base(FORM_TN, kD, 0, 0, w.dH0pre, kD, nullptr, 0, nullptr, 0);
+    f.perm = w.perm; f.b_ids = x; f.ngroups = m->n_chrom; f.groups = table_ptr(m->derived, TAB_GW0);
+    f.group_off = w.group_off; f.total_rows = T; f.max_group_dim = max_chrom_len(m);
+    if (m->p_feature > 0.f) { f.drop_on = 2; f.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
+    if ((rc = run_gemm(f, s))) return rc;
+  }
+  // derived -> reference parameters
+  prep_bwd_qk_kernel<<<kD, 256, 0, s>>>(*m);
+  MATCHA_CHECK_LAUNCH("prep_bwd_qk");
+  prep_bwd_g_kernel<<<kH, 256, 0, s>>>(*m);
+  MATCHA_CHECK_LAUNCH("prep_bwd_g");
+  if (active) {
+    if ((rc = launch_active_flags(w.counts, m->n_chrom, recon_on ? random_chrom : -1, T, active, s))) return rc;
+  }
+  return MATCHA_OK;
+}
+
+int matcha_node_embeddings(const matcha_model_desc* m, const int64_t* ids, int64_t T, float* out, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  int rc = validate(m);
+  if (rc) return rc;
+  MATCHA_REQUIRE(ids && out && workspace, "matcha_node_embeddings: NULL argument");
+  if (T == 0) return MATCHA_OK;
+  uintptr_t base = ((uintptr_t)workspace + 255) / 256 * 256;
+  Workspace w = carve(m, T, 1, 0, (void*)base);
+  MATCHA_REQUIRE((int64_t)(base - (uintptr_t)workspace) + w.bytes <= workspace_bytes,
+                 "workspace too small: need %lld bytes", (long long)(w.bytes + 256));
+  return run_encoder(m, ids, T, 0, 0, w, out, (cudaStream_t)stream);
+}
+
+int matcha_pair_tables(const matcha_model_desc* m, float* D, float* S, void* workspace, int64_t workspace_bytes,
+                       void* stream) {
+  int rc = validate(m);
+  if (rc) return rc;
+  MATCHA_REQUIRE(D && S && workspace, "matcha_pair_tables: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t T = m->n_nodes + 1;
+  uintptr_t base = ((uintptr_t)workspace + 255) / 256 * 256;
+  Workspace w = carve(m, T, 1, 0, (void*)base);
+  MATCHA_REQUIRE((int64_t)(base - (uintptr_t)workspace) + w.bytes <= workspace_bytes,
+                 "workspace too small: need %lld bytes", (long long)(w.bytes + 256));
+  // node ids 0..N are materialised in the H1d area (T*64 floats >= T int64); they are last read by
+  // run_mix_qkg, before run_pff overwrites H1d
+  int64_t* ids = reinterpret_cast<int64_t*>(w.H1d);
+  if ((rc = launch_iota_i64(ids, T, s))) return rc;
+  const DerivedLayout l = derived_layout();
+  if ((rc = run_encoder(m, ids, T, 0, 0, w, w.E, s))) return rc;
+  if ((rc = run_mix_qkg(m, ids, T, w, s))) return rc;
+  if ((rc = launch_pair_u(w.QKG, m->derived + l.bdyn, w.U, T, s))) return rc;
+  if ((rc = run_pff(m, T, 0, 0, w, s))) return rc;
+  return launch_pair_ds(w.H2, w.xhat, score_params(m), D, S, T, s);
+}
+
+int matcha_gemm(int32_t form, int32_t impl, const float* A, const float* B, float* C, const float* bias, int64_t M,
+                int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, void* stream) {
+  MATCHA_REQUIRE(form >= 0 && form <= 2 && A && B && C, "matcha_gemm: bad arguments");
+  GemmDesc d = gemm_base(form, M, N, K, A, lda, B, ldb, C, ldc);
+  d.bias = bias;
+  if (impl == 1) {
+    bool handled = false;
+    int rc = launch_gemm_tc(d, (cudaStream_t)stream, &handled);
+    if (rc) return rc;
+    if (!handled) { set_error("matcha_gemm: shape not eligible for the tcgen05 path"); return MATCHA_ERR_UNSUPPORTED; }
+    return MATCHA_OK;
+  }
+  return launch_gemm_simt(d, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,662 @@
+// Row-wise kernels of the Hyper-SAGNN hot path: everything that is not a dense contraction.
+// Layout rule: one HALF-WARP owns one token row (64 floats = 16 lanes x float4, one coalesced 256 B
+// access) or one hyperedge (its L <= 8 rows in turn); row reductions are 4 xor-shuffles.
+#include "rowwise.cuh"
+
+namespace matcha {
+namespace {
+
+constexpr int kBlock = 256;
+constexpr float kLnEps = 1e-5f;
+
+__device__ __forceinline__ float red16(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+__device__ __forceinline__ float sum4(float4 a) { return (a.x + a.y) + (a.z + a.w); }
+__device__ __forceinline__ float4 f4(float s) { return make_float4(s, s, s, s); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 fma4(float s, float4 a, float4 c) {
+  return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w));
+}
+
+struct LnOut { float4 xh; float rstd; };
+// LayerNorm statistics of one 64-wide row spread over 16 lanes (biased variance, eps 1e-5)
+__device__ __forceinline__ LnOut ln_norm(float4 v) {
+  const float mean = red16(sum4(v)) * (1.0f / kD);
+  const float4 c = v - f4(mean);
+  const float var = red16(dot4(c, c)) * (1.0f / kD);
+  LnOut o;
+  o.rstd = 1.0f / sqrtf(var + kLnEps);
+  o.xh = c * o.rstd;
+  return o;
+}
+// dx of y = LN(x) given gy = dy * gamma, normalised row xh and rstd
+__device__ __forceinline__ float4 ln_bwd(float4 gy, float4 xh, float rstd) {
+  const float m1 = red16(sum4(gy)) * (1.0f / kD);
+  const float m2 = red16(dot4(gy, xh)) * (1.0f / kD);
+  return (gy - f4(m1) - xh * m2) * rstd;
+}
+
+// block-level column reduction: every thread holds a float4 for columns [4*hl, 4*hl+4); add to dst[64]
+__device__ __forceinline__ void block_colsum_atomic(float4 v, float* smem64, float* dst) {
+  const int lane = threadIdx.x & 31, hl = threadIdx.x & 15;
+  v.x += __shfl_xor_sync(0xffffffffu, v.x, 16);
+  v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+  v.z += __shfl_xor_sync(0xffffffffu, v.z, 16);
+  v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
+  if (threadIdx.x < kD) smem64[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (lane < 16) {
+    atomicAdd(&smem64[hl * 4 + 0], v.x);
+    atomicAdd(&smem64[hl * 4 + 1], v.y);
+    atomicAdd(&smem64[hl * 4 + 2], v.z);
+    atomicAdd(&smem64[hl * 4 + 3], v.w);
+  }
+  __syncthreads();
+  if (threadIdx.x < kD && dst) atomicAdd(dst + threadIdx.x, smem64[threadIdx.x]);
+  __syncthreads();
+}
+
+inline int grid_for_halfwarps(int64_t n, int cap_blocks) {
+  int64_t blocks = (n * 16 + kBlock - 1) / kBlock;
+  if (blocks < 1) blocks = 1;
+  if (blocks > cap_blocks) blocks = cap_blocks;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------
+// token bucketing by chromosome (replaces the per-chromosome mask/nonzero loop of Modules.py:180-188)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int chrom_of(const ChromMeta& cm, int64_t id) {
+  if (id <= 0) return cm.n;  // pad bucket
+  for (int c = 0; c < cm.n; ++c)
+    if (id >= cm.start[c] && id < cm.end[c]) return c;
+  return cm.n;               // ids outside every range behave like padding (zero encoder output)
+}
+__global__ void bucket_count_kernel(const int64_t* __restrict__ x, int64_t T, const ChromMeta cm, int32_t* counts) {
+  __shared__ int32_t h[MATCHA_MAX_CHROM + 1];
+  for (int i = threadIdx.x; i <= cm.n; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&h[chrom_of(cm, x[t])], 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i <= cm.n; i += blockDim.x)
+    if (h[i]) atomicAdd(&counts[i], h[i]);
+}
+__global__ void bucket_scan_kernel(const int32_t* counts, int n, int32_t* group_off, int32_t* cursor) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int32_t acc = 0;
+    for (int c = 0; c < n; ++c) { group_off[c] = acc; cursor[c] = acc; acc += counts[c]; }
+    group_off[n] = acc;
+  }
+}
+__global__ void bucket_scatter_kernel(const int64_t* __restrict__ x, int64_t T, const ChromMeta cm, int32_t* cursor,
+                                      int32_t* perm) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+    int c = chrom_of(cm, x[t]);
+    if (c < cm.n) perm[atomicAdd(&cursor[c], 1)] = (int32_t)t;
+  }
+}
+__global__ void active_flags_kernel(const int32_t* counts, int n_chrom, int rchrom, int64_t T, int32_t* active) {
+  int c = threadIdx.x;
+  if (c < n_chrom) {
+    active[c] = counts[c] > 0;
+    int64_t elig = T - counts[n_chrom] - (rchrom >= 0 ? counts[rchrom] : 0);
+    active[n_chrom + c] = (c == rchrom && elig > 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm statistics of X (shared by MHA layer_norm1/2/3 and Classifier.layer_norm2: same input row)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) ln_fwd_kernel(const float* __restrict__ X, float* __restrict__ xhat,
+                                                         float* __restrict__ rstd, int64_t T) {
+  const int hl = threadIdx.x & 15;
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int64_t iters = (T + nhw - 1) / nhw;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t t = hw0 + it * nhw;
+    const bool valid = t < T;
+    const int64_t tt = valid ? t : T - 1;
+    LnOut o = ln_norm(ldg4(X + tt * kD + hl * 4));
+    if (valid) {
+      st4(xhat + t * kD + hl * 4, o.xh);
+      if (hl == 0) rstd[t] = o.rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// attention over the L tokens of one hyperedge (Modules.py:448-460, 563-572 with fc1 folded into G)
+//   S_h[i][j] = Q_h[i].K_h[j]  (1/sqrt(d) and LayerNorm affine folded into the projection),
+//   diagonal masked, softmax over j (pads are live keys), dyn_i = b_dyn + sum_h sum_j A_h[i][j] G_h[j]
+// ------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void softmax_offdiag(float (&A)[L][L]) {
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int j = 0; j < L; ++j) if (j != i) mx = fmaxf(mx, A[i][j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < L; ++j) if (j != i) { A[i][j] = expf(A[i][j] - mx); sum += A[i][j]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int j = 0; j < L; ++j) A[i][j] = (j != i) ? A[i][j] * inv : 0.f;
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kBlock) attn_fwd_kernel(const float* __restrict__ QKG, const int64_t* __restrict__ x,
+                                                           const float* __restrict__ b_dyn, float* __restrict__ U,
+                                                           int64_t B, const DropCfg drop) {
+  const int hl = threadIdx.x & 15;
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int64_t iters = (B + nhw - 1) / nhw;
+  const float4 bd = ldg4(b_dyn + hl * 4);
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t b = hw0 + it * nhw;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : B - 1;
+    const float* base = QKG + bb * L * kQKG + hl * 4;
+    float4 o[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) o[i] = bd;
+#pragma unroll 1
+    for (int h = 0; h < kH; ++h) {
+      float4 q[L], k[L];
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+        q[i] = ldg4(base + i * kQKG + h * kD);
+        k[i] = ldg4(base + i * kQKG + kH * kD + h * kD);
+      }
+      float A[L][L];
+#pragma unroll
+      for (int i = 0; i < L; ++i)
+#pragma unroll
+        for (int j = 0; j < L; ++j) A[i][j] = (i != j) ? red16(dot4(q[i], k[j])) : 0.f;
+      softmax_offdiag<L>(A);
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        const float4 g = ldg4(base + j * kQKG + 2 * kH * kD + h * kD);
+#pragma unroll
+        for (int i = 0; i < L; ++i) if (i != j) o[i] = fma4(A[i][j], g, o[i]);
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+        const int64_t t = b * L + i;
+        const float m = x[t] != 0 ? 1.f : 0.f;                       // non_pad_mask (Modules.py:614)
+        float4 v = drop_apply4(drop, (uint64_t)t, (uint32_t)(hl * 4), o[i]);   // dropout after fc1 (:572)
+        st4(U + t * kD + hl * 4, v * m);
+      }
+    }
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kBlock) attn_bwd_kernel(const float* __restrict__ QKG, const float* __restrict__ dU,
+                                                           const int64_t* __restrict__ x, float* __restrict__ dQKG,
+                                                           float* __restrict__ db_dyn, int64_t B, const DropCfg drop) {
+  __shared__ float red[kD];
+  const int hl = threadIdx.x & 15;
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int64_t iters = (B + nhw - 1) / nhw;
+  float4 acc_b = f4(0.f);
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t b = hw0 + it * nhw;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : B - 1;
+    const float* base = QKG + bb * L * kQKG + hl * 4;
+    float* dbase = dQKG + bb * L * kQKG + hl * 4;
+    float4 dd[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int64_t t = bb * L + i;
+      const float m = x[t] != 0 ? 1.f : 0.f;
+      dd[i] = ldg4(dU + t * kD + hl * 4) * drop_factor4(drop, (uint64_t)t, (uint32_t)(hl * 4)) * m;
+      if (valid) acc_b = acc_b + dd[i];
+    }
+#pragma unroll 1
+    for (int h = 0; h < kH; ++h) {
+      float4 q[L], k[L], g[L];
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+        q[i] = ldg4(base + i * kQKG + h * kD);
+        k[i] = ldg4(base + i * kQKG + kH * kD + h * kD);
+        g[i] = ldg4(base + i * kQKG + 2 * kH * kD + h * kD);
+      }
+      float A[L][L], dA[L][L];
+#pragma unroll
+      for (int i = 0; i < L; ++i)
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          A[i][j] = (i != j) ? red16(dot4(q[i], k[j])) : 0.f;
+          dA[i][j] = (i != j) ? red16(dot4(dd[i], g[j])) : 0.f;
+        }
+      softmax_offdiag<L>(A);
+      // dG_h[j] = sum_i A[i][j] * ddyn_i
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        float4 dg = f4(0.f);
+#pragma unroll
+        for (int i = 0; i < L; ++i) if (i != j) dg = fma4(A[i][j], dd[i], dg);
+        if (valid) st4(dbase + j * kQKG + 2 * kH * kD + h * kD, dg);
+      }
+      // softmax backward -> dS (stored in dA)
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < L; ++j) s = fmaf(A[i][j], dA[i][j], s);
+#pragma unroll
+        for (int j = 0; j < L; ++j) dA[i][j] = A[i][j] * (dA[i][j] - s);
+      }
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+        float4 dq = f4(0.f), dk = f4(0.f);
+#pragma unroll
+        for (int j = 0; j < L; ++j) if (j != i) { dq = fma4(dA[i][j], k[j], dq); dk = fma4(dA[j][i], q[j], dk); }
+        if (valid) {
+          st4(dbase + i * kQKG + h * kD, dq);
+          st4(dbase + i * kQKG + kH * kD + h * kD, dk);
+        }
+      }
+    }
+  }
+  block_colsum_atomic(acc_b, red, db_dyn);
+}
+
+// ------------------------------------------------------------------------------------------
+// scorer: pff_n1 LayerNorm + mask, Classifier.layer_norm1/2, (dyn - static)^2, Conv1d(d->1), masked mean
+// (Modules.py:373-374, 614, 290-311)
+// ------------------------------------------------------------------------------------------
+struct ScoreVec { float4 gp, bp, g1, b1, g2, b2, w; float cb; };
+__device__ __forceinline__ ScoreVec load_score_params(const ScoreParams& p, int hl) {
+  ScoreVec v;
+  v.gp = ldg4(p.pff_g + hl * 4); v.bp = ldg4(p.pff_b + hl * 4);
+  v.g1 = ldg4(p.ln1_g + hl * 4); v.b1 = ldg4(p.ln1_b + hl * 4);
+  v.g2 = ldg4(p.ln2_g + hl * 4); v.b2 = ldg4(p.ln2_b + hl * 4);
+  v.w = ldg4(p.cls_w + hl * 4);  v.cb = __ldg(p.cls_b);
+  return v;
+}
+
+template <int L>
+__global__ void __launch_bounds__(kBlock) score_fwd_kernel(const float* __restrict__ H2, const float* __restrict__ xhat,
+                                                            const int64_t* __restrict__ x, const ScoreParams p,
+                                                            float* __restrict__ logits, int64_t B) {
+  const int hl = threadIdx.x & 15;
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int64_t iters = (B + nhw - 1) / nhw;
+  const ScoreVec sv = load_score_params(p, hl);
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t b = hw0 + it * nhw;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : B - 1;
+    float zsum = 0.f, msum = 0.f;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int64_t t = bb * L + i;
+      const float m = x[t] != 0 ? 1.f : 0.f;
+      LnOut a = ln_norm(ldg4(H2 + t * kD + hl * 4));
+      const float4 dyn2 = (a.xh * sv.gp + sv.bp) * m;
+      LnOut c = ln_norm(dyn2);
+      const float4 D = c.xh * sv.g1 + sv.b1;
+      const float4 S = ldg4(xhat + t * kD + hl * 4) * sv.g2 + sv.b2;
+      const float4 df = D - S;
+      const float z = red16(dot4(df * df, sv.w)) + sv.cb;
+      zsum += z * m;
+      msum += m;
+    }
+    if (valid && hl == 0) logits[b] = zsum / (msum + 1e-15f);
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kBlock) score_bwd_kernel(const float* __restrict__ H2, const float* __restrict__ xhat,
+                                                            const float* __restrict__ rstd_x, const int64_t* __restrict__ x,
+                                                            const ScoreParams p, const float* __restrict__ dlogit,
+                                                            float* __restrict__ dH2, float* __restrict__ dXs,
+                                                            const ScoreGrads g, int64_t B) {
+  __shared__ float red[kD];
+  const int hl = threadIdx.x & 15;
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int64_t iters = (B + nhw - 1) / nhw;
+  const ScoreVec sv = load_score_params(p, hl);
+  float4 a_gp = f4(0.f), a_bp = f4(0.f), a_g1 = f4(0.f), a_b1 = f4(0.f), a_g2 = f4(0.f), a_b2 = f4(0.f), a_w = f4(0.f);
+  float a_cb = 0.f;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t b = hw0 + it * nhw;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : B - 1;
+    float msum = 0.f;
+#pragma unroll
+    for (int i = 0; i < L; ++i) msum += x[bb * L + i] != 0 ? 1.f : 0.f;
+    const float dl = valid ? dlogit[bb] / (msum + 1e-15f) : 0.f;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int64_t t = bb * L + i;
+      const float m = x[t] != 0 ? 1.f : 0.f;
+      const float dz = dl * m;
+      LnOut a = ln_norm(ldg4(H2 + t * kD + hl * 4));
+      const float4 dyn2 = (a.xh * sv.gp + sv.bp) * m;
+      LnOut c = ln_norm(dyn2);
+      const float4 D = c.xh * sv.g1 + sv.b1;
+      const float4 xh = ldg4(xhat + t * kD + hl * 4);
+      const float4 S = xh * sv.g2 + sv.b2;
+      const float4 df = D - S;
+      if (hl == 0) a_cb += dz;
+      a_w = a_w + df * df * dz;
+      const float4 dD = df * sv.w * (2.f * dz);
+      // Classifier.layer_norm1 backward
+      a_g1 = a_g1 + dD * c.xh; a_b1 = a_b1 + dD;
+      float4 ddyn2 = ln_bwd(dD * sv.g1, c.xh, c.rstd) * m;
+      // pff_n1.layer_norm backward
+      a_gp = a_gp + ddyn2 * a.xh; a_bp = a_bp + ddyn2;
+      const float4 dh2 = ln_bwd(ddyn2 * sv.gp, a.xh, a.rstd);
+      // Classifier.layer_norm2 (static branch) backward, directly w.r.t. X
+      const float4 dS = f4(0.f) - dD;
+      a_g2 = a_g2 + dS * xh; a_b2 = a_b2 + dS;
+      const float4 dxs = ln_bwd(dS * sv.g2, xh, rstd_x[t]);
+      if (valid) { st4(dH2 + t * kD + hl * 4, dh2); st4(dXs + t * kD + hl * 4, dxs); }
+    }
+  }
+  block_colsum_atomic(a_gp, red, g.pff_g); block_colsum_atomic(a_bp, red, g.pff_b);
+  block_colsum_atomic(a_g1, red, g.ln1_g); block_colsum_atomic(a_b1, red, g.ln1_b);
+  block_colsum_atomic(a_g2, red, g.ln2_g); block_colsum_atomic(a_b2, red, g.ln2_b);
+  block_colsum_atomic(a_w, red, g.cls_w);
+  // scalar bias gradient
+  float s = a_cb;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(g.cls_b, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// losses
+// ------------------------------------------------------------------------------------------
+__global__ void bce_kernel(const float* __restrict__ logits, const float* __restrict__ y, const float* __restrict__ w,
+                           float alpha, float* __restrict__ dlogit, float* __restrict__ loss_out, int64_t B) {
+  __shared__ float red[32];
+  float part = 0.f;
+  const float invB = 1.0f / (float)B;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const float z = logits[b], yy = y[b], ww = w[b];
+    // F.binary_cross_entropy_with_logits(pred, y, weight=w) (main.py:56)
+    part += ww * (fmaxf(z, 0.f) - z * yy + log1pf(expf(-fabsf(z))));
+    const float sig = 1.0f / (1.0f + expf(-z));
+    dlogit[b] = alpha * ww * (sig - yy) * invB;
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(loss_out, v * invB);
+  }
+}
+__global__ void finalize_loss_kernel(float* loss_out, const float* recon, float alpha, float beta) {
+  const float r = recon ? recon[0] : 0.f;
+  loss_out[1] = r;
+  loss_out[2] = alpha * loss_out[0] + beta * r;
+}
+
+// recon target gather + squared error (Modules.py:194-199); one warp per token row
+__global__ void __launch_bounds__(kBlock) recon_diff_kernel(float* __restrict__ pred, int64_t ld, const int64_t* __restrict__ x,
+                                                             int64_t T, const float* __restrict__ inter, int64_t inter_ld,
+                                                             int64_t r_start, int64_t r_end, const int32_t* __restrict__ counts,
+                                                             int rchrom, int n_chrom, float* __restrict__ recon_out) {
+  __shared__ float red[kBlock / 32];
+  const int lane = threadIdx.x & 31;
+  const int64_t n_r = r_end - r_start;
+  const int64_t elig = T - counts[n_chrom] - counts[rchrom];
+  const float gscale = elig > 0 ? 200.0f / ((float)elig * (float)n_r) : 0.f;
+  float part = 0.f;
+  for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < T; t += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t id = x[t];
+    const bool ok = id != 0 && (id < r_start || id >= r_end);
+    float* prow = pred + t * ld;
+    const float* trow = inter + (id - 1) * inter_ld + (r_start - 1);
+    for (int64_t j = lane; j < n_r; j += 32) {
+      float dv = 0.f;
+      if (ok) { dv = prow[j] - __ldg(trow + j); part = fmaf(dv, dv, part); }
+      prow[j] = dv * gscale;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int i = 0; i < kBlock / 32; ++i) v += red[i];
+    if (elig > 0 && v != 0.f) atomicAdd(recon_out, v * 100.0f / ((float)elig * (float)n_r));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// small backward helpers
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) ln_tanh_bwd_kernel(const float* __restrict__ dxhat, const float* __restrict__ dXs,
+                                                              const float* __restrict__ xhat, const float* __restrict__ rstd,
+                                                              const float* __restrict__ X, float* __restrict__ dP, int64_t T) {
+  const int hl = threadIdx.x & 15;
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int64_t iters = (T + nhw - 1) / nhw;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t t = hw0 + it * nhw;
+    const bool valid = t < T;
+    const int64_t tt = valid ? t : T - 1;
+    const float4 xh = ldg4(xhat + tt * kD + hl * 4);
+    float4 dx = ln_bwd(ldg4(dxhat + tt * kD + hl * 4), xh, rstd[tt]) + ldg4(dXs + tt * kD + hl * 4);
+    const float4 xv = ldg4(X + tt * kD + hl * 4);
+    dx = dx * (f4(1.f) - xv * xv);                      // X = tanh(P)  (Modules.py:270)
+    if (valid) st4(dP + t * kD + hl * 4, dx);
+  }
+}
+__global__ void enc_combine_bwd_kernel(const float4* __restrict__ dV0, const float4* __restrict__ dtE,
+                                       const float4* __restrict__ E, float beta, float4* __restrict__ dE, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = dV0[i];
+    if (dtE) {
+      const float4 e = E[i];
+      const float4 te = make_float4(tanhf(e.x), tanhf(e.y), tanhf(e.z), tanhf(e.w));
+      v = v + dtE[i] * (f4(1.f) - te * te) * beta;
+    }
+    dE[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k = 2 closed-form tables
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) pair_u_kernel(const float* __restrict__ QKG, const float* __restrict__ b_dyn,
+                                                         float* __restrict__ U, int64_t T) {
+  const int hl = threadIdx.x & 15;
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  for (int64_t t = hw0; t < T; t += nhw) {
+    float4 o = ldg4(b_dyn + hl * 4);
+#pragma unroll
+    for (int h = 0; h < kH; ++h) o = o + ldg4(QKG + t * kQKG + 2 * kH * kD + h * kD + hl * 4);
+    st4(U + t * kD + hl * 4, o);
+  }
+}
+__global__ void __launch_bounds__(kBlock) pair_ds_kernel(const float* __restrict__ H2, const float* __restrict__ xhat,
+                                                          const ScoreParams p, float* __restrict__ D, float* __restrict__ S,
+                                                          int64_t T) {
+  const int hl = threadIdx.x & 15;
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int64_t iters = (T + nhw - 1) / nhw;
+  const ScoreVec sv = load_score_params(p, hl);
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t t = hw0 + it * nhw;
+    const bool valid = t < T;
+    const int64_t tt = valid ? t : T - 1;
+    LnOut a = ln_norm(ldg4(H2 + tt * kD + hl * 4));
+    LnOut c = ln_norm(a.xh * sv.gp + sv.bp);
+    if (valid) {
+      st4(D + t * kD + hl * 4, c.xh * sv.g1 + sv.b1);
+      st4(S + t * kD + hl * 4, ldg4(xhat + t * kD + hl * 4) * sv.g2 + sv.b2);
+    }
+  }
+}
+
+__global__ void iota_i64_kernel(int64_t* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = i;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// launchers
+// ==========================================================================================
+int launch_bucket(const int64_t* x, int64_t T, const ChromMeta& cm, int32_t* counts, int32_t* group_off,
+                  int32_t* cursor, int32_t* perm, cudaStream_t s) {
+  if (int rc = check_cuda(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (cm.n + 1), s), "memset counts")) return rc;
+  int blocks = (int)((T + 1023) / 1024);
+  if (blocks < 1) blocks = 1;
+  if (blocks > kSMs * 4) blocks = kSMs * 4;
+  bucket_count_kernel<<<blocks, 256, 0, s>>>(x, T, cm, counts);
+  MATCHA_CHECK_LAUNCH("bucket_count");
+  bucket_scan_kernel<<<1, 32, 0, s>>>(counts, cm.n, group_off, cursor);
+  MATCHA_CHECK_LAUNCH("bucket_scan");
+  bucket_scatter_kernel<<<blocks, 256, 0, s>>>(x, T, cm, cursor, perm);
+  MATCHA_CHECK_LAUNCH("bucket_scatter");
+  return MATCHA_OK;
+}
+
+int launch_active_flags(const int32_t* counts, int n_chrom, int rchrom, int64_t T, int32_t* active, cudaStream_t s) {
+  active_flags_kernel<<<1, MATCHA_MAX_CHROM, 0, s>>>(counts, n_chrom, rchrom, T, active);
+  MATCHA_CHECK_LAUNCH("active_flags");
+  return MATCHA_OK;
+}
+
+int launch_ln_fwd(const float* X, float* xhat, float* rstd, int64_t T, cudaStream_t s) {
+  if (T <= 0) return MATCHA_OK;
+  ln_fwd_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(X, xhat, rstd, T);
+  MATCHA_CHECK_LAUNCH("ln_fwd");
+  return MATCHA_OK;
+}
+
+#define MATCHA_DISPATCH_L(L, CALL)                                              \
+  switch (L) {                                                                  \
+    case 2: { constexpr int LL = 2; CALL; } break;                              \
+    case 3: { constexpr int LL = 3; CALL; } break;                              \
+    case 4: { constexpr int LL = 4; CALL; } break;                              \
+    case 5: { constexpr int LL = 5; CALL; } break;                              \
+    case 6: { constexpr int LL = 6; CALL; } break;                              \
+    default:                                                                    \
+      set_error("hyperedge width L=%d unsupported (2..6)", (int)(L));           \
+      return MATCHA_ERR_UNSUPPORTED;                                            \
+  }
+
+int launch_attn_fwd(const float* QKG, const int64_t* x, const float* b_dyn, float* U, int64_t B, int L, DropCfg drop,
+                    cudaStream_t s) {
+  if (B <= 0) return MATCHA_OK;
+  const int grid = grid_for_halfwarps(B, kSMs * 8);
+  MATCHA_DISPATCH_L(L, (attn_fwd_kernel<LL><<<grid, kBlock, 0, s>>>(QKG, x, b_dyn, U, B, drop)));
+  MATCHA_CHECK_LAUNCH("attn_fwd");
+  return MATCHA_OK;
+}
+int launch_attn_bwd(const float* QKG, const float* dU, const int64_t* x, float* dQKG, float* db_dyn, int64_t B, int L,
+                    DropCfg drop, cudaStream_t s) {
+  if (B <= 0) return MATCHA_OK;
+  const int grid = grid_for_halfwarps(B, kSMs * 4);
+  MATCHA_DISPATCH_L(L, (attn_bwd_kernel<LL><<<grid, kBlock, 0, s>>>(QKG, dU, x, dQKG, db_dyn, B, drop)));
+  MATCHA_CHECK_LAUNCH("attn_bwd");
+  return MATCHA_OK;
+}
+int launch_score_fwd(const float* H2, const float* xhat, const int64_t* x, ScoreParams p, float* logits, int64_t B, int L,
+                     cudaStream_t s) {
+  if (B <= 0) return MATCHA_OK;
+  const int grid = grid_for_halfwarps(B, kSMs * 8);
+  MATCHA_DISPATCH_L(L, (score_fwd_kernel<LL><<<grid, kBlock, 0, s>>>(H2, xhat, x, p, logits, B)));
+  MATCHA_CHECK_LAUNCH("score_fwd");
+  return MATCHA_OK;
+}
+int launch_score_bwd(const float* H2, const float* xhat, const float* rstd_x, const int64_t* x, ScoreParams p,
+                     const float* dlogit, float* dH2, float* dXs, ScoreGrads g, int64_t B, int L, cudaStream_t s) {
+  if (B <= 0) return MATCHA_OK;
+  const int grid = grid_for_halfwarps(B, kSMs * 4);
+  MATCHA_DISPATCH_L(L, (score_bwd_kernel<LL><<<grid, kBlock, 0, s>>>(H2, xhat, rstd_x, x, p, dlogit, dH2, dXs, g, B)));
+  MATCHA_CHECK_LAUNCH("score_bwd");
+  return MATCHA_OK;
+}
+int launch_bce(const float* logits, const float* y, const float* w, float alpha, float* dlogit, float* loss_out, int64_t B,
+               cudaStream_t s) {
+  int blocks = (int)((B + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > kSMs * 2) blocks = kSMs * 2;
+  bce_kernel<<<blocks, 256, 0, s>>>(logits, y, w, alpha, dlogit, loss_out, B);
+  MATCHA_CHECK_LAUNCH("bce");
+  return MATCHA_OK;
+}
+int launch_finalize_loss(float* loss_out, const float* recon, float alpha, float beta, cudaStream_t s) {
+  finalize_loss_kernel<<<1, 1, 0, s>>>(loss_out, recon, alpha, beta);
+  MATCHA_CHECK_LAUNCH("finalize_loss");
+  return MATCHA_OK;
+}
+int launch_recon_diff(float* pred, int64_t ld, const int64_t* x, int64_t T, const float* inter, int64_t inter_ld,
+                      int64_t r_start, int64_t r_end, const int32_t* counts, int rchrom, int n_chrom, float* recon_out,
+                      cudaStream_t s) {
+  if (T <= 0) return MATCHA_OK;
+  int64_t blocks = (T * 32 + kBlock - 1) / kBlock;
+  if (blocks > kSMs * 8) blocks = kSMs * 8;
+  recon_diff_kernel<<<(int)blocks, kBlock, 0, s>>>(pred, ld, x, T, inter, inter_ld, r_start, r_end, counts, rchrom,
+                                                   n_chrom, recon_out);
+  MATCHA_CHECK_LAUNCH("recon_diff");
+  return MATCHA_OK;
+}
+int launch_ln_tanh_bwd(const float* dxhat, const float* dXs, const float* xhat, const float* rstd, const float* X,
+                       float* dP, int64_t T, cudaStream_t s) {
+  if (T <= 0) return MATCHA_OK;
+  ln_tanh_bwd_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(dxhat, dXs, xhat, rstd, X, dP, T);
+  MATCHA_CHECK_LAUNCH("ln_tanh_bwd");
+  return MATCHA_OK;
+}
+int launch_enc_combine_bwd(const float* dV0, const float* dtE, const float* E, float beta, float* dE, int64_t n,
+                           cudaStream_t s) {
+  if (n <= 0) return MATCHA_OK;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > kSMs * 16) blocks = kSMs * 16;
+  enc_combine_bwd_kernel<<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(dV0),
+                                                     reinterpret_cast<const float4*>(dtE),
+                                                     reinterpret_cast<const float4*>(E), beta,
+                                                     reinterpret_cast<float4*>(dE), n4);
+  MATCHA_CHECK_LAUNCH("enc_combine_bwd");
+  return MATCHA_OK;
+}
+int launch_iota_i64(int64_t* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return MATCHA_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kSMs * 8) blocks = kSMs * 8;
+  iota_i64_kernel<<<(int)blocks, 256, 0, s>>>(out, n);
+  MATCHA_CHECK_LAUNCH("iota_i64");
+  return MATCHA_OK;
+}
+int launch_pair_u(const float* QKG, const float* b_dyn, float* U, int64_t T, cudaStream_t s) {
+  if (T <= 0) return MATCHA_OK;
+  pair_u_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(QKG, b_dyn, U, T);
+  MATCHA_CHECK_LAUNCH("pair_u");
+  return MATCHA_OK;
+}
+int launch_pair_ds(const float* H2, const float* xhat, ScoreParams p, float* D, float* S, int64_t T, cudaStream_t s) {
+  if (T <= 0) return MATCHA_OK;
+  pair_ds_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(H2, xhat, p, D, S, T);
+  MATCHA_CHECK_LAUNCH("pair_ds");
+  return MATCHA_OK;
+}
+
+}  // namespace matcha

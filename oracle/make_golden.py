@@ -55,6 +55,7 @@ def build_reference(nums, d=64, seed=1):
         attrs.append(np.concatenate([ch, coor], -1))
     attr = np.concatenate([np.zeros((1, C + 1)), np.concatenate(attrs, 0)], 0).astype("float32")
 
+    build_reference.inter_raw = inter.copy()                 # kept to pin our own z-score restatement
     torch.manual_seed(seed)
     ne = Modules.MultipleEmbedding(feats, d, False, torch.as_tensor(num_list), chrom_range, inter.copy())
     model = Modules.Classifier(n_head=8, d_model=d, d_k=d, d_v=d, node_embedding=ne, diag_mask=True,
@@ -85,6 +86,7 @@ def main(out=os.path.join(HERE, "..", "tests", "golden", "ref_small.npz")):
     for c, f in enumerate(model.node_embedding.embeddings):
         arrays[f"feat/{c}"] = f.embedding.numpy()
     arrays["inter"] = model.node_embedding.inter_initial.embedding.numpy()      # z-scored by Modules.py:147-152
+    arrays["inter_raw"] = build_reference.inter_raw
     grads_any = {}
 
     rng = np.random.default_rng(5)

@@ -1,0 +1,351 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test calls the CUDA path through the
+C ABI (ctypes) and checks it against (a) golden vectors produced by the unmodified reference and/or
+(b) the CPU oracle on the same seeded inputs.  Tolerances: fp32, rtol 1e-4 on scores/embeddings
+(BASELINE.json north_star); sampled / indexed work bit-exact."""
+import ctypes as C
+import io
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import model_from_golden, oracle_from_model, step_seed
+from oracle import hypersagnn_oracle as O
+from oracle import sampler_oracle as SO
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model(golden):
+    return model_from_golden(golden)
+
+
+def _lib():
+    from matcha_b200 import _lib
+    return _lib
+
+
+# ------------------------------------------------------------------------------------------
+# building block: fp32 contraction kernel
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("form,M,N,K", [(0, 130, 1536, 64), (0, 37, 250, 24), (0, 64, 64, 250), (1, 300, 64, 1536),
+                                        (1, 65, 64, 133), (2, 1536, 64, 1000), (2, 64, 250, 777), (2, 133, 64, 4096)])
+def test_gemm_simt_matches_torch(form, M, N, K):
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(form * 1000 + M)
+    if form == 0:
+        A, B = torch.randn(M, K, device="cuda", generator=g), torch.randn(N, K, device="cuda", generator=g)
+        ref = A.double() @ B.double().t()
+    elif form == 1:
+        A, B = torch.randn(M, K, device="cuda", generator=g), torch.randn(K, N, device="cuda", generator=g)
+        ref = A.double() @ B.double()
+    else:
+        A, B = torch.randn(K, M, device="cuda", generator=g), torch.randn(K, N, device="cuda", generator=g)
+        ref = A.double().t() @ B.double()
+    bias = torch.randn(N, device="cuda", generator=g) if form == 0 else None
+    if bias is not None:
+        ref = ref + bias.double()
+    Cm = torch.zeros(M, N, device="cuda")
+    L.check(lib.matcha_gemm(form, 0, A.data_ptr(), B.data_ptr(), Cm.data_ptr(), L.ptr(bias), M, N, K, A.stride(0),
+                            B.stride(0), N, L.stream_ptr()), "matcha_gemm")
+    torch.cuda.synchronize()
+    err = (Cm.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-6, err
+
+
+# ------------------------------------------------------------------------------------------
+# Classifier.forward / get_node_embeddings vs the reference's own outputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [2, 3, 4, 5])
+def test_eval_logits_match_reference_golden(golden, model, L):
+    model.eval()
+    x = torch.from_numpy(golden[f"x/L{L}"]).cuda()
+    with torch.no_grad():
+        got = model(x)
+    assert got.shape == (x.shape[0], 1)          # raw logits [B, 1] like Modules.py:309-318
+    np.testing.assert_allclose(got.cpu().numpy(), golden[f"logits_eval/L{L}"], rtol=1e-4, atol=5e-5)
+
+
+def test_recon_loss_matches_reference_golden(golden, model, monkeypatch):
+    model.eval()
+    for L in (2, 5):
+        x = torch.from_numpy(golden[f"x/L{L}"]).cuda()
+        for r in range(len(golden["nums"])):
+            monkeypatch.setattr(np.random, "choice", lambda a, size=None, r=r: np.asarray([r]))
+            with torch.no_grad():
+                logits, rl = model(x, return_recon=True)
+            np.testing.assert_allclose(rl.cpu().numpy(), golden[f"recon_eval/L{L}/r{r}"], rtol=1e-4)
+            np.testing.assert_allclose(logits.cpu().numpy(), golden[f"logits_eval/L{L}"], rtol=1e-4, atol=5e-5)
+
+
+def test_embeddings_match_reference_golden(golden, model):
+    model.eval()
+    N = golden["embeddings"].shape[0]
+    ids = torch.arange(1, N + 1).view(-1, 1).cuda()
+    with torch.no_grad():
+        e = model.get_node_embeddings(ids)
+    assert e.shape == (N, 1, 64)
+    np.testing.assert_allclose(e[:, 0, :].cpu().numpy(), golden["embeddings"], rtol=1e-4, atol=2e-6)
+    with torch.no_grad():       # id 0 -> zero row (Modules.py:178)
+        z = model.get_node_embeddings(torch.zeros(3, 1, dtype=torch.long).cuda())
+    assert float(z.abs().max()) == 0.0
+
+
+def test_known_answer_facts(golden, model):
+    model.eval()
+    pw = golden["kat/pad_width"]
+    with torch.no_grad():
+        for i, x in enumerate([[3, 47, 90], [3, 47, 90, 0], [3, 47, 90, 0, 0]]):
+            assert abs(model(torch.tensor([x]).cuda()).item() - pw[i]) < 1e-4      # padded width changes the score
+        assert abs(model(torch.tensor([[90, 3, 47]]).cuda()).item() - golden["kat/permuted"][0]) < 1e-4
+
+
+@pytest.mark.parametrize("L", [3, 5])
+def test_gradients_match_reference_golden(golden, L, monkeypatch):
+    """Train mode, dropout p = 0, loss = 1.0 * bce + 0.5 * recon, driven exactly like main.py:164-183
+    (torch's BCE + loss.backward() through our autograd Function)."""
+    model = model_from_golden(golden)
+    model.train()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    r = int(golden[f"train_rchrom/L{L}"][0])
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([r]))
+    x = torch.from_numpy(golden[f"x/L{L}"]).cuda()
+    y, w = torch.from_numpy(golden[f"y/L{L}"]).cuda(), torch.from_numpy(golden[f"w/L{L}"]).cuda()
+    model.zero_grad(set_to_none=True)
+    pred, rl = model(x, return_recon=True)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w)
+    (bce * 1.0 + rl * 0.5).backward()
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), golden[f"train_logits/L{L}"], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(rl.detach().cpu().numpy(), golden[f"train_recon/L{L}"], rtol=1e-4)
+    meta = json.loads(str(golden["meta"]))
+    live = set(meta["live_keys_by_L"][str(L)])
+    got_live = set()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            got_live.add(k)
+            ref = golden[f"grad/L{L}/{k}"]
+            scale = float(np.abs(ref).max())
+            err = float(np.abs(p.grad.cpu().numpy() - ref).max())
+            assert err <= 3e-4 * scale + 2e-7, (k, err, scale)
+    assert got_live == live          # same parameters get a gradient as in the reference (others stay None)
+
+
+@pytest.mark.parametrize("L", [2, 4, 5])
+def test_train_step_with_dropout_matches_oracle(golden, L, monkeypatch):
+    """Dropout ON: the oracle regenerates the kernel's masks from the shared counter RNG, so logits and
+    gradients must still agree."""
+    model = model_from_golden(golden)
+    model.train()
+    eng = model._engine()
+    r = L % 3
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([r]))
+    x = torch.from_numpy(golden[f"x/L{L}"]).cuda()
+    y, w = torch.from_numpy(golden[f"y/L{L}"]).cuda(), torch.from_numpy(golden[f"w/L{L}"]).cuda()
+    pred, rl = model(x, return_recon=True)
+    (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.25 * rl.sum()).backward()
+    om = oracle_from_model(model).to(torch.float64)
+    out = O.loss_and_grads(om, x.cpu(), y.cpu().double(), w.cpu().double(), 1.0, 0.25, random_chrom=r, train=True,
+                           seed=step_seed(eng))
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), out["logits"].numpy(), rtol=2e-4, atol=1e-4)
+    np.testing.assert_allclose(rl.detach().cpu().numpy(), out["recon"].numpy(), rtol=1e-4)
+    sd = dict(model.named_parameters())
+    for k, gref in out["grads"].items():
+        p = sd[k]
+        gref = gref.numpy()
+        if p.grad is None:
+            assert np.abs(gref).max() == 0.0, k
+            continue
+        scale = float(np.abs(gref).max())
+        err = float(np.abs(p.grad.cpu().numpy() - gref).max())
+        assert err <= 5e-4 * scale + 2e-7, (k, err, scale)
+
+
+# ------------------------------------------------------------------------------------------
+# all-pairs scorer (k = 2 closed form) and tuple scorer
+# ------------------------------------------------------------------------------------------
+def test_pair_scorer_matches_reference_and_generic_path(golden, model):
+    from matcha_b200.scorer import PairScorer, pair_count, pair_index_to_ij
+    model.eval()
+    ps = PairScorer(model)
+    N = int(golden["chrom_range"][-1][1]) - 1
+    # whole node range as one "chromosome": pair order of generate_pair_wise (denoise_contact.py:67-74)
+    for md in (0, 2):
+        total = pair_count(1, N + 1, md)
+        ref_pairs = np.asarray([(i, j) for i in range(1, N + 1) for j in range(i + md, N + 1)], dtype=np.int64)
+        assert total == len(ref_pairs)
+        got = ps.score_range(1, N + 1, md).cpu().numpy()
+        ii, jj = pair_index_to_ij(np.arange(total), 1, N + 1, md)
+        assert (ii == ref_pairs[:, 0]).all() and (jj == ref_pairs[:, 1]).all()
+        sel = np.arange(0, total, 7)
+        keep = ref_pairs[sel][:, 0] != ref_pairs[sel][:, 1]        # (i, i) is not a 2-token hyperedge for the generic path
+        with torch.no_grad():
+            generic = model(torch.from_numpy(ref_pairs[sel][keep]).cuda()).cpu().numpy().reshape(-1)
+        np.testing.assert_allclose(got[sel][keep], generic, rtol=1e-4, atol=5e-5)
+        # sub-range (sharding) gives the same values
+        b, e = total // 3, total // 3 + 1000
+        np.testing.assert_array_equal(ps.score_range(1, N + 1, md, b, e).cpu().numpy(), got[b:e])
+    # golden pairs scored by the unmodified reference
+    pairs = golden["kat/pairs"]
+    got = ps.score_range(1, N + 1, 0).cpu().numpy()
+    n = N
+    idx = np.asarray([(i - 1) * n - (i - 1) * (i - 2) // 2 + (j - i) for i, j in pairs])
+    np.testing.assert_allclose(got[idx], golden["kat/pair_logits"].reshape(-1), rtol=1e-4, atol=5e-5)
+
+
+def test_score_tuples_pads_per_batch(golden, model):
+    from matcha_b200.scorer import score_tuples
+    samples = [[3, 47], [5, 9, 90], [1, 2], [7, 50, 60, 99]]
+    outs = score_tuples(model, samples, batch_size=2)
+    model.eval()
+    with torch.no_grad():
+        a = model(torch.tensor([[3, 47, 0], [5, 9, 90]]).cuda())
+        b = model(torch.tensor([[1, 2, 0, 0], [7, 50, 60, 99]]).cuda())
+    np.testing.assert_allclose(outs[0][1].cpu().numpy(), a.cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(outs[1][1].cpu().numpy(), b.cpu().numpy(), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# hash set + sampler: bit-exact vs the exact-set oracle
+# ------------------------------------------------------------------------------------------
+def _toy_kmers(rng, cr, n, L=5):
+    rows = np.zeros((n, L), dtype=np.int64)
+    for i in range(n):
+        k = int(rng.integers(2, L + 1))
+        c = int(rng.integers(0, len(cr)))
+        if rng.random() < 0.9:
+            ids = rng.choice(np.arange(cr[c][0], cr[c][1]), size=k, replace=False)
+        else:
+            ids = rng.choice(np.arange(1, cr[-1][1]), size=k, replace=False)
+        rows[i, :k] = np.sort(ids)
+    return np.unique(rows, axis=0)
+
+
+def test_hashset_membership_exact(golden):
+    from matcha_b200.sampler import KmerHashSet
+    rng = np.random.default_rng(3)
+    cr = golden["chrom_range"]
+    kmers = _toy_kmers(rng, cr, 20000)
+    hs = KmerHashSet(len(kmers), width=5).insert(kmers)
+    assert not hs.overflowed()
+    s = SO.build_set(kmers)
+    probe = np.concatenate([kmers[::3], _toy_kmers(rng, cr, 5000)])
+    got = hs.contains(probe).cpu().numpy()
+    want = np.asarray([SO.kmer_key(r) in s for r in probe])
+    assert (got == want).all()
+    assert got[: len(kmers[::3])].all()
+
+
+@pytest.mark.parametrize("min_dis", [0, 1])
+def test_negative_sampler_bit_exact_vs_oracle(golden, min_dis):
+    from matcha_b200.sampler import KmerHashSet, NegativeSampler
+    rng = np.random.default_rng(11)
+    cr = golden["chrom_range"]
+    kmers = _toy_kmers(rng, cr, 30000)
+    hs = KmerHashSet(len(kmers), width=5).insert(kmers)
+    pos = kmers[rng.choice(len(kmers), 96, replace=False)]
+    smp = NegativeSampler(hs, cr, min_dis=min_dis, neg_num=3, seed=2, max_rounds=64)
+    rounds = torch.zeros(96 * 3, dtype=torch.int32, device="cuda")
+    neg, valid = smp.sample(torch.from_numpy(pos).cuda(), rounds=rounds, step=5)
+    want_neg, want_valid, want_rounds = SO.sample_negatives(pos, SO.build_set(kmers), cr, 3, min_dis, seed=2, step=5)
+    assert (neg.cpu().numpy() == want_neg).all()
+    assert (valid.cpu().numpy() == want_valid).all()
+    assert (rounds.cpu().numpy() == want_rounds).all()
+    # domain properties: sorted, unique, never a positive, same chromosomes as the source positive
+    n = neg.cpu().numpy()
+    s = SO.build_set(kmers)
+    for g, row in enumerate(n):
+        live = row[row != 0]
+        assert (np.diff(live) > min_dis).all()
+        assert SO.kmer_key(row) not in s
+
+
+# ------------------------------------------------------------------------------------------
+# optimizer, persistence, fused trainer
+# ------------------------------------------------------------------------------------------
+def test_flat_adamw_matches_torch(golden):
+    from matcha_b200.engine import FlatAdamW
+    model = model_from_golden(golden)
+    eng = model._engine()
+    eng.ensure_bound()
+    live = eng.live_parameters()
+    ref_params = [p.detach().clone().requires_grad_(True) for p in live]
+    topt = torch.optim.AdamW(ref_params, lr=1e-3)
+    opt = FlatAdamW(eng)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for it in range(3):
+        eng.gflat.normal_(generator=g)
+        eng.active.fill_(1)
+        if it == 1:
+            eng.active[0] = 0                 # chromosome 0 absent: its encoder weights must not move
+        n_always = len(eng.layout) - len(eng.segments)
+        for i, ((p, o), rp) in enumerate(zip(eng.layout, ref_params)):
+            rp.grad = eng.grad_view(p, o).clone()
+            if it == 1 and i >= n_always and eng.segments[i - n_always][2] == 0:
+                rp.grad = None                # what autograd leaves when the chromosome is absent
+        topt.step()
+        opt.step()
+    for (p, o), rp in zip(eng.layout, ref_params):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), rp.detach().cpu().numpy(), rtol=2e-5, atol=2e-7)
+
+
+def test_whole_module_pickle_roundtrip(golden, model):
+    model.eval()
+    x = torch.from_numpy(golden["x/L4"]).cuda()
+    with torch.no_grad():
+        a = model(x)
+    buf = io.BytesIO()
+    torch.save(model, buf)                    # main.py:322,685 (model2load)
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)  # denoise_contact.py:99 (needs weights_only=False on torch >= 2.6)
+    m2.eval()
+    with torch.no_grad():
+        b = m2(x)
+    assert torch.equal(a, b)
+    assert str(m2.layer_norm1.weight.device).startswith("cuda")      # denoise_contact.py:101-104 reads this
+
+
+def test_fused_trainer_step_matches_oracle(golden):
+    """One Trainer.step (sampler -> fwd -> bce -> bwd -> AdamW) against the oracle chained the same way."""
+    from matcha_b200.sampler import KmerHashSet, NegativeSampler
+    from matcha_b200.trainer import Trainer
+    rng = np.random.default_rng(21)
+    cr = golden["chrom_range"]
+    kmers = _toy_kmers(rng, cr, 20000)
+    hs = KmerHashSet(len(kmers), width=5).insert(kmers)
+    model = model_from_golden(golden)
+    om = oracle_from_model(model).to(torch.float64)
+    smp = NegativeSampler(hs, cr, neg_num=3, seed=4)
+    tr = Trainer(model, smp, alpha=1.0, beta=0.3, seed=9)
+    pos = kmers[rng.choice(len(kmers), 32, replace=False)]
+    pw = rng.uniform(0.5, 3.0, 32).astype(np.float32)
+    before = {k: v.detach().cpu().double().clone() for k, v in model.named_parameters()}
+    tr.step(torch.from_numpy(pos).cuda(), torch.from_numpy(pw).cuda())
+    torch.cuda.synchronize()
+    eng = tr.e
+    neg, valid, _ = SO.sample_negatives(pos, SO.build_set(kmers), cr, 3, 0, seed=4, step=0)
+    x = torch.from_numpy(np.concatenate([pos, neg]))
+    y = torch.cat([torch.ones(32, 1), torch.zeros(96, 1)]).double()
+    w = torch.cat([torch.from_numpy(pw).view(-1, 1), torch.from_numpy(valid.astype(np.float32)).view(-1, 1)]).double()
+    rchrom = int(np.random.RandomState(9).randint(0, len(cr)))
+    out = O.loss_and_grads(om, x, y, w, 1.0, 0.3, random_chrom=rchrom, train=True, seed=step_seed(eng))
+    losses = tr.loss_out.cpu().numpy()
+    np.testing.assert_allclose(losses[0], out["bce"].item(), rtol=2e-4)
+    np.testing.assert_allclose(losses[1], out["recon"].item(), rtol=2e-4)
+    np.testing.assert_allclose(losses[2], out["loss"].item(), rtol=2e-4)
+    after = dict(model.named_parameters())
+    for k, gref in out["grads"].items():
+        if float(gref.abs().max()) == 0.0:
+            continue
+        p0 = before[k]
+        want, _, _ = O.adamw_step(p0, gref, torch.zeros_like(p0), torch.zeros_like(p0), 1)
+        got = after[k].detach().cpu().double()
+        # the first AdamW step moves a coordinate by ~lr * g / (|g| + eps): compare the update where the
+        # gradient is well above its own rounding error (near-zero gradients make the sign ill-conditioned)
+        mask = gref.abs() > 1e-3 * gref.abs().max()
+        upd_err = float((((got - p0) - (want - p0)).abs() * mask).max())
+        assert upd_err < 2e-5, (k, upd_err)
