@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- hyperedges/s trained (pos + neg, fwd + bwd + AdamW, negative sampling included) on the
+synthetic whole-genome 1 Mb SPRITE-like workload (BASELINE.json configs[1]: ~3.1k bins, k = 2..5, d = 64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One process per GPU (torchrun env for N > 1).  A step = one pass of the hot path over one batch:
+GPU negative sampler -> Classifier forward (train mode, dropout on) -> weighted BCE + beta * recon ->
+backward -> (NCCL all-reduce) -> AdamW.  `value` is measured with the positives already resident in HBM;
+`e2e` repeats the measurement with HOST (pinned) positives copied in and the loss copied out every step.
+`--impl reference` times the CPU oracle port of the reference path (the reference is pure Python and does
+not travel to the GPU box) on this box's host cores, reference batch (96 positives + 288 negatives).
+Prints ONE JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hyperedges_per_s_trained"
+UNIT = "hyperedges/s"
+WORKLOAD = "cfg2: synthetic SPRITE-like clusters, whole-genome 1 Mb (3067 bins, 23 chromosomes), k=2..5 mixed, embed_dim 64"
+POS_PER_STEP = 4096          # positives per GPU per step; x3 negatives -> 16384 hyperedges / GPU / step
+NEG_NUM = 3
+KMERS_PER_SIZE = 400_000
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "src": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            if sm:
+                out["sm_mhz"], out["sm_max_mhz"], out["samples"] = float(np.median(sm)), float(rows[0][2]), len(sm)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for i, n in enumerate(names):
+                if any(len(r) >= 9 and r[5 + i].strip().lower() == "active" for r in rows):
+                    out["reasons"].append(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (sampler + fwd + bwd + AdamW), reference batch size
+# ------------------------------------------------------------------------------------------
+def cpu_reference_arm(ds, steps, warmup, seed=0):
+    import torch
+    from oracle import hypersagnn_oracle as O
+    from oracle import sampler_oracle as SO
+    torch.set_num_threads(os.cpu_count())
+    # parameters come from our own module constructor (same shapes / init laws as main.py:609-623), moved to the CPU
+    from matcha_b200.synthetic import build_model
+    model = build_model(ds, seed=1)
+    sd = {k: v.detach().cpu().clone().float() for k, v in model.state_dict().items()}
+    feats = [e.embedding.detach().cpu().clone() for e in model.node_embedding.embeddings]
+    inter = model.node_embedding.inter_initial.embedding.detach().cpu().clone() if ds["inter"] is not None else None
+    del model
+    om = O.OracleModel(sd, feats, inter, ds["chrom_range"])
+    names = O.live_param_names(om)
+    pset = SO.build_set(ds["dict"])
+    rng = np.random.RandomState(seed)
+    m1 = {n: torch.zeros_like(om.params[n]) for n in names}
+    m2 = {n: torch.zeros_like(om.params[n]) for n in names}
+    P = 96
+    pos_all, w_all = ds["positives"], ds["pos_weight"]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        idx = rng.randint(0, len(pos_all), P)
+        pos, pw = pos_all[idx], w_all[idx]
+        neg, valid, _ = SO.sample_negatives(pos, pset, ds["chrom_range"], NEG_NUM, 0, seed=seed, step=it)
+        x = torch.from_numpy(np.concatenate([pos, neg]))
+        y = torch.cat([torch.ones(P, 1), torch.zeros(P * NEG_NUM, 1)])
+        w = torch.cat([torch.from_numpy(pw).view(-1, 1), torch.from_numpy(valid.astype(np.float32)).view(-1, 1)])
+        out = O.loss_and_grads(om, x, y, w, 1.0, 0.001, random_chrom=int(rng.randint(0, len(ds["nums"]))), train=True,
+                               seed=it)
+        with torch.no_grad():
+            for n in names:
+                p, a, b = O.adamw_step(om.params[n].detach(), out["grads"][n], m1[n], m2[n], it + 1)
+                om.params[n], m1[n], m2[n] = p, a, b
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    return {"value": P * (1 + NEG_NUM) / per_step, "ms_per_step": per_step * 1e3, "cores": os.cpu_count(),
+            "sample": f"{steps} steps of 96 positives + 288 negatives (reference batch, main.py:527-528) after {warmup} warm-up"}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kmers-per-size", type=int, default=KMERS_PER_SIZE)
+    ap.add_argument("--pos-per-step", type=int, default=POS_PER_STEP)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-impl", type=int, default=-1, help="-1 library default, 0 SIMT, 1 tcgen05")
+    args = ap.parse_args()
+    warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": WORKLOAD, "hyperedges_per_gpu_per_step": args.pos_per_step * (1 + NEG_NUM),
+              "positives_per_gpu_per_step": args.pos_per_step, "neg_num": NEG_NUM, "padded_width": 5,
+              "kmers_per_size": args.kmers_per_size, "parallelism": f"dp{world}",
+              "l2": "per-step activation stream (~1.4 GB) exceeds the 126 MB L2; no explicit flush"}
+
+    from matcha_b200.synthetic import make_dataset
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ds = make_dataset("cfg2", kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
+        r = cpu_reference_arm(ds, max(1, args.steps), max(1, args.warmup))
+        cfg = dict(config, hyperedges_per_gpu_per_step=384, positives_per_gpu_per_step=96,
+                   note="CPU oracle port of the reference path at the reference's batch size; the unmodified reference is "
+                        "Python that cannot travel to the GPU box")
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from matcha_b200 import _lib
+    from matcha_b200.parallel import init_from_env
+    from matcha_b200.sampler import KmerHashSet, NegativeSampler
+    from matcha_b200.synthetic import build_model
+    from matcha_b200.trainer import Trainer
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local)
+    init_from_env()
+    lib = _lib.load()
+    if args.gemm_impl >= 0:
+        lib.matcha_set_gemm_impl(args.gemm_impl)
+
+    ds = make_dataset("cfg2", kmers_per_size=args.kmers_per_size, seed=0)      # same data on every rank
+    model = build_model(ds, seed=1)
+    hs = KmerHashSet(len(ds["dict"]), width=5).insert(ds["dict"])
+    sampler = NegativeSampler(hs, ds["chrom_range"], min_dis=0, neg_num=NEG_NUM, seed=2 + rank)
+    trainer = Trainer(model, sampler, alpha=1.0, beta=0.001, seed=3, world_size=world, rank=rank)
+    P = args.pos_per_step
+    # this rank's positives: rows rank::world of a shuffled global pool
+    g = np.random.RandomState(7)
+    perm = g.permutation(len(ds["positives"]))
+    pos_host = torch.from_numpy(ds["positives"][perm][rank::world].copy()).pin_memory()
+    w_host = torch.from_numpy(ds["pos_weight"][perm][rank::world].copy()).pin_memory()
+    pos_dev, w_dev = pos_host.cuda(), w_host.cuda()
+    nb = len(pos_host) // P
+    assert nb >= 1, "not enough positives for one step"
+    T = P * (1 + NEG_NUM) * 5
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n_steps, host_io, start):
+        loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+        for i in range(n_steps):
+            b = (start + i) % nb
+            if host_io:
+                x = pos_host[b * P:(b + 1) * P].cuda(non_blocking=True)
+                w = w_host[b * P:(b + 1) * P].cuda(non_blocking=True)
+            else:
+                x, w = pos_dev[b * P:(b + 1) * P], w_dev[b * P:(b + 1) * P]
+            trainer.step(x, w)
+            if host_io:
+                loss_host.copy_(trainer.loss_out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()      # the caller reads the step's loss, as main.py:187-188 does
+
+    def timed(n_steps, host_io, start, profile=False):
+        barrier()
+        if profile:
+            lib.matcha_profile_enable(1)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        run(n_steps, host_io, start)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        prof = None
+        if profile:
+            lib.matcha_profile_enable(0)
+            n = lib.matcha_profile_labels()
+            tms, calls, kern = (C.c_float * n)(), (C.c_int64 * n)(), (C.c_int64 * n)()
+            _lib.check(lib.matcha_profile_read(tms, calls, kern, n), "profile_read")
+            prof = {lib.matcha_profile_label_name(i).decode(): (tms[i], calls[i], kern[i]) for i in range(n) if calls[i]}
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, prof
+
+    run(warmup, False, 0)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_dev, prof = timed(args.steps, False, warmup, profile=True)
+    clk = clocks.stop() if rank == 0 else None
+    run(2, True, 0)
+    ms_e2e, _ = timed(args.steps, True, warmup + args.steps)
+    losses = trainer.mean_losses()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    per_step = P * (1 + NEG_NUM) * world
+    value = per_step * args.steps / (ms_dev * 1e-3)
+    e2e = per_step * args.steps / (ms_e2e * 1e-3)
+    peaks = load_peaks()
+    # dominant call site and its roofline (algorithmic flops / bytes per launch)
+    d, qkg = 64, 1536
+    alg = {
+        "qkg_gemm": ("tensor", 2.0 * T * qkg * d), "qkg_wgrad": ("tensor", 2.0 * T * qkg * d), "qkg_dgrad": ("tensor", 2.0 * T * qkg * d),
+        "attn_fwd": ("hbm", T * (qkg + d) * 4.0), "attn_bwd": ("hbm", T * (2 * qkg + d) * 4.0),
+    }
+    top = max(prof.items(), key=lambda kv: kv[1][0])
+    tot_ms = sum(v[0] for v in prof.values())
+    name, (tms, calls, _) = top
+    per_launch_ms = tms / calls
+    if name in alg:
+        bound, work = alg[name]
+    else:
+        bound, work = "hbm", None
+    if work is None:
+        roof = {"bound": bound, "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
+    elif bound == "tensor":
+        ach = work / (per_launch_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None}
+    else:
+        ach = work / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                "traffic": None}
+    impl_used = args.gemm_impl if args.gemm_impl >= 0 else int(os.environ.get("MATCHA_GEMM_IMPL", "0") or 0)
+    roof.update({"kernel": name, "ms_per_launch": per_launch_ms, "share_of_step": tms / tot_ms, "peak_source": peaks["src"],
+                 "contractions": "tcgen05 bf16x3 split, fp32 accumulate" if impl_used == 1 else "fp32 SIMT"})
+    launches = int(sum(v[2] for v in prof.values()))
+    breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        small = make_dataset("cfg2", kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
+        r = cpu_reference_arm(small, args.cpu_baseline_steps, 3)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config, "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(P * 5 * 8 + P * 4), "d2h_bytes_per_step": 12,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clk, "kernel_ms_per_step": breakdown, "losses": losses}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -35,6 +35,16 @@ extern "C" {
 const char* matcha_last_error(void);
 int matcha_version(void);
 
+/* Optional per-call-site timing with CUDA events on the launching stream (bench.py's roofline figures).
+ * matcha_profile_read synchronises on the recorded events, fills ms / calls / kernel-launch counts per
+ * label (n >= matcha_profile_labels()) and resets the counters. */
+void matcha_profile_enable(int32_t on);
+int32_t matcha_profile_labels(void);
+const char* matcha_profile_label_name(int32_t i);
+int matcha_profile_read(float* ms, int64_t* calls, int64_t* kernels, int32_t n);
+/* 0 = SIMT fp32 contractions only, 1 = tcgen05 (bf16x3) where the shape is eligible */
+void matcha_set_gemm_impl(int32_t impl);
+
 /* ---------------------------------------------------------------------------------------------
  * Model description: where every live tensor of Modules.Classifier sits.
  * `params` / `grads` are flat fp32 device buffers with IDENTICAL layout; off_* are element offsets.

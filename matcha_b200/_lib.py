@@ -80,6 +80,11 @@ _MD = C.POINTER(ModelDesc)
 SYMBOLS = {
     "matcha_last_error": (C.c_char_p, []),
     "matcha_version": (C.c_int, []),
+    "matcha_profile_enable": (None, [_I32]),
+    "matcha_profile_labels": (_I32, []),
+    "matcha_profile_label_name": (C.c_char_p, [_I32]),
+    "matcha_profile_read": (C.c_int, [_P, _P, _P, _I32]),
+    "matcha_set_gemm_impl": (None, [_I32]),
     "matcha_derived_elems": (_I64, [_MD]),
     "matcha_workspace_bytes": (_I64, [_MD, _I64, _I32, _I32]),
     "matcha_prepare": (C.c_int, [_MD, _P]),

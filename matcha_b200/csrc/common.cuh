@@ -28,6 +28,26 @@ int check_cuda(cudaError_t e, const char* what);
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 
 // ------------------------------------------------------------------------------------------
+// Optional per-call-site timing (CUDA events on the launching stream) -- off unless
+// matcha_profile_enable(1) was called; used by bench.py for the roofline figures.
+// ------------------------------------------------------------------------------------------
+enum ProfLabel : int {
+  P_BUCKET = 0, P_ENC0, P_ENC1, P_RECON_PRED, P_RECON_DIFF, P_ATTR, P_MIX, P_LN, P_QKG, P_ATTN_FWD, P_PFF0, P_PFF1,
+  P_SCORE_FWD, P_BCE, P_SCORE_BWD, P_W_PFF1, P_D_PFF1, P_W_PFF0, P_D_PFF0, P_ATTN_BWD, P_W_QKG, P_D_QKG, P_LN_BWD,
+  P_W_NEXT, P_D_NEXT, P_W_ATTR, P_W_RECON, P_D_RECON, P_ENC_COMBINE, P_W_ENC1, P_D_ENC1, P_W_ENC0, P_PREP, P_PREP_BWD,
+  P_ADAMW, P_SAMPLER, P_PAIR_SCORE, P_MISC, P_COUNT
+};
+void prof_begin(int label, cudaStream_t s);
+void prof_end(int label, int n_kernels, cudaStream_t s);
+#define PROF(label, nk, call)                 \
+  ([&]() -> int {                             \
+    ::matcha::prof_begin(label, s);           \
+    int _prc = (call);                        \
+    ::matcha::prof_end(label, nk, s);         \
+    return _prc;                              \
+  }())
+
+// ------------------------------------------------------------------------------------------
 // Counter-based RNG, restated bit-exactly in oracle/hypersagnn_oracle.py (splitmix64).
 // ------------------------------------------------------------------------------------------
 constexpr uint64_t kGolden = 0x9E3779B97F4A7C15ull;

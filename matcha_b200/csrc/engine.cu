@@ -2,7 +2,10 @@
 // parameter preparation, forward, backward, AdamW.  Every dense product is a GemmDesc handed to
 // the contraction kernels; everything else is a row-wise kernel from rowwise.cu.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "common.cuh"
 #include "rowwise.cuh"
@@ -25,6 +28,46 @@ int check_cuda(cudaError_t e, const char* what) {
   return MATCHA_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------------------------------
+// profiling (see common.cuh): event pairs are created lazily and reused
+// ------------------------------------------------------------------------------------------
+namespace {
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> free_events;
+  struct Rec { int label; cudaEvent_t b, e; };
+  std::vector<Rec> recs;
+  cudaEvent_t open_begin[P_COUNT] = {};
+  int64_t kernels[P_COUNT] = {};
+  cudaEvent_t get() {
+    if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+ProfState g_prof;
+const char* kProfNames[P_COUNT] = {
+    "bucket_tokens", "enc0_gather_gemm", "enc1_gemm", "recon_pred_gemm", "recon_diff", "attr_gemm", "mix_gemm", "ln_fwd",
+    "qkg_gemm", "attn_fwd", "pff0_gemm", "pff1_gemm", "score_fwd", "bce_loss", "score_bwd", "pff1_wgrad", "pff1_dgrad",
+    "pff0_wgrad", "pff0_dgrad", "attn_bwd", "qkg_wgrad", "qkg_dgrad", "ln_tanh_bwd", "mix_wgrad", "mix_dgrad",
+    "attr_wgrad", "recon_wgrad", "recon_dgrad", "enc_combine_bwd", "enc1_wgrad", "enc1_dgrad", "enc0_wgrad", "param_prep",
+    "param_prep_bwd", "adamw", "neg_sampler", "pair_score", "misc"};
+}  // namespace
+void prof_begin(int label, cudaStream_t s) {
+  if (!g_prof.on) return;
+  cudaEvent_t b = g_prof.get();
+  cudaEventRecord(b, s);
+  g_prof.open_begin[label] = b;
+}
+void prof_end(int label, int n_kernels, cudaStream_t s) {
+  if (!g_prof.on) return;
+  cudaEvent_t e = g_prof.get();
+  cudaEventRecord(e, s);
+  g_prof.recs.push_back({label, g_prof.open_begin[label], e});
+  g_prof.kernels[label] += n_kernels;
+}
+
 static int g_gemm_impl = -1;  // -1 = read MATCHA_GEMM_IMPL on first use; 0 = SIMT only; 1 = tcgen05 where eligible
 static int gemm_impl() {
   if (g_gemm_impl < 0) {
@@ -33,28 +76,29 @@ static int gemm_impl() {
   }
   return g_gemm_impl;
 }
-static int run_gemm(const GemmDesc& d, cudaStream_t s) {
-  if (gemm_impl() == 1) {
-    bool handled = false;
-    int rc = launch_gemm_tc(d, s, &handled);
-    if (rc) return rc;
-    if (handled) return MATCHA_OK;
-  }
-  return launch_gemm_simt(d, s);
+static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
+  prof_begin(label, s);
+  int rc = MATCHA_OK;
+  bool handled = false;
+  if (gemm_impl() == 1) rc = launch_gemm_tc(d, s, &handled);
+  if (!rc && !handled) rc = launch_gemm_simt(d, s);
+  prof_end(label, 1, s);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------
 // derived-parameter layout
 // ------------------------------------------------------------------------------------------
 struct DerivedLayout {
-  int64_t wqkg, bqkg, bdyn, tables, total;  // float offsets
+  int64_t wqkg, bqkg, bdyn, bdyn_part, tables, total;  // float offsets
 };
 static __host__ __device__ DerivedLayout derived_layout() {
   DerivedLayout l;
   l.wqkg = 0;
   l.bqkg = l.wqkg + (int64_t)kQKG * kD;
   l.bdyn = l.bqkg + kQKG;
-  l.tables = l.bdyn + kD;
+  l.bdyn_part = l.bdyn + kD;        // per-head partial sums of b_dyn (summed in a fixed order: deterministic)
+  l.tables = l.bdyn_part + kH * kD;
   l.tables = (l.tables + 63) / 64 * 64;
   const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
   l.total = l.tables + 4 * table_floats;
@@ -129,12 +173,17 @@ __global__ void prep_g_kernel(const matcha_model_desc m) {
     m.derived[l.bqkg + 2 * kH * kD + h * kD + tid] = 0.f;
     float s = 0.f;
     for (int mm = 0; mm < kD; ++mm) s = fmaf(sF[tid][mm], sVb[mm], s);
-    if (h == 0) s += P[m.off_fc1_b + tid];
-    atomicAdd(m.derived + l.bdyn + tid, s);
+    m.derived[l.bdyn_part + h * kD + tid] = s;
   }
 }
 __global__ void prep_tables_kernel(const matcha_model_desc m) {
   const int c = threadIdx.x;
+  if (c < kD) {   // b_dyn = fc1.bias + sum_h (fc1_h Wv_h b_v), heads added in a fixed order
+    const DerivedLayout l = derived_layout();
+    float s = m.params[m.off_fc1_b + c];
+    for (int h = 0; h < kH; ++h) s += m.derived[l.bdyn_part + h * kD + c];
+    m.derived[l.bdyn + c] = s;
+  }
   if (c >= m.n_chrom) return;
   GemmGroup* t0 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_ENC0));
   GemmGroup* t1 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_ENC1));
@@ -326,18 +375,18 @@ static ChromMeta chrom_meta(const matcha_model_desc* m) {
 static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, int training, uint64_t seed,
                        const Workspace& w, float* E_out, cudaStream_t s) {
   int rc;
-  if ((rc = launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s))) return rc;
+  if ((rc = PROF(P_BUCKET, 3, launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s)))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(w.H0, 0, sizeof(float) * T * kD, s), "memset H0"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * kD, s), "memset E"))) return rc;
   GemmDesc d = gemm_base(FORM_NT, 0, kD, 0, nullptr, 0, nullptr, 0, w.H0, kD);
   d.perm = w.perm; d.a_ids = x; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, TAB_ENC0);
   d.group_off = w.group_off; d.total_rows = T; d.epi_act = 1;
   if (training && m->p_feature > 0.f) { d.drop_on = 1; d.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
-  if ((rc = run_gemm(d, s))) return rc;
+  if ((rc = run_gemm(d, s, P_ENC0))) return rc;
   GemmDesc e = gemm_base(FORM_NT, 0, kD, kD, w.H0, kD, nullptr, 0, E_out, kD);
   e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, TAB_ENC1);
   e.group_off = w.group_off; e.total_rows = T;
-  return run_gemm(e, s);
+  return run_gemm(e, s, P_ENC1);
 }
 
 // X = tanh(next_w(E + attribute_nn(attr[id]))), xhat, rstd, QKG
@@ -347,14 +396,14 @@ static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   const DerivedLayout l = derived_layout();
   GemmDesc a = gemm_base(FORM_NT, T, kD, m->attr_dim, m->attr_table, m->attr_dim, P + m->off_attr_w, m->attr_dim, w.V0, kD);
   a.a_ids = x; a.bias = P + m->off_attr_b; a.addend = w.E; a.ld_add = kD;
-  if ((rc = run_gemm(a, s))) return rc;
+  if ((rc = run_gemm(a, s, P_ATTR))) return rc;
   GemmDesc b = gemm_base(FORM_NT, T, kD, kD, w.V0, kD, P + m->off_next_w, kD, w.X, kD);
   b.bias = P + m->off_next_b; b.epi_act = 1;
-  if ((rc = run_gemm(b, s))) return rc;
-  if ((rc = launch_ln_fwd(w.X, w.xhat, w.rstd, T, s))) return rc;
+  if ((rc = run_gemm(b, s, P_MIX))) return rc;
+  if ((rc = PROF(P_LN, 1, launch_ln_fwd(w.X, w.xhat, w.rstd, T, s)))) return rc;
   GemmDesc q = gemm_base(FORM_NT, T, kQKG, kD, w.xhat, kD, m->derived + l.wqkg, kD, w.QKG, kQKG);
   q.bias = m->derived + l.bqkg;
-  return run_gemm(q, s);
+  return run_gemm(q, s, P_QKG);
 }
 
 // pff_n1 (two 1x1 convolutions with residual), input U, output H2 (pre-LayerNorm)
@@ -364,10 +413,10 @@ static int run_pff(const matcha_model_desc* m, int64_t T, int training, uint64_t
   GemmDesc a = gemm_base(FORM_NT, T, kD, kD, w.U, kD, P + m->off_pff_w0, kD, w.H1d, kD);
   a.bias = P + m->off_pff_b0; a.epi_act = 1;
   if (training && m->p_pff > 0.f) { a.epi_drop = 1; a.edrop = make_drop(seed, SITE_PFF, m->p_pff, true); }
-  if ((rc = run_gemm(a, s))) return rc;
+  if ((rc = run_gemm(a, s, P_PFF0))) return rc;
   GemmDesc b = gemm_base(FORM_NT, T, kD, kD, w.H1d, kD, P + m->off_pff_w1, kD, w.H2, kD);
   b.bias = P + m->off_pff_b1; b.addend = w.U; b.ld_add = kD;
-  return run_gemm(b, s);
+  return run_gemm(b, s, P_PFF1);
 }
 
 static ScoreParams score_params(const matcha_model_desc* m) {
@@ -388,6 +437,27 @@ using namespace matcha;
 extern "C" {
 
 const char* matcha_last_error(void) { return g_err; }
+
+void matcha_profile_enable(int32_t on) { g_prof.on = on != 0; }
+int32_t matcha_profile_labels(void) { return P_COUNT; }
+const char* matcha_profile_label_name(int32_t i) { return (i >= 0 && i < P_COUNT) ? kProfNames[i] : ""; }
+int matcha_profile_read(float* ms, int64_t* calls, int64_t* kernels, int32_t n) {
+  MATCHA_REQUIRE(ms && calls && kernels && n >= P_COUNT, "matcha_profile_read: need %d slots", (int)P_COUNT);
+  for (int i = 0; i < n; ++i) { ms[i] = 0.f; calls[i] = 0; kernels[i] = 0; }
+  for (auto& r : g_prof.recs) {
+    if (int rc = check_cuda(cudaEventSynchronize(r.e), "profile sync")) return rc;
+    float t = 0.f;
+    if (int rc = check_cuda(cudaEventElapsedTime(&t, r.b, r.e), "profile elapsed")) return rc;
+    ms[r.label] += t;
+    calls[r.label] += 1;
+    g_prof.free_events.push_back(r.b);
+    g_prof.free_events.push_back(r.e);
+  }
+  g_prof.recs.clear();
+  for (int i = 0; i < P_COUNT; ++i) { kernels[i] = g_prof.kernels[i]; g_prof.kernels[i] = 0; }
+  return MATCHA_OK;
+}
+void matcha_set_gemm_impl(int32_t impl) { g_gemm_impl = impl; }
 int matcha_version(void) { return 100; }
 
 int64_t matcha_derived_elems(const matcha_model_desc* m) {
@@ -405,13 +475,15 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const DerivedLayout l = derived_layout();
-  if ((rc = check_cuda(cudaMemsetAsync(m->derived + l.bdyn, 0, sizeof(float) * kD, s), "memset b_dyn"))) return rc;
+  (void)l;
+  prof_begin(P_PREP, s);
   prep_qk_kernel<<<2 * kH * kD, kD, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_qk");
   prep_g_kernel<<<kH, 256, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_g");
   prep_tables_kernel<<<1, MATCHA_MAX_CHROM, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_tables");
+  prof_end(P_PREP, 3, s);
   return MATCHA_OK;
 }
 
@@ -439,18 +511,18 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
       const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom];
       GemmDesc p = gemm_base(FORM_NT, T, re - rs, kD, w.E, kD, m->params + m->off_rw[random_chrom], kD, w.pred, w.pred_ld);
       p.a_act = 1; p.bias = m->params + m->off_rb[random_chrom];
-      if ((rc = run_gemm(p, s))) return rc;
-      if ((rc = launch_recon_diff(w.pred, w.pred_ld, x, T, m->inter, m->inter_ld, rs, re, w.counts, random_chrom,
-                                  m->n_chrom, w.recon, s))) return rc;
+      if ((rc = run_gemm(p, s, P_RECON_PRED))) return rc;
+      if ((rc = PROF(P_RECON_DIFF, 1, launch_recon_diff(w.pred, w.pred_ld, x, T, m->inter, m->inter_ld, rs, re, w.counts, random_chrom,
+                                  m->n_chrom, w.recon, s)))) return rc;
     }
     if (recon && (rc = check_cuda(cudaMemcpyAsync(recon, w.recon, sizeof(float), cudaMemcpyDeviceToDevice, s), "copy recon")))
       return rc;
   }
   if ((rc = run_mix_qkg(m, x, T, w, s))) return rc;
   DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, training != 0);
-  if ((rc = launch_attn_fwd(w.QKG, x, m->derived + l.bdyn, w.U, B, L, dattn, s))) return rc;
+  if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fwd(w.QKG, x, m->derived + l.bdyn, w.U, B, L, dattn, s)))) return rc;
   if ((rc = run_pff(m, T, training, seed, w, s))) return rc;
-  return launch_score_fwd(w.H2, w.xhat, x, score_params(m), logits, B, L, s);
+  return PROF(P_SCORE_FWD, 1, launch_score_fwd(w.H2, w.xhat, x, score_params(m), logits, B, L, s));
 }
 
 int matcha_bce_loss(const float* logits, const float* y, const float* wgt, int64_t B, float alpha, float beta,
@@ -459,8 +531,8 @@ int matcha_bce_loss(const float* logits, const float* y, const float* wgt, int64
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
   if ((rc = check_cuda(cudaMemsetAsync(loss_out, 0, 3 * sizeof(float), s), "memset loss"))) return rc;
-  if ((rc = launch_bce(logits, y, wgt, alpha, dlogit, loss_out, B, s))) return rc;
-  return launch_finalize_loss(loss_out, recon, alpha, beta, s);
+  if ((rc = PROF(P_BCE, 1, launch_bce(logits, y, wgt, alpha, dlogit, loss_out, B, s)))) return rc;
+  return PROF(P_BCE, 1, launch_finalize_loss(loss_out, recon, alpha, beta, s));
 }
 
 int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int32_t L, uint64_t seed,
@@ -490,45 +562,45 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   ScoreGrads sg;
   sg.pff_g = G + m->off_pff_g; sg.pff_b = G + m->off_pff_b; sg.ln1_g = G + m->off_ln1_g; sg.ln1_b = G + m->off_ln1_b;
   sg.ln2_g = G + m->off_ln2_g; sg.ln2_b = G + m->off_ln2_b; sg.cls_w = G + m->off_cls_w; sg.cls_b = G + m->off_cls_b;
-  if ((rc = launch_score_bwd(w.H2, w.xhat, w.rstd, x, score_params(m), dlogit, w.dH2, w.dXs, sg, B, L, s))) return rc;
+  if ((rc = PROF(P_SCORE_BWD, 1, launch_score_bwd(w.H2, w.xhat, w.rstd, x, score_params(m), dlogit, w.dH2, w.dXs, sg, B, L, s)))) return rc;
 
   // pff_n1 backward
   DropCfg dpff = make_drop(seed, SITE_PFF, m->p_pff, true);
   {
     GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dH2, kD, w.H1d, kD, G + m->off_pff_w1, kD);
     d.colsum = G + m->off_pff_b1; d.colsum_n = kD;
-    if ((rc = run_gemm(d, s))) return rc;
+    if ((rc = run_gemm(d, s, P_W_PFF1))) return rc;
     GemmDesc e = gemm_base(FORM_NN, T, kD, kD, w.dH2, kD, P + m->off_pff_w1, kD, w.dH1pre, kD);
     e.epi_act = 2; e.aux = w.H1d; e.ld_aux = kD;
     if (m->p_pff > 0.f) { e.epi_drop = 1; e.edrop = dpff; }
-    if ((rc = run_gemm(e, s))) return rc;
+    if ((rc = run_gemm(e, s, P_D_PFF1))) return rc;
     GemmDesc f = gemm_base(FORM_TN, kD, kD, T, w.dH1pre, kD, w.U, kD, G + m->off_pff_w0, kD);
     f.colsum = G + m->off_pff_b0; f.colsum_n = kD;
-    if ((rc = run_gemm(f, s))) return rc;
+    if ((rc = run_gemm(f, s, P_W_PFF0))) return rc;
     GemmDesc g = gemm_base(FORM_NN, T, kD, kD, w.dH1pre, kD, P + m->off_pff_w0, kD, w.dU, kD);
     g.addend = w.dH2; g.ld_add = kD;
-    if ((rc = run_gemm(g, s))) return rc;
+    if ((rc = run_gemm(g, s, P_D_PFF0))) return rc;
   }
   // attention backward
   DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, true);
-  if ((rc = launch_attn_bwd(w.QKG, w.dU, x, w.dQKG, DG + l.bdyn, B, L, dattn, s))) return rc;
+  if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_bwd(w.QKG, w.dU, x, w.dQKG, DG + l.bdyn, B, L, dattn, s)))) return rc;
   {
     GemmDesc d = gemm_base(FORM_TN, kQKG, kD, T, w.dQKG, kQKG, w.xhat, kD, DG + l.wqkg, kD);
     d.colsum = DG + l.bqkg; d.colsum_n = kH * kD;
-    if ((rc = run_gemm(d, s))) return rc;
+    if ((rc = run_gemm(d, s, P_W_QKG))) return rc;
     GemmDesc e = gemm_base(FORM_NN, T, kD, kQKG, w.dQKG, kQKG, m->derived + l.wqkg, kD, w.dxhat, kD);
-    if ((rc = run_gemm(e, s))) return rc;
+    if ((rc = run_gemm(e, s, P_D_QKG))) return rc;
   }
-  if ((rc = launch_ln_tanh_bwd(w.dxhat, w.dXs, w.xhat, w.rstd, w.X, w.dP, T, s))) return rc;
+  if ((rc = PROF(P_LN_BWD, 1, launch_ln_tanh_bwd(w.dxhat, w.dXs, w.xhat, w.rstd, w.X, w.dP, T, s)))) return rc;
   {
     GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dP, kD, w.V0, kD, G + m->off_next_w, kD);
     d.colsum = G + m->off_next_b; d.colsum_n = kD;
-    if ((rc = run_gemm(d, s))) return rc;
+    if ((rc = run_gemm(d, s, P_W_NEXT))) return rc;
     GemmDesc e = gemm_base(FORM_NN, T, kD, kD, w.dP, kD, P + m->off_next_w, kD, w.dV0, kD);
-    if ((rc = run_gemm(e, s))) return rc;
+    if ((rc = run_gemm(e, s, P_D_NEXT))) return rc;
     GemmDesc f = gemm_base(FORM_TN, kD, m->attr_dim, T, w.dV0, kD, m->attr_table, m->attr_dim, G + m->off_attr_w, m->attr_dim);
     f.b_ids = x; f.colsum = G + m->off_attr_b; f.colsum_n = kD;
-    if ((rc = run_gemm(f, s))) return rc;
+    if ((rc = run_gemm(f, s, P_W_ATTR))) return rc;
   }
   // reconstruction head backward (gdiff was left in w.pred by the forward pass, without the beta factor)
   const float* dtE = nullptr;
@@ -536,35 +608,37 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom], nr = re - rs;
     GemmDesc d = gemm_base(FORM_TN, nr, kD, T, w.pred, w.pred_ld, w.E, kD, G + m->off_rw[random_chrom], kD);
     d.b_act = 1; d.out_scale = beta; d.colsum = G + m->off_rb[random_chrom]; d.colsum_n = nr;
-    if ((rc = run_gemm(d, s))) return rc;
+    if ((rc = run_gemm(d, s, P_W_RECON))) return rc;
     GemmDesc e = gemm_base(FORM_NN, T, kD, nr, w.pred, w.pred_ld, P + m->off_rw[random_chrom], kD, w.dtE, kD);
-    if ((rc = run_gemm(e, s))) return rc;
+    if ((rc = run_gemm(e, s, P_D_RECON))) return rc;
     dtE = w.dtE;
   }
-  if ((rc = launch_enc_combine_bwd(w.dV0, dtE, w.E, beta, w.dE, T * kD, s))) return rc;
+  if ((rc = PROF(P_ENC_COMBINE, 1, launch_enc_combine_bwd(w.dV0, dtE, w.E, beta, w.dE, T * kD, s)))) return rc;
   // encoder backward (grouped by chromosome; token lists from the forward pass are still in the workspace)
   {
     GemmDesc d = gemm_base(FORM_TN, kD, kD, 0, w.dE, kD, w.H0, kD, nullptr, kD);
     d.perm = w.perm; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, TAB_GW1); d.group_off = w.group_off;
     d.total_rows = T; d.max_group_dim = kD;
-    if ((rc = run_gemm(d, s))) return rc;
+    if ((rc = run_gemm(d, s, P_W_ENC1))) return rc;
     GemmDesc e = gemm_base(FORM_NN, 0, kD, kD, w.dE, kD, nullptr, 0, w.dH0pre, kD);
     e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, TAB_ENC1); e.group_off = w.group_off;
     e.total_rows = T; e.epi_act = 2; e.aux = w.H0; e.ld_aux = kD;
-    if ((rc = run_gemm(e, s))) return rc;
+    if ((rc = run_gemm(e, s, P_D_ENC1))) return rc;
     GemmDesc f = gemm_base(FORM_TN, kD, 0, 0, w.dH0pre, kD, nullptr, 0, nullptr, 0);
     f.perm = w.perm; f.b_ids = x; f.ngroups = m->n_chrom; f.groups = table_ptr(m->derived, TAB_GW0);
     f.group_off = w.group_off; f.total_rows = T; f.max_group_dim = max_chrom_len(m);
     if (m->p_feature > 0.f) { f.drop_on = 2; f.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
-    if ((rc = run_gemm(f, s))) return rc;
+    if ((rc = run_gemm(f, s, P_W_ENC0))) return rc;
   }
   // derived -> reference parameters
+  prof_begin(P_PREP_BWD, s);
   prep_bwd_qk_kernel<<<kD, 256, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_bwd_qk");
   prep_bwd_g_kernel<<<kH, 256, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_bwd_g");
+  prof_end(P_PREP_BWD, 2, s);
   if (active) {
-    if ((rc = launch_active_flags(w.counts, m->n_chrom, recon_on ? random_chrom : -1, T, active, s))) return rc;
+    if ((rc = PROF(P_MISC, 1, launch_active_flags(w.counts, m->n_chrom, recon_on ? random_chrom : -1, T, active, s)))) return rc;
   }
   return MATCHA_OK;
 }
@@ -596,13 +670,13 @@ int matcha_pair_tables(const matcha_model_desc* m, float* D, float* S, void* wor
   // node ids 0..N are materialised in the H1d area (T*64 floats >= T int64); they are last read by
   // run_mix_qkg, before run_pff overwrites H1d
   int64_t* ids = reinterpret_cast<int64_t*>(w.H1d);
-  if ((rc = launch_iota_i64(ids, T, s))) return rc;
+  if ((rc = PROF(P_MISC, 1, launch_iota_i64(ids, T, s)))) return rc;
   const DerivedLayout l = derived_layout();
   if ((rc = run_encoder(m, ids, T, 0, 0, w, w.E, s))) return rc;
   if ((rc = run_mix_qkg(m, ids, T, w, s))) return rc;
-  if ((rc = launch_pair_u(w.QKG, m->derived + l.bdyn, w.U, T, s))) return rc;
+  if ((rc = PROF(P_MISC, 1, launch_pair_u(w.QKG, m->derived + l.bdyn, w.U, T, s)))) return rc;
   if ((rc = run_pff(m, T, 0, 0, w, s))) return rc;
-  return launch_pair_ds(w.H2, w.xhat, score_params(m), D, S, T, s);
+  return PROF(P_MISC, 1, launch_pair_ds(w.H2, w.xhat, score_params(m), D, S, T, s));
 }
 
 int matcha_gemm(int32_t form, int32_t impl, const float* A, const float* B, float* C, const float* bias, int64_t M,

@@ -55,6 +55,7 @@ extern "C" int matcha_adamw(float* params, const float* grads, float* exp_avg, f
   MATCHA_REQUIRE(params && grads && exp_avg && exp_avg_sq && step >= 1, "matcha_adamw: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   AdamCfg c{lr, beta1, beta2, eps, weight_decay, grad_scale};
+  prof_begin(P_ADAMW, s);
   if (n_always > 0) {
     const float bc1 = 1.f - powf(beta1, (float)step), bc2s = sqrtf(1.f - powf(beta2, (float)step));
     int64_t blocks = (n_always + 255) / 256;
@@ -71,5 +72,6 @@ extern "C" int matcha_adamw(float* params, const float* grads, float* exp_avg, f
     adamw_seg_step_kernel<<<(n_seg + 127) / 128, 128, 0, s>>>(n_seg, seg_flag, seg_step, active);
     MATCHA_CHECK_LAUNCH("adamw_seg_step");
   }
+  prof_end(P_ADAMW, n_seg > 0 ? 3 : 1, s);
   return MATCHA_OK;
 }

@@ -183,10 +183,12 @@ int matcha_neg_sample(const void* table, int64_t capacity, const int64_t* pos, i
   if (total == 0) return MATCHA_OK;
   int64_t blocks = (total + 127) / 128;
   if (blocks > kSMs * 16) blocks = kSMs * 16;
+  prof_begin(P_SAMPLER, (cudaStream_t)stream);
   neg_sample_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const ulonglong2*>(table),
                                                                   (uint64_t)capacity - 1, pos, P, L, neg_num, cm, min_dis,
                                                                   seed, step, max_rounds, neg, valid, rounds_used);
   MATCHA_CHECK_LAUNCH("neg_sample");
+  prof_end(P_SAMPLER, 1, (cudaStream_t)stream);
   return MATCHA_OK;
 }
 

@@ -125,6 +125,8 @@ int matcha_pair_score_range(const float* D, const float* S, const float* cls_w, 
   const int64_t ti0 = r0 / PT, ti1 = r1 / PT;
   const int64_t ntj = (n + PT - 1) / PT;
   int64_t done = ti0;
+  int nk = 0;
+  prof_begin(P_PAIR_SCORE, (cudaStream_t)stream);
   while (done <= ti1) {   // gridDim.y <= 65535
     const int64_t chunk = (ti1 - done + 1) > 32768 ? 32768 : (ti1 - done + 1);
     dim3 grid((unsigned)ntj, (unsigned)chunk);
@@ -132,7 +134,9 @@ int matcha_pair_score_range(const float* D, const float* S, const float* cls_w, 
                                                               apply_sigmoid, out);
     MATCHA_CHECK_LAUNCH("pair_score");
     done += chunk;
+    ++nk;
   }
+  prof_end(P_PAIR_SCORE, nk, (cudaStream_t)stream);
   return MATCHA_OK;
 }
 

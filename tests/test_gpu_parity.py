@@ -256,9 +256,13 @@ def test_negative_sampler_bit_exact_vs_oracle(golden, min_dis):
     assert (valid.cpu().numpy() == want_valid).all()
     assert (rounds.cpu().numpy() == want_rounds).all()
     # domain properties: sorted, unique, never a positive, same chromosomes as the source positive
-    n = neg.cpu().numpy()
+    n, v = neg.cpu().numpy(), valid.cpu().numpy()
     s = SO.build_set(kmers)
+    assert v.mean() > 0.9
     for g, row in enumerate(n):
+        if not v[g]:          # every same-chromosome corruption was a positive: the row is the positive, flagged
+            assert (row == pos[g // 3]).all()
+            continue
         live = row[row != 0]
         assert (np.diff(live) > min_dis).all()
         assert SO.kmer_key(row) not in s
