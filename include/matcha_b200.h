@@ -185,7 +185,10 @@ int64_t matcha_pair_count(int64_t lo, int64_t hi, int32_t min_dis);
  * impl 0 = SIMT fp32, 1 = tcgen05 (bf16x3 split, fp32 accumulate in TMEM)
  * --------------------------------------------------------------------------------------------- */
 int matcha_gemm(int32_t form, int32_t impl, const float* A, const float* B, float* C, const float* bias,
-                int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, void* stream);
+                int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, float* scratch,
+                int64_t scratch_floats, void* stream);
+/* floats of scratch the tcgen05 form-2 kernel needs for M output rows (split-K partial sums) */
+int64_t matcha_gemm_scratch_floats(int64_t M);
 
 #ifdef __cplusplus
 }

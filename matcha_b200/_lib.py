@@ -100,7 +100,8 @@ SYMBOLS = {
     "matcha_pair_tables": (C.c_int, [_MD, _P, _P, _P, _I64, _P]),
     "matcha_pair_score_range": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _I64, _I32, _I64, _I64, _I32, _P, _P]),
     "matcha_pair_count": (_I64, [_I64, _I64, _I32]),
-    "matcha_gemm": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
+    "matcha_gemm": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P]),
+    "matcha_gemm_scratch_floats": (_I64, [_I64]),
 }
 
 

@@ -144,7 +144,12 @@ struct GemmDesc {
   int ngroups; const GemmGroup* groups; const int32_t* group_off;
   int64_t max_group_dim;                    // TN grouped: max N over groups (grid sizing)
   int64_t total_rows;                       // grouped: total tokens (upper bound for grid sizing)
+  // tcgen05 TN path: split-K partial sums live here (gemm_tc_scratch_floats(M) floats)
+  float* scratch; int64_t scratch_floats;
 };
+
+constexpr int kTcMaxSplits = 128;
+int64_t gemm_tc_scratch_floats(int64_t M);
 
 int launch_gemm_simt(const GemmDesc& d, cudaStream_t stream);
 int launch_gemm_tc(const GemmDesc& d, cudaStream_t stream, bool* handled);

@@ -294,7 +294,8 @@ __global__ void prep_bwd_g_kernel(const matcha_model_desc m) {
 struct Workspace {
   int32_t *counts, *group_off, *cursor, *perm;
   float *H0, *E, *V0, *X, *xhat, *rstd, *QKG, *U, *H1d, *H2, *pred, *recon;
-  float *dlogit, *dH2, *dXs, *dH1pre, *dU, *dQKG, *dxhat, *dP, *dV0, *dtE, *dE, *dH0pre;
+  float *dlogit, *dH2, *dXs, *dH1pre, *dU, *dQKG, *dxhat, *dP, *dV0, *dtE, *dE, *dH0pre, *tc_scratch;
+  int64_t tc_scratch_floats;
   int64_t pred_ld;
   int64_t bytes;
 };
@@ -332,6 +333,8 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
     w.dQKG = (float*)take(sizeof(float) * T * kQKG);
     w.dxhat = (float*)take(row); w.dP = (float*)take(row); w.dV0 = (float*)take(row); w.dtE = (float*)take(row);
     w.dE = (float*)take(row); w.dH0pre = (float*)take(row);
+    w.tc_scratch_floats = gemm_tc_scratch_floats(kQKG);
+    w.tc_scratch = (float*)take(sizeof(float) * w.tc_scratch_floats);
   }
   w.bytes = off;
   return w;
@@ -587,6 +590,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   {
     GemmDesc d = gemm_base(FORM_TN, kQKG, kD, T, w.dQKG, kQKG, w.xhat, kD, DG + l.wqkg, kD);
     d.colsum = DG + l.bqkg; d.colsum_n = kH * kD;
+    d.scratch = w.tc_scratch; d.scratch_floats = w.tc_scratch_floats;
     if ((rc = run_gemm(d, s, P_W_QKG))) return rc;
     GemmDesc e = gemm_base(FORM_NN, T, kD, kQKG, w.dQKG, kQKG, m->derived + l.wqkg, kD, w.dxhat, kD);
     if ((rc = run_gemm(e, s, P_D_QKG))) return rc;
@@ -679,11 +683,15 @@ int matcha_pair_tables(const matcha_model_desc* m, float* D, float* S, void* wor
   return PROF(P_MISC, 1, launch_pair_ds(w.H2, w.xhat, score_params(m), D, S, T, s));
 }
 
+int64_t matcha_gemm_scratch_floats(int64_t M) { return gemm_tc_scratch_floats(M); }
+
 int matcha_gemm(int32_t form, int32_t impl, const float* A, const float* B, float* C, const float* bias, int64_t M,
-                int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, void* stream) {
+                int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, float* scratch, int64_t scratch_floats,
+                void* stream) {
   MATCHA_REQUIRE(form >= 0 && form <= 2 && A && B && C, "matcha_gemm: bad arguments");
   GemmDesc d = gemm_base(form, M, N, K, A, lda, B, ldb, C, ldc);
   d.bias = bias;
+  d.scratch = scratch; d.scratch_floats = scratch_floats;
   if (impl == 1) {
     bool handled = false;
     int rc = launch_gemm_tc(d, (cudaStream_t)stream, &handled);

@@ -1,10 +1,516 @@
-// tcgen05 contraction kernel (placeholder until the tensor-core path is wired in).
+// tcgen05 (5th-gen tensor core) contraction kernels for the three large products of the hyperedge
+// pipeline -- the QKG projection, its data gradient and its weight gradient (B*L tokens x 64 x 1536).
+//
+// Precision: fp32 operands are split on the fly into bf16 hi + bf16 lo and three MMAs are issued
+// (hi*hi + hi*lo + lo*hi) into an fp32 TMEM accumulator ("bf16x3"): ~2^-16 relative error per product,
+// which keeps the whole pipeline inside the rtol 1e-4 contract, at one third of the bf16 MMA rate.
+//
+// Operand staging is done by the CTA's own threads (global fp32 -> registers -> split -> st.shared in
+// the canonical no-swizzle UMMA layouts), because the fp32 -> 2 x bf16 split has to touch every element
+// anyway; `fence.proxy.async` publishes the tiles to the tensor-core proxy.  One elected thread issues
+// tcgen05.mma; completion is tracked with tcgen05.commit -> mbarrier; accumulators are read back with
+// tcgen05.ld (32 lanes x 32 columns per warp).  Canonical layouts (cute/arch/mma_sm100_desc.hpp):
+//   K-major  (k contiguous):  [k/8][row][8 elems]      LBO = rows * 16 B (next 8 k),  SBO = 128 B (next 8 rows)
+//   MN-major (mn contiguous): [k/8][mn/8][k%8][8 elems] LBO = mn * 16 B  (next 8 k),  SBO = 128 B (next 8 mn)
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace matcha {
+namespace {
+
+constexpr int kThreads = 128;
+constexpr uint32_t kSpinLimit = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell); base_offset 0, layout SWIZZLE_NONE
+  return d;
+}
+// bf16 x bf16 -> fp32, M x N tile, optional MN-major operands
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a descriptor / protocol bug must surface as a trap, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < kSpinLimit; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// fp32 x 8 -> bf16 hi x 8 (16 B) and bf16 lo x 8 (16 B), lo = bf16(x - float(hi))
+__device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ float4 ldg4z(const float* p, bool ok) {
+  return ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void sts16(uint8_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// issue the three bf16 passes of one K = 16 step:  hi*hi, hi*lo, lo*hi
+__device__ __forceinline__ void umma_x3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                        uint32_t a_lbo, uint32_t b_lbo, uint32_t idesc, bool first) {
+  umma_bf16(tmem_d, make_smem_desc(a_lo, a_lbo, 128), make_smem_desc(b_hi, b_lbo, 128), idesc, first ? 0u : 1u);
+  umma_bf16(tmem_d, make_smem_desc(a_hi, a_lbo, 128), make_smem_desc(b_lo, b_lbo, 128), idesc, 1u);
+  umma_bf16(tmem_d, make_smem_desc(a_hi, a_lbo, 128), make_smem_desc(b_hi, b_lbo, 128), idesc, 1u);
+}
+
+// ==========================================================================================
+// NT, K = 64:  C[M, N] = A[M, 64] . B[N, 64]^T (+ bias)        (QKG projection; N % BN == 0)
+// ==========================================================================================
+template <int BN>
+__global__ void __launch_bounds__(kThreads) tc_nt_k64_kernel(const float* __restrict__ A, int64_t lda,
+                                                             const float* __restrict__ B, int64_t ldb,
+                                                             float* __restrict__ C, int64_t ldc,
+                                                             const float* __restrict__ bias, int64_t M, int64_t N) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sAh = smem;                 // [8][128][16 B]
+  uint8_t* sAl = smem + 16384;
+  uint8_t* sBh = smem + 32768;         // [8][BN][16 B]
+  uint8_t* sBl = sBh + BN * 128;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * 128;
+  if (warp == 0) tmem_alloc(&tmem_base_s, BN);
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {  // A tile: thread = row
+    const int64_t r = m0 + tid;
+    const bool ok = r < M;
+    const float* src = A + (ok ? r : 0) * lda;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 hi, lo;
+      split8(ldg4z(src + q * 8, ok), ldg4z(src + q * 8 + 4, ok), hi, lo);
+      sts16(sAh + q * 2048 + tid * 16, hi);
+      sts16(sAl + q * 2048 + tid * 16, lo);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  constexpr uint32_t idesc = make_idesc(128, BN, false, false);
+  uint32_t phase = 0;
+  for (int64_t n0 = 0; n0 < N; n0 += BN) {
+    // B chunk: BN rows x 8 k-chunks
+#pragma unroll 4
+    for (int u = tid; u < BN * 8; u += kThreads) {
+      const int row = u % BN, q = u / BN;
+      const float* src = B + (n0 + row) * ldb + q * 8;
+      uint4 hi, lo;
+      split8(ldg4z(src, true), ldg4z(src + 4, true), hi, lo);
+      sts16(sBh + q * (BN * 16) + row * 16, hi);
+      sts16(sBl + q * (BN * 16) + row * 16, lo);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_x3(tmem_base, smem_u32(sAh) + ks * 4096, smem_u32(sAl) + ks * 4096, smem_u32(sBh) + ks * (BN * 32),
+                smem_u32(sBl) + ks * (BN * 32), 2048, BN * 16, idesc, ks == 0);
+      umma_commit(&mbar);
+    }
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    const int64_t r = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+      if (r < M) {
+        float* dst = C + r * ldc + n0 + cc * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc * 32 + j));
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          }
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, BN);
+}
+
+// ==========================================================================================
+// NN, N = 64:  C[M, 64] = A[M, K] . B[K, 64]        (data gradient of the QKG projection; K % 64 == 0)
+// ==========================================================================================
+__global__ void __launch_bounds__(kThreads) tc_nn_n64_kernel(const float* __restrict__ A, int64_t lda,
+                                                             const float* __restrict__ B, int64_t ldb,
+                                                             float* __restrict__ C, int64_t ldc, int64_t M, int64_t K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kBuf = 49152;   // per buffer: A hi 16 KB | A lo 16 KB | B hi 8 KB | B lo 8 KB
+  __shared__ uint64_t mbar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * 128;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  constexpr uint32_t idesc = make_idesc(128, 64, false, true);
+  const int64_t r = m0 + tid;
+  const bool rok = r < M;
+  const float* arow = A + (rok ? r : 0) * lda;
+  uint32_t phase[2] = {0, 0};
+  const int nk = (int)(K / 64);
+  for (int kc = 0; kc < nk; ++kc) {
+    const int buf = kc & 1;
+    uint8_t* sAh = smem + buf * kBuf;
+    uint8_t* sAl = sAh + 16384;
+    uint8_t* sBh = sAh + 32768;
+    uint8_t* sBl = sBh + 8192;
+    float4 ra[16], rb[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ra[i] = ldg4z(arow + kc * 64 + i * 4, rok);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // B chunk [64 k][64 n]: unit = (k, n-group of 8)
+      const int u = i * kThreads + tid, g = u & 7, k = u >> 3;
+      const float* src = B + (int64_t)(kc * 64 + k) * ldb + g * 8;
+      rb[2 * i] = ldg4z(src, true);
+      rb[2 * i + 1] = ldg4z(src + 4, true);
+    }
+    if (kc >= 2) { mbar_wait(&mbar[buf], phase[buf]); phase[buf] ^= 1; }   // MMAs of chunk kc-2 released this buffer
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 hi, lo;
+      split8(ra[2 * q], ra[2 * q + 1], hi, lo);
+      sts16(sAh + q * 2048 + tid * 16, hi);
+      sts16(sAl + q * 2048 + tid * 16, lo);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int u = i * kThreads + tid, g = u & 7, k = u >> 3;
+      uint4 hi, lo;
+      split8(rb[2 * i], rb[2 * i + 1], hi, lo);
+      const int off = (k >> 3) * 1024 + g * 128 + (k & 7) * 16;     // MN-major: [k/8][n/8][k%8][8]
+      sts16(sBh + off, hi);
+      sts16(sBl + off, lo);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_x3(tmem_base, smem_u32(sAh) + ks * 4096, smem_u32(sAl) + ks * 4096, smem_u32(sBh) + ks * 2048,
+                smem_u32(sBl) + ks * 2048, 2048, 1024, idesc, kc == 0 && ks == 0);
+      umma_commit(&mbar[buf]);
+    }
+  }
+  {  // tcgen05 ops of one thread complete in order: the last commit covers everything
+    const int buf = (nk - 1) & 1;
+    mbar_wait(&mbar[buf], phase[buf]);
+  }
+  tc_fence_after();
+  const int64_t ro = m0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int cc = 0; cc < 2; ++cc) {
+    float v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+    if (ro < M) {
+      float* dst = C + ro * ldc + cc * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+// ==========================================================================================
+// TN, N = 64:  part[s][M, 64] = A[Ks, M]^T . B[Ks, 64] over the token range of split s
+//              (weight gradient of the QKG projection; M % 512 == 0; also column sums of A)
+// ==========================================================================================
+__global__ void __launch_bounds__(kThreads) tc_tn_n64_kernel(const float* __restrict__ A, int64_t lda,
+                                                             const float* __restrict__ B, int64_t ldb, int64_t M,
+                                                             int64_t K, int64_t k_per_split, float* __restrict__ part,
+                                                             float* __restrict__ part_colsum) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kBuf = 36864;   // per buffer: A hi 16 KB | A lo 16 KB | B hi 2 KB | B lo 2 KB   (16 tokens x 512 / 64 columns)
+  __shared__ uint64_t mbar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_cs[kThreads][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mg = blockIdx.x;                       // group of 512 output rows (columns of A)
+  const int split = blockIdx.y;
+  const int64_t k_begin = (int64_t)split * k_per_split;
+  const int64_t k_end = (k_begin + k_per_split < K) ? k_begin + k_per_split : K;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  constexpr uint32_t idesc = make_idesc(128, 64, true, true);
+  const int ga = tid & 63, ta = tid >> 6;          // A units: column group ga (8 columns), tokens ta + 2 i
+  const int gb = tid & 7, tb = tid >> 3;           // B unit : column group gb, token tb
+  const float* acol = A + (int64_t)mg * 512 + ga * 8;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint32_t phase[2] = {0, 0};
+  const int nchunk = (int)((k_end - k_begin + 15) / 16);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int buf = ch & 1;
+    uint8_t* sAh = smem + buf * kBuf;
+    uint8_t* sAl = sAh + 16384;
+    uint8_t* sBh = sAh + 32768;
+    uint8_t* sBl = sBh + 2048;
+    const int64_t kb = k_begin + (int64_t)ch * 16;
+    float4 ra[16], rb[2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t k = kb + ta + 2 * i;
+      const bool ok = k < k_end;
+      const float* src = acol + (ok ? k : 0) * lda;
+      ra[2 * i] = ldg4z(src, ok);
+      ra[2 * i + 1] = ldg4z(src + 4, ok);
+    }
+    {
+      const int64_t k = kb + tb;
+      const bool ok = k < k_end;
+      const float* src = B + (ok ? k : 0) * ldb + gb * 8;
+      rb[0] = ldg4z(src, ok);
+      rb[1] = ldg4z(src + 4, ok);
+    }
+    if (ch >= 2) { mbar_wait(&mbar[buf], phase[buf]); phase[buf] ^= 1; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = ta + 2 * i;                                       // token within the chunk
+      uint4 hi, lo;
+      split8(ra[2 * i], ra[2 * i + 1], hi, lo);
+      const int off = (k >> 3) * 8192 + ga * 128 + (k & 7) * 16;      // MN-major: [k/8][m/8][k%8][8], 512 columns
+      sts16(sAh + off, hi);
+      sts16(sAl + off, lo);
+      cs[0] += ra[2 * i].x; cs[1] += ra[2 * i].y; cs[2] += ra[2 * i].z; cs[3] += ra[2 * i].w;
+      cs[4] += ra[2 * i + 1].x; cs[5] += ra[2 * i + 1].y; cs[6] += ra[2 * i + 1].z; cs[7] += ra[2 * i + 1].w;
+    }
+    {
+      uint4 hi, lo;
+      split8(rb[0], rb[1], hi, lo);
+      const int off = (tb >> 3) * 1024 + gb * 128 + (tb & 7) * 16;
+      sts16(sBh + off, hi);
+      sts16(sBl + off, lo);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)     // four 128-row output tiles share the B operand
+        umma_x3(tmem_base + j * 64, smem_u32(sAh) + j * 2048, smem_u32(sAl) + j * 2048, smem_u32(sBh), smem_u32(sBl), 8192,
+                1024, idesc, ch == 0);
+      umma_commit(&mbar[buf]);
+    }
+  }
+  if (nchunk > 0) {
+    const int buf = (nchunk - 1) & 1;
+    mbar_wait(&mbar[buf], phase[buf]);
+  }
+  tc_fence_after();
+  float* out = part + ((int64_t)split * M + (int64_t)mg * 512) * 64;
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      float v[32];
+      if (nchunk > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 64 + cc * 32, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      float* dst = out + (int64_t)(j * 128 + warp * 32 + lane) * 64 + cc * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  if (part_colsum) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_cs[tid][e] = cs[e];
+    __syncthreads();
+    if (tid < 64) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        part_colsum[(int64_t)split * M + (int64_t)mg * 512 + tid * 8 + e] = s_cs[tid][e] + s_cs[tid + 64][e];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+__global__ void tn_reduce_kernel(const float* __restrict__ part, const float* __restrict__ part_colsum, int splits,
+                                 int64_t M, float* __restrict__ C, int64_t ldc, float* __restrict__ colsum,
+                                 int64_t colsum_n, float scale) {
+  const int64_t total = M * 64;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total + M; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < total) {
+      float s = 0.f;
+      for (int sp = 0; sp < splits; ++sp) s += part[(int64_t)sp * total + i];
+      C[(i >> 6) * ldc + (i & 63)] += s * scale;
+    } else if (colsum && part_colsum) {
+      const int64_t m = i - total;
+      if (m < colsum_n) {
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += part_colsum[(int64_t)sp * M + m];
+        colsum[m] += s * scale;
+      }
+    }
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+bool plain(const GemmDesc& d) {
+  return d.ngroups == 0 && !d.perm && !d.a_ids && !d.b_ids && !d.a_act && !d.b_act && !d.drop_on && !d.addend &&
+         !d.epi_act && !d.epi_drop && (d.out_scale == 0.f || d.out_scale == 1.f);
+}
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
+}
+}  // namespace
+
+int64_t gemm_tc_scratch_floats(int64_t M) { return (int64_t)kTcMaxSplits * (M * 64 + M); }
+
 int launch_gemm_tc(const GemmDesc& d, cudaStream_t stream, bool* handled) {
-  (void)d; (void)stream;
   *handled = false;
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0) return MATCHA_OK;
+  const bool al = aligned16(d.A) && aligned16(d.B) && aligned16(d.C) && d.lda % 4 == 0 && d.ldb % 4 == 0 && d.ldc % 4 == 0;
+  if (!al) return MATCHA_OK;
+  if (d.form == FORM_NT && plain(d) && d.K == 64 && d.N % 256 == 0 && (!d.bias || aligned16(d.bias))) {
+    constexpr int smem = 32768 + 2 * 256 * 128;   // 96 KB -> two CTAs (2 x 256 TMEM columns) per SM
+    static bool once = false;
+    if (!once) { if (int rc = set_smem(tc_nt_k64_kernel<256>, smem)) return rc; once = true; }
+    tc_nt_k64_kernel<256><<<(unsigned)((d.M + 127) / 128), kThreads, smem, stream>>>(d.A, d.lda, d.B, d.ldb, d.C, d.ldc,
+                                                                                     d.bias, d.M, d.N);
+    MATCHA_CHECK_LAUNCH("tc_nt_k64");
+    *handled = true;
+  } else if (d.form == FORM_NN && plain(d) && !d.bias && d.N == 64 && d.K % 64 == 0) {
+    constexpr int smem = 2 * 49152;               // 96 KB
+    static bool once = false;
+    if (!once) { if (int rc = set_smem(tc_nn_n64_kernel, smem)) return rc; once = true; }
+    tc_nn_n64_kernel<<<(unsigned)((d.M + 127) / 128), kThreads, smem, stream>>>(d.A, d.lda, d.B, d.ldb, d.C, d.ldc, d.M, d.K);
+    MATCHA_CHECK_LAUNCH("tc_nn_n64");
+    *handled = true;
+  } else if (d.form == FORM_TN && d.ngroups == 0 && !d.perm && !d.a_ids && !d.b_ids && !d.a_act && !d.b_act && !d.drop_on &&
+             d.N == 64 && d.ldb == 64 && d.M % 512 == 0 && d.scratch && d.scratch_floats >= gemm_tc_scratch_floats(d.M) &&
+             d.K >= 2048) {
+    constexpr int smem = 81920;                   // 2 x 36 KB used; 80 KB requested so at most two CTAs (2 x 256 TMEM columns) share an SM
+    static bool once = false;
+    if (!once) { if (int rc = set_smem(tc_tn_n64_kernel, smem)) return rc; once = true; }
+    const int mgroups = (int)(d.M / 512);
+    int splits = (2 * kSMs + mgroups - 1) / mgroups;
+    if (splits > kTcMaxSplits) splits = kTcMaxSplits;
+    int64_t kps = (d.K + splits - 1) / splits;
+    kps = (kps + 15) / 16 * 16;
+    splits = (int)((d.K + kps - 1) / kps);
+    float* part = d.scratch;
+    float* part_cs = d.scratch + (int64_t)kTcMaxSplits * d.M * 64;
+    dim3 grid((unsigned)mgroups, (unsigned)splits);
+    tc_tn_n64_kernel<<<grid, kThreads, smem, stream>>>(d.A, d.lda, d.B, d.ldb, d.M, d.K, kps, part, d.colsum ? part_cs : nullptr);
+    MATCHA_CHECK_LAUNCH("tc_tn_n64");
+    const float scale = d.out_scale == 0.f ? 1.f : d.out_scale;
+    tn_reduce_kernel<<<kSMs * 2, 256, 0, stream>>>(part, d.colsum ? part_cs : nullptr, splits, d.M, d.C, d.ldc, d.colsum,
+                                                   d.colsum_n, scale);
+    MATCHA_CHECK_LAUNCH("tn_reduce");
+    *handled = true;
+  }
   return MATCHA_OK;
 }
+
 }  // namespace matcha
