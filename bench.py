@@ -287,7 +287,7 @@ def main():
         ach = work / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                 "traffic": None}
-    impl_used = args.gemm_impl if args.gemm_impl >= 0 else int(os.environ.get("MATCHA_GEMM_IMPL", "0") or 0)
+    impl_used = args.gemm_impl if args.gemm_impl >= 0 else int(os.environ.get("MATCHA_GEMM_IMPL", "1") or 1)
     roof.update({"kernel": name, "ms_per_launch": per_launch_ms, "share_of_step": tms / tot_ms, "peak_source": peaks["src"],
                  "contractions": "tcgen05 bf16x3 split, fp32 accumulate" if impl_used == 1 else "fp32 SIMT"})
     launches = int(sum(v[2] for v in prof.values()))

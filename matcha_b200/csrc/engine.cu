@@ -72,7 +72,7 @@ static int g_gemm_impl = -1;  // -1 = read MATCHA_GEMM_IMPL on first use; 0 = SI
 static int gemm_impl() {
   if (g_gemm_impl < 0) {
     const char* e = getenv("MATCHA_GEMM_IMPL");
-    g_gemm_impl = (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 1 : 0);
+    g_gemm_impl = (e && e[0] == '0') ? 0 : 1;   // tcgen05 for the eligible shapes unless MATCHA_GEMM_IMPL=0
   }
   return g_gemm_impl;
 }

@@ -56,6 +56,32 @@ def test_gemm_simt_matches_torch(form, M, N, K):
     assert err < 2e-6, err
 
 
+@pytest.mark.parametrize("form,M,N,K", [(0, 130, 1536, 64), (0, 4099, 512, 64), (1, 300, 64, 1536), (1, 5000, 64, 128),
+                                        (2, 1536, 64, 3000), (2, 512, 64, 20000)])
+def test_gemm_tcgen05_matches_fp64(form, M, N, K):
+    """tcgen05 path (bf16 hi/lo split x3, fp32 TMEM accumulator): ~2^-16 relative error per product."""
+    from tc_gemm_check import run
+    assert run(form, M, N, K, impl=1, bias=(form == 0)) < 3e-5
+
+
+def test_pipeline_agrees_between_simt_and_tcgen05(golden, model):
+    L = _lib()
+    lib = L.load()
+    model.eval()
+    x = torch.from_numpy(golden["x/L5"]).cuda().repeat(40, 1)        # 640 hyperedges -> 3200 tokens (>= 2048 for the TN path)
+    try:
+        lib.matcha_set_gemm_impl(0)
+        with torch.no_grad():
+            a = model(x)
+        lib.matcha_set_gemm_impl(1)
+        with torch.no_grad():
+            b = model(x)
+    finally:
+        lib.matcha_set_gemm_impl(1)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(b.cpu().numpy()[:16], golden["logits_eval/L5"], rtol=1e-4, atol=5e-5)
+
+
 # ------------------------------------------------------------------------------------------
 # Classifier.forward / get_node_embeddings vs the reference's own outputs
 # ------------------------------------------------------------------------------------------
