@@ -134,3 +134,45 @@ def build_model(ds, seed=1):
     model = M.Classifier(n_head=8, d_model=ds["d"], d_k=ds["d"], d_v=ds["d"], node_embedding=ne, diag_mask=True,
                          bottle_neck=ds["d"], attribute_dict=ds["attr"])
     return model.to(M.device)
+
+
+def write_temp_dir(ds, temp_dir, config_path=None):
+    """Write `ds` in the reference's on-disk formats (process.py:36-39,175-176; generate_kmers.py:140-141):
+    chrom_range.npy, node2chrom.npy, bin2node.npy, node2bin.npy, all_<k>_counter.npy,
+    all_<k>_freq_counter.npy, intra_adj.npy, inter_adj.npy -- plus a config.JSON with the reference's keys."""
+    import json
+    import os
+    os.makedirs(temp_dir, exist_ok=True)
+    cr, N, res = ds["chrom_range"], ds["N"], ds["res"]
+    np.save(os.path.join(temp_dir, "chrom_range.npy"), cr)
+    node2chrom, bin2node, node2bin = {}, {}, {}
+    for c, (s, e) in enumerate(cr):
+        for i in range(int(s), int(e)):
+            node2chrom[i] = c
+            name = "%s:%d" % (ds["chroms"][c], (i - int(s)) * res)
+            bin2node[name], node2bin[i] = i, name
+    np.save(os.path.join(temp_dir, "node2chrom.npy"), node2chrom, allow_pickle=True)
+    np.save(os.path.join(temp_dir, "bin2node.npy"), bin2node, allow_pickle=True)
+    np.save(os.path.join(temp_dir, "node2bin.npy"), node2bin, allow_pickle=True)
+    for k, rows in ds["kmers"].items():
+        np.save(os.path.join(temp_dir, "all_%d_counter.npy" % k), rows)
+        np.save(os.path.join(temp_dir, "all_%d_freq_counter.npy" % k), ds["freq"][k])
+    adj = np.zeros((N, N), dtype=np.float32)
+    for k, rows in ds["kmers"].items():
+        r, f = rows - 1, ds["freq"][k].astype(np.float32)
+        for a in range(k):
+            for b in range(a + 1, k):
+                np.add.at(adj, (r[:, a], r[:, b]), f)
+    adj = adj + adj.T
+    intra = np.zeros_like(adj)
+    for (s, e) in cr:
+        intra[s - 1:e - 1, s - 1:e - 1] = adj[s - 1:e - 1, s - 1:e - 1]
+    np.save(os.path.join(temp_dir, "intra_adj.npy"), intra)
+    np.save(os.path.join(temp_dir, "inter_adj.npy"), adj - intra)
+    cfg = {"cluster_path": "synthetic.cluster", "mcool_path": "synthetic.mcool", "resolution": res,
+           "chrom_list": list(ds["chroms"]), "chrom_size": "synthetic", "temp_dir": temp_dir, "max_cluster_size": 25,
+           "min_distance": 0, "k-mer_size": sorted(int(k) for k in ds["kmers"]), "min_freq_cutoff": 2,
+           "quantile_cutoff_for_positive": 0.6, "quantile_cutoff_for_unlabel": 0.4, "embed_dim": ds["d"]}
+    if config_path:
+        json.dump(cfg, open(config_path, "w"), indent=1)
+    return cfg

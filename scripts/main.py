@@ -1,0 +1,210 @@
+"""Training entry point with the reference's interface (Code/main.py): reads ./config.JSON and the
+`temp_dir` arrays written by process.py / generate_kmers.py, trains the Hyper-SAGNN classifier in the
+same two phases, and writes `temp_dir/model.chkpt`, `temp_dir/model2load` and `../embeddings.npy`.
+
+What differs from the reference is where the work runs: negatives are sampled on the GPU against an exact
+device hash set, and forward / loss / backward / AdamW are the fused sm_100a step of
+`matcha_b200.trainer.Trainer` (optionally data-parallel: launch with torchrun).  Hyper-edges are held
+zero-padded (numpy >= 1.24 rejects the ragged arrays of main.py:565).
+
+Environment overrides (tests / quick runs): MATCHA_EPOCHS1, MATCHA_EPOCHS2, MATCHA_BATCH, MATCHA_STEPS_PER_EPOCH.
+"""
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from Modules import Classifier, DataGenerator, MultipleEmbedding, device  # noqa: E402
+from utils import accuracy, build_hash, get_config, roc_auc_cuda  # noqa: E402
+
+from matcha_b200.hyper_sagnn import pad_edges  # noqa: E402
+from matcha_b200.parallel import init_from_env, shard_rows  # noqa: E402
+from matcha_b200.sampler import NegativeSampler  # noqa: E402
+from matcha_b200.trainer import Trainer  # noqa: E402
+
+
+def quantile_uniform(freq):
+    """QuantileTransformer(n_quantiles=1000, output_distribution='uniform') of main.py:555."""
+    from sklearn.preprocessing import QuantileTransformer
+    return QuantileTransformer(n_quantiles=1000, output_distribution="uniform").fit_transform(
+        freq.reshape((-1, 1))).reshape((-1))
+
+
+def load_kmers(temp_dir, size_list, cutoff, max_size):
+    data, weight = [], []
+    for size in size_list:
+        d = np.load(os.path.join(temp_dir, "all_%d_counter.npy" % size)).astype("int64")
+        w = quantile_uniform(np.load(os.path.join(temp_dir, "all_%d_freq_counter.npy" % size)).astype("float32"))
+        mask = w > cutoff
+        print("size", size, "before filter", len(d), "after filter", int(mask.sum()))
+        data.append(pad_edges(d[mask], max_size))
+        weight.append(w[mask])
+    return np.concatenate(data), np.concatenate(weight).astype("float32")
+
+
+def get_attributes(num, n_chrom):            # main.py:497-512
+    rows = []
+    for i in range(len(num)):
+        chrom = np.zeros((num[i], n_chrom))
+        chrom[:, i] = 1
+        coor = np.arange(num[i]).reshape((-1, 1)).astype("float32") / num[0]
+        rows.append(np.concatenate([chrom, coor], axis=-1))
+    allr = np.concatenate(rows, axis=0)
+    return np.concatenate([np.zeros((1, allr.shape[-1])), allr], axis=0).astype("float32")
+
+
+def save_embeddings(model, n_nodes):        # main.py:462-479: one call instead of N/96 tiny forwards
+    model.eval()
+    with torch.no_grad():
+        ids = torch.arange(1, n_nodes + 1, device=device).view(-1, 1)
+        emb = model.get_node_embeddings(ids).cpu().numpy()[:, 0, :]
+    np.save("../embeddings.npy", emb)
+    return emb
+
+
+def predict(model, samples, batch=int(1e5)):  # main.py:482-494
+    model.eval()
+    out = []
+    with torch.no_grad():
+        for j in range(math.ceil(len(samples) / batch)):
+            x = torch.from_numpy(pad_edges(samples[j * batch:(j + 1) * batch])).to(device)
+            out.append(model(x).cpu().numpy())
+    return np.concatenate(out, axis=0)
+
+
+def eval_epoch(model, trainer, sampler, data, weight, batch, rng):
+    """main.py:200-258: 10 000 sampled validation edges + fresh negatives, eval mode, metrics per size."""
+    model.eval()
+    idx = rng.permutation(len(data))[:10000]
+    preds, labels, sizes = [], [], []
+    bce_tot, n = 0.0, 0
+    with torch.no_grad():
+        for i in range(0, len(idx) - batch + 1, batch):
+            pos = torch.from_numpy(data[idx[i:i + batch]]).to(device)
+            neg, valid = sampler.sample(pos.contiguous())
+            x = torch.cat([pos, neg])
+            y = torch.cat([torch.ones(len(pos), 1, device=device), torch.zeros(len(neg), 1, device=device)])
+            w = torch.cat([torch.from_numpy(weight[idx[i:i + batch]]).to(device).view(-1, 1), valid.float().view(-1, 1)])
+            logit = model(x)
+            bce_tot += float(torch.nn.functional.binary_cross_entropy_with_logits(logit, y, weight=w))
+            n += 1
+            keep = w.view(-1) > 0
+            preds.append(torch.sigmoid(logit)[keep]); labels.append(y[keep]); sizes.append((x != 0).sum(1)[keep])
+    pred, label, size = torch.cat(preds), torch.cat(labels), torch.cat(sizes)
+    auc1, auc2 = roc_auc_cuda(label, pred, size, None)
+    model.train()
+    return bce_tot / max(1, n), accuracy(pred, label, size), auc1, auc2
+
+
+def train(model, trainer, sampler, training_data, validation_data, epochs, batch, steps_per_epoch, temp_dir, n_nodes,
+          min_size, max_size, rank, world, rng):
+    valid_best = [0.0]
+    edges, weights = training_data
+    gen = DataGenerator(edges, weights, int(batch), steps_per_epoch // max(1, (max_size - min_size + 1)) or 1,
+                        min_size=min_size, max_size=max_size)
+    for epoch_i in range(epochs):
+        if rank == 0:
+            save_embeddings(model, n_nodes)
+        print("[ Epoch", epoch_i, "of", epochs, "]")
+        start = time.time()
+        e_part, w_part = gen.next_iter()
+        perm = rng.permutation(len(e_part))
+        e_part, w_part = e_part[perm], w_part[perm].astype("float32")
+        model.train()
+        trainer.loss_sum.zero_(); trainer.steps = 0
+        nb = len(e_part) // batch
+        e_dev, w_dev = torch.from_numpy(e_part).to(device), torch.from_numpy(w_part).to(device)
+        for i in range(nb):
+            sl = slice(i * batch, (i + 1) * batch)
+            trainer.step(e_dev[sl][shard_rows(batch, rank, world)].contiguous(), w_dev[sl][shard_rows(batch, rank, world)].contiguous())
+        losses = trainer.mean_losses()
+        print("  - (Training)   bce: %7.4f, recon: %7.4f, steps: %d, elapse: %3.3f s" %
+              (losses["bce"], losses["recon"], nb, time.time() - start))
+        start = time.time()
+        v_bce, v_acc, v_auc1, v_auc2 = eval_epoch(model, trainer, sampler, validation_data[0], validation_data[1], batch, rng)
+        print("  - (Validation-hyper) bce: %7.4f,  acc: %s, auc: %s, aupr: %s, elapse: %3.3f s" %
+              (v_bce, v_acc, v_auc1, v_auc2, time.time() - start))
+        aupr = float(v_auc2.split(" ")[1])
+        if rank == 0 and aupr >= max(valid_best):
+            torch.save({"model_link": model.state_dict(), "epoch": epoch_i}, os.path.join(temp_dir, "model.chkpt"))
+            torch.save(model, os.path.join(temp_dir, "model2load"))
+        valid_best.append(aupr)
+
+
+def main():
+    config = get_config()
+    bottle_neck = config["embed_dim"]
+    size_list = config["k-mer_size"]
+    min_size, max_size = int(np.min(size_list)), int(np.max(size_list))
+    temp_dir = config["temp_dir"]
+    min_dis = config["min_distance"]
+    neg_num = 3
+    batch_size = int(os.environ.get("MATCHA_BATCH", 96))
+    steps_per_epoch = int(os.environ.get("MATCHA_STEPS_PER_EPOCH", 4000))
+    epochs1, epochs2 = int(os.environ.get("MATCHA_EPOCHS1", 3)), int(os.environ.get("MATCHA_EPOCHS2", 30))
+    rank, world, local = init_from_env()
+    rng = np.random.RandomState(0)
+
+    chrom_range = np.load(os.path.join(temp_dir, "chrom_range.npy"))
+    num = [int(v[1] - v[0]) for v in chrom_range]
+    num_list = np.cumsum(num)
+    data, weight = load_kmers(temp_dir, size_list, config["quantile_cutoff_for_positive"], max_size)
+
+    inter_initial = np.load(os.path.join(temp_dir, "inter_adj.npy")).astype("float32")
+    adj = np.load(os.path.join(temp_dir, "intra_adj.npy")).astype("float32")
+    embeddings_initial = []
+    for v in chrom_range:                                     # main.py:572-577
+        with np.errstate(invalid="ignore", divide="ignore"):
+            temp = np.corrcoef(adj[v[0] - 1:v[1] - 1, v[0] - 1:v[1] - 1]).astype("float32")
+        temp[np.isnan(temp)] = 0.0
+        embeddings_initial.append(temp)
+    attribute_dict = get_attributes(num, len(config["chrom_list"]))
+
+    weight /= np.mean(weight)
+    weight *= neg_num
+    index = rng.permutation(len(data))
+    split = int(0.8 * len(index))
+    train_data, test_data = data[index[:split]], data[index[split:]]
+    train_weight, test_weight = weight[index[:split]], weight[index[split:]]
+    print("train data amount", len(train_data))
+
+    node_embedding = MultipleEmbedding(embeddings_initial, bottle_neck, False, num_list, chrom_range, inter_initial).to(device)
+    model = Classifier(n_head=8, d_model=bottle_neck, d_k=bottle_neck, d_v=bottle_neck, node_embedding=node_embedding,
+                       diag_mask=True, bottle_neck=bottle_neck, attribute_dict=attribute_dict).to(device)
+    n_nodes = int(num_list[-1])
+    if rank == 0:
+        save_embeddings(model, n_nodes)
+    print("params to be trained", sum(int(np.prod(p.size())) for p in model.parameters() if p.requires_grad))
+
+    # phase 1 (main.py:637-643): reconstruction loss only.  The reference's dictionary is empty here, so
+    # its "negatives" equal the positives; with alpha = 0 they do not matter.
+    empty = build_hash(np.zeros((0, max_size), dtype=np.int64), max_size=max_size, capacity=1024)
+    sampler = NegativeSampler(empty, chrom_range, min_dis=min_dis, neg_num=neg_num, seed=2 + rank)
+    trainer = Trainer(model, sampler, alpha=0.0, beta=1.0, lr=1e-3, seed=1, world_size=world, rank=rank)
+    train(model, trainer, sampler, (train_data, train_weight), (test_data, test_weight), epochs1, batch_size,
+          steps_per_epoch, temp_dir, n_nodes, min_size, max_size, rank, world, rng)
+
+    # phase 2 (main.py:646-679): dictionary of all k-mers above the "unlabel" quantile, fresh AdamW
+    dict_data, _ = load_kmers(temp_dir, size_list, config["quantile_cutoff_for_unlabel"], max_size)
+    hashset = build_hash(dict_data, max_size=max_size)
+    print("Finish building Dict", hashset.count)
+    sampler = NegativeSampler(hashset, chrom_range, min_dis=min_dis, neg_num=neg_num, seed=2 + rank)
+    trainer = Trainer(model, sampler, alpha=1.0, beta=0.001, lr=1e-3, seed=2, world_size=world, rank=rank)
+    train(model, trainer, sampler, (train_data, train_weight), (test_data, test_weight), epochs2, batch_size,
+          steps_per_epoch, temp_dir, n_nodes, min_size, max_size, rank, world, rng)
+
+    if rank == 0:
+        ck = os.path.join(temp_dir, "model.chkpt")
+        if os.path.exists(ck):
+            model.load_state_dict(torch.load(ck, weights_only=False)["model_link"])
+        save_embeddings(model, n_nodes)
+        torch.save(model, os.path.join(temp_dir, "model2load"))
+
+
+if __name__ == "__main__":
+    main()
