@@ -146,10 +146,13 @@ struct GemmDesc {
   int64_t total_rows;                       // grouped: total tokens (upper bound for grid sizing)
   // tcgen05 TN path: split-K partial sums live here (gemm_tc_scratch_floats(M) floats)
   float* scratch; int64_t scratch_floats;
+  // tcgen05 NT path: B pre-split into bf16 hi|lo canonical chunks by launch_split_weights_k64 (N*64*4 bytes)
+  const uint8_t* b_split;
 };
 
 constexpr int kTcMaxSplits = 128;
 int64_t gemm_tc_scratch_floats(int64_t M);
+int launch_split_weights_k64(const float* W, int64_t ldw, int64_t N, void* out, cudaStream_t stream);
 
 int launch_gemm_simt(const GemmDesc& d, cudaStream_t stream);
 int launch_gemm_tc(const GemmDesc& d, cudaStream_t stream, bool* handled);

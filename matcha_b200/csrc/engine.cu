@@ -90,7 +90,7 @@ static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
 // derived-parameter layout
 // ------------------------------------------------------------------------------------------
 struct DerivedLayout {
-  int64_t wqkg, bqkg, bdyn, bdyn_part, tables, total;  // float offsets
+  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, tables, total;  // float offsets
 };
 static __host__ __device__ DerivedLayout derived_layout() {
   DerivedLayout l;
@@ -98,7 +98,8 @@ static __host__ __device__ DerivedLayout derived_layout() {
   l.bqkg = l.wqkg + (int64_t)kQKG * kD;
   l.bdyn = l.bqkg + kQKG;
   l.bdyn_part = l.bdyn + kD;        // per-head partial sums of b_dyn (summed in a fixed order: deterministic)
-  l.tables = l.bdyn_part + kH * kD;
+  l.wsplit = (l.bdyn_part + kH * kD + 255) / 256 * 256;   // W_qkg pre-split to bf16 hi|lo chunks (same byte count)
+  l.tables = l.wsplit + (int64_t)kQKG * kD;
   l.tables = (l.tables + 63) / 64 * 64;
   const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
   l.total = l.tables + 4 * table_floats;
@@ -406,6 +407,7 @@ static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   if ((rc = PROF(P_LN, 1, launch_ln_fwd(w.X, w.xhat, w.rstd, T, s)))) return rc;
   GemmDesc q = gemm_base(FORM_NT, T, kQKG, kD, w.xhat, kD, m->derived + l.wqkg, kD, w.QKG, kQKG);
   q.bias = m->derived + l.bqkg;
+  q.b_split = reinterpret_cast<const uint8_t*>(m->derived + l.wsplit);
   return run_gemm(q, s, P_QKG);
 }
 
@@ -486,7 +488,8 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   MATCHA_CHECK_LAUNCH("prep_g");
   prep_tables_kernel<<<1, MATCHA_MAX_CHROM, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_tables");
-  prof_end(P_PREP, 3, s);
+  if ((rc = launch_split_weights_k64(m->derived + l.wqkg, kD, kQKG, m->derived + l.wsplit, s))) return rc;
+  prof_end(P_PREP, 4, s);
   return MATCHA_OK;
 }
 
@@ -692,6 +695,10 @@ int matcha_gemm(int32_t form, int32_t impl, const float* A, const float* B, floa
   GemmDesc d = gemm_base(form, M, N, K, A, lda, B, ldb, C, ldc);
   d.bias = bias;
   d.scratch = scratch; d.scratch_floats = scratch_floats;
+  if (impl == 1 && form == 0 && K == 64 && N % 128 == 0 && scratch && scratch_floats >= N * 64 && ldb % 4 == 0) {
+    if (int rc = launch_split_weights_k64(B, ldb, N, scratch, (cudaStream_t)stream)) return rc;   // v2 kernel path
+    d.b_split = reinterpret_cast<const uint8_t*>(scratch);
+  }
   if (impl == 1) {
     bool handled = false;
     int rc = launch_gemm_tc(d, (cudaStream_t)stream, &handled);

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kThreads) tc_nn_n64_kernel(const float* __rest
                                                              const float* __restrict__ B, int64_t ldb,
                                                              float* __restrict__ C, int64_t ldc, int64_t M, int64_t K) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int kBuf = 49152;   // per buffer: A hi 16 KB | A lo 16 KB | B hi 8 KB | B lo 8 KB
+  constexpr int kBuf = 16 * 2064 + 16384;   // per buffer: A hi | A lo (8 padded planes each) | B hi 8 KB | B lo 8 KB
   __shared__ uint64_t mbar[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -239,34 +239,44 @@ __global__ void __launch_bounds__(kThreads) tc_nn_n64_kernel(const float* __rest
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   constexpr uint32_t idesc = make_idesc(128, 64, false, true);
-  const int64_t r = m0 + tid;
-  const bool rok = r < M;
-  const float* arow = A + (rok ? r : 0) * lda;
+  constexpr int kPlane = 2064;                     // padded K-major plane of the A tile (128 rows x 16 B + 16)
   uint32_t phase[2] = {0, 0};
   const int nk = (int)(K / 64);
-  for (int kc = 0; kc < nk; ++kc) {
-    const int buf = kc & 1;
-    uint8_t* sAh = smem + buf * kBuf;
-    uint8_t* sAl = sAh + 16384;
-    uint8_t* sBh = sAh + 32768;
-    uint8_t* sBl = sBh + 8192;
-    float4 ra[16], rb[8];
+  const int aq = tid & 7, ar0 = tid >> 3;          // A units: row = ar0 + 16 i, k-chunk aq
+  float4 ra[16], rb[8], na[16], nb[8];
+  auto load_chunk = [&](int kc, float4 (&xa)[16], float4 (&xb)[8]) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) ra[i] = ldg4z(arow + kc * 64 + i * 4, rok);
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = m0 + ar0 + 16 * i;
+      const bool ok = r < M;
+      const float* src = A + (ok ? r : 0) * lda + kc * 64 + aq * 8;
+      xa[2 * i] = ldg4z(src, ok);
+      xa[2 * i + 1] = ldg4z(src + 4, ok);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {   // B chunk [64 k][64 n]: unit = (k, n-group of 8)
       const int u = i * kThreads + tid, g = u & 7, k = u >> 3;
       const float* src = B + (int64_t)(kc * 64 + k) * ldb + g * 8;
-      rb[2 * i] = ldg4z(src, true);
-      rb[2 * i + 1] = ldg4z(src + 4, true);
+      xb[2 * i] = ldg4z(src, true);
+      xb[2 * i + 1] = ldg4z(src + 4, true);
     }
+  };
+  load_chunk(0, ra, rb);
+  for (int kc = 0; kc < nk; ++kc) {
+    const int buf = kc & 1;
+    uint8_t* sAh = smem + buf * kBuf;
+    uint8_t* sAl = sAh + 8 * kPlane;
+    uint8_t* sBh = sAh + 16 * kPlane;
+    uint8_t* sBl = sBh + 8192;
+    if (kc + 1 < nk) load_chunk(kc + 1, na, nb);   // in flight while this chunk is split and multiplied
     if (kc >= 2) { mbar_wait(&mbar[buf], phase[buf]); phase[buf] ^= 1; }   // MMAs of chunk kc-2 released this buffer
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int i = 0; i < 8; ++i) {
       uint4 hi, lo;
-      split8(ra[2 * q], ra[2 * q + 1], hi, lo);
-      sts16(sAh + q * 2048 + tid * 16, hi);
-      sts16(sAl + q * 2048 + tid * 16, lo);
+      split8(ra[2 * i], ra[2 * i + 1], hi, lo);
+      const int off = aq * kPlane + (ar0 + 16 * i) * 16;
+      sts16(sAh + off, hi);
+      sts16(sAl + off, lo);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -283,10 +293,14 @@ __global__ void __launch_bounds__(kThreads) tc_nn_n64_kernel(const float* __rest
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        umma_x3(tmem_base, smem_u32(sAh) + ks * 4096, smem_u32(sAl) + ks * 4096, smem_u32(sBh) + ks * 2048,
-                smem_u32(sBl) + ks * 2048, 2048, 1024, idesc, kc == 0 && ks == 0);
+        umma_x3(tmem_base, smem_u32(sAh) + ks * 2 * kPlane, smem_u32(sAl) + ks * 2 * kPlane, smem_u32(sBh) + ks * 2048,
+                smem_u32(sBl) + ks * 2048, kPlane, 1024, idesc, kc == 0 && ks == 0);
       umma_commit(&mbar[buf]);
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ra[i] = na[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rb[i] = nb[i];
   }
   {  // tcgen05 ops of one thread complete in order: the last commit covers everything
     const int buf = (nk - 1) & 1;
@@ -344,29 +358,31 @@ __global__ void __launch_bounds__(kThreads) tc_tn_n64_kernel(const float* __rest
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   uint32_t phase[2] = {0, 0};
   const int nchunk = (int)((k_end - k_begin + 15) / 16);
+  float4 ra[16], rb[2], na[16], nb[2];
+  auto load_chunk = [&](int ch, float4 (&xa)[16], float4 (&xb)[2]) {
+    const int64_t kb = k_begin + (int64_t)ch * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t k = kb + ta + 2 * i;
+      const bool ok = k < k_end;
+      const float* src = acol + (ok ? k : 0) * lda;
+      xa[2 * i] = ldg4z(src, ok);
+      xa[2 * i + 1] = ldg4z(src + 4, ok);
+    }
+    const int64_t k = kb + tb;
+    const bool ok = k < k_end;
+    const float* src = B + (ok ? k : 0) * ldb + gb * 8;
+    xb[0] = ldg4z(src, ok);
+    xb[1] = ldg4z(src + 4, ok);
+  };
+  if (nchunk > 0) load_chunk(0, ra, rb);
   for (int ch = 0; ch < nchunk; ++ch) {
     const int buf = ch & 1;
     uint8_t* sAh = smem + buf * kBuf;
     uint8_t* sAl = sAh + 16384;
     uint8_t* sBh = sAh + 32768;
     uint8_t* sBl = sBh + 2048;
-    const int64_t kb = k_begin + (int64_t)ch * 16;
-    float4 ra[16], rb[2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int64_t k = kb + ta + 2 * i;
-      const bool ok = k < k_end;
-      const float* src = acol + (ok ? k : 0) * lda;
-      ra[2 * i] = ldg4z(src, ok);
-      ra[2 * i + 1] = ldg4z(src + 4, ok);
-    }
-    {
-      const int64_t k = kb + tb;
-      const bool ok = k < k_end;
-      const float* src = B + (ok ? k : 0) * ldb + gb * 8;
-      rb[0] = ldg4z(src, ok);
-      rb[1] = ldg4z(src + 4, ok);
-    }
+    if (ch + 1 < nchunk) load_chunk(ch + 1, na, nb);   // next chunk's loads fly while this one is split and multiplied
     if (ch >= 2) { mbar_wait(&mbar[buf], phase[buf]); phase[buf] ^= 1; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -396,6 +412,9 @@ __global__ void __launch_bounds__(kThreads) tc_tn_n64_kernel(const float* __rest
                 1024, idesc, ch == 0);
       umma_commit(&mbar[buf]);
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ra[i] = na[i];
+    rb[0] = nb[0]; rb[1] = nb[1];
   }
   if (nchunk > 0) {
     const int buf = (nchunk - 1) & 1;
@@ -454,6 +473,178 @@ __global__ void tn_reduce_kernel(const float* __restrict__ part, const float* __
   }
 }
 
+// ==========================================================================================
+// v2 of the NT, K = 64 product (the QKG projection), warp-specialised and pipelined.
+//   Transposed tile: D[128 features, 128 tokens] = Wsplit[chunk](128 x 64) . xhat_tile(128 x 64)^T, so a TMEM
+//   lane is an output FEATURE: the bias is one register per thread and every STG.32 of a warp writes 32
+//   consecutive floats of one token row (one full 128-byte line).
+//   warp 0: bulk-copies pre-split weight chunks (bf16 hi | lo, canonical K-major, 32 KB) into a 3-stage ring
+//   warp 1: issues tcgen05.mma (3 bf16 passes x 4 K-steps per chunk) into a 4-deep ring of TMEM accumulators
+//   warps 2-9: split + stage the token tile (double buffered), then drain accumulators (LDTM -> +bias -> STG)
+// ==========================================================================================
+constexpr int kV2Threads = 320;
+constexpr int kV2WStages = 3, kV2AccStages = 4;
+constexpr int kV2WBytes = 32768;                 // one weight chunk: hi 16 KB | lo 16 KB
+constexpr int kV2XPlane = 2064;                  // 128 rows x 16 B + 16 B pad: conflict-free staging stores
+constexpr int kV2XHalf = 8 * kV2XPlane;          // hi (or lo) part of one token tile
+constexpr int kV2XBytes = 2 * kV2XHalf;          // one token tile: hi | lo
+constexpr int kV2Smem = kV2WStages * kV2WBytes + 2 * kV2XBytes;   // 160 KB
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// fp32 [N, 64] row-major  ->  per 128-row chunk: bf16 hi [8][128][8] | bf16 lo [8][128][8]   (N % 128 == 0)
+__global__ void split_weights_k64_kernel(const float* __restrict__ W, int64_t ldw, int64_t N, uint8_t* __restrict__ out) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // unit = (row, k-chunk of 8)
+  if (u >= N * 8) return;
+  const int64_t row = u >> 3;
+  const int q = (int)(u & 7);
+  const float* src = W + row * ldw + q * 8;
+  uint4 hi, lo;
+  split8(__ldg(reinterpret_cast<const float4*>(src)), __ldg(reinterpret_cast<const float4*>(src + 4)), hi, lo);
+  uint8_t* chunk = out + (row >> 7) * kV2WBytes;
+  const int r = (int)(row & 127);
+  *reinterpret_cast<uint4*>(chunk + q * 2048 + r * 16) = hi;
+  *reinterpret_cast<uint4*>(chunk + 16384 + q * 2048 + r * 16) = lo;
+}
+
+__global__ void __launch_bounds__(kV2Threads, 1) tc_qkg_fwd_v2_kernel(const float* __restrict__ A, int64_t lda,
+                                                                      const uint8_t* __restrict__ Wsplit,
+                                                                      const float* __restrict__ bias, float* __restrict__ C,
+                                                                      int64_t ldc, int64_t M, int N) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;                                   // [kV2WStages][32 KB]
+  uint8_t* sX = smem + kV2WStages * kV2WBytes;          // [2][32 KB]
+  __shared__ uint64_t w_full[kV2WStages], w_empty[kV2WStages], x_full[2], x_empty[2], acc_full[kV2AccStages],
+      acc_empty[kV2AccStages];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunk = N / 128;
+  const int64_t ntiles = (M + 127) / 128;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 32) {
+    for (int i = 0; i < kV2WStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 256); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < kV2AccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ---------------- weight-chunk producer ----------------
+    if (lane == 0) {
+      int ws = 0; uint32_t wp = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int fc = 0; fc < nchunk; ++fc) {
+          mbar_wait(&w_empty[ws], wp ^ 1);
+          mbar_expect_tx(&w_full[ws], kV2WBytes);
+          bulk_g2s(sW + ws * kV2WBytes, Wsplit + (int64_t)fc * kV2WBytes, kV2WBytes, &w_full[ws]);
+          if (++ws == kV2WStages) { ws = 0; wp ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 128, false, false);
+      int ws = 0, as = 0, xs = 0; uint32_t wp = 0, ap = 0, xp = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&x_full[xs], xp);
+        const uint32_t xh = smem_u32(sX + xs * kV2XBytes), xl = xh + kV2XHalf;
+        for (int fc = 0; fc < nchunk; ++fc) {
+          mbar_wait(&w_full[ws], wp);
+          mbar_wait(&acc_empty[as], ap ^ 1);
+          tc_fence_after();
+          const uint32_t wh = smem_u32(sW + ws * kV2WBytes), wl = wh + 16384;
+          const uint32_t d = tmem_base + as * 128;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_x3(d, wh + ks * 4096, wl + ks * 4096, xh + ks * 2 * kV2XPlane, xl + ks * 2 * kV2XPlane, 2048, kV2XPlane, idesc, ks == 0);
+          umma_commit(&w_empty[ws]);       // weight stage may be refilled once these MMAs retire
+          umma_commit(&acc_full[as]);      // accumulator ready for the epilogue warps
+          if (++ws == kV2WStages) { ws = 0; wp ^= 1; }
+          if (++as == kV2AccStages) { as = 0; ap ^= 1; }
+        }
+        umma_commit(&x_empty[xs]);         // token tile buffer may be overwritten
+        if (++xs == 2) { xs = 0; xp ^= 1; }
+      }
+    }
+  } else {
+    // ---------------- token-tile staging + epilogue (warps 2..9) ----------------
+    const int et = tid - 64;               // 0..255
+    const int ew = et >> 5;                // 0..7
+    const int lane_grp = warp & 3;         // TMEM lane quarter this warp may read (warp id % 4)
+    const int tok_half = ew >> 2;          // which 64 tokens of the tile
+    int as = 0; uint32_t ap = 0;
+    auto stage_tile = [&](int64_t tile, int buf) {
+      // 128 rows x 8 k-chunks = 1024 units; thread -> (row = u >> 3, q = u & 7): 8 lanes cover one 256-byte row
+      uint8_t* xh = sX + buf * kV2XBytes;
+      uint8_t* xl = xh + kV2XHalf;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int u = i * 256 + et, row = u >> 3, q = u & 7;
+        const int64_t r = tile * 128 + row;
+        const bool ok = r < M;
+        const float* src = A + (ok ? r : 0) * lda + q * 8;
+        uint4 hi, lo;
+        split8(ldg4z(src, ok), ldg4z(src + 4, ok), hi, lo);
+        sts16(xh + q * kV2XPlane + row * 16, hi);
+        sts16(xl + q * kV2XPlane + row * 16, lo);
+      }
+      fence_async_smem();
+      mbar_arrive(&x_full[buf]);
+    };
+    int64_t tile = blockIdx.x;
+    if (tile < ntiles) stage_tile(tile, 0);
+    int stage_buf = 1; uint32_t stage_phase = 0;   // phase of x_empty for the NEXT buffer to fill
+    for (; tile < ntiles; tile += gridDim.x) {
+      const int64_t next = tile + gridDim.x;
+      if (next < ntiles) {
+        mbar_wait(&x_empty[stage_buf], stage_phase ^ 1);
+        stage_tile(next, stage_buf);
+        if (++stage_buf == 2) { stage_buf = 0; stage_phase ^= 1; }
+      }
+      for (int fc = 0; fc < nchunk; ++fc) {
+        mbar_wait(&acc_full[as], ap);
+        tc_fence_after();
+        const int feat = fc * 128 + lane_grp * 32 + lane;
+        const float b = bias ? __ldg(bias + feat) : 0.f;
+        float v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + as * 128 + tok_half * 64;
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32, v1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        const int64_t t0 = tile * 128 + tok_half * 64;
+        float* dst = C + t0 * ldc + feat;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (t0 + j < M) dst[(int64_t)j * ldc] = v0[j] + b;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (t0 + 32 + j < M) dst[(int64_t)(32 + j) * ldc] = v1[j] + b;
+        if (++as == kV2AccStages) { as = 0; ap ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 bool plain(const GemmDesc& d) {
   return d.ngroups == 0 && !d.perm && !d.a_ids && !d.b_ids && !d.a_act && !d.b_act && !d.drop_on && !d.addend &&
@@ -465,6 +656,13 @@ int set_smem(K kernel, int bytes) {
 }
 }  // namespace
 
+int launch_split_weights_k64(const float* W, int64_t ldw, int64_t N, void* out, cudaStream_t stream) {
+  if (N % 128 != 0) { set_error("split_weights: N must be a multiple of 128"); return MATCHA_ERR_ARG; }
+  split_weights_k64_kernel<<<(unsigned)((N * 8 + 255) / 256), 256, 0, stream>>>(W, ldw, N, reinterpret_cast<uint8_t*>(out));
+  MATCHA_CHECK_LAUNCH("split_weights_k64");
+  return MATCHA_OK;
+}
+
 int64_t gemm_tc_scratch_floats(int64_t M) { return (int64_t)kTcMaxSplits * (M * 64 + M); }
 
 int launch_gemm_tc(const GemmDesc& d, cudaStream_t stream, bool* handled) {
@@ -472,7 +670,15 @@ int launch_gemm_tc(const GemmDesc& d, cudaStream_t stream, bool* handled) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return MATCHA_OK;
   const bool al = aligned16(d.A) && aligned16(d.B) && aligned16(d.C) && d.lda % 4 == 0 && d.ldb % 4 == 0 && d.ldc % 4 == 0;
   if (!al) return MATCHA_OK;
-  if (d.form == FORM_NT && plain(d) && d.K == 64 && d.N % 256 == 0 && (!d.bias || aligned16(d.bias))) {
+  if (d.form == FORM_NT && plain(d) && d.K == 64 && d.N % 128 == 0 && d.b_split && d.M >= 128) {
+    static bool once = false;
+    if (!once) { if (int rc = set_smem(tc_qkg_fwd_v2_kernel, kV2Smem)) return rc; once = true; }
+    const int64_t ntiles = (d.M + 127) / 128;
+    const unsigned grid = (unsigned)(ntiles < kSMs ? ntiles : kSMs);
+    tc_qkg_fwd_v2_kernel<<<grid, kV2Threads, kV2Smem, stream>>>(d.A, d.lda, d.b_split, d.bias, d.C, d.ldc, d.M, (int)d.N);
+    MATCHA_CHECK_LAUNCH("tc_qkg_fwd_v2");
+    *handled = true;
+  } else if (d.form == FORM_NT && plain(d) && d.K == 64 && d.N % 256 == 0 && (!d.bias || aligned16(d.bias))) {
     constexpr int smem = 32768 + 2 * 256 * 128;   // 96 KB -> two CTAs (2 x 256 TMEM columns) per SM
     static bool once = false;
     if (!once) { if (int rc = set_smem(tc_nt_k64_kernel<256>, smem)) return rc; once = true; }
@@ -481,7 +687,7 @@ int launch_gemm_tc(const GemmDesc& d, cudaStream_t stream, bool* handled) {
     MATCHA_CHECK_LAUNCH("tc_nt_k64");
     *handled = true;
   } else if (d.form == FORM_NN && plain(d) && !d.bias && d.N == 64 && d.K % 64 == 0) {
-    constexpr int smem = 2 * 49152;               // 96 KB
+    constexpr int smem = 2 * (16 * 2064 + 16384);   // ~97 KB -> two CTAs per SM
     static bool once = false;
     if (!once) { if (int rc = set_smem(tc_nn_n64_kernel, smem)) return rc; once = true; }
     tc_nn_n64_kernel<<<(unsigned)((d.M + 127) / 128), kThreads, smem, stream>>>(d.A, d.lda, d.B, d.ldb, d.C, d.ldc, d.M, d.K);

@@ -53,6 +53,8 @@ class KmerHashSet:
     def insert(self, kmers):
         """kmers [n, k] int64, rows sorted ascending, zero padded to the right (k <= width)."""
         rows = self._as_rows(kmers)
+        if rows.shape[0] == 0:
+            return self
         if (self.count + rows.shape[0]) * 2 > self.capacity:
             raise MatchaError("hash set over capacity: construct it with a larger capacity_hint")
         check(self.lib.matcha_hashset_insert(ptr(self.table), self.capacity, ptr(rows), rows.shape[0], self.width,

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from matcha_b200 import _lib as L  # noqa: E402
 
 
-def run(form, M, N, K, impl, bias=False, seed=0):
+def run(form, M, N, K, impl, bias=False, seed=0, v2=True):
     lib = L.load()
     g = torch.Generator(device="cuda").manual_seed(seed)
     if form == 0:
@@ -25,7 +25,7 @@ def run(form, M, N, K, impl, bias=False, seed=0):
     if b is not None:
         ref = ref + b.double()
     C = torch.zeros(M, N, device="cuda")
-    ns = lib.matcha_gemm_scratch_floats(M) if form == 2 else 0
+    ns = lib.matcha_gemm_scratch_floats(M) if form == 2 else (N * 64 if (form == 0 and v2) else 0)
     scratch = torch.empty(max(ns, 1), device="cuda")
     L.check(lib.matcha_gemm(form, impl, A.data_ptr(), B.data_ptr(), C.data_ptr(), L.ptr(b), M, N, K, A.stride(0),
                             B.stride(0), N, scratch.data_ptr(), ns, L.stream_ptr()), "matcha_gemm")
@@ -38,6 +38,9 @@ if __name__ == "__main__":
     cases = [(0, 128, 256, 64, True), (0, 1000, 1536, 64, True), (0, 81920, 1536, 64, False),
              (1, 128, 64, 64, False), (1, 333, 64, 1536, False), (1, 81920, 64, 1536, False),
              (2, 512, 64, 4096, False), (2, 1536, 64, 5000, False), (2, 1536, 64, 81920, False)]
+    e = run(0, 1000, 1536, 64, 1, True, v2=False)
+    print(f"form 0 v1 kernel (no pre-split weights): rel err {e:.2e}", flush=True)
+    ok &= e < 3e-5
     for form, M, N, K, bias in cases:
         e1 = run(form, M, N, K, 1, bias)
         e0 = run(form, M, N, K, 0, bias)
