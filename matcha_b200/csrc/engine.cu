@@ -76,6 +76,8 @@ static int gemm_impl() {
   }
   return g_gemm_impl;
 }
+static bool use_tiles(int64_t T) { return gemm_impl() == 1 && T >= kTilePathMinTokens; }
+
 static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
   prof_begin(label, s);
   int rc = MATCHA_OK;
@@ -90,7 +92,7 @@ static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
 // derived-parameter layout
 // ------------------------------------------------------------------------------------------
 struct DerivedLayout {
-  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, tables, total;  // float offsets
+  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, tables, total;  // float offsets
 };
 static __host__ __device__ DerivedLayout derived_layout() {
   DerivedLayout l;
@@ -99,7 +101,8 @@ static __host__ __device__ DerivedLayout derived_layout() {
   l.bdyn = l.bqkg + kQKG;
   l.bdyn_part = l.bdyn + kD;        // per-head partial sums of b_dyn (summed in a fixed order: deterministic)
   l.wsplit = (l.bdyn_part + kH * kD + 255) / 256 * 256;   // W_qkg pre-split to bf16 hi|lo chunks (same byte count)
-  l.tables = l.wsplit + (int64_t)kQKG * kD;
+  l.wtsplit = l.wsplit + (int64_t)kQKG * kD;             // W_qkg^T pre-split, MN-major chunks (data-gradient B operand)
+  l.tables = l.wtsplit + (int64_t)kQKG * kD;
   l.tables = (l.tables + 63) / 64 * 64;
   const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
   l.total = l.tables + 4 * table_floats;
@@ -295,6 +298,7 @@ __global__ void prep_bwd_g_kernel(const matcha_model_desc m) {
 struct Workspace {
   int32_t *counts, *group_off, *cursor, *perm;
   float *H0, *E, *V0, *X, *xhat, *rstd, *QKG, *U, *H1d, *H2, *pred, *recon;
+  uint8_t *xhat_t, *dqkg_t;   // MMA-ready tiles (rowwise.cuh); dqkg_t aliases dQKG
   float *dlogit, *dH2, *dXs, *dH1pre, *dU, *dQKG, *dxhat, *dP, *dV0, *dtE, *dE, *dH0pre, *tc_scratch;
   int64_t tc_scratch_floats;
   int64_t pred_ld;
@@ -324,6 +328,7 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
   const int64_t row = sizeof(float) * T * kD;
   w.H0 = (float*)take(row); w.E = (float*)take(row); w.V0 = (float*)take(row); w.X = (float*)take(row);
   w.xhat = (float*)take(row); w.rstd = (float*)take(sizeof(float) * (T + 1));
+  w.xhat_t = (uint8_t*)take(num_token_tiles(T) * (int64_t)kXTileBytes);
   w.QKG = (float*)take(sizeof(float) * T * kQKG);
   w.U = (float*)take(row); w.H1d = (float*)take(row); w.H2 = (float*)take(row);
   w.pred_ld = m->inter ? (max_chrom_len(m) + 3) / 4 * 4 : 0;
@@ -331,7 +336,8 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
   if (training) {
     w.dlogit = (float*)take(sizeof(float) * (B + 1));
     w.dH2 = (float*)take(row); w.dXs = (float*)take(row); w.dH1pre = (float*)take(row); w.dU = (float*)take(row);
-    w.dQKG = (float*)take(sizeof(float) * T * kQKG);
+    w.dQKG = (float*)take(num_token_tiles(T) * (int64_t)kGChunks * kGTileBytes);   // >= T * 1536 * 4 bytes
+    w.dqkg_t = reinterpret_cast<uint8_t*>(w.dQKG);
     w.dxhat = (float*)take(row); w.dP = (float*)take(row); w.dV0 = (float*)take(row); w.dtE = (float*)take(row);
     w.dE = (float*)take(row); w.dH0pre = (float*)take(row);
     w.tc_scratch_floats = gemm_tc_scratch_floats(kQKG);
@@ -404,7 +410,11 @@ static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   GemmDesc b = gemm_base(FORM_NT, T, kD, kD, w.V0, kD, P + m->off_next_w, kD, w.X, kD);
   b.bias = P + m->off_next_b; b.epi_act = 1;
   if ((rc = run_gemm(b, s, P_MIX))) return rc;
-  if ((rc = PROF(P_LN, 1, launch_ln_fwd(w.X, w.xhat, w.rstd, T, s)))) return rc;
+  const bool tiles = use_tiles(T);
+  if ((rc = PROF(P_LN, 1, launch_ln_fwd(w.X, w.xhat, w.rstd, T, tiles ? w.xhat_t : nullptr, s)))) return rc;
+  if (tiles)
+    return PROF(P_QKG, 1, tc_qkg_forward_tiles(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wsplit),
+                                               m->derived + l.bqkg, w.QKG, T, s));
   GemmDesc q = gemm_base(FORM_NT, T, kQKG, kD, w.xhat, kD, m->derived + l.wqkg, kD, w.QKG, kQKG);
   q.bias = m->derived + l.bqkg;
   q.b_split = reinterpret_cast<const uint8_t*>(m->derived + l.wsplit);
@@ -489,7 +499,8 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   prep_tables_kernel<<<1, MATCHA_MAX_CHROM, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_tables");
   if ((rc = launch_split_weights_k64(m->derived + l.wqkg, kD, kQKG, m->derived + l.wsplit, s))) return rc;
-  prof_end(P_PREP, 4, s);
+  if ((rc = launch_split_wT(m->derived + l.wqkg, m->derived + l.wtsplit, s))) return rc;
+  prof_end(P_PREP, 5, s);
   return MATCHA_OK;
 }
 
@@ -589,8 +600,20 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   }
   // attention backward
   DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, true);
-  if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_bwd(w.QKG, w.dU, x, w.dQKG, DG + l.bdyn, B, L, dattn, s)))) return rc;
-  {
+  if (use_tiles(T)) {
+    // tile path: the attention backward emits dQKG directly as bf16 hi|lo MMA tiles; rows of the last tile beyond T are zero
+    const int64_t nt = num_token_tiles(T);
+    if (T % kTileTok != 0 &&
+        (rc = check_cuda(cudaMemsetAsync(w.dqkg_t + (nt - 1) * (int64_t)kGChunks * kGTileBytes, 0, (size_t)kGChunks * kGTileBytes, s),
+                         "memset dQKG tail tile")))
+      return rc;
+    if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_bwd(w.QKG, w.dU, x, nullptr, w.dqkg_t, DG + l.bdyn, B, L, dattn, s)))) return rc;
+    if ((rc = PROF(P_W_QKG, 2, tc_qkg_wgrad_tiles(w.dqkg_t, w.xhat_t, w.tc_scratch, w.tc_scratch_floats, DG + l.wqkg,
+                                                  DG + l.bqkg, kH * kD, T, s)))) return rc;
+    if ((rc = PROF(P_D_QKG, 1, tc_qkg_dgrad_tiles(w.dqkg_t, reinterpret_cast<const uint8_t*>(m->derived + l.wtsplit), w.dxhat,
+                                                  T, s)))) return rc;
+  } else {
+    if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_bwd(w.QKG, w.dU, x, w.dQKG, nullptr, DG + l.bdyn, B, L, dattn, s)))) return rc;
     GemmDesc d = gemm_base(FORM_TN, kQKG, kD, T, w.dQKG, kQKG, w.xhat, kD, DG + l.wqkg, kD);
     d.colsum = DG + l.bqkg; d.colsum_n = kH * kD;
     d.scratch = w.tc_scratch; d.scratch_floats = w.tc_scratch_floats;

@@ -1,6 +1,8 @@
 // Row-wise kernels of the Hyper-SAGNN hot path: everything that is not a dense contraction.
 // Layout rule: one HALF-WARP owns one token row (64 floats = 16 lanes x float4, one coalesced 256 B
 // access) or one hyperedge (its L <= 8 rows in turn); row reductions are 4 xor-shuffles.
+#include <cuda_bf16.h>
+
 #include "rowwise.cuh"
 
 namespace matcha {
@@ -67,6 +69,8 @@ __device__ __forceinline__ void block_colsum_atomic(float4 v, float* smem64, flo
   __syncthreads();
 }
 
+__device__ __forceinline__ int64_t num_token_tiles_dev(int64_t T) { return (T + kTileTok - 1) / kTileTok; }
+
 inline int grid_for_halfwarps(int64_t n, int cap_blocks) {
   int64_t blocks = (n * 16 + kBlock - 1) / kBlock;
   if (blocks < 1) blocks = 1;
@@ -119,11 +123,30 @@ __global__ void active_flags_kernel(const int32_t* counts, int n_chrom, int rchr
 // ------------------------------------------------------------------------------------------
 // LayerNorm statistics of X (shared by MHA layer_norm1/2/3 and Classifier.layer_norm2: same input row)
 // ------------------------------------------------------------------------------------------
+// fp32 x4 -> 4 bf16 hi (8 B) + 4 bf16 lo (8 B), lo = bf16(x - float(hi))
+__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  uint32_t h[2], l[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint2(h[0], h[1]);
+  lo = make_uint2(l[0], l[1]);
+}
+// byte offset, inside a tile half, of columns [4*hl, 4*hl+4) of token `tok` (0..127)
+__device__ __forceinline__ int tile_off(int hl, int tok) { return (hl >> 1) * kPlaneBytes + tok * 16 + (hl & 1) * 8; }
+
 __global__ void __launch_bounds__(kBlock) ln_fwd_kernel(const float* __restrict__ X, float* __restrict__ xhat,
-                                                         float* __restrict__ rstd, int64_t T) {
+                                                         float* __restrict__ rstd, int64_t T, uint8_t* __restrict__ xt) {
   const int hl = threadIdx.x & 15;
   const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
-  const int64_t iters = (T + nhw - 1) / nhw;
+  const int64_t Tp = xt ? num_token_tiles_dev(T) * kTileTok : T;     // tile path: also zero the tail rows of the last tile
+  const int64_t iters = (Tp + nhw - 1) / nhw;
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t t = hw0 + it * nhw;
     const bool valid = t < T;
@@ -132,6 +155,19 @@ __global__ void __launch_bounds__(kBlock) ln_fwd_kernel(const float* __restrict_
     if (valid) {
       st4(xhat + t * kD + hl * 4, o.xh);
       if (hl == 0) rstd[t] = o.rstd;
+    }
+    if (xt && t < Tp) {
+      uint8_t* tile = xt + (t / kTileTok) * (int64_t)kXTileBytes;
+      const int tok = (int)(t % kTileTok);
+      uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
+      if (valid) split4(o.xh, hi, lo);
+      *reinterpret_cast<uint2*>(tile + tile_off(hl, tok)) = hi;
+      *reinterpret_cast<uint2*>(tile + kXHalfBytes + tile_off(hl, tok)) = lo;
+      if (hl < 4) {   // planes 8 (ones column) and 9 (zeros) of both halves: 16 bytes each per token
+        uint4 v = make_uint4((hl == 0 && valid) ? 0x00003F80u : 0u, 0u, 0u, 0u);     // bf16(1.0) in column 64
+        uint8_t* dst = tile + (hl >> 1) * kXHalfBytes + (8 + (hl & 1)) * kPlaneBytes + tok * 16;
+        *reinterpret_cast<uint4*>(dst) = v;
+      }
     }
   }
 }
@@ -206,10 +242,26 @@ __global__ void __launch_bounds__(kBlock) attn_fwd_kernel(const float* __restric
   }
 }
 
-template <int L>
+// store 4 consecutive gradient columns of token t: fp32 row-major, or pre-split tile (chunk fc, columns 4*hl..)
+template <bool SPLIT>
+__device__ __forceinline__ void store_dqkg(float* dQKG, uint8_t* gt, int64_t t, int fc, int hl, float4 v) {
+  if (!SPLIT) {
+    st4(dQKG + t * kQKG + fc * kD + hl * 4, v);
+  } else {
+    uint2 hi, lo;
+    split4(v, hi, lo);
+    uint8_t* tile = gt + ((t / kTileTok) * kGChunks + fc) * (int64_t)kGTileBytes;
+    const int off = tile_off(hl, (int)(t % kTileTok));
+    *reinterpret_cast<uint2*>(tile + off) = hi;
+    *reinterpret_cast<uint2*>(tile + kGHalfBytes + off) = lo;
+  }
+}
+
+template <int L, bool SPLIT>
 __global__ void __launch_bounds__(kBlock) attn_bwd_kernel(const float* __restrict__ QKG, const float* __restrict__ dU,
                                                            const int64_t* __restrict__ x, float* __restrict__ dQKG,
-                                                           float* __restrict__ db_dyn, int64_t B, const DropCfg drop) {
+                                                           uint8_t* __restrict__ gt, float* __restrict__ db_dyn, int64_t B,
+                                                           const DropCfg drop) {
   __shared__ float red[kD];
   const int hl = threadIdx.x & 15;
   const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
@@ -220,7 +272,6 @@ __global__ void __launch_bounds__(kBlock) attn_bwd_kernel(const float* __restric
     const bool valid = b < B;
     const int64_t bb = valid ? b : B - 1;
     const float* base = QKG + bb * L * kQKG + hl * 4;
-    float* dbase = dQKG + bb * L * kQKG + hl * 4;
     float4 dd[L];
 #pragma unroll
     for (int i = 0; i < L; ++i) {
@@ -253,7 +304,7 @@ __global__ void __launch_bounds__(kBlock) attn_bwd_kernel(const float* __restric
         float4 dg = f4(0.f);
 #pragma unroll
         for (int i = 0; i < L; ++i) if (i != j) dg = fma4(A[i][j], dd[i], dg);
-        if (valid) st4(dbase + j * kQKG + 2 * kH * kD + h * kD, dg);
+        if (valid) store_dqkg<SPLIT>(dQKG, gt, bb * L + j, 2 * kH + h, hl, dg);
       }
       // softmax backward -> dS (stored in dA)
 #pragma unroll
@@ -270,8 +321,8 @@ __global__ void __launch_bounds__(kBlock) attn_bwd_kernel(const float* __restric
 #pragma unroll
         for (int j = 0; j < L; ++j) if (j != i) { dq = fma4(dA[i][j], k[j], dq); dk = fma4(dA[j][i], q[j], dk); }
         if (valid) {
-          st4(dbase + i * kQKG + h * kD, dq);
-          st4(dbase + i * kQKG + kH * kD + h * kD, dk);
+          store_dqkg<SPLIT>(dQKG, gt, bb * L + i, h, hl, dq);
+          store_dqkg<SPLIT>(dQKG, gt, bb * L + i, kH + h, hl, dk);
         }
       }
     }
@@ -542,9 +593,9 @@ int launch_active_flags(const int32_t* counts, int n_chrom, int rchrom, int64_t 
   return MATCHA_OK;
 }
 
-int launch_ln_fwd(const float* X, float* xhat, float* rstd, int64_t T, cudaStream_t s) {
+int launch_ln_fwd(const float* X, float* xhat, float* rstd, int64_t T, uint8_t* xhat_tiles, cudaStream_t s) {
   if (T <= 0) return MATCHA_OK;
-  ln_fwd_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(X, xhat, rstd, T);
+  ln_fwd_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(X, xhat, rstd, T, xhat_tiles);
   MATCHA_CHECK_LAUNCH("ln_fwd");
   return MATCHA_OK;
 }
@@ -569,11 +620,15 @@ int launch_attn_fwd(const float* QKG, const int64_t* x, const float* b_dyn, floa
   MATCHA_CHECK_LAUNCH("attn_fwd");
   return MATCHA_OK;
 }
-int launch_attn_bwd(const float* QKG, const float* dU, const int64_t* x, float* dQKG, float* db_dyn, int64_t B, int L,
-                    DropCfg drop, cudaStream_t s) {
+int launch_attn_bwd(const float* QKG, const float* dU, const int64_t* x, float* dQKG, uint8_t* dqkg_tiles, float* db_dyn,
+                    int64_t B, int L, DropCfg drop, cudaStream_t s) {
   if (B <= 0) return MATCHA_OK;
   const int grid = grid_for_halfwarps(B, kSMs * 4);
-  MATCHA_DISPATCH_L(L, (attn_bwd_kernel<LL><<<grid, kBlock, 0, s>>>(QKG, dU, x, dQKG, db_dyn, B, drop)));
+  if (dqkg_tiles) {
+    MATCHA_DISPATCH_L(L, (attn_bwd_kernel<LL, true><<<grid, kBlock, 0, s>>>(QKG, dU, x, dQKG, dqkg_tiles, db_dyn, B, drop)));
+  } else {
+    MATCHA_DISPATCH_L(L, (attn_bwd_kernel<LL, false><<<grid, kBlock, 0, s>>>(QKG, dU, x, dQKG, dqkg_tiles, db_dyn, B, drop)));
+  }
   MATCHA_CHECK_LAUNCH("attn_bwd");
   return MATCHA_OK;
 }

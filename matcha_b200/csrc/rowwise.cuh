@@ -8,6 +8,23 @@ constexpr int kD = 64;            // embed_dim handled by this build
 constexpr int kH = 8;             // heads
 constexpr int kQKG = 3 * kH * kD; // 1536 columns: [Q (8x64) | K (8x64) | G (8x64)]
 
+// ------------------------------------------------------------------------------------------
+// MMA-ready tiles written by producers for the tcgen05 kernels of qkg_tiles.cu.
+// A tile covers 128 tokens x 64 columns as bf16 hi | bf16 lo, each [plane = column/8][token][8 columns]
+// (2048-byte planes).  xhat tiles carry two extra planes per half: a ones column (column 64) that makes the
+// weight-gradient MMA also produce the bias gradient, and a zero plane (UMMA N must be a multiple of 16).
+// ------------------------------------------------------------------------------------------
+constexpr int kTileTok = 128;
+constexpr int kPlaneBytes = 2048;
+constexpr int kXPlanes = 10;
+constexpr int kXHalfBytes = kXPlanes * kPlaneBytes;    // 20480
+constexpr int kXTileBytes = 2 * kXHalfBytes;           // 40960 per 128 tokens
+constexpr int kGHalfBytes = 8 * kPlaneBytes;           // 16384
+constexpr int kGTileBytes = 2 * kGHalfBytes;           // 32768 per (128 tokens, 64-column chunk)
+constexpr int kGChunks = kQKG / 64;                    // 24 chunks: Q heads 0-7, K heads 0-7, G heads 0-7
+constexpr int64_t kTilePathMinTokens = 1024;           // below this the SIMT path (fp32 tensors) is used
+__host__ __device__ inline int64_t num_token_tiles(int64_t T) { return (T + kTileTok - 1) / kTileTok; }
+
 struct ChromMeta {
   int32_t n;
   int64_t start[MATCHA_MAX_CHROM];
@@ -18,7 +35,8 @@ struct ChromMeta {
 int launch_bucket(const int64_t* x, int64_t T, const ChromMeta& cm, int32_t* counts, int32_t* group_off,
                   int32_t* cursor, int32_t* perm, cudaStream_t s);
 
-int launch_ln_fwd(const float* X, float* xhat, float* rstd, int64_t T, cudaStream_t s);
+// xhat_tiles (optional): also emit the pre-split tiles (num_token_tiles(T) * kXTileBytes bytes, tail rows zeroed)
+int launch_ln_fwd(const float* X, float* xhat, float* rstd, int64_t T, uint8_t* xhat_tiles, cudaStream_t s);
 int launch_attn_fwd(const float* QKG, const int64_t* x, const float* b_dyn, float* U, int64_t B, int L,
                     DropCfg drop, cudaStream_t s);
 struct ScoreParams {
@@ -39,8 +57,18 @@ struct ScoreGrads {
 };
 int launch_score_bwd(const float* H2, const float* xhat, const float* rstd_x, const int64_t* x, ScoreParams p,
                      const float* dlogit, float* dH2, float* dXs, ScoreGrads g, int64_t B, int L, cudaStream_t s);
-int launch_attn_bwd(const float* QKG, const float* dU, const int64_t* x, float* dQKG, float* db_dyn, int64_t B,
-                    int L, DropCfg drop, cudaStream_t s);
+// dQKG is written as fp32 [T, 1536], or -- when dqkg_tiles != NULL -- only as pre-split tiles
+// [token tile][24 chunks][kGTileBytes] (the caller zeroes the tail rows of the last tile)
+int launch_attn_bwd(const float* QKG, const float* dU, const int64_t* x, float* dQKG, uint8_t* dqkg_tiles, float* db_dyn,
+                    int64_t B, int L, DropCfg drop, cudaStream_t s);
+
+// tcgen05 tile kernels (qkg_tiles.cu)
+int launch_split_wT(const float* W, void* out, cudaStream_t s);     // W [1536, 64] fp32 -> MN-major chunks for the dgrad
+int tc_qkg_forward_tiles(const uint8_t* xhat_tiles, const uint8_t* w_split, const float* bias, float* QKG, int64_t T,
+                         cudaStream_t s);
+int tc_qkg_dgrad_tiles(const uint8_t* dqkg_tiles, const uint8_t* wT_split, float* dxhat, int64_t T, cudaStream_t s);
+int tc_qkg_wgrad_tiles(const uint8_t* dqkg_tiles, const uint8_t* xhat_tiles, float* scratch, int64_t scratch_floats,
+                       float* dW, float* dbias, int64_t dbias_n, int64_t T, cudaStream_t s);
 // dP = (LNbwd(dxhat) + dXs) * (1 - X^2)
 int launch_ln_tanh_bwd(const float* dxhat, const float* dXs, const float* xhat, const float* rstd, const float* X,
                        float* dP, int64_t T, cudaStream_t s);
