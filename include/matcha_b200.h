@@ -44,6 +44,9 @@ const char* matcha_profile_label_name(int32_t i);
 int matcha_profile_read(float* ms, int64_t* calls, int64_t* kernels, int32_t n);
 /* 0 = SIMT fp32 contractions only, 1 = tcgen05 (bf16x3) where the shape is eligible */
 void matcha_set_gemm_impl(int32_t impl);
+/* 1 (default) = fused hyperedge-tile kernels (QKG projection + attention in one tcgen05 kernel) where eligible,
+ * 0 = decomposed pipeline (projection, attention, ... as separate launches); also MATCHA_FUSED=0 */
+void matcha_set_fused(int32_t on);
 
 /* ---------------------------------------------------------------------------------------------
  * Model description: where every live tensor of Modules.Classifier sits.

@@ -77,6 +77,18 @@ static int gemm_impl() {
   return g_gemm_impl;
 }
 static bool use_tiles(int64_t T) { return gemm_impl() == 1 && T >= kTilePathMinTokens; }
+static int g_fused = -1;      // -1 = read MATCHA_FUSED on first use; 0 = decomposed pipeline; 1 = fused hyperedge-tile kernels
+static int fused_impl() {
+  if (g_fused < 0) {
+    const char* e = getenv("MATCHA_FUSED");
+    g_fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_fused;
+}
+// the fused attention forward serves eval passes (training still needs the QKG tape of the decomposed backward)
+static bool use_fused_fwd(int64_t T, int L, int training) {
+  return fused_impl() == 1 && gemm_impl() == 1 && !training && L >= 2 && L <= 6 && T >= kTilePathMinTokens;
+}
 
 static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
   prof_begin(label, s);
@@ -92,7 +104,7 @@ static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
 // derived-parameter layout
 // ------------------------------------------------------------------------------------------
 struct DerivedLayout {
-  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, tables, total;  // float offsets
+  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, wheads, tables, total;  // float offsets
 };
 static __host__ __device__ DerivedLayout derived_layout() {
   DerivedLayout l;
@@ -102,7 +114,8 @@ static __host__ __device__ DerivedLayout derived_layout() {
   l.bdyn_part = l.bdyn + kD;        // per-head partial sums of b_dyn (summed in a fixed order: deterministic)
   l.wsplit = (l.bdyn_part + kH * kD + 255) / 256 * 256;   // W_qkg pre-split to bf16 hi|lo chunks (same byte count)
   l.wtsplit = l.wsplit + (int64_t)kQKG * kD;             // W_qkg^T pre-split, MN-major chunks (data-gradient B operand)
-  l.tables = l.wtsplit + (int64_t)kQKG * kD;
+  l.wheads = l.wtsplit + (int64_t)kQKG * kD;             // per-head [Q_h | K_h | G_h] chunks for the fused attention kernels
+  l.tables = l.wheads + (int64_t)kH * kHeadWBytes / 4;
   l.tables = (l.tables + 63) / 64 * 64;
   const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
   l.total = l.tables + 4 * table_floats;
@@ -328,7 +341,11 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
   const int64_t row = sizeof(float) * T * kD;
   w.H0 = (float*)take(row); w.E = (float*)take(row); w.V0 = (float*)take(row); w.X = (float*)take(row);
   w.xhat = (float*)take(row); w.rstd = (float*)take(sizeof(float) * (T + 1));
-  w.xhat_t = (uint8_t*)take(num_token_tiles(T) * (int64_t)kXTileBytes);
+  {
+    int64_t nt = num_token_tiles(T);
+    if (L >= 2 && L <= 6 && num_atiles(T, L) > nt) nt = num_atiles(T, L);
+    w.xhat_t = (uint8_t*)take(nt * (int64_t)kXTileBytes);
+  }
   w.QKG = (float*)take(sizeof(float) * T * kQKG);
   w.U = (float*)take(row); w.H1d = (float*)take(row); w.H2 = (float*)take(row);
   w.pred_ld = m->inter ? (max_chrom_len(m) + 3) / 4 * 4 : 0;
@@ -400,7 +417,8 @@ static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, 
 }
 
 // X = tanh(next_w(E + attribute_nn(attr[id]))), xhat, rstd, QKG
-static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, const Workspace& w, cudaStream_t s) {
+static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, const Workspace& w, cudaStream_t s,
+                       int fused_L = 0) {
   int rc;
   const float* P = m->params;
   const DerivedLayout l = derived_layout();
@@ -410,6 +428,8 @@ static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   GemmDesc b = gemm_base(FORM_NT, T, kD, kD, w.V0, kD, P + m->off_next_w, kD, w.X, kD);
   b.bias = P + m->off_next_b; b.epi_act = 1;
   if ((rc = run_gemm(b, s, P_MIX))) return rc;
+  if (fused_L > 0)   // fused attention: hyperedge-aligned tiles; the QKG projection happens inside the attention kernel
+    return PROF(P_LN, 1, launch_ln_fwd_atiles(w.X, w.xhat, w.rstd, T, fused_L, w.xhat_t, s));
   const bool tiles = use_tiles(T);
   if ((rc = PROF(P_LN, 1, launch_ln_fwd(w.X, w.xhat, w.rstd, T, tiles ? w.xhat_t : nullptr, s)))) return rc;
   if (tiles)
@@ -473,6 +493,7 @@ int matcha_profile_read(float* ms, int64_t* calls, int64_t* kernels, int32_t n) 
   return MATCHA_OK;
 }
 void matcha_set_gemm_impl(int32_t impl) { g_gemm_impl = impl; }
+void matcha_set_fused(int32_t on) { g_fused = on != 0; }
 int matcha_version(void) { return 100; }
 
 int64_t matcha_derived_elems(const matcha_model_desc* m) {
@@ -500,7 +521,8 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   MATCHA_CHECK_LAUNCH("prep_tables");
   if ((rc = launch_split_weights_k64(m->derived + l.wqkg, kD, kQKG, m->derived + l.wsplit, s))) return rc;
   if ((rc = launch_split_wT(m->derived + l.wqkg, m->derived + l.wtsplit, s))) return rc;
-  prof_end(P_PREP, 5, s);
+  if ((rc = launch_split_w_heads(m->derived + l.wqkg, m->derived + l.wheads, s))) return rc;
+  prof_end(P_PREP, 6, s);
   return MATCHA_OK;
 }
 
@@ -535,9 +557,14 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
     if (recon && (rc = check_cuda(cudaMemcpyAsync(recon, w.recon, sizeof(float), cudaMemcpyDeviceToDevice, s), "copy recon")))
       return rc;
   }
-  if ((rc = run_mix_qkg(m, x, T, w, s))) return rc;
+  const bool fused = use_fused_fwd(T, L, training);
+  if ((rc = run_mix_qkg(m, x, T, w, s, fused ? L : 0))) return rc;
   DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, training != 0);
-  if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fwd(w.QKG, x, m->derived + l.bdyn, w.U, B, L, dattn, s)))) return rc;
+  if (fused) {
+    if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fused_fwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wheads),
+                                                        m->derived + l.bqkg, m->derived + l.bdyn, x, w.U, nullptr, B, L, dattn, s))))
+      return rc;
+  } else if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fwd(w.QKG, x, m->derived + l.bdyn, w.U, B, L, dattn, s)))) return rc;
   if ((rc = run_pff(m, T, training, seed, w, s))) return rc;
   return PROF(P_SCORE_FWD, 1, launch_score_fwd(w.H2, w.xhat, x, score_params(m), logits, B, L, s));
 }

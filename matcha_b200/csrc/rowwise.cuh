@@ -24,6 +24,11 @@ constexpr int kGTileBytes = 2 * kGHalfBytes;           // 32768 per (128 tokens,
 constexpr int kGChunks = kQKG / 64;                    // 24 chunks: Q heads 0-7, K heads 0-7, G heads 0-7
 constexpr int64_t kTilePathMinTokens = 1024;           // below this the SIMT path (fp32 tensors) is used
 __host__ __device__ inline int64_t num_token_tiles(int64_t T) { return (T + kTileTok - 1) / kTileTok; }
+// Hyperedge-aligned tiles of the fused attention kernels (attn_fused.cu): warp-row q of tile i holds the
+// rows_per_warp(L) consecutive tokens starting at (4 i + q) * rows_per_warp(L); the other lanes are zero rows.
+__host__ __device__ inline int rows_per_warp(int L) { return (32 / L) * L; }
+__host__ __device__ inline int64_t num_atiles(int64_t T, int L) { return (T + 4 * rows_per_warp(L) - 1) / (4 * rows_per_warp(L)); }
+constexpr int kHeadWBytes = 2 * 192 * 64 * 2;          // per-head [Q_h | K_h | G_h] weights, bf16 hi | lo (49152)
 
 struct ChromMeta {
   int32_t n;
@@ -61,6 +66,14 @@ int launch_score_bwd(const float* H2, const float* xhat, const float* rstd_x, co
 // [token tile][24 chunks][kGTileBytes] (the caller zeroes the tail rows of the last tile)
 int launch_attn_bwd(const float* QKG, const float* dU, const int64_t* x, float* dQKG, uint8_t* dqkg_tiles, float* db_dyn,
                     int64_t B, int L, DropCfg drop, cudaStream_t s);
+
+// fused attention kernels (attn_fused.cu)
+int launch_split_w_heads(const float* W, void* out, cudaStream_t s);   // W_qkg [1536, 64] -> 8 per-head chunks (kHeadWBytes)
+int launch_ln_fwd_atiles(const float* X, float* xhat, float* rstd, int64_t T, int L, uint8_t* xhat_tiles, cudaStream_t s);
+// U = dropout(sum_h softmax(Q_h K_h^T) G_h + b_dyn) * non_pad_mask straight from hyperedge-aligned xhat tiles;
+// probs (optional) [T, 8, 4 (L <= 5) or 8] keeps the attention weights for the backward pass
+int launch_attn_fused_fwd(const uint8_t* xhat_tiles, const uint8_t* wheads, const float* bq, const float* b_dyn,
+                          const int64_t* x, float* U, float* probs, int64_t B, int L, DropCfg drop, cudaStream_t s);
 
 // tcgen05 tile kernels (qkg_tiles.cu)
 int launch_split_wT(const float* W, void* out, cudaStream_t s);     // W [1536, 64] fp32 -> MN-major chunks for the dgrad

@@ -416,3 +416,39 @@ def test_tile_path_gradients_match_simt_path(golden, monkeypatch):
         g1 = grads[1][0][k]
         scale = float(np.abs(g0).max())
         assert float(np.abs(g1 - g0).max()) <= 5e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
+
+
+# ------------------------------------------------------------------------------------------
+# fused hyperedge-tile kernels (attn_fused.cu) vs the decomposed pipeline and the reference golden
+# ------------------------------------------------------------------------------------------
+def _random_hyperedges(golden, B, L, seed, kmin=2):
+    rng = np.random.default_rng(seed)
+    N = int(golden["chrom_range"][-1][1]) - 1
+    x = np.zeros((B, L), dtype=np.int64)
+    for b in range(B):
+        k = int(rng.integers(kmin, L + 1))
+        x[b, :k] = np.sort(rng.choice(np.arange(1, N + 1), size=k, replace=False))
+    return x
+
+
+@pytest.mark.parametrize("L,B", [(2, 700), (3, 411), (4, 777), (5, 333), (5, 4099), (6, 300)])
+def test_fused_attention_forward_matches_decomposed(golden, model, L, B):
+    """Eval logits through the fused tcgen05 attention kernel (QKG in TMEM, shuffle softmax) vs the decomposed
+    pipeline on the same inputs; B chosen so the last hyperedge-aligned tile is ragged."""
+    lib = _lib().load()
+    model.eval()
+    x = torch.from_numpy(_random_hyperedges(golden, B, L, seed=L * 1000 + B)).cuda()
+    if f"x/L{L}" in golden.files:
+        x[:16] = torch.from_numpy(golden[f"x/L{L}"]).cuda()
+    try:
+        lib.matcha_set_fused(0)
+        with torch.no_grad():
+            a = model(x).cpu().numpy()
+        lib.matcha_set_fused(1)
+        with torch.no_grad():
+            b = model(x).cpu().numpy()
+    finally:
+        lib.matcha_set_fused(1)
+    np.testing.assert_allclose(b, a, rtol=1e-4, atol=5e-5)
+    if f"logits_eval/L{L}" in golden.files:
+        np.testing.assert_allclose(b[:16], golden[f"logits_eval/L{L}"], rtol=1e-4, atol=5e-5)
