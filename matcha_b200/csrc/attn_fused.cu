@@ -298,6 +298,396 @@ attn_fused_fwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ==========================================================================================
+// fused attention backward
+//   grid = 4 head pairs x S token splits (one CTA per SM).  A CTA keeps its head pair's weights resident in shared
+//   memory (one copy serves the recompute, K-major, and the data gradient, MN-major) and its 384 x 64 slice of the
+//   weight gradient resident in TMEM across all of its tiles.  Per tile, three stages (G, K, Q):
+//     tcgen05  R = xhat . W_piece^T                  (recompute, N = 128: both heads of the pair)
+//     SIMT     thread = (token row, head): shuffles within the hyperedge -> dG / dQ / dK rows -> bf16 hi|lo d-tile
+//     tcgen05  dxhat += d-tile . W_piece   and   dW_piece += d-tile^T . xhat
+//   TMEM columns: dxhat 0..63 | R0 64..191 | R1 192..319 | dW_G, dW_K, dW_Q 320..511.
+// ==========================================================================================
+constexpr int kBThreads = 320;
+constexpr int kBWPiece = 32768;                 // piece pair: 128 rows x 64 k, hi 16 KB | lo 16 KB
+constexpr int kBWBytes = 3 * kBWPiece;          // G | K | Q
+constexpr int kBXBytes = 32768;
+constexpr int kBDHalf = 32768;                  // d-tile pair: 16 planes x 2048
+constexpr int kBDBytes = 2 * kBDHalf;
+constexpr int kBSmem = kBWBytes + 2 * kBXBytes + kBDBytes;   // 229376
+constexpr uint32_t kColDX = 0, kColR = 64, kColDW = 320;
+
+// W_qkg [1536, 64] -> per head pair hp, piece p (0 = G, 1 = K, 2 = Q): K-major [k/8][128 rows][8] hi | lo,
+// rows 0..63 = head 2 hp, rows 64..127 = head 2 hp + 1
+__global__ void split_w_pairs_kernel(const float* __restrict__ W, uint8_t* __restrict__ out) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;       // unit = (hp, piece, row r, k-group g)
+  if (u >= 4 * 3 * 128 * 8) return;
+  const int g = u & 7, r = (u >> 3) & 127, p = (u >> 10) % 3, hp = u / (3 * 1024);
+  const int head = 2 * hp + (r >> 6);
+  const int base = (p == 0) ? 2 * kH * kD : (p == 1 ? kH * kD : 0);
+  const float* src = W + (int64_t)(base + head * kD + (r & 63)) * kD + g * 8;
+  uint4 hi, lo;
+  split8(__ldg(reinterpret_cast<const float4*>(src)), __ldg(reinterpret_cast<const float4*>(src + 4)), hi, lo);
+  uint8_t* chunk = out + (int64_t)hp * kBWBytes + p * kBWPiece;
+  const int off = g * 2048 + r * 16;
+  *reinterpret_cast<uint4*>(chunk + off) = hi;
+  *reinterpret_cast<uint4*>(chunk + 16384 + off) = lo;
+}
+
+// column sums of a [32 lanes x 64] register tile: 62 shuffles; lane l ends with the sums of columns col0, col0 + 1
+__device__ __forceinline__ void warp_colsum64(const float (&v)[64], int lane, float& s0, float& s1, int& col0) {
+  float a[32], b[16], c[8], d[4];
+  bool up = (lane & 16) != 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float send = up ? v[i] : v[32 + i], keep = up ? v[32 + i] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  up = (lane & 8) != 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float send = up ? a[i] : a[16 + i], keep = up ? a[16 + i] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = (lane & 4) != 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = up ? b[i] : b[8 + i], keep = up ? b[8 + i] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  up = (lane & 2) != 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = up ? c[i] : c[4 + i], keep = up ? c[4 + i] : c[i];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  up = (lane & 1) != 0;
+  {
+    const float send0 = up ? d[0] : d[2], keep0 = up ? d[2] : d[0];
+    const float send1 = up ? d[1] : d[3], keep1 = up ? d[3] : d[1];
+    s0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 1);
+    s1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 1);
+  }
+  col0 = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
+}
+
+// one 64-wide fp32 row -> bf16 hi | lo planes of the d-tile pair (thread = tile row r, planes p0 .. p0 + 7)
+__device__ __forceinline__ void store_drow(uint8_t* sD, int p0, int r, const float (&o)[64]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 hi, lo;
+    split8(make_float4(o[8 * j], o[8 * j + 1], o[8 * j + 2], o[8 * j + 3]),
+           make_float4(o[8 * j + 4], o[8 * j + 5], o[8 * j + 6], o[8 * j + 7]), hi, lo);
+    sts16(sD + (p0 + j) * 2048 + r * 16, hi);
+    sts16(sD + kBDHalf + (p0 + j) * 2048 + r * 16, lo);
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kBThreads, 1)
+attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict__ wpairs, const float* __restrict__ bq,
+                      const int64_t* __restrict__ x, const float* __restrict__ dU, const float* __restrict__ probs,
+                      float* __restrict__ dxhat_parts, float* __restrict__ part, float* __restrict__ dbq,
+                      float* __restrict__ db_dyn, int64_t T, const DropCfg drop) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sX = smem + kBWBytes;
+  uint8_t* sD = smem + kBWBytes + 2 * kBXBytes;
+  __shared__ uint64_t w_full, x_full[2], x_empty[2], r_full[2], r_empty[2], d_full, d_empty, dx_full, dx_empty, done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sBq[2 * kD], sDbq[2 * kD], sDbd[kD];
+  constexpr int RPW = (32 / L) * L;
+  constexpr int PL = (L - 1 <= 4) ? 4 : 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hp = blockIdx.x & 3, sp = blockIdx.x >> 2, S = gridDim.x >> 2;
+  const int64_t ntiles = (T + 4 * RPW - 1) / (4 * RPW);
+  const int64_t my_tiles = (ntiles - sp + S - 1) / S;          // tiles sp, sp + S, ...
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 32) {
+    mbar_init(&w_full, 1); mbar_init(&d_full, 8); mbar_init(&d_empty, 1); mbar_init(&dx_full, 1); mbar_init(&dx_empty, 8);
+    mbar_init(&done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 2 * kD) { sBq[tid] = __ldg(bq + (2 * hp) * kD + tid); sDbq[tid] = 0.f; }
+  if (tid < kD) sDbd[tid] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&w_full, kBWBytes);
+      for (int p = 0; p < 3; ++p)
+        bulk_g2s(sW + p * kBWPiece, wpairs + (int64_t)hp * kBWBytes + p * kBWPiece, kBWPiece, &w_full);
+      for (int64_t k = 0; k < my_tiles; ++k) {
+        const int b = (int)(k & 1);
+        mbar_wait(&x_empty[b], (uint32_t)((k >> 1) & 1) ^ 1u);
+        mbar_expect_tx(&x_full[b], kBXBytes);
+        const uint8_t* src = xt + (sp + k * S) * (int64_t)kXTileBytes;
+        bulk_g2s(sX + b * kBXBytes, src, 16384, &x_full[b]);
+        bulk_g2s(sX + b * kBXBytes + 16384, src + kXHalfBytes, 16384, &x_full[b]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idescR = make_idesc(128, 128, false, false);
+      constexpr uint32_t idescD = make_idesc(128, 64, false, true);
+      constexpr uint32_t idescW = make_idesc(128, 64, true, true);
+      const int64_t N = 3 * my_tiles;
+      const uint32_t dh = smem_u32(sD), dl = dh + kBDHalf;
+      mbar_wait(&w_full, 0);
+      auto recompute = [&](int64_t n) {
+        const int64_t k = n / 3;
+        const int g = (int)(n - 3 * k), xb = (int)(k & 1), rb = (int)(n & 1);
+        if (g == 0) mbar_wait(&x_full[xb], (uint32_t)((k >> 1) & 1));
+        mbar_wait(&r_empty[rb], (uint32_t)((n >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t xh = smem_u32(sX + xb * kBXBytes), xl = xh + 16384;
+        const uint32_t wh = smem_u32(sW + g * kBWPiece), wl = wh + 16384;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_x3s(tmem_base + kColR + rb * 128, xh + ks * 4096, xl + ks * 4096, wh + ks * 4096, wl + ks * 4096, 2048, 128,
+                   2048, 128, idescR, ks == 0);
+        umma_commit(&r_full[rb]);
+      };
+      if (N > 0) recompute(0);
+      for (int64_t n = 0; n < N; ++n) {
+        if (n + 1 < N) recompute(n + 1);
+        const int64_t k = n / 3;
+        const int g = (int)(n - 3 * k), xb = (int)(k & 1);
+        mbar_wait(&d_full, (uint32_t)(n & 1));
+        if (g == 0) mbar_wait(&dx_empty, (uint32_t)(k & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t xh = smem_u32(sX + xb * kBXBytes), xl = xh + 16384;
+        const uint32_t wh = smem_u32(sW + g * kBWPiece), wl = wh + 16384;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // dxhat[128 tok, 64] += d[128 tok, 128 f] . W_piece[128 f, 64]   (B MN-major)
+          umma_x3s(tmem_base + kColDX, dh + ks * 4096, dl + ks * 4096, wh + ks * 256, wl + ks * 256, 2048, 128, 128, 2048,
+                   idescD, g == 0 && ks == 0);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // dW_piece[128 f, 64] += d^T[128 f, 128 tok] . xhat[128 tok, 64]  (both MN-major)
+          umma_x3s(tmem_base + kColDW + g * 64, dh + ks * 256, dl + ks * 256, xh + ks * 256, xl + ks * 256, 128, 2048, 128,
+                   2048, idescW, k == 0 && ks == 0);
+        umma_commit(&d_empty);
+        if (g == 2) { umma_commit(&dx_full); umma_commit(&x_empty[xb]); }
+      }
+      umma_commit(&done);
+    }
+  } else {
+    const int hl = (warp - 2) >> 2, q = warp & 3, head = 2 * hp + hl;
+    const int r = q * 32 + lane;
+    const bool live_lane = lane < RPW;
+    const int gI = lane / L, pos = lane - gI * L;
+    int src[L - 1];
+#pragma unroll
+    for (int s = 1; s < L; ++s) src[s - 1] = live_lane ? gI * L + (pos + s) % L : lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    int64_t n = 0;
+    for (int64_t k = 0; k < my_tiles; ++k) {
+      const int64_t tile = sp + k * S;
+      const int64_t t = (tile * 4 + q) * RPW + lane;
+      const bool live = live_lane && t < T;
+      float A[L - 1], AT[L - 1], dS[L - 1];
+      {
+        const float* pp = probs + (t * kH + head) * PL;
+#pragma unroll
+        for (int s = 0; s < L - 1; ++s) A[s] = live ? __ldg(pp + s) : 0.f;
+#pragma unroll
+        for (int s = 1; s < L; ++s) AT[s - 1] = __shfl_sync(0xffffffffu, A[L - s - 1], src[s - 1]);   // weight of row (i+s) on row i
+      }
+      float o[kD];
+      // ---------------- stage G: dA = dd . G_j,  dG_i = sum_j A_ji dd_j ----------------
+      {
+        float dd[kD];
+        const float m = (live && x[t] != 0) ? 1.f : 0.f;
+#pragma unroll
+        for (int c = 0; c < kD; c += 4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) {
+            v = __ldg(reinterpret_cast<const float4*>(dU + t * kD + c));
+            const float4 f = drop_factor4(drop, (uint64_t)t, (uint32_t)c);
+            v = make_float4(v.x * f.x * m, v.y * f.y * m, v.z * f.z * m, v.w * f.w * m);
+          }
+          dd[c] = v.x; dd[c + 1] = v.y; dd[c + 2] = v.z; dd[c + 3] = v.w;
+        }
+        if (hp == 0 && hl == 0) {          // db_dyn = sum over tokens of the masked, dropout-scaled gradient
+          float s0, s1; int col0;
+          warp_colsum64(dd, lane, s0, s1, col0);
+          atomicAdd(&sDbd[col0], s0);
+          atomicAdd(&sDbd[col0 + 1], s1);
+        }
+        float dA[L - 1];
+#pragma unroll
+        for (int s = 0; s < L - 1; ++s) dA[s] = 0.f;
+        const int rb = (int)(n & 1);
+        mbar_wait(&r_full[rb], (uint32_t)((n >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t gv[32];
+          tmem_ld32_issue(tlane + kColR + rb * 128 + hl * 64 + half * 32, gv);
+          tmem_ld_wait(gv);
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+#pragma unroll
+            for (int s = 0; s < L - 1; ++s)
+              dA[s] = fmaf(dd[half * 32 + c], __uint_as_float(__shfl_sync(0xffffffffu, gv[c], src[s])), dA[s]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r_empty[rb]);
+#pragma unroll
+        for (int c = 0; c < kD; ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int s = 0; s < L - 1; ++s) acc = fmaf(AT[s], __shfl_sync(0xffffffffu, dd[c], src[s]), acc);
+          o[c] = acc;
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int s = 0; s < L - 1; ++s) dot = fmaf(A[s], dA[s], dot);
+#pragma unroll
+        for (int s = 0; s < L - 1; ++s) dS[s] = A[s] * (dA[s] - dot);
+        mbar_wait(&d_empty, (uint32_t)(n & 1) ^ 1u);
+        store_drow(sD, hl * 8, r, o);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_full);
+        ++n;
+      }
+      // ---------------- stage K: dQ_i = sum_j dS_ij K_j ----------------
+      {
+        const int rb = (int)(n & 1);
+        mbar_wait(&r_full[rb], (uint32_t)((n >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t kv[32];
+          tmem_ld32_issue(tlane + kColR + rb * 128 + hl * 64 + half * 32, kv);
+          tmem_ld_wait(kv);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int s = 0; s < L - 1; ++s) acc = fmaf(dS[s], __uint_as_float(__shfl_sync(0xffffffffu, kv[c], src[s])), acc);
+            o[half * 32 + c] = acc;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r_empty[rb]);
+        {                                   // gradient of the folded Q bias
+          float s0, s1; int col0;
+          warp_colsum64(o, lane, s0, s1, col0);
+          atomicAdd(&sDbq[hl * kD + col0], s0);
+          atomicAdd(&sDbq[hl * kD + col0 + 1], s1);
+        }
+        mbar_wait(&d_empty, (uint32_t)(n & 1) ^ 1u);
+        store_drow(sD, hl * 8, r, o);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_full);
+        ++n;
+      }
+      // ---------------- stage Q: dK_i = sum_j dS_ji Q_j ----------------
+      {
+        float dST[L - 1];
+#pragma unroll
+        for (int s = 1; s < L; ++s) dST[s - 1] = __shfl_sync(0xffffffffu, dS[L - s - 1], src[s - 1]);
+        const int rb = (int)(n & 1);
+        mbar_wait(&r_full[rb], (uint32_t)((n >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t qv[32];
+          tmem_ld32_issue(tlane + kColR + rb * 128 + hl * 64 + half * 32, qv);
+          tmem_ld_wait(qv);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float qc = live_lane ? __uint_as_float(qv[c]) + sBq[hl * kD + half * 32 + c] : 0.f;
+            float acc = 0.f;
+#pragma unroll
+            for (int s = 0; s < L - 1; ++s) acc = fmaf(dST[s], __shfl_sync(0xffffffffu, qc, src[s]), acc);
+            o[half * 32 + c] = acc;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r_empty[rb]);
+        mbar_wait(&d_empty, (uint32_t)(n & 1) ^ 1u);
+        store_drow(sD, hl * 8, r, o);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_full);
+        ++n;
+      }
+      // ---------------- dxhat of this (tile, head pair) ----------------
+      {
+        mbar_wait(&dx_full, (uint32_t)(k & 1));
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32_issue(tlane + kColDX + hl * 32, v);
+        tmem_ld_wait(v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dx_empty);
+        if (live) {
+          float* dst = dxhat_parts + ((int64_t)hp * T + t) * kD + hl * 32;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                                              __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+        }
+      }
+    }
+    // ---------------- weight-gradient slice of this CTA -> split-K partial ----------------
+    mbar_wait(&done, 0);
+    tc_fence_after();
+    {
+      const int f = q * 32 + lane;                 // TMEM lane = feature row of the piece pair
+      const int hrow = (2 * hp + (f >> 6)) * kD + (f & 63);
+#pragma unroll 1
+      for (int g = 0; g < 3; ++g) {
+        uint32_t v[32];
+        tmem_ld32_issue(tlane + kColDW + g * 64 + hl * 32, v);
+        tmem_ld_wait(v);
+        const int row = ((g == 0) ? 2 * kH * kD : (g == 1 ? kH * kD : 0)) + hrow;
+        float* dst = part + ((int64_t)sp * kQKG + row) * kD + hl * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                                            __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int i = tid - 64;
+    if (i < 2 * kD) atomicAdd(dbq + (2 * hp) * kD + i, sDbq[i]);
+    if (hp == 0 && i >= 2 * kD && i < 3 * kD) atomicAdd(db_dyn + (i - 2 * kD), sDbd[i - 2 * kD]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void attn_wgrad_reduce_kernel(const float* __restrict__ part, int splits, float* __restrict__ dW) {
+  const int64_t total = (int64_t)kQKG * kD / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < splits; ++sp) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part) + (int64_t)sp * total + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float4* d = reinterpret_cast<float4*>(dW) + i;
+    float4 cur = *d;
+    *d = make_float4(cur.x + s.x, cur.y + s.y, cur.z + s.z, cur.w + s.w);
+  }
+}
+
 template <typename K>
 int set_smem_attr_a(K kernel, int bytes) {
   return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
@@ -315,7 +705,45 @@ int launch_fwd_L(const uint8_t* xt, const uint8_t* wheads, const float* bq, cons
   return MATCHA_OK;
 }
 
+template <int L>
+int launch_bwd_L(const uint8_t* xt, const uint8_t* wpairs, const float* bq, const int64_t* x, const float* dU,
+                 const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn, int64_t T,
+                 DropCfg drop, cudaStream_t s) {
+  static bool once = false;
+  if (!once) { if (int rc = set_smem_attr_a(attn_fused_bwd_kernel<L>, kBSmem)) return rc; once = true; }
+  const int64_t ntiles = num_atiles(T, L);
+  const int S = (int)(ntiles < kSMs / 4 ? ntiles : kSMs / 4);
+  attn_fused_bwd_kernel<L><<<4 * S, kBThreads, kBSmem, s>>>(xt, wpairs, bq, x, dU, probs, dxhat_parts, part, dbq, db_dyn, T, drop);
+  MATCHA_CHECK_LAUNCH("attn_fused_bwd");
+  attn_wgrad_reduce_kernel<<<kSMs, 256, 0, s>>>(part, S, dW);
+  MATCHA_CHECK_LAUNCH("attn_wgrad_reduce");
+  return MATCHA_OK;
+}
+
 }  // namespace
+
+int launch_split_w_pairs(const float* W, void* out, cudaStream_t s) {
+  split_w_pairs_kernel<<<(4 * 3 * 128 * 8 + 255) / 256, 256, 0, s>>>(W, reinterpret_cast<uint8_t*>(out));
+  MATCHA_CHECK_LAUNCH("split_w_pairs");
+  return MATCHA_OK;
+}
+
+int64_t attn_fused_bwd_scratch_floats() { return (int64_t)(kSMs / 4) * kQKG * kD; }
+
+int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, const float* dU,
+                          const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn,
+                          int64_t B, int L, DropCfg drop, cudaStream_t s) {
+  if (B <= 0) return MATCHA_OK;
+  const int64_t T = B * L;
+  switch (L) {
+    case 2: return launch_bwd_L<2>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
+    case 3: return launch_bwd_L<3>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
+    case 4: return launch_bwd_L<4>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
+    case 5: return launch_bwd_L<5>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
+    case 6: return launch_bwd_L<6>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
+    default: set_error("attn_fused_bwd: padded width L=%d unsupported (2..6)", L); return MATCHA_ERR_ARG;
+  }
+}
 
 int launch_split_w_heads(const float* W, void* out, cudaStream_t s) {
   split_w_heads_kernel<<<(kH * 192 * 8 + 255) / 256, 256, 0, s>>>(W, reinterpret_cast<uint8_t*>(out));

@@ -85,9 +85,9 @@ static int fused_impl() {
   }
   return g_fused;
 }
-// the fused attention forward serves eval passes (training still needs the QKG tape of the decomposed backward)
-static bool use_fused_fwd(int64_t T, int L, int training) {
-  return fused_impl() == 1 && gemm_impl() == 1 && !training && L >= 2 && L <= 6 && T >= kTilePathMinTokens;
+// fused attention forward (eval and training) and backward: QKG and its gradient never leave the SM
+static bool use_fused(int64_t T, int L) {
+  return fused_impl() == 1 && gemm_impl() == 1 && L >= 2 && L <= 6 && T >= kTilePathMinTokens;
 }
 
 static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
@@ -104,7 +104,7 @@ static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
 // derived-parameter layout
 // ------------------------------------------------------------------------------------------
 struct DerivedLayout {
-  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, wheads, tables, total;  // float offsets
+  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, wheads, wpairs, tables, total;  // float offsets
 };
 static __host__ __device__ DerivedLayout derived_layout() {
   DerivedLayout l;
@@ -115,7 +115,8 @@ static __host__ __device__ DerivedLayout derived_layout() {
   l.wsplit = (l.bdyn_part + kH * kD + 255) / 256 * 256;   // W_qkg pre-split to bf16 hi|lo chunks (same byte count)
   l.wtsplit = l.wsplit + (int64_t)kQKG * kD;             // W_qkg^T pre-split, MN-major chunks (data-gradient B operand)
   l.wheads = l.wtsplit + (int64_t)kQKG * kD;             // per-head [Q_h | K_h | G_h] chunks for the fused attention kernels
-  l.tables = l.wheads + (int64_t)kH * kHeadWBytes / 4;
+  l.wpairs = l.wheads + (int64_t)kH * kHeadWBytes / 4;   // per-head-pair G | K | Q piece pairs for the fused backward
+  l.tables = l.wpairs + (int64_t)4 * kPairWBytes / 4;
   l.tables = (l.tables + 63) / 64 * 64;
   const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
   l.total = l.tables + 4 * table_floats;
@@ -310,7 +311,7 @@ __global__ void prep_bwd_g_kernel(const matcha_model_desc m) {
 // ------------------------------------------------------------------------------------------
 struct Workspace {
   int32_t *counts, *group_off, *cursor, *perm;
-  float *H0, *E, *V0, *X, *xhat, *rstd, *QKG, *U, *H1d, *H2, *pred, *recon;
+  float *H0, *E, *V0, *X, *xhat, *rstd, *QKG, *U, *H1d, *H2, *pred, *recon, *probs;
   uint8_t *xhat_t, *dqkg_t;   // MMA-ready tiles (rowwise.cuh); dqkg_t aliases dQKG
   float *dlogit, *dH2, *dXs, *dH1pre, *dU, *dQKG, *dxhat, *dP, *dV0, *dtE, *dE, *dH0pre, *tc_scratch;
   int64_t tc_scratch_floats;
@@ -357,6 +358,7 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
     w.dqkg_t = reinterpret_cast<uint8_t*>(w.dQKG);
     w.dxhat = (float*)take(row); w.dP = (float*)take(row); w.dV0 = (float*)take(row); w.dtE = (float*)take(row);
     w.dE = (float*)take(row); w.dH0pre = (float*)take(row);
+    w.probs = (float*)take(sizeof(float) * T * kH * 8);       // attention weights kept by the fused forward
     w.tc_scratch_floats = gemm_tc_scratch_floats(kQKG);
     w.tc_scratch = (float*)take(sizeof(float) * w.tc_scratch_floats);
   }
@@ -522,7 +524,8 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   if ((rc = launch_split_weights_k64(m->derived + l.wqkg, kD, kQKG, m->derived + l.wsplit, s))) return rc;
   if ((rc = launch_split_wT(m->derived + l.wqkg, m->derived + l.wtsplit, s))) return rc;
   if ((rc = launch_split_w_heads(m->derived + l.wqkg, m->derived + l.wheads, s))) return rc;
-  prof_end(P_PREP, 6, s);
+  if (m->grads && (rc = launch_split_w_pairs(m->derived + l.wqkg, m->derived + l.wpairs, s))) return rc;
+  prof_end(P_PREP, 7, s);
   return MATCHA_OK;
 }
 
@@ -557,12 +560,13 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
     if (recon && (rc = check_cuda(cudaMemcpyAsync(recon, w.recon, sizeof(float), cudaMemcpyDeviceToDevice, s), "copy recon")))
       return rc;
   }
-  const bool fused = use_fused_fwd(T, L, training);
+  const bool fused = use_fused(T, L);
   if ((rc = run_mix_qkg(m, x, T, w, s, fused ? L : 0))) return rc;
   DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, training != 0);
   if (fused) {
     if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fused_fwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wheads),
-                                                        m->derived + l.bqkg, m->derived + l.bdyn, x, w.U, nullptr, B, L, dattn, s))))
+                                                        m->derived + l.bqkg, m->derived + l.bdyn, x, w.U, training ? w.probs : nullptr, B, L,
+                                                        dattn, s))))
       return rc;
   } else if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fwd(w.QKG, x, m->derived + l.bdyn, w.U, B, L, dattn, s)))) return rc;
   if ((rc = run_pff(m, T, training, seed, w, s))) return rc;
@@ -627,7 +631,15 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   }
   // attention backward
   DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, true);
-  if (use_tiles(T)) {
+  int dx_parts = 1;
+  if (use_fused(T, L)) {
+    // fused path: recompute + attention backward + data / weight gradients of the QKG projection in one kernel; the
+    // per-head-pair dxhat partials live in the (otherwise unused) dQKG area
+    dx_parts = 4;
+    if ((rc = PROF(P_ATTN_BWD, 2, launch_attn_fused_bwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wpairs),
+                                                        m->derived + l.bqkg, x, w.dU, w.probs, w.dQKG, w.tc_scratch,
+                                                        DG + l.wqkg, DG + l.bqkg, DG + l.bdyn, B, L, dattn, s)))) return rc;
+  } else if (use_tiles(T)) {
     // tile path: the attention backward emits dQKG directly as bf16 hi|lo MMA tiles; rows of the last tile beyond T are zero
     const int64_t nt = num_token_tiles(T);
     if (T % kTileTok != 0 &&
@@ -648,7 +660,8 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     GemmDesc e = gemm_base(FORM_NN, T, kD, kQKG, w.dQKG, kQKG, m->derived + l.wqkg, kD, w.dxhat, kD);
     if ((rc = run_gemm(e, s, P_D_QKG))) return rc;
   }
-  if ((rc = PROF(P_LN_BWD, 1, launch_ln_tanh_bwd(w.dxhat, w.dXs, w.xhat, w.rstd, w.X, w.dP, T, s)))) return rc;
+  if ((rc = PROF(P_LN_BWD, 1, launch_ln_tanh_bwd(dx_parts > 1 ? w.dQKG : w.dxhat, dx_parts, T * kD, w.dXs, w.xhat, w.rstd, w.X,
+                                                 w.dP, T, s)))) return rc;
   {
     GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dP, kD, w.V0, kD, G + m->off_next_w, kD);
     d.colsum = G + m->off_next_b; d.colsum_n = kD;

@@ -499,7 +499,8 @@ __global__ void __launch_bounds__(kBlock) recon_diff_kernel(float* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // small backward helpers
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) ln_tanh_bwd_kernel(const float* __restrict__ dxhat, const float* __restrict__ dXs,
+__global__ void __launch_bounds__(kBlock) ln_tanh_bwd_kernel(const float* __restrict__ dxhat, int nparts, int64_t part_stride,
+                                                              const float* __restrict__ dXs,
                                                               const float* __restrict__ xhat, const float* __restrict__ rstd,
                                                               const float* __restrict__ X, float* __restrict__ dP, int64_t T) {
   const int hl = threadIdx.x & 15;
@@ -510,7 +511,9 @@ __global__ void __launch_bounds__(kBlock) ln_tanh_bwd_kernel(const float* __rest
     const bool valid = t < T;
     const int64_t tt = valid ? t : T - 1;
     const float4 xh = ldg4(xhat + tt * kD + hl * 4);
-    float4 dx = ln_bwd(ldg4(dxhat + tt * kD + hl * 4), xh, rstd[tt]) + ldg4(dXs + tt * kD + hl * 4);
+    float4 gy = ldg4(dxhat + tt * kD + hl * 4);
+    for (int p = 1; p < nparts; ++p) gy = gy + ldg4(dxhat + p * part_stride + tt * kD + hl * 4);
+    float4 dx = ln_bwd(gy, xh, rstd[tt]) + ldg4(dXs + tt * kD + hl * 4);
     const float4 xv = ldg4(X + tt * kD + hl * 4);
     dx = dx * (f4(1.f) - xv * xv);                      // X = tanh(P)  (Modules.py:270)
     if (valid) st4(dP + t * kD + hl * 4, dx);
@@ -673,10 +676,10 @@ int launch_recon_diff(float* pred, int64_t ld, const int64_t* x, int64_t T, cons
   MATCHA_CHECK_LAUNCH("recon_diff");
   return MATCHA_OK;
 }
-int launch_ln_tanh_bwd(const float* dxhat, const float* dXs, const float* xhat, const float* rstd, const float* X,
-                       float* dP, int64_t T, cudaStream_t s) {
+int launch_ln_tanh_bwd(const float* dxhat, int nparts, int64_t part_stride, const float* dXs, const float* xhat,
+                       const float* rstd, const float* X, float* dP, int64_t T, cudaStream_t s) {
   if (T <= 0) return MATCHA_OK;
-  ln_tanh_bwd_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(dxhat, dXs, xhat, rstd, X, dP, T);
+  ln_tanh_bwd_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(dxhat, nparts, part_stride, dXs, xhat, rstd, X, dP, T);
   MATCHA_CHECK_LAUNCH("ln_tanh_bwd");
   return MATCHA_OK;
 }

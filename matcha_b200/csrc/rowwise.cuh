@@ -75,6 +75,18 @@ int launch_ln_fwd_atiles(const float* X, float* xhat, float* rstd, int64_t T, in
 int launch_attn_fused_fwd(const uint8_t* xhat_tiles, const uint8_t* wheads, const float* bq, const float* b_dyn,
                           const int64_t* x, float* U, float* probs, int64_t B, int L, DropCfg drop, cudaStream_t s);
 
+// backward of the same block: recompute per head pair, shuffle attention backward, tcgen05 data and weight gradients.
+//   wpairs       launch_split_w_pairs output (4 head pairs x 3 pieces x 32 KB)
+//   dxhat_parts  [4, T, 64] per-head-pair partial data gradients (summed by launch_ln_tanh_bwd)
+//   part         attn_fused_bwd_scratch_floats() floats of split-K partials; dW [1536, 64] += their sum
+//   dbq [512], db_dyn [64] accumulate (atomics)
+int launch_split_w_pairs(const float* W, void* out, cudaStream_t s);
+int64_t attn_fused_bwd_scratch_floats();
+int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, const float* dU,
+                          const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn,
+                          int64_t B, int L, DropCfg drop, cudaStream_t s);
+constexpr int kPairWBytes = 3 * 32768;                 // per head pair: G | K | Q piece pairs, bf16 hi | lo
+
 // tcgen05 tile kernels (qkg_tiles.cu)
 int launch_split_wT(const float* W, void* out, cudaStream_t s);     // W [1536, 64] fp32 -> MN-major chunks for the dgrad
 int tc_qkg_forward_tiles(const uint8_t* xhat_tiles, const uint8_t* w_split, const float* bias, float* QKG, int64_t T,
@@ -82,9 +94,9 @@ int tc_qkg_forward_tiles(const uint8_t* xhat_tiles, const uint8_t* w_split, cons
 int tc_qkg_dgrad_tiles(const uint8_t* dqkg_tiles, const uint8_t* wT_split, float* dxhat, int64_t T, cudaStream_t s);
 int tc_qkg_wgrad_tiles(const uint8_t* dqkg_tiles, const uint8_t* xhat_tiles, float* scratch, int64_t scratch_floats,
                        float* dW, float* dbias, int64_t dbias_n, int64_t T, cudaStream_t s);
-// dP = (LNbwd(dxhat) + dXs) * (1 - X^2)
-int launch_ln_tanh_bwd(const float* dxhat, const float* dXs, const float* xhat, const float* rstd, const float* X,
-                       float* dP, int64_t T, cudaStream_t s);
+// dP = (LNbwd(sum of nparts dxhat partials, part_stride floats apart) + dXs) * (1 - X^2)
+int launch_ln_tanh_bwd(const float* dxhat, int nparts, int64_t part_stride, const float* dXs, const float* xhat,
+                       const float* rstd, const float* X, float* dP, int64_t T, cudaStream_t s);
 // dE = dV0 + beta * dtE * (1 - tanh(E)^2)   (dtE may be NULL)
 int launch_enc_combine_bwd(const float* dV0, const float* dtE, const float* E, float beta, float* dE, int64_t n,
                            cudaStream_t s);
