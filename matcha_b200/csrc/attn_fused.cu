@@ -463,15 +463,17 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         mbar_wait(&d_full, (uint32_t)(n & 1));
         if (g == 0) mbar_wait(&dx_empty, (uint32_t)(k & 1) ^ 1u);
         tc_fence_after();
+        // stage g recomputes piece g (G, K, Q) but its d-tile holds the gradient of piece gp (dG, dQ, dK)
+        const int gp = (g == 0) ? 0 : (g == 1 ? 2 : 1);
         const uint32_t xh = smem_u32(sX + xb * kBXBytes), xl = xh + 16384;
-        const uint32_t wh = smem_u32(sW + g * kBWPiece), wl = wh + 16384;
+        const uint32_t wh = smem_u32(sW + gp * kBWPiece), wl = wh + 16384;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)   // dxhat[128 tok, 64] += d[128 tok, 128 f] . W_piece[128 f, 64]   (B MN-major)
           umma_x3s(tmem_base + kColDX, dh + ks * 4096, dl + ks * 4096, wh + ks * 256, wl + ks * 256, 2048, 128, 128, 2048,
                    idescD, g == 0 && ks == 0);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)   // dW_piece[128 f, 64] += d^T[128 f, 128 tok] . xhat[128 tok, 64]  (both MN-major)
-          umma_x3s(tmem_base + kColDW + g * 64, dh + ks * 256, dl + ks * 256, xh + ks * 256, xl + ks * 256, 128, 2048, 128,
+          umma_x3s(tmem_base + kColDW + gp * 64, dh + ks * 256, dl + ks * 256, xh + ks * 256, xl + ks * 256, 128, 2048, 128,
                    2048, idescW, k == 0 && ks == 0);
         umma_commit(&d_empty);
         if (g == 2) { umma_commit(&dx_full); umma_commit(&x_empty[xb]); }
