@@ -261,9 +261,12 @@ attn_fused_fwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
 #pragma unroll
         for (int s = 0; s < L - 1; ++s) S[s] *= inv;
         if (probs && live) {
+          float pr[PL];
+#pragma unroll
+          for (int s = 0; s < PL; ++s) pr[s] = (s < L - 1) ? S[s < L - 1 ? s : 0] : 0.f;
           float* pp = probs + (t * kH + h) * PL;
 #pragma unroll
-          for (int s = 0; s < L - 1; ++s) pp[s] = S[s];
+          for (int s = 0; s < PL; s += 4) *reinterpret_cast<float4*>(pp + s) = make_float4(pr[s], pr[s + 1], pr[s + 2], pr[s + 3]);
         }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -386,9 +389,8 @@ __device__ __forceinline__ void store_drow(uint8_t* sD, int p0, int r, const flo
 template <int L>
 __global__ void __launch_bounds__(kBThreads, 1)
 attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict__ wpairs, const float* __restrict__ bq,
-                      const int64_t* __restrict__ x, const float* __restrict__ dU, const float* __restrict__ probs,
-                      float* __restrict__ dxhat_parts, float* __restrict__ part, float* __restrict__ dbq,
-                      float* __restrict__ db_dyn, int64_t T, const DropCfg drop) {
+                      const float* __restrict__ dd_in, const float* __restrict__ probs, float* __restrict__ dxhat_parts,
+                      float* __restrict__ part, float* __restrict__ dbq, float* __restrict__ db_dyn, int64_t T) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sX = smem + kBWBytes;
@@ -490,32 +492,54 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
     for (int s = 1; s < L; ++s) src[s - 1] = live_lane ? gI * L + (pos + s) % L : lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     int64_t n = 0;
+    int64_t t_prev = 0;
+    bool live_prev = false;
+    // dxhat of the previous tile is drained one stage late, so the tensor pipe finishes that tile's last data-gradient
+    // MMAs underneath this tile's first shuffle phase
+    auto drain_dxhat = [&](int64_t kk, int64_t tt, bool lv) {
+      mbar_wait(&dx_full, (uint32_t)(kk & 1));
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32_issue(tlane + kColDX + hl * 32, v);
+      tmem_ld_wait(v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dx_empty);
+      if (lv) {
+        float* dst = dxhat_parts + ((int64_t)hp * T + tt) * kD + hl * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                                            __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+      }
+    };
     for (int64_t k = 0; k < my_tiles; ++k) {
       const int64_t tile = sp + k * S;
       const int64_t t = (tile * 4 + q) * RPW + lane;
       const bool live = live_lane && t < T;
+      const int64_t tl = live ? t : 0;              // clamped row: loads are issued unconditionally, results masked
       float A[L - 1], AT[L - 1], dS[L - 1];
-      {
-        const float* pp = probs + (t * kH + head) * PL;
-#pragma unroll
-        for (int s = 0; s < L - 1; ++s) A[s] = live ? __ldg(pp + s) : 0.f;
-#pragma unroll
-        for (int s = 1; s < L; ++s) AT[s - 1] = __shfl_sync(0xffffffffu, A[L - s - 1], src[s - 1]);   // weight of row (i+s) on row i
-      }
       float o[kD];
       // ---------------- stage G: dA = dd . G_j,  dG_i = sum_j A_ji dd_j ----------------
       {
-        float dd[kD];
-        const float m = (live && x[t] != 0) ? 1.f : 0.f;
+        float dd[kD];                                // gradient wrt the attention output, already masked / dropout-scaled
 #pragma unroll
         for (int c = 0; c < kD; c += 4) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live) {
-            v = __ldg(reinterpret_cast<const float4*>(dU + t * kD + c));
-            const float4 f = drop_factor4(drop, (uint64_t)t, (uint32_t)c);
-            v = make_float4(v.x * f.x * m, v.y * f.y * m, v.z * f.z * m, v.w * f.w * m);
+          const float4 v = __ldg(reinterpret_cast<const float4*>(dd_in + tl * kD + c));
+          dd[c] = live ? v.x : 0.f; dd[c + 1] = live ? v.y : 0.f; dd[c + 2] = live ? v.z : 0.f; dd[c + 3] = live ? v.w : 0.f;
+        }
+        {
+          const float* pp = probs + (tl * kH + head) * PL;
+          float pr[PL];
+#pragma unroll
+          for (int s = 0; s < PL; s += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(pp + s));
+            pr[s] = v.x; pr[s + 1] = v.y; pr[s + 2] = v.z; pr[s + 3] = v.w;
           }
-          dd[c] = v.x; dd[c + 1] = v.y; dd[c + 2] = v.z; dd[c + 3] = v.w;
+#pragma unroll
+          for (int s = 0; s < L - 1; ++s) A[s] = live ? pr[s] : 0.f;
+#pragma unroll
+          for (int s = 1; s < L; ++s) AT[s - 1] = __shfl_sync(0xffffffffu, A[L - s - 1], src[s - 1]);   // weight of row (i+s) on row i
         }
         if (hp == 0 && hl == 0) {          // db_dyn = sum over tokens of the masked, dropout-scaled gradient
           float s0, s1; int col0;
@@ -555,6 +579,7 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         for (int s = 0; s < L - 1; ++s) dot = fmaf(A[s], dA[s], dot);
 #pragma unroll
         for (int s = 0; s < L - 1; ++s) dS[s] = A[s] * (dA[s] - dot);
+        if (k > 0) drain_dxhat(k - 1, t_prev, live_prev);
         mbar_wait(&d_empty, (uint32_t)(n & 1) ^ 1u);
         store_drow(sD, hl * 8, r, o);
         fence_async_smem();
@@ -628,25 +653,10 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         if (lane == 0) mbar_arrive(&d_full);
         ++n;
       }
-      // ---------------- dxhat of this (tile, head pair) ----------------
-      {
-        mbar_wait(&dx_full, (uint32_t)(k & 1));
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32_issue(tlane + kColDX + hl * 32, v);
-        tmem_ld_wait(v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&dx_empty);
-        if (live) {
-          float* dst = dxhat_parts + ((int64_t)hp * T + t) * kD + hl * 32;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
-                                                              __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
-        }
-      }
+      t_prev = t;
+      live_prev = live;
     }
+    if (my_tiles > 0) drain_dxhat(my_tiles - 1, t_prev, live_prev);
     // ---------------- weight-gradient slice of this CTA -> split-K partial ----------------
     mbar_wait(&done, 0);
     tc_fence_after();
@@ -708,14 +718,14 @@ int launch_fwd_L(const uint8_t* xt, const uint8_t* wheads, const float* bq, cons
 }
 
 template <int L>
-int launch_bwd_L(const uint8_t* xt, const uint8_t* wpairs, const float* bq, const int64_t* x, const float* dU,
+int launch_bwd_L(const uint8_t* xt, const uint8_t* wpairs, const float* bq, const float* dd,
                  const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn, int64_t T,
-                 DropCfg drop, cudaStream_t s) {
+                 cudaStream_t s) {
   static bool once = false;
   if (!once) { if (int rc = set_smem_attr_a(attn_fused_bwd_kernel<L>, kBSmem)) return rc; once = true; }
   const int64_t ntiles = num_atiles(T, L);
   const int S = (int)(ntiles < kSMs / 4 ? ntiles : kSMs / 4);
-  attn_fused_bwd_kernel<L><<<4 * S, kBThreads, kBSmem, s>>>(xt, wpairs, bq, x, dU, probs, dxhat_parts, part, dbq, db_dyn, T, drop);
+  attn_fused_bwd_kernel<L><<<4 * S, kBThreads, kBSmem, s>>>(xt, wpairs, bq, dd, probs, dxhat_parts, part, dbq, db_dyn, T);
   MATCHA_CHECK_LAUNCH("attn_fused_bwd");
   attn_wgrad_reduce_kernel<<<kSMs, 256, 0, s>>>(part, S, dW);
   MATCHA_CHECK_LAUNCH("attn_wgrad_reduce");
@@ -732,17 +742,36 @@ int launch_split_w_pairs(const float* W, void* out, cudaStream_t s) {
 
 int64_t attn_fused_bwd_scratch_floats() { return (int64_t)(kSMs / 4) * kQKG * kD; }
 
-int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, const float* dU,
+// dU <- dU * dropout factor * non_pad_mask, in place (the gradient wrt the pre-dropout attention output)
+__global__ void mask_drop_kernel(float* __restrict__ dU, const int64_t* __restrict__ x, int64_t T, const DropCfg drop) {
+  const int64_t n4 = T * (kD / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i >> 4;
+    const int c = (int)(i & 15) * 4;
+    float4 v = reinterpret_cast<float4*>(dU)[i];
+    const float m = x[t] != 0 ? 1.f : 0.f;
+    const float4 f = drop_factor4(drop, (uint64_t)t, (uint32_t)c);
+    reinterpret_cast<float4*>(dU)[i] = make_float4(v.x * f.x * m, v.y * f.y * m, v.z * f.z * m, v.w * f.w * m);
+  }
+}
+
+int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, float* dU,
                           const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn,
                           int64_t B, int L, DropCfg drop, cudaStream_t s) {
   if (B <= 0) return MATCHA_OK;
   const int64_t T = B * L;
+  {
+    int64_t blocks = (T * 16 + 255) / 256;
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    mask_drop_kernel<<<(unsigned)blocks, 256, 0, s>>>(dU, x, T, drop);
+    MATCHA_CHECK_LAUNCH("mask_drop");
+  }
   switch (L) {
-    case 2: return launch_bwd_L<2>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
-    case 3: return launch_bwd_L<3>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
-    case 4: return launch_bwd_L<4>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
-    case 5: return launch_bwd_L<5>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
-    case 6: return launch_bwd_L<6>(xhat_tiles, wpairs, bq, x, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, drop, s);
+    case 2: return launch_bwd_L<2>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
+    case 3: return launch_bwd_L<3>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
+    case 4: return launch_bwd_L<4>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
+    case 5: return launch_bwd_L<5>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
+    case 6: return launch_bwd_L<6>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
     default: set_error("attn_fused_bwd: padded width L=%d unsupported (2..6)", L); return MATCHA_ERR_ARG;
   }
 }

@@ -79,10 +79,10 @@ int launch_attn_fused_fwd(const uint8_t* xhat_tiles, const uint8_t* wheads, cons
 //   wpairs       launch_split_w_pairs output (4 head pairs x 3 pieces x 32 KB)
 //   dxhat_parts  [4, T, 64] per-head-pair partial data gradients (summed by launch_ln_tanh_bwd)
 //   part         attn_fused_bwd_scratch_floats() floats of split-K partials; dW [1536, 64] += their sum
-//   dbq [512], db_dyn [64] accumulate (atomics)
+//   dbq [512], db_dyn [64] accumulate (atomics); dU is masked / dropout-scaled IN PLACE first
 int launch_split_w_pairs(const float* W, void* out, cudaStream_t s);
 int64_t attn_fused_bwd_scratch_floats();
-int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, const float* dU,
+int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, float* dU,
                           const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn,
                           int64_t B, int L, DropCfg drop, cudaStream_t s);
 constexpr int kPairWBytes = 3 * 32768;                 // per head pair: G | K | Q piece pairs, bf16 hi | lo
