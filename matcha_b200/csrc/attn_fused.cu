@@ -168,7 +168,7 @@ attn_fused_fwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         for (int s = 0; s < 2; ++s) {
           const int64_t tile = 2 * pair + s;
           if (tile >= ntiles) break;
-          mbar_wait(&x_empty[s], xp[s] ^ 1);
+          mbar_wait_backoff(&x_empty[s], xp[s] ^ 1);
           mbar_expect_tx(&x_full[s], kAXBytes);
           const uint8_t* src = xt + tile * (int64_t)kXTileBytes;
           bulk_g2s(sX + s * kAXBytes, src, 16384, &x_full[s]);
@@ -176,7 +176,7 @@ attn_fused_fwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
           xp[s] ^= 1;
         }
         for (int h = 0; h < kH; ++h) {
-          mbar_wait(&w_empty[ws], wp ^ 1);
+          mbar_wait_backoff(&w_empty[ws], wp ^ 1);
           mbar_expect_tx(&w_full[ws], kAWBytes);
           bulk_g2s(sW + ws * kAWBytes, wheads + (int64_t)h * kAWBytes, kAWBytes, &w_full[ws]);
           if (++ws == 2) { ws = 0; wp ^= 1; }
@@ -190,11 +190,11 @@ attn_fused_fwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
       for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
         const int nsub = (2 * pair + 1 < ntiles) ? 2 : 1;
         for (int h = 0; h < kH; ++h) {
-          mbar_wait(&w_full[ws], wp);
+          mbar_wait_backoff(&w_full[ws], wp);
           const uint32_t wh = smem_u32(sW + ws * kAWBytes), wl = wh + kAWHalf;
           for (int s = 0; s < nsub; ++s) {
-            if (h == 0) { mbar_wait(&x_full[s], xp[s]); xp[s] ^= 1; }
-            mbar_wait(&acc_empty[s], ap[s] ^ 1);
+            if (h == 0) { mbar_wait_backoff(&x_full[s], xp[s]); xp[s] ^= 1; }
+            mbar_wait_backoff(&acc_empty[s], ap[s] ^ 1);
             ap[s] ^= 1;
             tc_fence_after();
             const uint32_t xh = smem_u32(sX + s * kAXBytes), xl = xh + 16384;
@@ -428,7 +428,7 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         bulk_g2s(sW + p * kBWPiece, wpairs + (int64_t)hp * kBWBytes + p * kBWPiece, kBWPiece, &w_full);
       for (int64_t k = 0; k < my_tiles; ++k) {
         const int b = (int)(k & 1);
-        mbar_wait(&x_empty[b], (uint32_t)((k >> 1) & 1) ^ 1u);
+        mbar_wait_backoff(&x_empty[b], (uint32_t)((k >> 1) & 1) ^ 1u);
         mbar_expect_tx(&x_full[b], kBXBytes);
         const uint8_t* src = xt + (sp + k * S) * (int64_t)kXTileBytes;
         bulk_g2s(sX + b * kBXBytes, src, 16384, &x_full[b]);
@@ -442,12 +442,12 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
       constexpr uint32_t idescW = make_idesc(128, 64, true, true);
       const int64_t N = 3 * my_tiles;
       const uint32_t dh = smem_u32(sD), dl = dh + kBDHalf;
-      mbar_wait(&w_full, 0);
+      mbar_wait_backoff(&w_full, 0);
       auto recompute = [&](int64_t n) {
         const int64_t k = n / 3;
         const int g = (int)(n - 3 * k), xb = (int)(k & 1), rb = (int)(n & 1);
-        if (g == 0) mbar_wait(&x_full[xb], (uint32_t)((k >> 1) & 1));
-        mbar_wait(&r_empty[rb], (uint32_t)((n >> 1) & 1) ^ 1u);
+        if (g == 0) mbar_wait_backoff(&x_full[xb], (uint32_t)((k >> 1) & 1));
+        mbar_wait_backoff(&r_empty[rb], (uint32_t)((n >> 1) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t xh = smem_u32(sX + xb * kBXBytes), xl = xh + 16384;
         const uint32_t wh = smem_u32(sW + g * kBWPiece), wl = wh + 16384;
@@ -462,8 +462,8 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         if (n + 1 < N) recompute(n + 1);
         const int64_t k = n / 3;
         const int g = (int)(n - 3 * k), xb = (int)(k & 1);
-        mbar_wait(&d_full, (uint32_t)(n & 1));
-        if (g == 0) mbar_wait(&dx_empty, (uint32_t)(k & 1) ^ 1u);
+        mbar_wait_backoff(&d_full, (uint32_t)(n & 1));
+        if (g == 0) mbar_wait_backoff(&dx_empty, (uint32_t)(k & 1) ^ 1u);
         tc_fence_after();
         // stage g recomputes piece g (G, K, Q) but its d-tile holds the gradient of piece gp (dG, dQ, dK)
         const int gp = (g == 0) ? 0 : (g == 1 ? 2 : 1);
@@ -513,34 +513,43 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
                                                             __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
       }
     };
+    // rows of the next tile are fetched as soon as the current tile's registers are free, so their latency hides
+    // under the K and Q stages
+    float dd[kD];                                    // gradient wrt the attention output, already masked / dropout-scaled
+    float pr[PL];
+    auto fetch_rows = [&](int64_t kk) {
+      const int64_t tt = ((sp + kk * S) * 4 + q) * RPW + lane;
+      const bool lv = live_lane && tt < T;
+      const int64_t tl = lv ? tt : 0;               // clamped row: loads are issued unconditionally, results masked on use
+#pragma unroll
+      for (int c = 0; c < kD; c += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dd_in + tl * kD + c));
+        dd[c] = v.x; dd[c + 1] = v.y; dd[c + 2] = v.z; dd[c + 3] = v.w;
+      }
+      const float* pp = probs + (tl * kH + head) * PL;
+#pragma unroll
+      for (int s = 0; s < PL; s += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(pp + s));
+        pr[s] = v.x; pr[s + 1] = v.y; pr[s + 2] = v.z; pr[s + 3] = v.w;
+      }
+    };
+    if (my_tiles > 0) fetch_rows(0);
     for (int64_t k = 0; k < my_tiles; ++k) {
       const int64_t tile = sp + k * S;
       const int64_t t = (tile * 4 + q) * RPW + lane;
       const bool live = live_lane && t < T;
-      const int64_t tl = live ? t : 0;              // clamped row: loads are issued unconditionally, results masked
       float A[L - 1], AT[L - 1], dS[L - 1];
       float o[kD];
       // ---------------- stage G: dA = dd . G_j,  dG_i = sum_j A_ji dd_j ----------------
       {
-        float dd[kD];                                // gradient wrt the attention output, already masked / dropout-scaled
+        if (!live) {
 #pragma unroll
-        for (int c = 0; c < kD; c += 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(dd_in + tl * kD + c));
-          dd[c] = live ? v.x : 0.f; dd[c + 1] = live ? v.y : 0.f; dd[c + 2] = live ? v.z : 0.f; dd[c + 3] = live ? v.w : 0.f;
+          for (int c = 0; c < kD; ++c) dd[c] = 0.f;
         }
-        {
-          const float* pp = probs + (tl * kH + head) * PL;
-          float pr[PL];
 #pragma unroll
-          for (int s = 0; s < PL; s += 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(pp + s));
-            pr[s] = v.x; pr[s + 1] = v.y; pr[s + 2] = v.z; pr[s + 3] = v.w;
-          }
+        for (int s = 0; s < L - 1; ++s) A[s] = live ? pr[s] : 0.f;
 #pragma unroll
-          for (int s = 0; s < L - 1; ++s) A[s] = live ? pr[s] : 0.f;
-#pragma unroll
-          for (int s = 1; s < L; ++s) AT[s - 1] = __shfl_sync(0xffffffffu, A[L - s - 1], src[s - 1]);   // weight of row (i+s) on row i
-        }
+        for (int s = 1; s < L; ++s) AT[s - 1] = __shfl_sync(0xffffffffu, A[L - s - 1], src[s - 1]);   // weight of row (i+s) on row i
         if (hp == 0 && hl == 0) {          // db_dyn = sum over tokens of the masked, dropout-scaled gradient
           float s0, s1; int col0;
           warp_colsum64(dd, lane, s0, s1, col0);
@@ -579,6 +588,7 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         for (int s = 0; s < L - 1; ++s) dot = fmaf(A[s], dA[s], dot);
 #pragma unroll
         for (int s = 0; s < L - 1; ++s) dS[s] = A[s] * (dA[s] - dot);
+        if (k + 1 < my_tiles) fetch_rows(k + 1);
         if (k > 0) drain_dxhat(k - 1, t_prev, live_prev);
         mbar_wait(&d_empty, (uint32_t)(n & 1) ^ 1u);
         store_drow(sD, hl * 8, r, o);
