@@ -47,6 +47,9 @@ void matcha_set_gemm_impl(int32_t impl);
 /* 1 (default) = fused hyperedge-tile kernels (QKG projection + attention in one tcgen05 kernel) where eligible,
  * 0 = decomposed pipeline (projection, attention, ... as separate launches); also MATCHA_FUSED=0 */
 void matcha_set_fused(int32_t on);
+/* 1 (default) = the 64-wide layers around the attention block run as tcgen05 row-chain kernels (needs the fused
+ * path), 0 = SIMT fp32 contractions; also MATCHA_CHAIN=0 */
+void matcha_set_chain(int32_t on);
 
 /* ---------------------------------------------------------------------------------------------
  * Model description: where every live tensor of Modules.Classifier sits.

@@ -767,10 +767,10 @@ __global__ void mask_drop_kernel(float* __restrict__ dU, const int64_t* __restri
 
 int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, float* dU,
                           const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn,
-                          int64_t B, int L, DropCfg drop, cudaStream_t s) {
+                          int64_t B, int L, DropCfg drop, int premasked, cudaStream_t s) {
   if (B <= 0) return MATCHA_OK;
   const int64_t T = B * L;
-  {
+  if (!premasked) {
     int64_t blocks = (T * 16 + 255) / 256;
     if (blocks > kSMs * 16) blocks = kSMs * 16;
     mask_drop_kernel<<<(unsigned)blocks, 256, 0, s>>>(dU, x, T, drop);

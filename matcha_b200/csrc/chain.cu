@@ -1,0 +1,813 @@
+// "Row-chain" kernels: the 64-wide position-wise layers around the attention block (Modules.py:263-270 attribute mix,
+// :353-376 pff_n1, :290-311 scorer) as chains of tcgen05 contractions whose activations stay in registers.
+//
+// One CTA = 128 threads = the 128 rows of one hyperedge-aligned tile (rowwise.cuh); thread r owns tile row r, which is
+// also TMEM lane r.  A stage = { the thread splits its fp32 row into bf16 hi | lo and stores it into the shared A tile
+// (and, when a consumer needs it, into the same tile in global memory) -> one thread issues the bf16x3 MMAs against a
+// pre-split 64x64 weight resident in shared memory -> every thread reads its output row back with tcgen05.ld }.
+// Several CTAs per SM (<= 64 KB shared memory, 64 TMEM columns each) overlap each other's load / MMA / store phases.
+#include "rowwise.cuh"
+#include "tc_common.cuh"
+
+namespace matcha {
+namespace {
+
+constexpr int kCThreads = 128;
+constexpr int kCTile = 32768;                 // A tile: hi 16 KB (8 planes x 128 rows x 16 B) | lo 16 KB
+constexpr int kCW = kChainWBytes;             // one 64x64 weight: hi 8 KB | lo 8 KB
+constexpr float kLnEpsC = 1e-5f;
+
+// ------------------------------------------------------------------------------------------
+// parameter preparation: W [64][64] row-major -> (a) K-major [k/8][n][8] for Y = X W^T, (b) the layout of W read as
+// B[N = column, K = row] MN-major ([row/8][col/8][row%8][8 cols]) for dX = dY W.  LBO 1024 / SBO 128 in both.
+// ------------------------------------------------------------------------------------------
+__global__ void split_w64_kernel(const float* __restrict__ W, uint8_t* __restrict__ out_k, uint8_t* __restrict__ out_mn) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;       // unit = (row r, group g of 8 columns)
+  if (u >= 64 * 8) return;
+  const int g = u & 7, r = u >> 3;
+  const float* src = W + r * 64 + g * 8;
+  uint4 hi, lo;
+  split8(__ldg(reinterpret_cast<const float4*>(src)), __ldg(reinterpret_cast<const float4*>(src + 4)), hi, lo);
+  const int off_k = g * 1024 + r * 16;
+  *reinterpret_cast<uint4*>(out_k + off_k) = hi;
+  *reinterpret_cast<uint4*>(out_k + 8192 + off_k) = lo;
+  const int off_mn = (r >> 3) * 1024 + g * 128 + (r & 7) * 16;
+  *reinterpret_cast<uint4*>(out_mn + off_mn) = hi;
+  *reinterpret_cast<uint4*>(out_mn + 8192 + off_mn) = lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage helpers
+// ------------------------------------------------------------------------------------------
+struct ChainCtx {
+  uint8_t* sA;
+  uint64_t* bar;
+  uint32_t tmem;       // TMEM base (64 columns)
+  uint32_t phase;
+  int r;               // tile row of this thread
+};
+
+// split one fp32 row into the shared A tile and (optionally) the same tile in global memory
+__device__ __forceinline__ void put_row(uint8_t* sA, uint8_t* gT, int r, const float (&v)[64]) {   // gT: kCTile layout
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 hi, lo;
+    split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+           make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+    sts16(sA + j * 2048 + r * 16, hi);
+    sts16(sA + 16384 + j * 2048 + r * 16, lo);
+    if (gT) {
+      *reinterpret_cast<uint4*>(gT + j * 2048 + r * 16) = hi;
+      *reinterpret_cast<uint4*>(gT + 16384 + j * 2048 + r * 16) = lo;
+    }
+  }
+}
+// only the global copy (rows that feed a later weight-gradient kernel but no MMA of this kernel)
+__device__ __forceinline__ void put_row_global(uint8_t* gT, int half_bytes, int r, const float (&v)[64]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 hi, lo;
+    split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+           make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+    *reinterpret_cast<uint4*>(gT + j * 2048 + r * 16) = hi;
+    *reinterpret_cast<uint4*>(gT + half_bytes + j * 2048 + r * 16) = lo;
+  }
+}
+
+__device__ __forceinline__ void tmem_ld32_issue_c(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// the row is already in the A tile: publish it, run [128 x 64] . W (64 x 64, pre-split at shared address w_hi), read the
+// output row back.  Must be called by all 128 threads.
+__device__ __forceinline__ void run_stage(ChainCtx& c, uint32_t w_hi, uint32_t idesc, float (&out)[64]) {
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    const uint32_t ah = smem_u32(c.sA), al = ah + 16384;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      umma_x3s(c.tmem, ah + ks * 4096, al + ks * 4096, w_hi + ks * 2048, w_hi + 8192 + ks * 2048, 2048, 128, 1024, 128, idesc,
+               ks == 0);
+    umma_commit(c.bar);
+  }
+  mbar_wait(c.bar, c.phase);
+  c.phase ^= 1;
+  tc_fence_after();
+  const uint32_t taddr = c.tmem + ((uint32_t)((c.r >> 5) * 32) << 16);
+  uint32_t a[32], b[32];
+  tmem_ld32_issue_c(taddr, a);
+  tmem_ld32_issue_c(taddr + 32, b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { asm volatile("" : "+r"(a[i])); asm volatile("" : "+r"(b[i])); }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { out[i] = __uint_as_float(a[i]); out[32 + i] = __uint_as_float(b[i]); }
+  tc_fence_before();
+}
+
+__device__ __forceinline__ void load_weight(uint8_t* dst, const uint8_t* src) {   // 16 KB, all 128 threads
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < kCW / 16 / kCThreads; ++i) d[threadIdx.x + i * kCThreads] = __ldg(s + threadIdx.x + i * kCThreads);
+}
+
+// LayerNorm statistics of a row held by one thread (biased variance, eps 1e-5); v <- normalised row
+__device__ __forceinline__ float ln_row(float (&v)[64]) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; ++c) s += v[c];
+  const float mean = s * (1.0f / 64);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; ++c) { v[c] -= mean; q = fmaf(v[c], v[c], q); }
+  const float rstd = 1.0f / sqrtf(q * (1.0f / 64) + kLnEpsC);
+#pragma unroll
+  for (int c = 0; c < 64; ++c) v[c] *= rstd;
+  return rstd;
+}
+
+// ==========================================================================================
+// F1: V0 = E + attribute_nn(attr[id]);  X = tanh(next_w V0 + b);  xhat, rstd = LayerNorm statistics of X
+// ==========================================================================================
+struct MixArgs {
+  const float* E; const int64_t* x; const float* attr_table; int attr_dim; const float* attr_w; const float* attr_b;
+  const uint8_t* w_next; const float* next_b;
+  float* V0; float* X; float* xhat; float* rstd;
+  uint8_t* xt;       // hyperedge-aligned xhat tiles (kXTileBytes each)
+  uint8_t* v0t;      // V0 tiles (32 KB each: hi 16 KB | lo 16 KB) for the weight-gradient kernel, or NULL
+  uint8_t* attrt;    // attribute-row tiles [128 x 32] hi 8 KB | lo 8 KB, or NULL
+  int64_t T;
+};
+
+template <int L>
+__global__ void __launch_bounds__(kCThreads) chain_mix_fwd_kernel(const MixArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + kCTile;
+  float* sWt = reinterpret_cast<float*>(smem + kCTile + kCW);     // attribute_nn.weight^T [attr_dim][64]
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sNb[64], sAb[64];
+  constexpr int RPW = (32 / L) * L;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (a.T + 4 * RPW - 1) / (4 * RPW);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  load_weight(sW, a.w_next);
+  for (int i = tid; i < a.attr_dim * 64; i += kCThreads) sWt[i] = __ldg(a.attr_w + (i & 63) * a.attr_dim + (i >> 6));
+  if (tid < 64) { sNb[tid] = __ldg(a.next_b + tid); sAb[tid] = __ldg(a.attr_b + tid); }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
+  constexpr uint32_t idesc = make_idesc(128, 64, false, false);
+  const uint32_t w_hi = smem_u32(sW);
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t t = (tile * 4 + warp) * RPW + lane;
+    const bool live = lane < RPW && t < a.T;
+    float v[64];
+#pragma unroll
+    for (int cc = 0; cc < 64; ++cc) v[cc] = 0.f;
+    if (live) {
+      const int64_t id = a.x[t];
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 4) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(a.E + t * 64 + cc));
+        v[cc] = e.x + sAb[cc]; v[cc + 1] = e.y + sAb[cc + 1]; v[cc + 2] = e.z + sAb[cc + 2]; v[cc + 3] = e.w + sAb[cc + 3];
+      }
+      const float* arow = a.attr_table + id * a.attr_dim;
+      float av[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) av[k] = (k < a.attr_dim) ? __ldg(arow + k) : 0.f;
+      if (a.attrt) {       // attribute rows for the attribute_nn weight gradient: 4 planes of 8 columns
+        uint8_t* gt = a.attrt + tile * 16384;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 hi, lo;
+          split8(make_float4(av[8 * j], av[8 * j + 1], av[8 * j + 2], av[8 * j + 3]),
+                 make_float4(av[8 * j + 4], av[8 * j + 5], av[8 * j + 6], av[8 * j + 7]), hi, lo);
+          *reinterpret_cast<uint4*>(gt + j * 2048 + tid * 16) = hi;
+          *reinterpret_cast<uint4*>(gt + 8192 + j * 2048 + tid * 16) = lo;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {        // attribute rows are one-hot + one scalar (main.py:497-512): skip the zeros
+        if (k < a.attr_dim && av[k] != 0.f) {
+          const float* wt = sWt + k * 64;
+#pragma unroll
+          for (int cc = 0; cc < 64; ++cc) v[cc] = fmaf(av[k], wt[cc], v[cc]);
+        }
+      }
+      if (a.V0) {
+#pragma unroll
+        for (int cc = 0; cc < 64; cc += 4)
+          *reinterpret_cast<float4*>(a.V0 + t * 64 + cc) = make_float4(v[cc], v[cc + 1], v[cc + 2], v[cc + 3]);
+      }
+    } else if (a.attrt) {
+      uint8_t* gt = a.attrt + tile * 16384;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        *reinterpret_cast<uint4*>(gt + j * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(gt + 8192 + j * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    put_row(sA, a.v0t ? a.v0t + tile * (int64_t)kCTile : nullptr, tid, v);
+    float o[64];
+    run_stage(c, w_hi, idesc, o);
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < 64; ++cc) o[cc] = tanhf(o[cc] + sNb[cc]);
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 4)
+        *reinterpret_cast<float4*>(a.X + t * 64 + cc) = make_float4(o[cc], o[cc + 1], o[cc + 2], o[cc + 3]);
+      const float rs = ln_row(o);
+      a.rstd[t] = rs;
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 4)
+        *reinterpret_cast<float4*>(a.xhat + t * 64 + cc) = make_float4(o[cc], o[cc + 1], o[cc + 2], o[cc + 3]);
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 64; ++cc) o[cc] = 0.f;
+    }
+    put_row_global(a.xt + tile * (int64_t)kXTileBytes, kXHalfBytes, tid, o);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 64);
+}
+
+// ==========================================================================================
+// F3: pff_n1 (two 1x1 convolutions, tanh, dropout, residual) + scorer (LayerNorms, (dyn - static)^2, masked mean)
+// ==========================================================================================
+struct PffArgs {
+  const float* U; const float* xhat; const int64_t* x;
+  const uint8_t* w0; const uint8_t* w1; const float* b0; const float* b1;
+  ScoreParams p; DropCfg drop;
+  float* H1d; float* H2; float* logits;
+  uint8_t* ut; uint8_t* h1t;       // U / H1d tiles for the weight-gradient kernel (training) or NULL
+  int64_t T;
+};
+
+template <int L>
+__global__ void __launch_bounds__(kCThreads) chain_pff_fwd_kernel(const PffArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW0 = smem + kCTile;
+  uint8_t* sW1 = smem + kCTile + kCW;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sP[9][64];        // b0, b1, pff_g, pff_b, ln1_g, ln1_b, ln2_g, ln2_b, cls_w
+  __shared__ float sCb;
+  constexpr int RPW = (32 / L) * L;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (a.T + 4 * RPW - 1) / (4 * RPW);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  if (tid == 0) { mbar_init(&bar, 1); sCb = __ldg(a.p.cls_b); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  load_weight(sW0, a.w0);
+  load_weight(sW1, a.w1);
+  if (tid < 64) {
+    sP[0][tid] = __ldg(a.b0 + tid); sP[1][tid] = __ldg(a.b1 + tid);
+    sP[2][tid] = __ldg(a.p.pff_g + tid); sP[3][tid] = __ldg(a.p.pff_b + tid);
+    sP[4][tid] = __ldg(a.p.ln1_g + tid); sP[5][tid] = __ldg(a.p.ln1_b + tid);
+    sP[6][tid] = __ldg(a.p.ln2_g + tid); sP[7][tid] = __ldg(a.p.ln2_b + tid);
+    sP[8][tid] = __ldg(a.p.cls_w + tid);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
+  constexpr uint32_t idesc = make_idesc(128, 64, false, false);
+  const uint32_t w0_hi = smem_u32(sW0), w1_hi = smem_u32(sW1);
+  const bool live_lane = lane < RPW;
+  const int g = lane / L, pos = lane - g * L;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t t = (tile * 4 + warp) * RPW + lane;
+    const bool live = live_lane && t < a.T;
+    float u[64];
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 4) {
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) e = __ldg(reinterpret_cast<const float4*>(a.U + t * 64 + cc));
+      u[cc] = e.x; u[cc + 1] = e.y; u[cc + 2] = e.z; u[cc + 3] = e.w;
+    }
+    put_row(sA, a.ut ? a.ut + tile * (int64_t)kCTile : nullptr, tid, u);
+    float h[64];
+    run_stage(c, w0_hi, idesc, h);
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 4) {
+        float4 v = make_float4(tanhf(h[cc] + sP[0][cc]), tanhf(h[cc + 1] + sP[0][cc + 1]), tanhf(h[cc + 2] + sP[0][cc + 2]),
+                               tanhf(h[cc + 3] + sP[0][cc + 3]));
+        v = drop_apply4(a.drop, (uint64_t)t, (uint32_t)cc, v);          // dropout inside pff_n1 (Modules.py:359-360)
+        h[cc] = v.x; h[cc + 1] = v.y; h[cc + 2] = v.z; h[cc + 3] = v.w;
+        if (a.H1d) *reinterpret_cast<float4*>(a.H1d + t * 64 + cc) = v;
+      }
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 64; ++cc) h[cc] = 0.f;
+    }
+    put_row(sA, a.h1t ? a.h1t + tile * (int64_t)kCTile : nullptr, tid, h);
+    float o[64];
+    run_stage(c, w1_hi, idesc, o);
+    float z = 0.f, m = 0.f;
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < 64; ++cc) o[cc] = o[cc] + sP[1][cc] + u[cc];    // residual (Modules.py:371-372)
+      if (a.H2) {
+#pragma unroll
+        for (int cc = 0; cc < 64; cc += 4)
+          *reinterpret_cast<float4*>(a.H2 + t * 64 + cc) = make_float4(o[cc], o[cc + 1], o[cc + 2], o[cc + 3]);
+      }
+      m = a.x[t] != 0 ? 1.f : 0.f;
+      ln_row(o);                                                            // pff_n1.layer_norm
+#pragma unroll
+      for (int cc = 0; cc < 64; ++cc) o[cc] = fmaf(o[cc], sP[2][cc], sP[3][cc]) * m;
+      ln_row(o);                                                            // Classifier.layer_norm1
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 4) {
+        const float4 xh = __ldg(reinterpret_cast<const float4*>(a.xhat + t * 64 + cc));
+        const float xv[4] = {xh.x, xh.y, xh.z, xh.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float D = fmaf(o[cc + j], sP[4][cc + j], sP[5][cc + j]);
+          const float S = fmaf(xv[j], sP[6][cc + j], sP[7][cc + j]);          // Classifier.layer_norm2 of the layer input
+          const float df = D - S;
+          z = fmaf(df * df, sP[8][cc + j], z);
+        }
+      }
+      z += sCb;
+    }
+    // masked mean over the L tokens of the hyperedge (all inside this warp)
+    float zs = z * m, ms = m;
+#pragma unroll
+    for (int s = 1; s < L; ++s) {
+      const int src = live_lane ? g * L + (pos + s) % L : lane;
+      zs += __shfl_sync(0xffffffffu, z * m, src);
+      ms += __shfl_sync(0xffffffffu, m, src);
+    }
+    if (live && pos == 0) a.logits[t / L] = zs / (ms + 1e-15f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 64);
+}
+
+
+// ==========================================================================================
+// B1: pff_n1 backward.  dH2 -> dH1pre = (dH2 W1) * tanh' * dropout -> dU = dH1pre W0 + dH2 -> masked / dropout-scaled
+// gradient of the attention output.  The dH2 and dH1pre tiles go to global memory for the weight-gradient kernel.
+// ==========================================================================================
+struct PffBwdArgs {
+  const float* dH2; const float* H1d; const int64_t* x;
+  const uint8_t* w1mn; const uint8_t* w0mn;
+  DropCfg dpff, dattn;
+  float* dd;                      // out [T, 64]
+  uint8_t* dh2t; uint8_t* dh1t;   // out tiles (32 KB each)
+  int64_t T;
+};
+
+template <int L>
+__global__ void __launch_bounds__(kCThreads) chain_pff_bwd_kernel(const PffBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW1 = smem + kCTile;
+  uint8_t* sW0 = smem + kCTile + kCW;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  constexpr int RPW = (32 / L) * L;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (a.T + 4 * RPW - 1) / (4 * RPW);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  load_weight(sW1, a.w1mn);
+  load_weight(sW0, a.w0mn);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
+  constexpr uint32_t idesc = make_idesc(128, 64, false, true);      // B = W read as [N = column, K = row], MN-major
+  const uint32_t w1_hi = smem_u32(sW1), w0_hi = smem_u32(sW0);
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t t = (tile * 4 + warp) * RPW + lane;
+    const bool live = lane < RPW && t < a.T;
+    const int64_t tl = live ? t : 0;
+    float g[64];
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 4) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(a.dH2 + tl * 64 + cc));
+      g[cc] = live ? e.x : 0.f; g[cc + 1] = live ? e.y : 0.f; g[cc + 2] = live ? e.z : 0.f; g[cc + 3] = live ? e.w : 0.f;
+    }
+    put_row(sA, a.dh2t + tile * (int64_t)kCTile, tid, g);
+    float o[64];
+    run_stage(c, w1_hi, idesc, o);
+    // gradient through H1d = dropout(tanh(.)): dy * f * (1 - (y / f)^2), f = keep * scale
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 4) {
+      const float4 yv = __ldg(reinterpret_cast<const float4*>(a.H1d + tl * 64 + cc));
+      const float4 f = drop_factor4(a.dpff, (uint64_t)t, (uint32_t)cc);
+      const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, ff[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float h = ff[j] > 0.f ? yy[j] / ff[j] : 0.f;
+        o[cc + j] = live ? o[cc + j] * ff[j] * (1.f - h * h) : 0.f;
+      }
+    }
+    put_row(sA, a.dh1t + tile * (int64_t)kCTile, tid, o);
+    run_stage(c, w0_hi, idesc, o);
+    if (live) {
+      const float m = a.x[t] != 0 ? 1.f : 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 4) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(a.dH2 + t * 64 + cc));     // residual branch (L2 hit)
+        const float4 f = drop_factor4(a.dattn, (uint64_t)t, (uint32_t)cc);
+        *reinterpret_cast<float4*>(a.dd + t * 64 + cc) = make_float4((o[cc] + e.x) * f.x * m, (o[cc + 1] + e.y) * f.y * m,
+                                                                      (o[cc + 2] + e.z) * f.z * m, (o[cc + 3] + e.w) * f.w * m);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 64);
+}
+
+// ==========================================================================================
+// B3: LayerNorm / tanh / next_w backward.  dP = (LNbwd(sum of dxhat partials) + dXs) * (1 - X^2);  dV0 = dP next_w;
+// dE = dV0 + beta * dtE * (1 - tanh(E)^2).  dP and dV0 tiles go to global memory for the weight-gradient kernel.
+// ==========================================================================================
+struct MixBwdArgs {
+  const float* dxhat; int nparts; int64_t part_stride;
+  const float* dXs; const float* xhat; const float* rstd; const float* X;
+  const float* dtE; const float* E; float beta;     // dtE may be NULL
+  const uint8_t* wnmn;
+  float* dE;                       // out [T, 64]
+  uint8_t* dpt; uint8_t* dv0t;     // out tiles
+  int64_t T;
+};
+
+template <int L>
+__global__ void __launch_bounds__(kCThreads) chain_mix_bwd_kernel(const MixBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + kCTile;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  constexpr int RPW = (32 / L) * L;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (a.T + 4 * RPW - 1) / (4 * RPW);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  load_weight(sW, a.wnmn);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
+  constexpr uint32_t idesc = make_idesc(128, 64, false, true);
+  const uint32_t w_hi = smem_u32(sW);
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t t = (tile * 4 + warp) * RPW + lane;
+    const bool live = lane < RPW && t < a.T;
+    const int64_t tl = live ? t : 0;
+    float g[64];
+    {
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 4) {
+        float4 e = __ldg(reinterpret_cast<const float4*>(a.dxhat + tl * 64 + cc));
+        for (int p = 1; p < a.nparts; ++p) {
+          const float4 e2 = __ldg(reinterpret_cast<const float4*>(a.dxhat + p * a.part_stride + tl * 64 + cc));
+          e.x += e2.x; e.y += e2.y; e.z += e2.z; e.w += e2.w;
+        }
+        const float4 xh = __ldg(reinterpret_cast<const float4*>(a.xhat + tl * 64 + cc));
+        g[cc] = e.x; g[cc + 1] = e.y; g[cc + 2] = e.z; g[cc + 3] = e.w;
+        m1 += (e.x + e.y) + (e.z + e.w);
+        m2 = fmaf(e.x, xh.x, fmaf(e.y, xh.y, fmaf(e.z, xh.z, fmaf(e.w, xh.w, m2))));
+      }
+      m1 *= (1.0f / 64); m2 *= (1.0f / 64);
+      const float rs = __ldg(a.rstd + tl);
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 4) {
+        const float4 xh = __ldg(reinterpret_cast<const float4*>(a.xhat + tl * 64 + cc));
+        const float4 ds = __ldg(reinterpret_cast<const float4*>(a.dXs + tl * 64 + cc));
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(a.X + tl * 64 + cc));
+        const float xx[4] = {xh.x, xh.y, xh.z, xh.w}, dd[4] = {ds.x, ds.y, ds.z, ds.w}, vv[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dx = (g[cc + j] - m1 - xx[j] * m2) * rs + dd[j];
+          g[cc + j] = live ? dx * (1.f - vv[j] * vv[j]) : 0.f;           // X = tanh(P)  (Modules.py:270)
+        }
+      }
+    }
+    put_row(sA, a.dpt + tile * (int64_t)kCTile, tid, g);
+    float o[64];
+    run_stage(c, w_hi, idesc, o);
+    if (!live) {
+#pragma unroll
+      for (int cc = 0; cc < 64; ++cc) o[cc] = 0.f;
+    }
+    put_row_global(a.dv0t + tile * (int64_t)kCTile, 16384, tid, o);
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 4) {
+        float4 v = make_float4(o[cc], o[cc + 1], o[cc + 2], o[cc + 3]);
+        if (a.dtE) {
+          const float4 e = __ldg(reinterpret_cast<const float4*>(a.E + t * 64 + cc));
+          const float4 d = __ldg(reinterpret_cast<const float4*>(a.dtE + t * 64 + cc));
+          const float te[4] = {tanhf(e.x), tanhf(e.y), tanhf(e.z), tanhf(e.w)};
+          v.x += d.x * (1.f - te[0] * te[0]) * a.beta; v.y += d.y * (1.f - te[1] * te[1]) * a.beta;
+          v.z += d.z * (1.f - te[2] * te[2]) * a.beta; v.w += d.w * (1.f - te[3] * te[3]) * a.beta;
+        }
+        *reinterpret_cast<float4*>(a.dE + t * 64 + cc) = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 64);
+}
+
+// ==========================================================================================
+// W: two stacked 64-wide weight gradients per launch.  D[128, N] += [A1 | A2]^T . [B1 | B2 | ones]  over the tokens of
+// this CTA's tiles (TMEM-resident accumulator): rows 0..63 x columns of B1 = A1^T B1, rows 64..127 x columns of B2 =
+// A2^T B2, the ones column = the two bias gradients.  Pure bulk copies + MMAs: every operand arrives pre-split.
+// ==========================================================================================
+constexpr int kWThreadsP = 192;      // producer warp, MMA warp, 4 readout warps
+struct WgradPairArgs {
+  const uint8_t* a1; const uint8_t* a2;      // 32 KB tiles
+  const uint8_t* b1;                          // 32 KB tiles
+  const uint8_t* b2; int b2_planes; int b2_tile_bytes;     // 8 planes (32 KB tiles) or 4 planes (16 KB tiles)
+  int64_t ntiles;
+  float* part;                                // [grid][128][N]
+};
+
+__global__ void __launch_bounds__(kWThreadsP, 1) wgrad_pair_kernel(const WgradPairArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nbp = 8 + a.b2_planes + 2;                 // B planes per half: B1 | B2 | ones | zeros
+  const int b_half = nbp * 2048;
+  uint8_t* sAp = smem;                                  // hi: A1 planes 0-7, A2 planes 8-15 (32 KB) | lo (32 KB)
+  uint8_t* sB = smem + 65536;                           // hi [nbp planes] | lo [nbp planes]
+  __shared__ uint64_t full, empty, done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = nbp * 8;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (tid == 32) {
+    mbar_init(&full, 1); mbar_init(&empty, 1); mbar_init(&done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // constant planes: ones column (bf16 1.0 in column 0 of the plane, hi half only) and zeros
+  for (int i = tid; i < 2 * 128; i += kWThreadsP) {
+    const int pl = i >> 7, row = i & 127;
+    *reinterpret_cast<uint4*>(sB + (8 + a.b2_planes + pl) * 2048 + row * 16) = make_uint4(pl == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sB + b_half + (8 + a.b2_planes + pl) * 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int64_t my_tiles = (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int b2_half = a.b2_planes * 2048;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int64_t k = 0; k < my_tiles; ++k) {
+        const int64_t tile = blockIdx.x + k * gridDim.x;
+        mbar_wait_backoff(&empty, (uint32_t)(k & 1) ^ 1u);
+        mbar_expect_tx(&full, 4 * 16384 + 2 * 16384 + 2 * b2_half);
+        const uint8_t* s1 = a.a1 + tile * (int64_t)kCTile;
+        const uint8_t* s2 = a.a2 + tile * (int64_t)kCTile;
+        bulk_g2s(sAp, s1, 16384, &full);
+        bulk_g2s(sAp + 16384, s2, 16384, &full);
+        bulk_g2s(sAp + 32768, s1 + 16384, 16384, &full);
+        bulk_g2s(sAp + 49152, s2 + 16384, 16384, &full);
+        const uint8_t* t1 = a.b1 + tile * (int64_t)kCTile;
+        const uint8_t* t2 = a.b2 + tile * (int64_t)a.b2_tile_bytes;
+        bulk_g2s(sB, t1, 16384, &full);
+        bulk_g2s(sB + b_half, t1 + 16384, 16384, &full);
+        bulk_g2s(sB + 16384, t2, b2_half, &full);
+        bulk_g2s(sB + b_half + 16384, t2 + b2_half, b2_half, &full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, N, true, true);
+      const uint32_t ah = smem_u32(sAp), al = ah + 32768, bh = smem_u32(sB), bl = bh + b_half;
+      for (int64_t k = 0; k < my_tiles; ++k) {
+        mbar_wait_backoff(&full, (uint32_t)(k & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)      // K = 16 tokens per step; both operands MN-major (LBO 128: next 8 tokens, SBO 2048: next plane)
+          umma_x3s(tmem_base, ah + ks * 256, al + ks * 256, bh + ks * 256, bl + ks * 256, 128, 2048, 128, 2048, idesc,
+                   k == 0 && ks == 0);
+        umma_commit(&empty);
+      }
+      umma_commit(&done);
+    }
+  } else {
+    const int q = warp & 3;
+    if (my_tiles > 0) mbar_wait(&done, 0);
+    tc_fence_after();
+    const int row = q * 32 + lane;
+    float* dst = a.part + ((int64_t)blockIdx.x * 128 + row) * N;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      if (my_tiles > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// sum the per-CTA partials and add the four blocks into the gradient buffers
+struct WgradPairOut {
+  float* w1; int ld1; int n1; float* bias1;       // rows 0..63,  columns [0, n1)
+  float* w2; int ld2; int n2; float* bias2;       // rows 64..127, columns [64, 64 + n2)
+};
+__global__ void wgrad_pair_reduce_kernel(const float* __restrict__ part, int nparts, int N, int ones_col, const WgradPairOut o) {
+  const int total = 128 * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int row = i / N, col = i - row * N;
+    float* dst = nullptr;
+    if (row < 64) {
+      if (col < o.n1) dst = o.w1 + row * o.ld1 + col;
+      else if (col == ones_col) dst = o.bias1 + row;
+    } else {
+      if (col >= 64 && col < 64 + o.n2) dst = o.w2 + (row - 64) * o.ld2 + (col - 64);
+      else if (col == ones_col) dst = o.bias2 + (row - 64);
+    }
+    if (!dst) continue;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * total + i];
+    *dst += s;
+  }
+}
+
+template <typename K>
+int set_smem_attr_c(K kernel, int bytes) {
+  return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
+}
+inline unsigned chain_grid(int64_t ntiles, int per_sm) {
+  const int64_t cap = (int64_t)kSMs * per_sm;
+  return (unsigned)(ntiles < cap ? ntiles : cap);
+}
+
+template <int L>
+int launch_mix_L(const MixArgs& a, cudaStream_t s) {
+  const int smem = kCTile + kCW + a.attr_dim * 64 * 4;
+  static int set_for = 0;
+  if (set_for < smem) { if (int rc = set_smem_attr_c(chain_mix_fwd_kernel<L>, smem)) return rc; set_for = smem; }
+  chain_mix_fwd_kernel<L><<<chain_grid(num_atiles(a.T, L), 3), kCThreads, smem, s>>>(a);
+  MATCHA_CHECK_LAUNCH("chain_mix_fwd");
+  return MATCHA_OK;
+}
+template <int L>
+int launch_pff_L(const PffArgs& a, cudaStream_t s) {
+  constexpr int smem = kCTile + 2 * kCW;
+  static bool once = false;
+  if (!once) { if (int rc = set_smem_attr_c(chain_pff_fwd_kernel<L>, smem)) return rc; once = true; }
+  chain_pff_fwd_kernel<L><<<chain_grid(num_atiles(a.T, L), 3), kCThreads, smem, s>>>(a);
+  MATCHA_CHECK_LAUNCH("chain_pff_fwd");
+  return MATCHA_OK;
+}
+
+
+template <int L>
+int launch_pff_bwd_L(const PffBwdArgs& a, cudaStream_t s) {
+  constexpr int smem = kCTile + 2 * kCW;
+  static bool once = false;
+  if (!once) { if (int rc = set_smem_attr_c(chain_pff_bwd_kernel<L>, smem)) return rc; once = true; }
+  chain_pff_bwd_kernel<L><<<chain_grid(num_atiles(a.T, L), 3), kCThreads, smem, s>>>(a);
+  MATCHA_CHECK_LAUNCH("chain_pff_bwd");
+  return MATCHA_OK;
+}
+template <int L>
+int launch_mix_bwd_L(const MixBwdArgs& a, cudaStream_t s) {
+  constexpr int smem = kCTile + kCW;
+  static bool once = false;
+  if (!once) { if (int rc = set_smem_attr_c(chain_mix_bwd_kernel<L>, smem)) return rc; once = true; }
+  chain_mix_bwd_kernel<L><<<chain_grid(num_atiles(a.T, L), 3), kCThreads, smem, s>>>(a);
+  MATCHA_CHECK_LAUNCH("chain_mix_bwd");
+  return MATCHA_OK;
+}
+
+}  // namespace
+
+int64_t wgrad_pair_scratch_floats() { return (int64_t)kSMs * 128 * 144; }
+
+// [A1 | A2]^T [B1 | B2 | 1]: see wgrad_pair_kernel.  b2_planes = 8 (64 columns) or 4 (32 columns, attribute rows)
+int launch_wgrad_pair(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, const uint8_t* b2, int b2_planes, int64_t ntiles,
+                      float* scratch, float* w1, int ld1, int n1, float* bias1, float* w2, int ld2, int n2, float* bias2,
+                      cudaStream_t s) {
+  if (ntiles <= 0) return MATCHA_OK;
+  const int nbp = 8 + b2_planes + 2, N = nbp * 8;
+  const int smem = 65536 + 2 * nbp * 2048;
+  static int set_for = 0;
+  if (set_for < smem) { if (int rc = set_smem_attr_c(wgrad_pair_kernel, smem)) return rc; set_for = smem; }
+  const unsigned grid = (unsigned)(ntiles < kSMs ? ntiles : kSMs);
+  WgradPairArgs a{a1, a2, b1, b2, b2_planes, b2_planes * 4096, ntiles, scratch};
+  wgrad_pair_kernel<<<grid, kWThreadsP, smem, s>>>(a);
+  MATCHA_CHECK_LAUNCH("wgrad_pair");
+  WgradPairOut o{w1, ld1, n1, bias1, w2, ld2, n2, bias2};
+  wgrad_pair_reduce_kernel<<<(128 * N + 255) / 256, 256, 0, s>>>(scratch, (int)grid, N, (8 + b2_planes) * 8, o);
+  MATCHA_CHECK_LAUNCH("wgrad_pair_reduce");
+  return MATCHA_OK;
+}
+
+int launch_chain_pff_bwd(const float* dH2, const float* H1d, const int64_t* x, const void* w1_mn, const void* w0_mn,
+                         DropCfg dpff, DropCfg dattn, float* dd, uint8_t* dh2_tiles, uint8_t* dh1_tiles, int64_t B, int L,
+                         cudaStream_t s) {
+  if (B <= 0) return MATCHA_OK;
+  PffBwdArgs a{dH2, H1d, x, reinterpret_cast<const uint8_t*>(w1_mn), reinterpret_cast<const uint8_t*>(w0_mn), dpff, dattn, dd,
+               dh2_tiles, dh1_tiles, B * L};
+  switch (L) {
+    case 2: return launch_pff_bwd_L<2>(a, s);
+    case 3: return launch_pff_bwd_L<3>(a, s);
+    case 4: return launch_pff_bwd_L<4>(a, s);
+    case 5: return launch_pff_bwd_L<5>(a, s);
+    case 6: return launch_pff_bwd_L<6>(a, s);
+    default: set_error("chain_pff_bwd: padded width L=%d unsupported (2..6)", L); return MATCHA_ERR_ARG;
+  }
+}
+
+int launch_chain_mix_bwd(const float* dxhat, int nparts, int64_t part_stride, const float* dXs, const float* xhat,
+                         const float* rstd, const float* X, const float* dtE, const float* E, float beta, const void* wn_mn,
+                         float* dE, uint8_t* dp_tiles, uint8_t* dv0_tiles, int64_t B, int L, cudaStream_t s) {
+  if (B <= 0) return MATCHA_OK;
+  MixBwdArgs a{dxhat, nparts, part_stride, dXs, xhat, rstd, X, dtE, E, beta, reinterpret_cast<const uint8_t*>(wn_mn), dE,
+               dp_tiles, dv0_tiles, B * L};
+  switch (L) {
+    case 2: return launch_mix_bwd_L<2>(a, s);
+    case 3: return launch_mix_bwd_L<3>(a, s);
+    case 4: return launch_mix_bwd_L<4>(a, s);
+    case 5: return launch_mix_bwd_L<5>(a, s);
+    case 6: return launch_mix_bwd_L<6>(a, s);
+    default: set_error("chain_mix_bwd: padded width L=%d unsupported (2..6)", L); return MATCHA_ERR_ARG;
+  }
+}
+
+int launch_split_w64(const float* W, void* out_k, void* out_mn, cudaStream_t s) {
+  split_w64_kernel<<<2, 256, 0, s>>>(W, reinterpret_cast<uint8_t*>(out_k), reinterpret_cast<uint8_t*>(out_mn));
+  MATCHA_CHECK_LAUNCH("split_w64");
+  return MATCHA_OK;
+}
+
+int launch_chain_mix_fwd(const float* E, const int64_t* x, const float* attr_table, int attr_dim, const float* attr_w,
+                         const float* attr_b, const void* w_next_k, const float* next_b, float* V0, float* X, float* xhat,
+                         float* rstd, uint8_t* xhat_tiles, uint8_t* v0_tiles, uint8_t* attr_tiles, int64_t B, int L,
+                         cudaStream_t s) {
+  if (B <= 0) return MATCHA_OK;
+  if (attr_dim > 32) { set_error("chain_mix_fwd: attribute width %d > 32", attr_dim); return MATCHA_ERR_UNSUPPORTED; }
+  MixArgs a{E, x, attr_table, attr_dim, attr_w, attr_b, reinterpret_cast<const uint8_t*>(w_next_k), next_b, V0, X, xhat, rstd,
+            xhat_tiles, v0_tiles, attr_tiles, B * L};
+  switch (L) {
+    case 2: return launch_mix_L<2>(a, s);
+    case 3: return launch_mix_L<3>(a, s);
+    case 4: return launch_mix_L<4>(a, s);
+    case 5: return launch_mix_L<5>(a, s);
+    case 6: return launch_mix_L<6>(a, s);
+    default: set_error("chain_mix_fwd: padded width L=%d unsupported (2..6)", L); return MATCHA_ERR_ARG;
+  }
+}
+
+int launch_chain_pff_fwd(const float* U, const float* xhat, const int64_t* x, const void* w0_k, const void* w1_k,
+                         const float* b0, const float* b1, ScoreParams p, DropCfg drop, float* H1d, float* H2, float* logits,
+                         uint8_t* u_tiles, uint8_t* h1_tiles, int64_t B, int L, cudaStream_t s) {
+  if (B <= 0) return MATCHA_OK;
+  PffArgs a{U, xhat, x, reinterpret_cast<const uint8_t*>(w0_k), reinterpret_cast<const uint8_t*>(w1_k), b0, b1, p, drop,
+            H1d, H2, logits, u_tiles, h1_tiles, B * L};
+  switch (L) {
+    case 2: return launch_pff_L<2>(a, s);
+    case 3: return launch_pff_L<3>(a, s);
+    case 4: return launch_pff_L<4>(a, s);
+    case 5: return launch_pff_L<5>(a, s);
+    case 6: return launch_pff_L<6>(a, s);
+    default: set_error("chain_pff_fwd: padded width L=%d unsupported (2..6)", L); return MATCHA_ERR_ARG;
+  }
+}
+
+}  // namespace matcha

@@ -86,6 +86,16 @@ static int fused_impl() {
   return g_fused;
 }
 // fused attention forward (eval and training) and backward: QKG and its gradient never leave the SM
+enum { CW_NEXT_K = 0, CW_NEXT_MN, CW_PFF0_K, CW_PFF0_MN, CW_PFF1_K, CW_PFF1_MN };
+static int g_chain = -1;      // row-chain kernels for the 64-wide layers (MATCHA_CHAIN=0 keeps the SIMT contractions)
+static bool use_fused(int64_t T, int L);
+static bool use_chain(const matcha_model_desc* m, int64_t T, int L) {
+  if (g_chain < 0) {
+    const char* e = getenv("MATCHA_CHAIN");
+    g_chain = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_chain == 1 && use_fused(T, L) && m->attr_dim <= 32;
+}
 static bool use_fused(int64_t T, int L) {
   return fused_impl() == 1 && gemm_impl() == 1 && L >= 2 && L <= 6 && T >= kTilePathMinTokens;
 }
@@ -104,7 +114,7 @@ static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
 // derived-parameter layout
 // ------------------------------------------------------------------------------------------
 struct DerivedLayout {
-  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, wheads, wpairs, tables, total;  // float offsets
+  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, wheads, wpairs, wchain, tables, total;  // float offsets
 };
 static __host__ __device__ DerivedLayout derived_layout() {
   DerivedLayout l;
@@ -116,7 +126,8 @@ static __host__ __device__ DerivedLayout derived_layout() {
   l.wtsplit = l.wsplit + (int64_t)kQKG * kD;             // W_qkg^T pre-split, MN-major chunks (data-gradient B operand)
   l.wheads = l.wtsplit + (int64_t)kQKG * kD;             // per-head [Q_h | K_h | G_h] chunks for the fused attention kernels
   l.wpairs = l.wheads + (int64_t)kH * kHeadWBytes / 4;   // per-head-pair G | K | Q piece pairs for the fused backward
-  l.tables = l.wpairs + (int64_t)4 * kPairWBytes / 4;
+  l.wchain = l.wpairs + (int64_t)4 * kPairWBytes / 4;    // next_w, pff_w0, pff_w1: K-major and MN-major pre-split copies
+  l.tables = l.wchain + (int64_t)6 * kChainWBytes / 4;
   l.tables = (l.tables + 63) / 64 * 64;
   const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
   l.total = l.tables + 4 * table_floats;
@@ -313,6 +324,8 @@ struct Workspace {
   int32_t *counts, *group_off, *cursor, *perm;
   float *H0, *E, *V0, *X, *xhat, *rstd, *QKG, *U, *H1d, *H2, *pred, *recon, *probs;
   uint8_t *xhat_t, *dqkg_t;   // MMA-ready tiles (rowwise.cuh); dqkg_t aliases dQKG
+  uint8_t *v0_t, *attr_t, *u_t, *h1_t, *dh2_t, *dh1_t, *dp_t, *dv0_t;   // row-chain tiles kept for the weight-gradient kernel
+  float* wpair_scratch;
   float *dlogit, *dH2, *dXs, *dH1pre, *dU, *dQKG, *dxhat, *dP, *dV0, *dtE, *dE, *dH0pre, *tc_scratch;
   int64_t tc_scratch_floats;
   int64_t pred_ld;
@@ -359,6 +372,13 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
     w.dxhat = (float*)take(row); w.dP = (float*)take(row); w.dV0 = (float*)take(row); w.dtE = (float*)take(row);
     w.dE = (float*)take(row); w.dH0pre = (float*)take(row);
     w.probs = (float*)take(sizeof(float) * T * kH * 8);       // attention weights kept by the fused forward
+    if (L >= 2 && L <= 6) {
+      const int64_t nat = num_atiles(T, L);
+      w.v0_t = (uint8_t*)take(nat * 32768); w.u_t = (uint8_t*)take(nat * 32768); w.h1_t = (uint8_t*)take(nat * 32768);
+      w.dh2_t = (uint8_t*)take(nat * 32768); w.dh1_t = (uint8_t*)take(nat * 32768); w.dp_t = (uint8_t*)take(nat * 32768);
+      w.dv0_t = (uint8_t*)take(nat * 32768); w.attr_t = (uint8_t*)take(nat * 16384);
+      w.wpair_scratch = (float*)take(sizeof(float) * wgrad_pair_scratch_floats());
+    }
     w.tc_scratch_floats = gemm_tc_scratch_floats(kQKG);
     w.tc_scratch = (float*)take(sizeof(float) * w.tc_scratch_floats);
   }
@@ -420,10 +440,15 @@ static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, 
 
 // X = tanh(next_w(E + attribute_nn(attr[id]))), xhat, rstd, QKG
 static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, const Workspace& w, cudaStream_t s,
-                       int fused_L = 0) {
+                       int fused_L = 0, int training = 0) {
   int rc;
   const float* P = m->params;
   const DerivedLayout l = derived_layout();
+  if (fused_L > 0 && use_chain(m, T, fused_L))     // attribute mix + next_w + LayerNorm statistics + tiles in one kernel
+    return PROF(P_MIX, 1, launch_chain_mix_fwd(w.E, x, m->attr_table, m->attr_dim, P + m->off_attr_w, P + m->off_attr_b,
+                                               m->derived + l.wchain + CW_NEXT_K * (kChainWBytes / 4), P + m->off_next_b, w.V0,
+                                               w.X, w.xhat, w.rstd, w.xhat_t, training ? w.v0_t : nullptr, training ? w.attr_t : nullptr,
+                                               T / fused_L, fused_L, s));
   GemmDesc a = gemm_base(FORM_NT, T, kD, m->attr_dim, m->attr_table, m->attr_dim, P + m->off_attr_w, m->attr_dim, w.V0, kD);
   a.a_ids = x; a.bias = P + m->off_attr_b; a.addend = w.E; a.ld_add = kD;
   if ((rc = run_gemm(a, s, P_ATTR))) return rc;
@@ -496,6 +521,7 @@ int matcha_profile_read(float* ms, int64_t* calls, int64_t* kernels, int32_t n) 
 }
 void matcha_set_gemm_impl(int32_t impl) { g_gemm_impl = impl; }
 void matcha_set_fused(int32_t on) { g_fused = on != 0; }
+void matcha_set_chain(int32_t on) { g_chain = on != 0; }
 int matcha_version(void) { return 100; }
 
 int64_t matcha_derived_elems(const matcha_model_desc* m) {
@@ -525,7 +551,14 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   if ((rc = launch_split_wT(m->derived + l.wqkg, m->derived + l.wtsplit, s))) return rc;
   if ((rc = launch_split_w_heads(m->derived + l.wqkg, m->derived + l.wheads, s))) return rc;
   if (m->grads && (rc = launch_split_w_pairs(m->derived + l.wqkg, m->derived + l.wpairs, s))) return rc;
-  prof_end(P_PREP, 7, s);
+  {
+    float* wc = m->derived + l.wchain;
+    const int64_t st = kChainWBytes / 4;
+    if ((rc = launch_split_w64(m->params + m->off_next_w, wc + CW_NEXT_K * st, wc + CW_NEXT_MN * st, s))) return rc;
+    if ((rc = launch_split_w64(m->params + m->off_pff_w0, wc + CW_PFF0_K * st, wc + CW_PFF0_MN * st, s))) return rc;
+    if ((rc = launch_split_w64(m->params + m->off_pff_w1, wc + CW_PFF1_K * st, wc + CW_PFF1_MN * st, s))) return rc;
+  }
+  prof_end(P_PREP, 10, s);
   return MATCHA_OK;
 }
 
@@ -561,7 +594,7 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
       return rc;
   }
   const bool fused = use_fused(T, L);
-  if ((rc = run_mix_qkg(m, x, T, w, s, fused ? L : 0))) return rc;
+  if ((rc = run_mix_qkg(m, x, T, w, s, fused ? L : 0, training))) return rc;
   DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, training != 0);
   if (fused) {
     if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fused_fwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wheads),
@@ -569,6 +602,14 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
                                                         dattn, s))))
       return rc;
   } else if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fwd(w.QKG, x, m->derived + l.bdyn, w.U, B, L, dattn, s)))) return rc;
+  if (fused && use_chain(m, T, L)) {
+    const float* wc = m->derived + l.wchain;
+    return PROF(P_PFF0, 1, launch_chain_pff_fwd(w.U, w.xhat, x, wc + CW_PFF0_K * (kChainWBytes / 4), wc + CW_PFF1_K * (kChainWBytes / 4),
+                                                m->params + m->off_pff_b0, m->params + m->off_pff_b1, score_params(m),
+                                                make_drop(seed, SITE_PFF, m->p_pff, training != 0), training ? w.H1d : nullptr,
+                                                training ? w.H2 : nullptr, logits, training ? w.u_t : nullptr,
+                                                training ? w.h1_t : nullptr, B, L, s));
+  }
   if ((rc = run_pff(m, T, training, seed, w, s))) return rc;
   return PROF(P_SCORE_FWD, 1, launch_score_fwd(w.H2, w.xhat, x, score_params(m), logits, B, L, s));
 }
@@ -614,7 +655,20 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
 
   // pff_n1 backward
   DropCfg dpff = make_drop(seed, SITE_PFF, m->p_pff, true);
-  {
+  DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, true);
+  const bool chain = use_chain(m, T, L);
+  const int64_t nat = chain ? num_atiles(T, L) : 0;
+  const float* wc = m->derived + l.wchain;
+  if (chain) {
+    // dH2 -> dH1pre -> masked gradient of the attention output in one tcgen05 row-chain kernel; both weight gradients
+    // (and bias gradients) of pff_n1 in one stacked tile kernel
+    if ((rc = PROF(P_D_PFF1, 1, launch_chain_pff_bwd(w.dH2, w.H1d, x, wc + CW_PFF1_MN * (kChainWBytes / 4),
+                                                     wc + CW_PFF0_MN * (kChainWBytes / 4), dpff, dattn, w.dU, w.dh2_t, w.dh1_t, B,
+                                                     L, s)))) return rc;
+    if ((rc = PROF(P_W_PFF1, 2, launch_wgrad_pair(w.dh2_t, w.dh1_t, w.h1_t, w.u_t, 8, nat, w.wpair_scratch, G + m->off_pff_w1, kD,
+                                                  kD, G + m->off_pff_b1, G + m->off_pff_w0, kD, kD, G + m->off_pff_b0, s))))
+      return rc;
+  } else {
     GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dH2, kD, w.H1d, kD, G + m->off_pff_w1, kD);
     d.colsum = G + m->off_pff_b1; d.colsum_n = kD;
     if ((rc = run_gemm(d, s, P_W_PFF1))) return rc;
@@ -630,7 +684,6 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     if ((rc = run_gemm(g, s, P_D_PFF0))) return rc;
   }
   // attention backward
-  DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, true);
   int dx_parts = 1;
   if (use_fused(T, L)) {
     // fused path: recompute + attention backward + data / weight gradients of the QKG projection in one kernel; the
@@ -638,7 +691,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     dx_parts = 4;
     if ((rc = PROF(P_ATTN_BWD, 2, launch_attn_fused_bwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wpairs),
                                                         m->derived + l.bqkg, x, w.dU, w.probs, w.dQKG, w.tc_scratch,
-                                                        DG + l.wqkg, DG + l.bqkg, DG + l.bdyn, B, L, dattn, s)))) return rc;
+                                                        DG + l.wqkg, DG + l.bqkg, DG + l.bdyn, B, L, dattn, chain ? 1 : 0, s)))) return rc;
   } else if (use_tiles(T)) {
     // tile path: the attention backward emits dQKG directly as bf16 hi|lo MMA tiles; rows of the last tile beyond T are zero
     const int64_t nt = num_token_tiles(T);
@@ -660,18 +713,6 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     GemmDesc e = gemm_base(FORM_NN, T, kD, kQKG, w.dQKG, kQKG, m->derived + l.wqkg, kD, w.dxhat, kD);
     if ((rc = run_gemm(e, s, P_D_QKG))) return rc;
   }
-  if ((rc = PROF(P_LN_BWD, 1, launch_ln_tanh_bwd(dx_parts > 1 ? w.dQKG : w.dxhat, dx_parts, T * kD, w.dXs, w.xhat, w.rstd, w.X,
-                                                 w.dP, T, s)))) return rc;
-  {
-    GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dP, kD, w.V0, kD, G + m->off_next_w, kD);
-    d.colsum = G + m->off_next_b; d.colsum_n = kD;
-    if ((rc = run_gemm(d, s, P_W_NEXT))) return rc;
-    GemmDesc e = gemm_base(FORM_NN, T, kD, kD, w.dP, kD, P + m->off_next_w, kD, w.dV0, kD);
-    if ((rc = run_gemm(e, s, P_D_NEXT))) return rc;
-    GemmDesc f = gemm_base(FORM_TN, kD, m->attr_dim, T, w.dV0, kD, m->attr_table, m->attr_dim, G + m->off_attr_w, m->attr_dim);
-    f.b_ids = x; f.colsum = G + m->off_attr_b; f.colsum_n = kD;
-    if ((rc = run_gemm(f, s, P_W_ATTR))) return rc;
-  }
   // reconstruction head backward (gdiff was left in w.pred by the forward pass, without the beta factor)
   const float* dtE = nullptr;
   if (recon_on) {
@@ -683,7 +724,28 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     if ((rc = run_gemm(e, s, P_D_RECON))) return rc;
     dtE = w.dtE;
   }
-  if ((rc = PROF(P_ENC_COMBINE, 1, launch_enc_combine_bwd(w.dV0, dtE, w.E, beta, w.dE, T * kD, s)))) return rc;
+  if (chain) {
+    // LayerNorm / tanh / next_w backward and the encoder-gradient combine in one row-chain kernel; the next_w and
+    // attribute_nn weight / bias gradients in one stacked tile kernel
+    if ((rc = PROF(P_LN_BWD, 1, launch_chain_mix_bwd(dx_parts > 1 ? w.dQKG : w.dxhat, dx_parts, T * kD, w.dXs, w.xhat, w.rstd, w.X,
+                                                     dtE, w.E, beta, wc + CW_NEXT_MN * (kChainWBytes / 4), w.dE, w.dp_t, w.dv0_t, B,
+                                                     L, s)))) return rc;
+    if ((rc = PROF(P_W_NEXT, 2, launch_wgrad_pair(w.dp_t, w.dv0_t, w.v0_t, w.attr_t, 4, nat, w.wpair_scratch, G + m->off_next_w, kD,
+                                                  kD, G + m->off_next_b, G + m->off_attr_w, m->attr_dim, m->attr_dim,
+                                                  G + m->off_attr_b, s)))) return rc;
+  } else {
+    if ((rc = PROF(P_LN_BWD, 1, launch_ln_tanh_bwd(dx_parts > 1 ? w.dQKG : w.dxhat, dx_parts, T * kD, w.dXs, w.xhat, w.rstd, w.X,
+                                                   w.dP, T, s)))) return rc;
+    GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dP, kD, w.V0, kD, G + m->off_next_w, kD);
+    d.colsum = G + m->off_next_b; d.colsum_n = kD;
+    if ((rc = run_gemm(d, s, P_W_NEXT))) return rc;
+    GemmDesc e = gemm_base(FORM_NN, T, kD, kD, w.dP, kD, P + m->off_next_w, kD, w.dV0, kD);
+    if ((rc = run_gemm(e, s, P_D_NEXT))) return rc;
+    GemmDesc f = gemm_base(FORM_TN, kD, m->attr_dim, T, w.dV0, kD, m->attr_table, m->attr_dim, G + m->off_attr_w, m->attr_dim);
+    f.b_ids = x; f.colsum = G + m->off_attr_b; f.colsum_n = kD;
+    if ((rc = run_gemm(f, s, P_W_ATTR))) return rc;
+    if ((rc = PROF(P_ENC_COMBINE, 1, launch_enc_combine_bwd(w.dV0, dtE, w.E, beta, w.dE, T * kD, s)))) return rc;
+  }
   // encoder backward (grouped by chromosome; token lists from the forward pass are still in the workspace)
   {
     GemmDesc d = gemm_base(FORM_TN, kD, kD, 0, w.dE, kD, w.H0, kD, nullptr, kD);

@@ -79,13 +79,41 @@ int launch_attn_fused_fwd(const uint8_t* xhat_tiles, const uint8_t* wheads, cons
 //   wpairs       launch_split_w_pairs output (4 head pairs x 3 pieces x 32 KB)
 //   dxhat_parts  [4, T, 64] per-head-pair partial data gradients (summed by launch_ln_tanh_bwd)
 //   part         attn_fused_bwd_scratch_floats() floats of split-K partials; dW [1536, 64] += their sum
-//   dbq [512], db_dyn [64] accumulate (atomics); dU is masked / dropout-scaled IN PLACE first
+//   dbq [512], db_dyn [64] accumulate (atomics); dU is masked / dropout-scaled IN PLACE first unless `premasked`
 int launch_split_w_pairs(const float* W, void* out, cudaStream_t s);
 int64_t attn_fused_bwd_scratch_floats();
 int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, float* dU,
                           const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn,
-                          int64_t B, int L, DropCfg drop, cudaStream_t s);
+                          int64_t B, int L, DropCfg drop, int premasked, cudaStream_t s);
 constexpr int kPairWBytes = 3 * 32768;                 // per head pair: G | K | Q piece pairs, bf16 hi | lo
+
+// row-chain kernels (chain.cu): the 64-wide layers around the attention block on tensor cores, thread = tile row
+constexpr int kChainWBytes = 16384;                    // one 64x64 weight, bf16 hi 8 KB | lo 8 KB
+int launch_split_w64(const float* W, void* out_k, void* out_mn, cudaStream_t s);
+// V0 = E + attribute_nn(attr[id]); X = tanh(next_w V0 + b); xhat / rstd; hyperedge-aligned xhat tiles
+// (optional: V0, V0 tiles and attribute-row tiles for the backward pass)
+int launch_chain_mix_fwd(const float* E, const int64_t* x, const float* attr_table, int attr_dim, const float* attr_w,
+                         const float* attr_b, const void* w_next_k, const float* next_b, float* V0, float* X, float* xhat,
+                         float* rstd, uint8_t* xhat_tiles, uint8_t* v0_tiles, uint8_t* attr_tiles, int64_t B, int L,
+                         cudaStream_t s);
+// pff_n1 + scorer: U -> H1d -> H2 -> logits (H1d / H2 / tiles optional: kept for the backward pass)
+int launch_chain_pff_fwd(const float* U, const float* xhat, const int64_t* x, const void* w0_k, const void* w1_k,
+                         const float* b0, const float* b1, ScoreParams p, DropCfg drop, float* H1d, float* H2, float* logits,
+                         uint8_t* u_tiles, uint8_t* h1_tiles, int64_t B, int L, cudaStream_t s);
+// backward of pff_n1 from dH2: writes the masked / dropout-scaled gradient of the attention output (dd) and the dH2 /
+// dH1pre tiles (32 KB each) consumed by launch_wgrad_pair
+int launch_chain_pff_bwd(const float* dH2, const float* H1d, const int64_t* x, const void* w1_mn, const void* w0_mn,
+                         DropCfg dpff, DropCfg dattn, float* dd, uint8_t* dh2_tiles, uint8_t* dh1_tiles, int64_t B, int L,
+                         cudaStream_t s);
+// LayerNorm / tanh / next_w backward: dE = dV0 + beta * dtE * (1 - tanh(E)^2), plus the dP / dV0 tiles
+int launch_chain_mix_bwd(const float* dxhat, int nparts, int64_t part_stride, const float* dXs, const float* xhat,
+                         const float* rstd, const float* X, const float* dtE, const float* E, float beta, const void* wn_mn,
+                         float* dE, uint8_t* dp_tiles, uint8_t* dv0_tiles, int64_t B, int L, cudaStream_t s);
+// two stacked 64-row weight gradients (+ bias gradients) from pre-split tiles: w1 [64, n1] += A1^T B1, w2 [64, n2] += A2^T B2
+int64_t wgrad_pair_scratch_floats();
+int launch_wgrad_pair(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, const uint8_t* b2, int b2_planes, int64_t ntiles,
+                      float* scratch, float* w1, int ld1, int n1, float* bias1, float* w2, int ld2, int n2, float* bias2,
+                      cudaStream_t s);
 
 // tcgen05 tile kernels (qkg_tiles.cu)
 int launch_split_wT(const float* W, void* out, cudaStream_t s);     // W [1536, 64] fp32 -> MN-major chunks for the dgrad

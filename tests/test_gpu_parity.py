@@ -485,3 +485,40 @@ def test_fused_attention_training_matches_decomposed(golden, monkeypatch, L, B):
         g1 = res[1][0][k]
         scale = float(np.abs(g0).max())
         assert float(np.abs(g1 - g0).max()) <= 5e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
+
+
+@pytest.mark.parametrize("L,B", [(5, 333), (4, 300), (3, 411), (2, 640), (5, 2100)])
+def test_chain_kernels_match_simt_layers(golden, monkeypatch, L, B):
+    """The tcgen05 row-chain kernels (attribute mix + next_w + LayerNorm, pff_n1 + scorer and their backward
+    counterparts) vs the SIMT fp32 layers, inside the fused pipeline: eval logits, train logits, every gradient."""
+    lib = _lib().load()
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([1]))
+    rng = np.random.default_rng(B + 1)
+    x = torch.from_numpy(_random_hyperedges(golden, B, L, seed=11 * L + B)).cuda()
+    y = torch.from_numpy((rng.random((B, 1)) < 0.3).astype("float32")).cuda()
+    w = torch.from_numpy(rng.uniform(0.5, 3, (B, 1)).astype("float32")).cuda()
+    res = {}
+    try:
+        for chain in (0, 1):
+            lib.matcha_set_chain(chain)
+            model = model_from_golden(golden)
+            model.eval()
+            with torch.no_grad():
+                ev = model(x).cpu().numpy()
+            model.train()
+            eng = model._engine()
+            eng.seed_base = 123
+            eng.tape_id = 0
+            pred, rl = model(x, return_recon=True)
+            (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.1 * rl.sum()).backward()
+            res[chain] = ({k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None},
+                          pred.detach().cpu().numpy(), ev)
+    finally:
+        lib.matcha_set_chain(1)
+    np.testing.assert_allclose(res[1][2], res[0][2], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-4, atol=5e-5)
+    assert res[0][0].keys() == res[1][0].keys()
+    for k, g0 in res[0][0].items():
+        g1 = res[1][0][k]
+        scale = float(np.abs(g0).max())
+        assert float(np.abs(g1 - g0).max()) <= 5e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
