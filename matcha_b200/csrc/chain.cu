@@ -117,6 +117,63 @@ __device__ __forceinline__ void run_stage(ChainCtx& c, uint32_t w_hi, uint32_t i
   tc_fence_before();
 }
 
+// Coalesced row I/O.  A warp's RPW tile rows are consecutive tokens, i.e. one contiguous run of fp32 in global memory:
+// the warp moves it with fully coalesced 128-bit accesses through a padded staging area (68 floats per row: conflict
+// free for both access patterns) and every thread picks up / drops off its own 64-float row there.
+constexpr int kStageRow = 68;
+constexpr int kStageWarp = 32 * kStageRow;          // floats per warp
+constexpr int kStageBytes = 4 * kStageWarp * 4;     // 34816
+__device__ __forceinline__ void warp_load_rows(const float* __restrict__ g, int nrows, float* stage, int lane, float (&v)[64]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 4, c4 = idx & 15;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nrows) e = __ldg(reinterpret_cast<const float4*>(g) + idx);
+    *reinterpret_cast<float4*>(stage + row * kStageRow + c4 * 4) = e;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float4 e = *reinterpret_cast<const float4*>(stage + lane * kStageRow + k * 4);
+    v[4 * k] = e.x; v[4 * k + 1] = e.y; v[4 * k + 2] = e.z; v[4 * k + 3] = e.w;
+  }
+  __syncwarp();
+}
+// v += rows (same traffic pattern, accumulating)
+__device__ __forceinline__ void warp_add_rows(const float* __restrict__ g, int nrows, float* stage, int lane, float (&v)[64]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 4, c4 = idx & 15;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nrows) e = __ldg(reinterpret_cast<const float4*>(g) + idx);
+    *reinterpret_cast<float4*>(stage + row * kStageRow + c4 * 4) = e;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float4 e = *reinterpret_cast<const float4*>(stage + lane * kStageRow + k * 4);
+    v[4 * k] += e.x; v[4 * k + 1] += e.y; v[4 * k + 2] += e.z; v[4 * k + 3] += e.w;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_store_rows(float* __restrict__ g, int nrows, float* stage, int lane, const float (&v)[64]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    *reinterpret_cast<float4*>(stage + lane * kStageRow + k * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 4, c4 = idx & 15;
+    if (row < nrows) reinterpret_cast<float4*>(g)[idx] = *reinterpret_cast<const float4*>(stage + row * kStageRow + c4 * 4);
+  }
+  __syncwarp();
+}
+// live rows of this warp's slice of the tile
+__device__ __forceinline__ int warp_rows(int64_t t0, int rpw, int64_t T) {
+  const int64_t n = T - t0;
+  return n <= 0 ? 0 : (n < rpw ? (int)n : rpw);
+}
+
 __device__ __forceinline__ void load_weight(uint8_t* dst, const uint8_t* src) {   // 16 KB, all 128 threads
   const uint4* s = reinterpret_cast<const uint4*>(src);
   uint4* d = reinterpret_cast<uint4*>(dst);
@@ -157,7 +214,8 @@ __global__ void __launch_bounds__(kCThreads) chain_mix_fwd_kernel(const MixArgs 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kCTile;
-  float* sWt = reinterpret_cast<float*>(smem + kCTile + kCW);     // attribute_nn.weight^T [attr_dim][64]
+  float* sStage = reinterpret_cast<float*>(smem + kCTile + kCW);
+  float* sWt = reinterpret_cast<float*>(smem + kCTile + kCW + kStageBytes);     // attribute_nn.weight^T [attr_dim][64]
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float sNb[64], sAb[64];
@@ -176,34 +234,34 @@ __global__ void __launch_bounds__(kCThreads) chain_mix_fwd_kernel(const MixArgs 
   ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
   constexpr uint32_t idesc = make_idesc(128, 64, false, false);
   const uint32_t w_hi = smem_u32(sW);
+  float* stage = sStage + warp * kStageWarp;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t t = (tile * 4 + warp) * RPW + lane;
-    const bool live = lane < RPW && t < a.T;
+    const int64_t t0 = (tile * 4 + warp) * RPW, t = t0 + lane;
+    const int nrows = warp_rows(t0, RPW, a.T);
+    const bool live = lane < nrows;
     float v[64];
-#pragma unroll
-    for (int cc = 0; cc < 64; ++cc) v[cc] = 0.f;
-    if (live) {
-      const int64_t id = a.x[t];
-#pragma unroll
-      for (int cc = 0; cc < 64; cc += 4) {
-        const float4 e = __ldg(reinterpret_cast<const float4*>(a.E + t * 64 + cc));
-        v[cc] = e.x + sAb[cc]; v[cc + 1] = e.y + sAb[cc + 1]; v[cc + 2] = e.z + sAb[cc + 2]; v[cc + 3] = e.w + sAb[cc + 3];
-      }
+    warp_load_rows(a.E + t0 * 64, nrows, stage, lane, v);
+    float av[32];
+    {
+      const int64_t id = live ? a.x[t] : 0;
       const float* arow = a.attr_table + id * a.attr_dim;
-      float av[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) av[k] = (k < a.attr_dim) ? __ldg(arow + k) : 0.f;
-      if (a.attrt) {       // attribute rows for the attribute_nn weight gradient: 4 planes of 8 columns
-        uint8_t* gt = a.attrt + tile * 16384;
+      for (int k = 0; k < 32; ++k) av[k] = (live && k < a.attr_dim) ? __ldg(arow + k) : 0.f;
+    }
+    if (a.attrt) {       // attribute rows for the attribute_nn weight gradient: 4 planes of 8 columns (zeros for dead rows)
+      uint8_t* gt = a.attrt + tile * 16384;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 hi, lo;
-          split8(make_float4(av[8 * j], av[8 * j + 1], av[8 * j + 2], av[8 * j + 3]),
-                 make_float4(av[8 * j + 4], av[8 * j + 5], av[8 * j + 6], av[8 * j + 7]), hi, lo);
-          *reinterpret_cast<uint4*>(gt + j * 2048 + tid * 16) = hi;
-          *reinterpret_cast<uint4*>(gt + 8192 + j * 2048 + tid * 16) = lo;
-        }
+      for (int j = 0; j < 4; ++j) {
+        uint4 hi, lo;
+        split8(make_float4(av[8 * j], av[8 * j + 1], av[8 * j + 2], av[8 * j + 3]),
+               make_float4(av[8 * j + 4], av[8 * j + 5], av[8 * j + 6], av[8 * j + 7]), hi, lo);
+        *reinterpret_cast<uint4*>(gt + j * 2048 + tid * 16) = hi;
+        *reinterpret_cast<uint4*>(gt + 8192 + j * 2048 + tid * 16) = lo;
       }
+    }
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < 64; ++cc) v[cc] += sAb[cc];
 #pragma unroll
       for (int k = 0; k < 32; ++k) {        // attribute rows are one-hot + one scalar (main.py:497-512): skip the zeros
         if (k < a.attr_dim && av[k] != 0.f) {
@@ -212,37 +270,27 @@ __global__ void __launch_bounds__(kCThreads) chain_mix_fwd_kernel(const MixArgs 
           for (int cc = 0; cc < 64; ++cc) v[cc] = fmaf(av[k], wt[cc], v[cc]);
         }
       }
-      if (a.V0) {
-#pragma unroll
-        for (int cc = 0; cc < 64; cc += 4)
-          *reinterpret_cast<float4*>(a.V0 + t * 64 + cc) = make_float4(v[cc], v[cc + 1], v[cc + 2], v[cc + 3]);
-      }
-    } else if (a.attrt) {
-      uint8_t* gt = a.attrt + tile * 16384;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        *reinterpret_cast<uint4*>(gt + j * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(gt + 8192 + j * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
-      }
     }
+    if (a.V0) warp_store_rows(a.V0 + t0 * 64, nrows, stage, lane, v);
     put_row(sA, a.v0t ? a.v0t + tile * (int64_t)kCTile : nullptr, tid, v);
     float o[64];
     run_stage(c, w_hi, idesc, o);
     if (live) {
 #pragma unroll
       for (int cc = 0; cc < 64; ++cc) o[cc] = tanhf(o[cc] + sNb[cc]);
-#pragma unroll
-      for (int cc = 0; cc < 64; cc += 4)
-        *reinterpret_cast<float4*>(a.X + t * 64 + cc) = make_float4(o[cc], o[cc + 1], o[cc + 2], o[cc + 3]);
-      const float rs = ln_row(o);
-      a.rstd[t] = rs;
-#pragma unroll
-      for (int cc = 0; cc < 64; cc += 4)
-        *reinterpret_cast<float4*>(a.xhat + t * 64 + cc) = make_float4(o[cc], o[cc + 1], o[cc + 2], o[cc + 3]);
     } else {
 #pragma unroll
       for (int cc = 0; cc < 64; ++cc) o[cc] = 0.f;
     }
+    warp_store_rows(a.X + t0 * 64, nrows, stage, lane, o);
+    const float rs = ln_row(o);
+    if (live) {
+      a.rstd[t] = rs;
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 64; ++cc) o[cc] = 0.f;
+    }
+    warp_store_rows(a.xhat + t0 * 64, nrows, stage, lane, o);
     put_row_global(a.xt + tile * (int64_t)kXTileBytes, kXHalfBytes, tid, o);
   }
   tc_fence_before();
@@ -268,6 +316,7 @@ __global__ void __launch_bounds__(kCThreads) chain_pff_fwd_kernel(const PffArgs 
   uint8_t* sA = smem;
   uint8_t* sW0 = smem + kCTile;
   uint8_t* sW1 = smem + kCTile + kCW;
+  float* sStage = reinterpret_cast<float*>(smem + kCTile + 2 * kCW);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float sP[9][64];        // b0, b1, pff_g, pff_b, ln1_g, ln1_b, ln2_g, ln2_b, cls_w
@@ -293,18 +342,15 @@ __global__ void __launch_bounds__(kCThreads) chain_pff_fwd_kernel(const PffArgs 
   ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
   constexpr uint32_t idesc = make_idesc(128, 64, false, false);
   const uint32_t w0_hi = smem_u32(sW0), w1_hi = smem_u32(sW1);
+  float* stage = sStage + warp * kStageWarp;
   const bool live_lane = lane < RPW;
   const int g = lane / L, pos = lane - g * L;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t t = (tile * 4 + warp) * RPW + lane;
-    const bool live = live_lane && t < a.T;
+    const int64_t t0 = (tile * 4 + warp) * RPW, t = t0 + lane;
+    const int nrows = warp_rows(t0, RPW, a.T);
+    const bool live = lane < nrows;
     float u[64];
-#pragma unroll
-    for (int cc = 0; cc < 64; cc += 4) {
-      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live) e = __ldg(reinterpret_cast<const float4*>(a.U + t * 64 + cc));
-      u[cc] = e.x; u[cc + 1] = e.y; u[cc + 2] = e.z; u[cc + 3] = e.w;
-    }
+    warp_load_rows(a.U + t0 * 64, nrows, stage, lane, u);
     put_row(sA, a.ut ? a.ut + tile * (int64_t)kCTile : nullptr, tid, u);
     float h[64];
     run_stage(c, w0_hi, idesc, h);
@@ -315,40 +361,32 @@ __global__ void __launch_bounds__(kCThreads) chain_pff_fwd_kernel(const PffArgs 
                                tanhf(h[cc + 3] + sP[0][cc + 3]));
         v = drop_apply4(a.drop, (uint64_t)t, (uint32_t)cc, v);          // dropout inside pff_n1 (Modules.py:359-360)
         h[cc] = v.x; h[cc + 1] = v.y; h[cc + 2] = v.z; h[cc + 3] = v.w;
-        if (a.H1d) *reinterpret_cast<float4*>(a.H1d + t * 64 + cc) = v;
       }
     } else {
 #pragma unroll
       for (int cc = 0; cc < 64; ++cc) h[cc] = 0.f;
     }
+    if (a.H1d) warp_store_rows(a.H1d + t0 * 64, nrows, stage, lane, h);
     put_row(sA, a.h1t ? a.h1t + tile * (int64_t)kCTile : nullptr, tid, h);
     float o[64];
     run_stage(c, w1_hi, idesc, o);
+#pragma unroll
+    for (int cc = 0; cc < 64; ++cc) o[cc] = o[cc] + sP[1][cc] + u[cc];      // residual (Modules.py:371-372)
+    if (a.H2) warp_store_rows(a.H2 + t0 * 64, nrows, stage, lane, o);
+    warp_load_rows(a.xhat + t0 * 64, nrows, stage, lane, u);                // u now holds the normalised layer input
     float z = 0.f, m = 0.f;
     if (live) {
-#pragma unroll
-      for (int cc = 0; cc < 64; ++cc) o[cc] = o[cc] + sP[1][cc] + u[cc];    // residual (Modules.py:371-372)
-      if (a.H2) {
-#pragma unroll
-        for (int cc = 0; cc < 64; cc += 4)
-          *reinterpret_cast<float4*>(a.H2 + t * 64 + cc) = make_float4(o[cc], o[cc + 1], o[cc + 2], o[cc + 3]);
-      }
       m = a.x[t] != 0 ? 1.f : 0.f;
       ln_row(o);                                                            // pff_n1.layer_norm
 #pragma unroll
       for (int cc = 0; cc < 64; ++cc) o[cc] = fmaf(o[cc], sP[2][cc], sP[3][cc]) * m;
       ln_row(o);                                                            // Classifier.layer_norm1
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 4) {
-        const float4 xh = __ldg(reinterpret_cast<const float4*>(a.xhat + t * 64 + cc));
-        const float xv[4] = {xh.x, xh.y, xh.z, xh.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float D = fmaf(o[cc + j], sP[4][cc + j], sP[5][cc + j]);
-          const float S = fmaf(xv[j], sP[6][cc + j], sP[7][cc + j]);          // Classifier.layer_norm2 of the layer input
-          const float df = D - S;
-          z = fmaf(df * df, sP[8][cc + j], z);
-        }
+      for (int cc = 0; cc < 64; ++cc) {
+        const float D = fmaf(o[cc], sP[4][cc], sP[5][cc]);
+        const float S = fmaf(u[cc], sP[6][cc], sP[7][cc]);                  // Classifier.layer_norm2 of the layer input
+        const float df = D - S;
+        z = fmaf(df * df, sP[8][cc], z);
       }
       z += sCb;
     }
@@ -366,7 +404,6 @@ __global__ void __launch_bounds__(kCThreads) chain_pff_fwd_kernel(const PffArgs 
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base_s, 64);
 }
-
 
 // ==========================================================================================
 // B1: pff_n1 backward.  dH2 -> dH1pre = (dH2 W1) * tanh' * dropout -> dU = dH1pre W0 + dH2 -> masked / dropout-scaled
@@ -387,6 +424,7 @@ __global__ void __launch_bounds__(kCThreads) chain_pff_bwd_kernel(const PffBwdAr
   uint8_t* sA = smem;
   uint8_t* sW1 = smem + kCTile;
   uint8_t* sW0 = smem + kCTile + kCW;
+  float* sStage = reinterpret_cast<float*>(smem + kCTile + 2 * kCW);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   constexpr int RPW = (32 / L) * L;
@@ -403,43 +441,38 @@ __global__ void __launch_bounds__(kCThreads) chain_pff_bwd_kernel(const PffBwdAr
   ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
   constexpr uint32_t idesc = make_idesc(128, 64, false, true);      // B = W read as [N = column, K = row], MN-major
   const uint32_t w1_hi = smem_u32(sW1), w0_hi = smem_u32(sW0);
+  float* stage = sStage + warp * kStageWarp;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t t = (tile * 4 + warp) * RPW + lane;
-    const bool live = lane < RPW && t < a.T;
-    const int64_t tl = live ? t : 0;
+    const int64_t t0 = (tile * 4 + warp) * RPW, t = t0 + lane;
+    const int nrows = warp_rows(t0, RPW, a.T);
+    const bool live = lane < nrows;
     float g[64];
-#pragma unroll
-    for (int cc = 0; cc < 64; cc += 4) {
-      const float4 e = __ldg(reinterpret_cast<const float4*>(a.dH2 + tl * 64 + cc));
-      g[cc] = live ? e.x : 0.f; g[cc + 1] = live ? e.y : 0.f; g[cc + 2] = live ? e.z : 0.f; g[cc + 3] = live ? e.w : 0.f;
-    }
+    warp_load_rows(a.dH2 + t0 * 64, nrows, stage, lane, g);
     put_row(sA, a.dh2t + tile * (int64_t)kCTile, tid, g);
     float o[64];
     run_stage(c, w1_hi, idesc, o);
+    warp_load_rows(a.H1d + t0 * 64, nrows, stage, lane, g);
     // gradient through H1d = dropout(tanh(.)): dy * f * (1 - (y / f)^2), f = keep * scale
 #pragma unroll
     for (int cc = 0; cc < 64; cc += 4) {
-      const float4 yv = __ldg(reinterpret_cast<const float4*>(a.H1d + tl * 64 + cc));
       const float4 f = drop_factor4(a.dpff, (uint64_t)t, (uint32_t)cc);
-      const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, ff[4] = {f.x, f.y, f.z, f.w};
+      const float ff[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float h = ff[j] > 0.f ? yy[j] / ff[j] : 0.f;
+        const float h = ff[j] > 0.f ? g[cc + j] / ff[j] : 0.f;
         o[cc + j] = live ? o[cc + j] * ff[j] * (1.f - h * h) : 0.f;
       }
     }
     put_row(sA, a.dh1t + tile * (int64_t)kCTile, tid, o);
     run_stage(c, w0_hi, idesc, o);
-    if (live) {
-      const float m = a.x[t] != 0 ? 1.f : 0.f;
+    warp_add_rows(a.dH2 + t0 * 64, nrows, stage, lane, o);            // residual branch (second read: L2 hit)
+    const float m = (live && a.x[t] != 0) ? 1.f : 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 4) {
-        const float4 e = __ldg(reinterpret_cast<const float4*>(a.dH2 + t * 64 + cc));     // residual branch (L2 hit)
-        const float4 f = drop_factor4(a.dattn, (uint64_t)t, (uint32_t)cc);
-        *reinterpret_cast<float4*>(a.dd + t * 64 + cc) = make_float4((o[cc] + e.x) * f.x * m, (o[cc + 1] + e.y) * f.y * m,
-                                                                      (o[cc + 2] + e.z) * f.z * m, (o[cc + 3] + e.w) * f.w * m);
-      }
+    for (int cc = 0; cc < 64; cc += 4) {
+      const float4 f = drop_factor4(a.dattn, (uint64_t)t, (uint32_t)cc);
+      o[cc] *= f.x * m; o[cc + 1] *= f.y * m; o[cc + 2] *= f.z * m; o[cc + 3] *= f.w * m;
     }
+    warp_store_rows(a.dd + t0 * 64, nrows, stage, lane, o);
   }
   tc_fence_before();
   __syncthreads();
@@ -465,6 +498,7 @@ __global__ void __launch_bounds__(kCThreads) chain_mix_bwd_kernel(const MixBwdAr
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kCTile;
+  float* sStage = reinterpret_cast<float*>(smem + kCTile + kCW);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   constexpr int RPW = (32 / L) * L;
@@ -480,40 +514,28 @@ __global__ void __launch_bounds__(kCThreads) chain_mix_bwd_kernel(const MixBwdAr
   ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
   constexpr uint32_t idesc = make_idesc(128, 64, false, true);
   const uint32_t w_hi = smem_u32(sW);
+  float* stage = sStage + warp * kStageWarp;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t t = (tile * 4 + warp) * RPW + lane;
-    const bool live = lane < RPW && t < a.T;
-    const int64_t tl = live ? t : 0;
-    float g[64];
+    const int64_t t0 = (tile * 4 + warp) * RPW, t = t0 + lane;
+    const int nrows = warp_rows(t0, RPW, a.T);
+    const bool live = lane < nrows;
+    float g[64], r[64];
+    warp_load_rows(a.dxhat + t0 * 64, nrows, stage, lane, g);
+    for (int p = 1; p < a.nparts; ++p) warp_add_rows(a.dxhat + p * a.part_stride + t0 * 64, nrows, stage, lane, g);
+    warp_load_rows(a.xhat + t0 * 64, nrows, stage, lane, r);
     {
       float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 4) {
-        float4 e = __ldg(reinterpret_cast<const float4*>(a.dxhat + tl * 64 + cc));
-        for (int p = 1; p < a.nparts; ++p) {
-          const float4 e2 = __ldg(reinterpret_cast<const float4*>(a.dxhat + p * a.part_stride + tl * 64 + cc));
-          e.x += e2.x; e.y += e2.y; e.z += e2.z; e.w += e2.w;
-        }
-        const float4 xh = __ldg(reinterpret_cast<const float4*>(a.xhat + tl * 64 + cc));
-        g[cc] = e.x; g[cc + 1] = e.y; g[cc + 2] = e.z; g[cc + 3] = e.w;
-        m1 += (e.x + e.y) + (e.z + e.w);
-        m2 = fmaf(e.x, xh.x, fmaf(e.y, xh.y, fmaf(e.z, xh.z, fmaf(e.w, xh.w, m2))));
-      }
+      for (int cc = 0; cc < 64; ++cc) { m1 += g[cc]; m2 = fmaf(g[cc], r[cc], m2); }
       m1 *= (1.0f / 64); m2 *= (1.0f / 64);
-      const float rs = __ldg(a.rstd + tl);
+      const float rs = live ? __ldg(a.rstd + t) : 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 4) {
-        const float4 xh = __ldg(reinterpret_cast<const float4*>(a.xhat + tl * 64 + cc));
-        const float4 ds = __ldg(reinterpret_cast<const float4*>(a.dXs + tl * 64 + cc));
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(a.X + tl * 64 + cc));
-        const float xx[4] = {xh.x, xh.y, xh.z, xh.w}, dd[4] = {ds.x, ds.y, ds.z, ds.w}, vv[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float dx = (g[cc + j] - m1 - xx[j] * m2) * rs + dd[j];
-          g[cc + j] = live ? dx * (1.f - vv[j] * vv[j]) : 0.f;           // X = tanh(P)  (Modules.py:270)
-        }
-      }
+      for (int cc = 0; cc < 64; ++cc) g[cc] = (g[cc] - m1 - r[cc] * m2) * rs;          // LayerNorm backward
     }
+    warp_add_rows(a.dXs + t0 * 64, nrows, stage, lane, g);                              // + static-branch gradient
+    warp_load_rows(a.X + t0 * 64, nrows, stage, lane, r);
+#pragma unroll
+    for (int cc = 0; cc < 64; ++cc) g[cc] = live ? g[cc] * (1.f - r[cc] * r[cc]) : 0.f; // X = tanh(P)  (Modules.py:270)
     put_row(sA, a.dpt + tile * (int64_t)kCTile, tid, g);
     float o[64];
     run_stage(c, w_hi, idesc, o);
@@ -522,20 +544,16 @@ __global__ void __launch_bounds__(kCThreads) chain_mix_bwd_kernel(const MixBwdAr
       for (int cc = 0; cc < 64; ++cc) o[cc] = 0.f;
     }
     put_row_global(a.dv0t + tile * (int64_t)kCTile, 16384, tid, o);
-    if (live) {
+    if (a.dtE) {
+      warp_load_rows(a.E + t0 * 64, nrows, stage, lane, r);
+      warp_load_rows(a.dtE + t0 * 64, nrows, stage, lane, g);
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 4) {
-        float4 v = make_float4(o[cc], o[cc + 1], o[cc + 2], o[cc + 3]);
-        if (a.dtE) {
-          const float4 e = __ldg(reinterpret_cast<const float4*>(a.E + t * 64 + cc));
-          const float4 d = __ldg(reinterpret_cast<const float4*>(a.dtE + t * 64 + cc));
-          const float te[4] = {tanhf(e.x), tanhf(e.y), tanhf(e.z), tanhf(e.w)};
-          v.x += d.x * (1.f - te[0] * te[0]) * a.beta; v.y += d.y * (1.f - te[1] * te[1]) * a.beta;
-          v.z += d.z * (1.f - te[2] * te[2]) * a.beta; v.w += d.w * (1.f - te[3] * te[3]) * a.beta;
-        }
-        *reinterpret_cast<float4*>(a.dE + t * 64 + cc) = v;
+      for (int cc = 0; cc < 64; ++cc) {
+        const float te = tanhf(r[cc]);
+        o[cc] = fmaf(g[cc] * (1.f - te * te), a.beta, o[cc]);
       }
     }
+    warp_store_rows(a.dE + t0 * 64, nrows, stage, lane, o);
   }
   tc_fence_before();
   __syncthreads();
@@ -671,26 +689,30 @@ template <typename K>
 int set_smem_attr_c(K kernel, int bytes) {
   return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
 }
-inline unsigned chain_grid(int64_t ntiles, int per_sm) {
+// persistent grid = resident CTAs (occupancy query), so every CTA starts at once and loops over its tiles
+template <typename K>
+unsigned chain_grid(K kernel, int smem, int64_t ntiles) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kCThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t cap = (int64_t)kSMs * per_sm;
   return (unsigned)(ntiles < cap ? ntiles : cap);
 }
 
 template <int L>
 int launch_mix_L(const MixArgs& a, cudaStream_t s) {
-  const int smem = kCTile + kCW + a.attr_dim * 64 * 4;
+  const int smem = kCTile + kCW + kStageBytes + a.attr_dim * 64 * 4;
   static int set_for = 0;
   if (set_for < smem) { if (int rc = set_smem_attr_c(chain_mix_fwd_kernel<L>, smem)) return rc; set_for = smem; }
-  chain_mix_fwd_kernel<L><<<chain_grid(num_atiles(a.T, L), 3), kCThreads, smem, s>>>(a);
+  chain_mix_fwd_kernel<L><<<chain_grid(chain_mix_fwd_kernel<L>, smem, num_atiles(a.T, L)), kCThreads, smem, s>>>(a);
   MATCHA_CHECK_LAUNCH("chain_mix_fwd");
   return MATCHA_OK;
 }
 template <int L>
 int launch_pff_L(const PffArgs& a, cudaStream_t s) {
-  constexpr int smem = kCTile + 2 * kCW;
+  constexpr int smem = kCTile + 2 * kCW + kStageBytes;
   static bool once = false;
   if (!once) { if (int rc = set_smem_attr_c(chain_pff_fwd_kernel<L>, smem)) return rc; once = true; }
-  chain_pff_fwd_kernel<L><<<chain_grid(num_atiles(a.T, L), 3), kCThreads, smem, s>>>(a);
+  chain_pff_fwd_kernel<L><<<chain_grid(chain_pff_fwd_kernel<L>, smem, num_atiles(a.T, L)), kCThreads, smem, s>>>(a);
   MATCHA_CHECK_LAUNCH("chain_pff_fwd");
   return MATCHA_OK;
 }
@@ -698,19 +720,19 @@ int launch_pff_L(const PffArgs& a, cudaStream_t s) {
 
 template <int L>
 int launch_pff_bwd_L(const PffBwdArgs& a, cudaStream_t s) {
-  constexpr int smem = kCTile + 2 * kCW;
+  constexpr int smem = kCTile + 2 * kCW + kStageBytes;
   static bool once = false;
   if (!once) { if (int rc = set_smem_attr_c(chain_pff_bwd_kernel<L>, smem)) return rc; once = true; }
-  chain_pff_bwd_kernel<L><<<chain_grid(num_atiles(a.T, L), 3), kCThreads, smem, s>>>(a);
+  chain_pff_bwd_kernel<L><<<chain_grid(chain_pff_bwd_kernel<L>, smem, num_atiles(a.T, L)), kCThreads, smem, s>>>(a);
   MATCHA_CHECK_LAUNCH("chain_pff_bwd");
   return MATCHA_OK;
 }
 template <int L>
 int launch_mix_bwd_L(const MixBwdArgs& a, cudaStream_t s) {
-  constexpr int smem = kCTile + kCW;
+  constexpr int smem = kCTile + kCW + kStageBytes;
   static bool once = false;
   if (!once) { if (int rc = set_smem_attr_c(chain_mix_bwd_kernel<L>, smem)) return rc; once = true; }
-  chain_mix_bwd_kernel<L><<<chain_grid(num_atiles(a.T, L), 3), kCThreads, smem, s>>>(a);
+  chain_mix_bwd_kernel<L><<<chain_grid(chain_mix_bwd_kernel<L>, smem, num_atiles(a.T, L)), kCThreads, smem, s>>>(a);
   MATCHA_CHECK_LAUNCH("chain_mix_bwd");
   return MATCHA_OK;
 }

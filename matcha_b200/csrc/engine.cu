@@ -446,7 +446,7 @@ static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   const DerivedLayout l = derived_layout();
   if (fused_L > 0 && use_chain(m, T, fused_L))     // attribute mix + next_w + LayerNorm statistics + tiles in one kernel
     return PROF(P_MIX, 1, launch_chain_mix_fwd(w.E, x, m->attr_table, m->attr_dim, P + m->off_attr_w, P + m->off_attr_b,
-                                               m->derived + l.wchain + CW_NEXT_K * (kChainWBytes / 4), P + m->off_next_b, w.V0,
+                                               m->derived + l.wchain + CW_NEXT_K * (kChainWBytes / 4), P + m->off_next_b, nullptr,
                                                w.X, w.xhat, w.rstd, w.xhat_t, training ? w.v0_t : nullptr, training ? w.attr_t : nullptr,
                                                T / fused_L, fused_L, s));
   GemmDesc a = gemm_base(FORM_NT, T, kD, m->attr_dim, m->attr_table, m->attr_dim, P + m->off_attr_w, m->attr_dim, w.V0, kD);
