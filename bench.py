@@ -245,6 +245,45 @@ def main():
             ms = float(t.item())
         return ms, prof
 
+    def pair_scorer_bench(iters=5):
+        """Second metric of BASELINE.json: pair-scores/s of the denoise all-pairs scorer (denoise_contact.py:67-88) on
+        configs[3]'s shape -- chr1 at 10 kb, 24,897 bins, n(n+1)/2 = 3.1e8 pairs generated on the device -- sharded by
+        contiguous pair range across ranks with no communication.  The per-node tables are synthetic (the kernel's cost
+        does not depend on their values); their construction from a model is covered by the parity tests."""
+        n, d = 24897, 64
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        D = torch.randn(n + 1, d, device="cuda", generator=gen)
+        S = torch.randn(n + 1, d, device="cuda", generator=gen)
+        cw = torch.rand(d, device="cuda", generator=gen)
+        cb = torch.zeros(1, device="cuda")
+        total = int(lib.matcha_pair_count(1, n + 1, 0))
+        b, e = total * rank // world, total * (rank + 1) // world
+        out = torch.empty(e - b, dtype=torch.float32, device="cuda")
+        nbytes = int(lib.matcha_pair_tc_workspace_bytes(1, n + 1))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.matcha_pair_tc_prepare(_lib.ptr(D), _lib.ptr(S), _lib.ptr(cw), d, 1, n + 1, _lib.ptr(ws), nbytes,
+                                              _lib.stream_ptr()), "matcha_pair_tc_prepare")
+
+        def once():
+            _lib.check(lib.matcha_pair_tc_score_range(_lib.ptr(ws), _lib.ptr(cb), 1, n + 1, 0, b, e, 1, _lib.ptr(out),
+                                                      _lib.stream_ptr()), "matcha_pair_tc_score_range")
+        for _ in range(3):
+            once()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(iters):
+            once()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1) / iters
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        del out
+        return total, ms
+
     run(warmup, False, 0)
     clocks = ClockSampler(local)
     if rank == 0:
@@ -255,6 +294,7 @@ def main():
     run(2, True, 0)
     ms_e2e, _ = timed(args.steps, True, warmup + args.steps)
     losses = trainer.mean_losses()
+    pair_total, pair_ms = pair_scorer_bench()
 
     if rank != 0:
         if world > 1:
@@ -266,10 +306,18 @@ def main():
     peaks = load_peaks()
     # dominant call site and its roofline (algorithmic flops / bytes per launch)
     d, qkg = 64, 1536
-    alg = {
-        "qkg_gemm": ("tensor", 2.0 * T * qkg * d), "qkg_wgrad": ("tensor", 2.0 * T * qkg * d), "qkg_dgrad": ("tensor", 2.0 * T * qkg * d),
-        "attn_fwd": ("hbm", T * (qkg + d) * 4.0), "attn_bwd": ("hbm", T * (2 * qkg + d) * 4.0),
-    }
+    impl_env = os.environ.get("MATCHA_GEMM_IMPL", "1") if args.gemm_impl < 0 else str(args.gemm_impl)
+    fused = os.environ.get("MATCHA_FUSED", "1") != "0" and impl_env != "0"
+    if fused:
+        # fused hyperedge-tile kernels: QKG never leaves the SM, so the bound is the tensor pipe.  ALGORITHMIC flops only:
+        # forward = the QKG projection; backward = its data + weight gradients (the in-kernel recompute of QKG and the three
+        # bf16 passes of the fp32-accurate split are implementation cost, not counted)
+        alg = {"attn_fwd": ("tensor", 2.0 * T * qkg * d), "attn_bwd": ("tensor", 2.0 * 2.0 * T * qkg * d)}
+    else:
+        alg = {
+            "qkg_gemm": ("tensor", 2.0 * T * qkg * d), "qkg_wgrad": ("tensor", 2.0 * T * qkg * d), "qkg_dgrad": ("tensor", 2.0 * T * qkg * d),
+            "attn_fwd": ("hbm", T * (qkg + d) * 4.0), "attn_bwd": ("hbm", T * (2 * qkg + d) * 4.0),
+        }
     top = max(prof.items(), key=lambda kv: kv[1][0])
     tot_ms = sum(v[0] for v in prof.values())
     name, (tms, calls, _) = top
@@ -289,8 +337,24 @@ def main():
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                 "traffic": None}
     impl_used = args.gemm_impl if args.gemm_impl >= 0 else int(os.environ.get("MATCHA_GEMM_IMPL", "1") or 1)
-    roof.update({"kernel": name, "ms_per_launch": per_launch_ms, "share_of_step": tms / tot_ms, "peak_source": peaks["src"],
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (bytes per launch), if one exists
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "top_kernel_traffic.json")))
+        ent = tr.get(name if not fused else "fused_" + name)
+        if ent and ent.get("tokens") == T:
+            roof["traffic"] = ent["dram_read_bytes"] + ent["dram_write_bytes"]
+    except Exception:
+        pass
+    roof.update({"kernel": ("fused_" + name) if fused and name in alg else name, "ms_per_launch": per_launch_ms,
+                 "share_of_step": tms / tot_ms, "peak_source": peaks["src"],
                  "contractions": "tcgen05 bf16x3 split, fp32 accumulate" if impl_used == 1 else "fp32 SIMT"})
+    pair_rate = pair_total / (pair_ms * 1e-3)
+    pair = {"value": pair_rate, "unit": "pair-scores/s", "ms_per_pass": pair_ms, "pairs": pair_total,
+            "workload": "cfg4 shape: chr1 at 10 kb, 24,897 bins, all n(n+1)/2 pairs generated on the device, sigmoid applied, "
+                        "sharded by pair range over the ranks",
+            "roofline": {"bound": "hbm", "achieved": pair_rate * 4.0 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": pair_rate * 4.0 / 1e9 / peaks["hbm_gbs"] / world, "peak_source": peaks["src"],
+                         "note": "4 bytes written per pair; tables (12.7 MB) stay in L2"}}
     launches = int(sum(v[2] for v in prof.values()))
     breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
 
@@ -305,7 +369,7 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": config, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(P * 5 * 8 + P * 4), "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clk, "kernel_ms_per_step": breakdown, "losses": losses}
+            "gpu_launches": launches, "clocks": clk, "kernel_ms_per_step": breakdown, "losses": losses, "pair_scores": pair}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmatcha_b200.so")
-SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu"]
+SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu", "pair_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 MAX_CHROM = 64
@@ -102,6 +102,9 @@ SYMBOLS = {
     "matcha_pair_tables": (C.c_int, [_MD, _P, _P, _P, _I64, _P]),
     "matcha_pair_score_range": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _I64, _I32, _I64, _I64, _I32, _P, _P]),
     "matcha_pair_count": (_I64, [_I64, _I64, _I32]),
+    "matcha_pair_tc_workspace_bytes": (_I64, [_I64, _I64]),
+    "matcha_pair_tc_prepare": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I64, _P]),
+    "matcha_pair_tc_score_range": (C.c_int, [_P, _P, _I64, _I64, _I32, _I64, _I64, _I32, _P, _P]),
     "matcha_gemm": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P]),
     "matcha_gemm_scratch_floats": (_I64, [_I64]),
 }

@@ -50,9 +50,24 @@ class PairScorer:
         m = self.model
         self.cls_w = m.pff_classifier.PWF_Conv0.weight.data.reshape(-1)
         self.cls_b = m.pff_classifier.PWF_Conv0.bias.data.reshape(-1)
+        self._packed = {}
 
-    def score_range(self, lo, hi, min_dis=0, p_begin=0, p_end=None, sigmoid=False, out=None):
-        """Scores of pairs [p_begin, p_end) of chromosome ids [lo, hi) -> fp32 tensor on the device."""
+    def _pack(self, lo, hi):
+        """Operand blocks of the tensor-core scorer for chromosome ids [lo, hi), built once per table refresh."""
+        key = (int(lo), int(hi))
+        ws = self._packed.get(key)
+        if ws is None:
+            eng = self.engine
+            nbytes = int(eng.lib.matcha_pair_tc_workspace_bytes(key[0], key[1]))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=eng.dev)
+            check(eng.lib.matcha_pair_tc_prepare(ptr(self.D), ptr(self.S), ptr(self.cls_w), eng.d, key[0], key[1], ptr(ws),
+                                                 nbytes, stream_ptr()), "matcha_pair_tc_prepare")
+            self._packed[key] = ws
+        return ws
+
+    def score_range(self, lo, hi, min_dis=0, p_begin=0, p_end=None, sigmoid=False, out=None, impl="tc"):
+        """Scores of pairs [p_begin, p_end) of chromosome ids [lo, hi) -> fp32 tensor on the device.
+        impl "tc" = tcgen05 contraction form (default), "simt" = fp32 FMA form (cross-check)."""
         total = pair_count(lo, hi, min_dis)
         p_end = total if p_end is None else p_end
         if not (0 <= p_begin <= p_end <= total):
@@ -60,9 +75,15 @@ class PairScorer:
         eng = self.engine
         if out is None:
             out = torch.empty(p_end - p_begin, dtype=torch.float32, device=eng.dev)
-        check(eng.lib.matcha_pair_score_range(ptr(self.D), ptr(self.S), ptr(self.cls_w), ptr(self.cls_b), eng.d,
-                                              int(lo), int(hi), int(min_dis), int(p_begin), int(p_end),
-                                              1 if sigmoid else 0, ptr(out), stream_ptr()), "matcha_pair_score_range")
+        if impl == "tc":
+            ws = self._pack(lo, hi)
+            check(eng.lib.matcha_pair_tc_score_range(ptr(ws), ptr(self.cls_b), int(lo), int(hi), int(min_dis), int(p_begin),
+                                                     int(p_end), 1 if sigmoid else 0, ptr(out), stream_ptr()),
+                  "matcha_pair_tc_score_range")
+        else:
+            check(eng.lib.matcha_pair_score_range(ptr(self.D), ptr(self.S), ptr(self.cls_w), ptr(self.cls_b), eng.d,
+                                                  int(lo), int(hi), int(min_dis), int(p_begin), int(p_end),
+                                                  1 if sigmoid else 0, ptr(out), stream_ptr()), "matcha_pair_score_range")
         return out
 
     def score_chromosome(self, chrom_id, min_dis=0, sigmoid=False, rank=0, world=1):

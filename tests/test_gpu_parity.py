@@ -522,3 +522,31 @@ def test_chain_kernels_match_simt_layers(golden, monkeypatch, L, B):
         g1 = res[1][0][k]
         scale = float(np.abs(g0).max())
         assert float(np.abs(g1 - g0).max()) <= 5e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
+
+
+@pytest.mark.parametrize("n,min_dis", [(1000, 0), (777, 3), (300, 130), (2500, 1)])
+def test_pair_scorer_tensor_core_matches_simt(n, min_dis):
+    """tcgen05 all-pairs scorer (u_i + u_j - PA_i.PB_j + b) vs the fp32 FMA form on random tables, incl. a ragged last
+    block, min_distance inside and beyond one block, and an interior sub-range (the multi-GPU shard)."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    lo = 5
+    D = torch.randn(lo + n, 64, device="cuda", generator=g)
+    S = torch.randn(lo + n, 64, device="cuda", generator=g)
+    w = (torch.rand(64, device="cuda", generator=g) - 0.5) * 0.25
+    b = torch.full((1,), 0.1, device="cuda")
+    total = int(lib.matcha_pair_count(lo, lo + n, min_dis))
+    nbytes = int(lib.matcha_pair_tc_workspace_bytes(lo, lo + n))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    L.check(lib.matcha_pair_tc_prepare(L.ptr(D), L.ptr(S), L.ptr(w), 64, lo, lo + n, L.ptr(ws), nbytes, L.stream_ptr()), "prep")
+    for (pb, pe) in [(0, total), (total // 3, 2 * total // 3 + 1)]:
+        for sig in (0, 1):
+            ref = torch.full((pe - pb,), -7.0, device="cuda")
+            out = torch.full((pe - pb,), -9.0, device="cuda")
+            L.check(lib.matcha_pair_score_range(L.ptr(D), L.ptr(S), L.ptr(w), L.ptr(b), 64, lo, lo + n, min_dis, pb, pe, sig,
+                                                L.ptr(ref), L.stream_ptr()), "simt")
+            L.check(lib.matcha_pair_tc_score_range(L.ptr(ws), L.ptr(b), lo, lo + n, min_dis, pb, pe, sig, L.ptr(out),
+                                                   L.stream_ptr()), "tc")
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=5e-5)
