@@ -169,6 +169,14 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
         mbar_wait(&acc_full[grp], (uint32_t)((k >> 1) & 1));
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 128;
+        const int cc = lane & 15, half = lane >> 4;
+        const int64_t full = a.n - a.md;
+        const int64_t i_first = ti * 128 + q * 32, j_first = tj * 128;
+        // interior tile: every (i, j) of this warp's 32 x 128 slab is a valid pair inside [p_begin, p_end) -> no checks
+        const int64_t i_last = i_first + 31, j_last = j_first + 127;
+        const bool interior = i_last < a.n && j_last < a.n && j_first >= i_last + a.md &&
+                              tri_prefix(i_first, a.n, a.md) - (i_first + a.md) + j_first >= a.p_begin &&
+                              tri_prefix(i_last, a.n, a.md) - (i_last + a.md) + j_last < a.p_end;
 #pragma unroll 1
         for (int ch = 0; ch < 8; ++ch) {
           float v[16];
@@ -177,21 +185,36 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
           for (int c4 = 0; c4 < 16; c4 += 4)
             *reinterpret_cast<float4*>(stage + lane * kPStageRow + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);
           __syncwarp();
-          const int cc = lane & 15;
-          const int64_t j = tj * 128 + ch * 16 + cc;
-          const float uj = j < a.n ? __ldg(a.u + j) : 0.f;
+          const int64_t j = j_first + ch * 16 + cc;
+          const float ujb = (j < a.n ? __ldg(a.u + j) : 0.f) + bias;
+          if (interior) {
+            // p(i, j) = rowbase(i) + j with rowbase(i + 1) - rowbase(i) = full - i - 1: two rows per iteration
+            int64_t i = i_first + half;
+            float* dst = a.out + (tri_prefix(i, a.n, a.md) - (i + a.md) + j - a.p_begin);
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+              const int rr = it * 2 + half;
+              const float acc = stage[rr * kPStageRow + cc];
+              float val = __shfl_sync(0xffffffffu, ui, rr) + ujb - acc;
+              if (a.apply_sigmoid) val = __fdividef(1.0f, 1.0f + __expf(-val));
+              *dst = val;
+              dst += 2 * (full - i) - 3;           // rowbase(i + 2) - rowbase(i)
+              i += 2;
+            }
+          } else {
 #pragma unroll 4
-          for (int it = 0; it < 16; ++it) {
-            const int rr = it * 2 + (lane >> 4);
-            const float acc = stage[rr * kPStageRow + cc];
-            const float ur = __shfl_sync(0xffffffffu, ui, rr);
-            const int64_t i = ti * 128 + q * 32 + rr;
-            if (i < a.n && j < a.n && j >= i + a.md) {
-              const int64_t p = tri_prefix(i, a.n, a.md) - (i + a.md) + j;
-              if (p >= a.p_begin && p < a.p_end) {
-                float val = ur + uj - acc + bias;
-                if (a.apply_sigmoid) val = __fdividef(1.0f, 1.0f + __expf(-val));
-                a.out[p - a.p_begin] = val;
+            for (int it = 0; it < 16; ++it) {
+              const int rr = it * 2 + half;
+              const float acc = stage[rr * kPStageRow + cc];
+              const float ur = __shfl_sync(0xffffffffu, ui, rr);
+              const int64_t i = i_first + rr;
+              if (i < a.n && j < a.n && j >= i + a.md) {
+                const int64_t p = tri_prefix(i, a.n, a.md) - (i + a.md) + j;
+                if (p >= a.p_begin && p < a.p_end) {
+                  float val = ur + ujb - acc;
+                  if (a.apply_sigmoid) val = __fdividef(1.0f, 1.0f + __expf(-val));
+                  a.out[p - a.p_begin] = val;
+                }
               }
             }
           }
