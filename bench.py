@@ -261,11 +261,11 @@ def main():
         out = torch.empty(e - b, dtype=torch.float32, device="cuda")
         nbytes = int(lib.matcha_pair_tc_workspace_bytes(1, n + 1))
         ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        _lib.check(lib.matcha_pair_tc_prepare(_lib.ptr(D), _lib.ptr(S), _lib.ptr(cw), d, 1, n + 1, _lib.ptr(ws), nbytes,
+        _lib.check(lib.matcha_pair_tc_prepare(_lib.ptr(D), _lib.ptr(S), _lib.ptr(cw), _lib.ptr(cb), d, 1, n + 1, _lib.ptr(ws), nbytes,
                                               _lib.stream_ptr()), "matcha_pair_tc_prepare")
 
         def once():
-            _lib.check(lib.matcha_pair_tc_score_range(_lib.ptr(ws), _lib.ptr(cb), 1, n + 1, 0, b, e, 1, _lib.ptr(out),
+            _lib.check(lib.matcha_pair_tc_score_range(_lib.ptr(ws), 1, n + 1, 0, b, e, 1, _lib.ptr(out),
                                                       _lib.stream_ptr()), "matcha_pair_tc_score_range")
         for _ in range(3):
             once()

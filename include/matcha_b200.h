@@ -184,14 +184,14 @@ int matcha_pair_score_range(const float* D, const float* S, const float* cls_w, 
                             int32_t apply_sigmoid, float* out, void* stream);
 int64_t matcha_pair_count(int64_t lo, int64_t hi, int32_t min_dis);
 /* Tensor-core form of the same scorer (tcgen05, bf16x3 split): logit = u_i + u_j - PA_i . PB_j + b with
- * PA = [w.S | D], PB = [D | w.S].  matcha_pair_tc_prepare packs the tables of one chromosome (ids [lo, hi)) into
+ * PA = [w.S | D], PB = [D | w.S]; u and b ride in 16 extra k columns as exact bf16 pieces.  matcha_pair_tc_prepare packs the tables of one chromosome (ids [lo, hi)) into
  * `workspace` (dev, 256-byte aligned, matcha_pair_tc_workspace_bytes(lo, hi) bytes); matcha_pair_tc_score_range then
  * writes the same out[p] as matcha_pair_score_range (apply_sigmoid uses the fast exponential: 1e-6 relative). */
 int64_t matcha_pair_tc_workspace_bytes(int64_t lo, int64_t hi);
-int matcha_pair_tc_prepare(const float* D, const float* S, const float* cls_w, int32_t d, int64_t lo, int64_t hi,
-                           void* workspace, int64_t workspace_bytes, void* stream);
-int matcha_pair_tc_score_range(const void* workspace, const float* cls_b, int64_t lo, int64_t hi, int32_t min_dis,
-                               int64_t p_begin, int64_t p_end, int32_t apply_sigmoid, float* out, void* stream);
+int matcha_pair_tc_prepare(const float* D, const float* S, const float* cls_w, const float* cls_b, int32_t d, int64_t lo,
+                           int64_t hi, void* workspace, int64_t workspace_bytes, void* stream);
+int matcha_pair_tc_score_range(const void* workspace, int64_t lo, int64_t hi, int32_t min_dis, int64_t p_begin, int64_t p_end,
+                               int32_t apply_sigmoid, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Building blocks exposed for tests (dense fp32 contractions used by the passes above).

@@ -15,11 +15,17 @@ namespace matcha {
 namespace {
 
 constexpr int kPD = 64;
-constexpr int kPBlk = 65536;                 // one block: 128 nodes x 128 k, hi 32 KB ([16 planes][128][8]) | lo 32 KB
+// one block = 128 nodes x 144 k: hi [18 planes][128][8] (36 KB) | lo [16 planes] (32 KB).  k 0..127 carry the contraction
+// operands; k 128..143 (hi half only, one extra bf16 pass) carry -log2(e) * u as three exact bf16 pieces against ones, so
+// the accumulator already holds t = -log2(e) * logit and the epilogue is ex2 / add / rcp / store.
+constexpr int kPHi = 18 * 2048;
+constexpr int kPBlk = kPHi + 16 * 2048;      // 69632
 constexpr int kPThreads = 320;
 constexpr int kPStageRow = 20;               // floats per staged row (16 + 4 pad)
 constexpr int kPStageWarp = 32 * kPStageRow;
-constexpr int kPSmem = 3 * kPBlk + 8 * kPStageWarp * 4;      // A + 2 x B + staging = 217 088
+constexpr int kPSmem = 3 * kPBlk + 8 * kPStageWarp * 4;      // A + 2 x B + staging = 229 376
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 __host__ __device__ __forceinline__ int64_t tri_prefix(int64_t r, int64_t n, int64_t md) {
   const int64_t full = n - md;               // items in row 0 when row q holds max(0, n - md - q)
@@ -34,49 +40,68 @@ __host__ __device__ __forceinline__ int64_t tri_row_of(int64_t p, int64_t n, int
 }
 
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf16_bits(float x) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf16_val(uint32_t b) { return __uint_as_float(b << 16); }
+
 __global__ void pair_prep_kernel(const float* __restrict__ D, const float* __restrict__ S, const float* __restrict__ w,
-                                 int64_t lo, int64_t n, int64_t nblocks, uint8_t* __restrict__ PA, uint8_t* __restrict__ PB,
-                                 float* __restrict__ u) {
-  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (relative node r, group g of 8 of the 128 k)
-  if (unit >= nblocks * 128 * 16) return;
-  const int g = (int)(unit & 15);
-  const int64_t r = unit >> 4;
-  float a[8], b[8];
+                                 const float* __restrict__ cls_b, int64_t lo, int64_t n, int64_t nblocks,
+                                 uint8_t* __restrict__ PA, uint8_t* __restrict__ PB) {
+  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (relative node r, plane g of 18)
+  if (unit >= nblocks * 128 * 18) return;
+  const int g = (int)(unit % 18);
+  const int64_t r = unit / 18;
+  const int64_t off = (r >> 7) * kPBlk + g * 2048 + (r & 127) * 16;
+  if (g < 16) {
+    float a[8], b[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
-  if (r < n) {
-    const int c0 = (g & 7) * 8;
-    const float* dr = D + (lo + r) * kPD + c0;
-    const float* sr = S + (lo + r) * kPD + c0;
-    float ws[8], dv[8];
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
+    if (r < n) {
+      const int c0 = (g & 7) * 8;
+      const float* dr = D + (lo + r) * kPD + c0;
+      const float* sr = S + (lo + r) * kPD + c0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { ws[i] = __ldg(w + c0 + i) * __ldg(sr + i); dv[i] = __ldg(dr + i); }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { a[i] = g < 8 ? ws[i] : dv[i]; b[i] = g < 8 ? dv[i] : ws[i]; }
-    if (g == 0) {
+      for (int i = 0; i < 8; ++i) {
+        const float ws = __ldg(w + c0 + i) * __ldg(sr + i), dv = __ldg(dr + i);
+        a[i] = g < 8 ? ws : dv;                       // PA = [w.S | D]
+        b[i] = (g < 8 ? dv : ws) * kLog2e;            // PB = log2(e) * [D | w.S]
+      }
+    }
+    uint4 hi, lo4;
+    split8(make_float4(a[0], a[1], a[2], a[3]), make_float4(a[4], a[5], a[6], a[7]), hi, lo4);
+    *reinterpret_cast<uint4*>(PA + off) = hi;
+    *reinterpret_cast<uint4*>(PA + off + kPHi) = lo4;
+    split8(make_float4(b[0], b[1], b[2], b[3]), make_float4(b[4], b[5], b[6], b[7]), hi, lo4);
+    *reinterpret_cast<uint4*>(PB + off) = hi;
+    *reinterpret_cast<uint4*>(PB + off + kPHi) = lo4;
+  } else if (g == 16) {
+    // k 128..130: three bf16 pieces of -log2(e) u (A side) against ones (B side); k 131..133: ones against the pieces of
+    // -log2(e) (u + b); the sum of the pieces is exact to 2^-24
+    uint32_t pa[4] = {0u, 0u, 0u, 0u}, pb[4] = {0u, 0u, 0u, 0u};
+    if (r < n) {
       float acc = 0.f;
       for (int c = 0; c < kPD; ++c) {
         const float dd = __ldg(D + (lo + r) * kPD + c), ss = __ldg(S + (lo + r) * kPD + c);
         acc = fmaf(__ldg(w + c), fmaf(dd, dd, ss * ss), acc);
       }
-      u[r] = 0.5f * acc;
+      const float u = 0.5f * acc;
+      const float xa = -kLog2e * u, xb = -kLog2e * (u + __ldg(cls_b));
+      const uint32_t ah = bf16_bits(xa), am = bf16_bits(xa - bf16_val(ah)), al = bf16_bits(xa - bf16_val(ah) - bf16_val(am));
+      const uint32_t bh = bf16_bits(xb), bm = bf16_bits(xb - bf16_val(bh)), bl = bf16_bits(xb - bf16_val(bh) - bf16_val(bm));
+      const uint32_t one = 0x3F80u;
+      pa[0] = ah | (am << 16); pa[1] = al | (one << 16); pa[2] = one | (one << 16);
+      pb[0] = one | (one << 16); pb[1] = one | (bh << 16); pb[2] = bm | (bl << 16);
     }
-  } else if (g == 0) {
-    u[r] = 0.f;
+    *reinterpret_cast<uint4*>(PA + off) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+    *reinterpret_cast<uint4*>(PB + off) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+  } else {
+    *reinterpret_cast<uint4*>(PA + off) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(PB + off) = make_uint4(0u, 0u, 0u, 0u);
   }
-  uint4 hi, lo4;
-  const int64_t off = (r >> 7) * kPBlk + g * 2048 + (r & 127) * 16;
-  split8(make_float4(a[0], a[1], a[2], a[3]), make_float4(a[4], a[5], a[6], a[7]), hi, lo4);
-  *reinterpret_cast<uint4*>(PA + off) = hi;
-  *reinterpret_cast<uint4*>(PA + off + 32768) = lo4;
-  split8(make_float4(b[0], b[1], b[2], b[3]), make_float4(b[4], b[5], b[6], b[7]), hi, lo4);
-  *reinterpret_cast<uint4*>(PB + off) = hi;
-  *reinterpret_cast<uint4*>(PB + off + 32768) = lo4;
 }
 
 // ------------------------------------------------------------------------------------------
 struct PairArgs {
-  const uint8_t* PA; const uint8_t* PB; const float* u; const float* cls_b;
+  const uint8_t* PA; const uint8_t* PB;
   int64_t n; int md; int64_t nb; int bmd;          // nodes, min distance, 128-node blocks, md / 128
   int64_t f_begin, f_end;                          // flat tile range of this launch
   int64_t p_begin, p_end;
@@ -84,6 +109,8 @@ struct PairArgs {
   float* out;
 };
 
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void flat_to_tile(int64_t f, int64_t nb, int bmd, int64_t& ti, int64_t& tj) {
   ti = tri_row_of(f, nb, bmd);
   tj = ti + bmd + (f - tri_prefix(ti, nb, bmd));
@@ -136,18 +163,20 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
       constexpr uint32_t idesc = make_idesc(128, 128, false, false);
       int64_t ti, tj, cur_ti = -1, na = 0;
       flat_to_tile(f0, a.nb, a.bmd, ti, tj);
-      const uint32_t ah = smem_u32(sAop), al = ah + 32768;
+      const uint32_t ah = smem_u32(sAop), al = ah + kPHi;
       for (int64_t f = f0, k = 0; f < f1; ++f, ++k) {
         if (ti != cur_ti) { mbar_wait_backoff(&a_full, (uint32_t)(na & 1)); cur_ti = ti; ++na; }
         const int s = (int)(k & 1);
         mbar_wait_backoff(&b_full[s], (uint32_t)((k >> 1) & 1));
         mbar_wait_backoff(&acc_empty[s], (uint32_t)((k >> 1) & 1) ^ 1u);
         tc_fence_after();
-        const uint32_t bh = smem_u32(sBop + s * kPBlk), bl = bh + 32768;
+        const uint32_t bh = smem_u32(sBop + s * kPBlk), bl = bh + kPHi;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
           umma_x3s(tmem_base + s * 128, ah + ks * 4096, al + ks * 4096, bh + ks * 4096, bl + ks * 4096, 2048, 128, 2048, 128,
                    idesc, ks == 0);
+        // k 128..143: the u / bias pieces (exact in bf16), hi * hi pass only
+        umma_bf16(tmem_base + s * 128, make_smem_desc(ah + 8 * 4096, 2048, 128), make_smem_desc(bh + 8 * 4096, 2048, 128), idesc, 1u);
         umma_commit(&b_empty[s]);
         umma_commit(&acc_full[s]);
         int64_t nti = ti, ntj = tj + 1;
@@ -159,13 +188,10 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
   } else if (f0 < f1) {
     const int grp = (warp - 2) >> 2, q = warp & 3;          // epilogue warpgroup <-> TMEM stage; lane quarter
     float* stage = sStage + (warp - 2) * kPStageWarp;
-    const float bias = __ldg(a.cls_b);
     int64_t ti, tj;
     flat_to_tile(f0, a.nb, a.bmd, ti, tj);
     for (int64_t f = f0, k = 0; f < f1; ++f, ++k) {
       if ((int)(k & 1) == grp) {
-        const int64_t i_own = ti * 128 + q * 32 + lane;
-        const float ui = i_own < a.n ? __ldg(a.u + i_own) : 0.f;
         mbar_wait(&acc_full[grp], (uint32_t)((k >> 1) & 1));
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 128;
@@ -186,35 +212,27 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
             *reinterpret_cast<float4*>(stage + lane * kPStageRow + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);
           __syncwarp();
           const int64_t j = j_first + ch * 16 + cc;
-          const float ujb = (j < a.n ? __ldg(a.u + j) : 0.f) + bias;
           if (interior) {
             // p(i, j) = rowbase(i) + j with rowbase(i + 1) - rowbase(i) = full - i - 1: two rows per iteration
-            int64_t i = i_first + half;
-            float* dst = a.out + (tri_prefix(i, a.n, a.md) - (i + a.md) + j - a.p_begin);
+            const int64_t i0 = i_first + half;
+            float* dst = a.out + (tri_prefix(i0, a.n, a.md) - (i0 + a.md) + j - a.p_begin);
+            int64_t stride = 2 * (full - i0) - 3;      // rowbase(i + 2) - rowbase(i), shrinking by 4 per iteration
 #pragma unroll
             for (int it = 0; it < 16; ++it) {
-              const int rr = it * 2 + half;
-              const float acc = stage[rr * kPStageRow + cc];
-              float val = __shfl_sync(0xffffffffu, ui, rr) + ujb - acc;
-              if (a.apply_sigmoid) val = __fdividef(1.0f, 1.0f + __expf(-val));
-              *dst = val;
-              dst += 2 * (full - i) - 3;           // rowbase(i + 2) - rowbase(i)
-              i += 2;
+              const float t = stage[(it * 2 + half) * kPStageRow + cc];          // -log2(e) * logit
+              *dst = a.apply_sigmoid ? fast_rcp(1.0f + fast_ex2(t)) : -kLn2 * t;
+              dst += stride;
+              stride -= 4;
             }
           } else {
 #pragma unroll 4
             for (int it = 0; it < 16; ++it) {
               const int rr = it * 2 + half;
-              const float acc = stage[rr * kPStageRow + cc];
-              const float ur = __shfl_sync(0xffffffffu, ui, rr);
+              const float t = stage[rr * kPStageRow + cc];
               const int64_t i = i_first + rr;
               if (i < a.n && j < a.n && j >= i + a.md) {
                 const int64_t p = tri_prefix(i, a.n, a.md) - (i + a.md) + j;
-                if (p >= a.p_begin && p < a.p_end) {
-                  float val = ur + ujb - acc;
-                  if (a.apply_sigmoid) val = __fdividef(1.0f, 1.0f + __expf(-val));
-                  a.out[p - a.p_begin] = val;
-                }
+                if (p >= a.p_begin && p < a.p_end) a.out[p - a.p_begin] = a.apply_sigmoid ? fast_rcp(1.0f + fast_ex2(t)) : -kLn2 * t;
               }
             }
           }
@@ -239,17 +257,17 @@ using namespace matcha;
 
 extern "C" {
 
-// workspace: PA | PB blocks (64 KB per 128 nodes each) | u
+// workspace: PA | PB blocks (68 KB per 128 nodes each)
 int64_t matcha_pair_tc_workspace_bytes(int64_t lo, int64_t hi) {
   const int64_t n = hi - lo;
   if (n <= 0) return 0;
   const int64_t nb = (n + 127) / 128;
-  return 2 * nb * (int64_t)kPBlk + nb * 128 * 4 + 256;
+  return 2 * nb * (int64_t)kPBlk + 256;
 }
 
-int matcha_pair_tc_prepare(const float* D, const float* S, const float* cls_w, int32_t d, int64_t lo, int64_t hi,
-                           void* workspace, int64_t workspace_bytes, void* stream) {
-  MATCHA_REQUIRE(D && S && cls_w && workspace, "pair_tc_prepare: NULL argument");
+int matcha_pair_tc_prepare(const float* D, const float* S, const float* cls_w, const float* cls_b, int32_t d, int64_t lo,
+                           int64_t hi, void* workspace, int64_t workspace_bytes, void* stream) {
+  MATCHA_REQUIRE(D && S && cls_w && cls_b && workspace, "pair_tc_prepare: NULL argument");
   if (d != kPD) { set_error("pair_tc_prepare: embed_dim %d unsupported (64)", d); return MATCHA_ERR_UNSUPPORTED; }
   MATCHA_REQUIRE(((uintptr_t)workspace & 255) == 0, "pair_tc_prepare: workspace must be 256-byte aligned");
   const int64_t n = hi - lo;
@@ -257,16 +275,15 @@ int matcha_pair_tc_prepare(const float* D, const float* S, const float* cls_w, i
   const int64_t nb = (n + 127) / 128;
   uint8_t* PA = reinterpret_cast<uint8_t*>(workspace);
   uint8_t* PB = PA + nb * (int64_t)kPBlk;
-  float* u = reinterpret_cast<float*>(PB + nb * (int64_t)kPBlk);
-  const int64_t units = nb * 128 * 16;
-  pair_prep_kernel<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(D, S, cls_w, lo, n, nb, PA, PB, u);
+  const int64_t units = nb * 128 * 18;
+  pair_prep_kernel<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(D, S, cls_w, cls_b, lo, n, nb, PA, PB);
   MATCHA_CHECK_LAUNCH("pair_prep");
   return MATCHA_OK;
 }
 
-int matcha_pair_tc_score_range(const void* workspace, const float* cls_b, int64_t lo, int64_t hi, int32_t min_dis,
-                               int64_t p_begin, int64_t p_end, int32_t apply_sigmoid, float* out, void* stream) {
-  MATCHA_REQUIRE(workspace && cls_b && out, "pair_tc_score_range: NULL argument");
+int matcha_pair_tc_score_range(const void* workspace, int64_t lo, int64_t hi, int32_t min_dis, int64_t p_begin, int64_t p_end,
+                               int32_t apply_sigmoid, float* out, void* stream) {
+  MATCHA_REQUIRE(workspace && out, "pair_tc_score_range: NULL argument");
   MATCHA_REQUIRE(min_dis >= 0, "pair_tc_score_range: negative min_distance");
   const int64_t n = hi - lo;
   const int64_t total = tri_prefix(n, n, min_dis);
@@ -279,8 +296,7 @@ int matcha_pair_tc_score_range(const void* workspace, const float* cls_b, int64_
   PairArgs a;
   a.PA = reinterpret_cast<const uint8_t*>(workspace);
   a.PB = a.PA + nb * (int64_t)kPBlk;
-  a.u = reinterpret_cast<const float*>(a.PB + nb * (int64_t)kPBlk);
-  a.cls_b = cls_b; a.n = n; a.md = min_dis; a.nb = nb; a.bmd = bmd;
+  a.n = n; a.md = min_dis; a.nb = nb; a.bmd = bmd;
   a.f_begin = tri_prefix(r0 / 128, nb, bmd);
   a.f_end = tri_prefix(r1 / 128 + 1, nb, bmd);
   a.p_begin = p_begin; a.p_end = p_end; a.apply_sigmoid = apply_sigmoid; a.out = out;

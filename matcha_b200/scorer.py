@@ -60,8 +60,8 @@ class PairScorer:
             eng = self.engine
             nbytes = int(eng.lib.matcha_pair_tc_workspace_bytes(key[0], key[1]))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=eng.dev)
-            check(eng.lib.matcha_pair_tc_prepare(ptr(self.D), ptr(self.S), ptr(self.cls_w), eng.d, key[0], key[1], ptr(ws),
-                                                 nbytes, stream_ptr()), "matcha_pair_tc_prepare")
+            check(eng.lib.matcha_pair_tc_prepare(ptr(self.D), ptr(self.S), ptr(self.cls_w), ptr(self.cls_b), eng.d, key[0], key[1],
+                                                 ptr(ws), nbytes, stream_ptr()), "matcha_pair_tc_prepare")
             self._packed[key] = ws
         return ws
 
@@ -77,7 +77,7 @@ class PairScorer:
             out = torch.empty(p_end - p_begin, dtype=torch.float32, device=eng.dev)
         if impl == "tc":
             ws = self._pack(lo, hi)
-            check(eng.lib.matcha_pair_tc_score_range(ptr(ws), ptr(self.cls_b), int(lo), int(hi), int(min_dis), int(p_begin),
+            check(eng.lib.matcha_pair_tc_score_range(ptr(ws), int(lo), int(hi), int(min_dis), int(p_begin),
                                                      int(p_end), 1 if sigmoid else 0, ptr(out), stream_ptr()),
                   "matcha_pair_tc_score_range")
         else:

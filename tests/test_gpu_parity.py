@@ -539,14 +539,14 @@ def test_pair_scorer_tensor_core_matches_simt(n, min_dis):
     total = int(lib.matcha_pair_count(lo, lo + n, min_dis))
     nbytes = int(lib.matcha_pair_tc_workspace_bytes(lo, lo + n))
     ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-    L.check(lib.matcha_pair_tc_prepare(L.ptr(D), L.ptr(S), L.ptr(w), 64, lo, lo + n, L.ptr(ws), nbytes, L.stream_ptr()), "prep")
+    L.check(lib.matcha_pair_tc_prepare(L.ptr(D), L.ptr(S), L.ptr(w), L.ptr(b), 64, lo, lo + n, L.ptr(ws), nbytes, L.stream_ptr()), "prep")
     for (pb, pe) in [(0, total), (total // 3, 2 * total // 3 + 1)]:
         for sig in (0, 1):
             ref = torch.full((pe - pb,), -7.0, device="cuda")
             out = torch.full((pe - pb,), -9.0, device="cuda")
             L.check(lib.matcha_pair_score_range(L.ptr(D), L.ptr(S), L.ptr(w), L.ptr(b), 64, lo, lo + n, min_dis, pb, pe, sig,
                                                 L.ptr(ref), L.stream_ptr()), "simt")
-            L.check(lib.matcha_pair_tc_score_range(L.ptr(ws), L.ptr(b), lo, lo + n, min_dis, pb, pe, sig, L.ptr(out),
+            L.check(lib.matcha_pair_tc_score_range(L.ptr(ws), lo, lo + n, min_dis, pb, pe, sig, L.ptr(out),
                                                    L.stream_ptr()), "tc")
             torch.cuda.synchronize()
             np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=5e-5)
