@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmatcha_b200.so")
-SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu", "pair_tc.cu"]
+SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 MAX_CHROM = 64

@@ -395,9 +395,11 @@ static int validate(const matcha_model_desc* m) {
   MATCHA_REQUIRE(m->n_chrom >= 1 && m->n_chrom <= MATCHA_MAX_CHROM, "n_chrom=%d out of range", m->n_chrom);
   MATCHA_REQUIRE(m->params && m->derived, "params / derived buffers missing");
   MATCHA_REQUIRE(m->attr_dim >= 1 && m->attr_table, "attribute table missing");
+  const bool csr = model_uses_csr(m);
   for (int c = 0; c < m->n_chrom; ++c) {
-    if (!m->feat[c]) {
-      set_error("chromosome %d: dense feature rows missing (CSR-only features are not wired into this entry point)", c);
+    const bool has_csr = m->feat_indptr[c] && m->feat_indices[c] && m->feat_values[c];
+    if (csr ? (m->feat[c] || !has_csr) : !m->feat[c]) {
+      set_error("chromosome %d: feature rows must be all dense or all CSR", c);
       return MATCHA_ERR_UNSUPPORTED;
     }
   }
@@ -427,11 +429,16 @@ static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   if ((rc = PROF(P_BUCKET, 3, launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s)))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(w.H0, 0, sizeof(float) * T * kD, s), "memset H0"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * kD, s), "memset E"))) return rc;
-  GemmDesc d = gemm_base(FORM_NT, 0, kD, 0, nullptr, 0, nullptr, 0, w.H0, kD);
-  d.perm = w.perm; d.a_ids = x; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, TAB_ENC0);
-  d.group_off = w.group_off; d.total_rows = T; d.epi_act = 1;
-  if (training && m->p_feature > 0.f) { d.drop_on = 1; d.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
-  if ((rc = run_gemm(d, s, P_ENC0))) return rc;
+  if (model_uses_csr(m)) {
+    const DropCfg fd = make_drop(seed, SITE_FEATURE, m->p_feature, training != 0);
+    if ((rc = PROF(P_ENC0, 1, launch_enc0_csr_fwd(m, derived_layout().total, x, w.perm, w.group_off, w.H0, fd, s)))) return rc;
+  } else {
+    GemmDesc d = gemm_base(FORM_NT, 0, kD, 0, nullptr, 0, nullptr, 0, w.H0, kD);
+    d.perm = w.perm; d.a_ids = x; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, TAB_ENC0);
+    d.group_off = w.group_off; d.total_rows = T; d.epi_act = 1;
+    if (training && m->p_feature > 0.f) { d.drop_on = 1; d.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
+    if ((rc = run_gemm(d, s, P_ENC0))) return rc;
+  }
   GemmDesc e = gemm_base(FORM_NT, 0, kD, kD, w.H0, kD, nullptr, 0, E_out, kD);
   e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, TAB_ENC1);
   e.group_off = w.group_off; e.total_rows = T;
@@ -524,10 +531,14 @@ void matcha_set_fused(int32_t on) { g_fused = on != 0; }
 void matcha_set_chain(int32_t on) { g_chain = on != 0; }
 int matcha_version(void) { return 100; }
 
-int64_t matcha_derived_elems(const matcha_model_desc* m) {
-  (void)m;
-  return derived_layout().total;
+// CSR models keep W0T_c [n_c, 64] (and, in derived_grad, its gradient) after the fixed-size part
+static int64_t w0t_floats(const matcha_model_desc* m) {
+  if (!m || !model_uses_csr(m)) return 0;
+  int64_t n = 0;
+  for (int c = 0; c < m->n_chrom; ++c) n += (m->chrom_end[c] - m->chrom_start[c]) * kD;
+  return n;
 }
+int64_t matcha_derived_elems(const matcha_model_desc* m) { return derived_layout().total + w0t_floats(m); }
 
 int64_t matcha_workspace_bytes(const matcha_model_desc* m, int64_t B, int32_t L, int32_t training) {
   if (!m || B < 0 || L < 1) return -1;
@@ -558,6 +569,7 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
     if ((rc = launch_split_w64(m->params + m->off_pff_w0, wc + CW_PFF0_K * st, wc + CW_PFF0_MN * st, s))) return rc;
     if ((rc = launch_split_w64(m->params + m->off_pff_w1, wc + CW_PFF1_K * st, wc + CW_PFF1_MN * st, s))) return rc;
   }
+  if (model_uses_csr(m) && (rc = launch_csr_prepare(m, l.total, s))) return rc;
   prof_end(P_PREP, 10, s);
   return MATCHA_OK;
 }
@@ -756,11 +768,17 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, TAB_ENC1); e.group_off = w.group_off;
     e.total_rows = T; e.epi_act = 2; e.aux = w.H0; e.ld_aux = kD;
     if ((rc = run_gemm(e, s, P_D_ENC1))) return rc;
-    GemmDesc f = gemm_base(FORM_TN, kD, 0, 0, w.dH0pre, kD, nullptr, 0, nullptr, 0);
-    f.perm = w.perm; f.b_ids = x; f.ngroups = m->n_chrom; f.groups = table_ptr(m->derived, TAB_GW0);
-    f.group_off = w.group_off; f.total_rows = T; f.max_group_dim = max_chrom_len(m);
-    if (m->p_feature > 0.f) { f.drop_on = 2; f.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
-    if ((rc = run_gemm(f, s, P_W_ENC0))) return rc;
+    if (model_uses_csr(m)) {
+      if ((rc = check_cuda(cudaMemsetAsync(DG + l.total, 0, sizeof(float) * w0t_floats(m), s), "memset dW0T"))) return rc;
+      if ((rc = PROF(P_W_ENC0, 2, launch_enc0_csr_wgrad(m, l.total, x, w.perm, w.group_off, w.dH0pre,
+                                                        make_drop(seed, SITE_FEATURE, m->p_feature, true), s)))) return rc;
+    } else {
+      GemmDesc f = gemm_base(FORM_TN, kD, 0, 0, w.dH0pre, kD, nullptr, 0, nullptr, 0);
+      f.perm = w.perm; f.b_ids = x; f.ngroups = m->n_chrom; f.groups = table_ptr(m->derived, TAB_GW0);
+      f.group_off = w.group_off; f.total_rows = T; f.max_group_dim = max_chrom_len(m);
+      if (m->p_feature > 0.f) { f.drop_on = 2; f.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
+      if ((rc = run_gemm(f, s, P_W_ENC0))) return rc;
+    }
   }
   // derived -> reference parameters
   prof_begin(P_PREP_BWD, s);

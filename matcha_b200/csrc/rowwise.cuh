@@ -115,6 +115,16 @@ int launch_wgrad_pair(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, c
                       float* scratch, float* w1, int ld1, int n1, float* bias1, float* w2, int ld2, int n2, float* bias2,
                       cudaStream_t s);
 
+// CSR first encoder layer (csr_encoder.cu): feature rows given as CSR (feat[c] == NULL, feat_indptr/indices/values set).
+// W0T_c [n_c, 64] copies live in the derived buffer from float offset w0t_base (chromosome after chromosome); the same
+// offsets of derived_grad accumulate dW0T_c.
+bool model_uses_csr(const matcha_model_desc* m);
+int launch_csr_prepare(const matcha_model_desc* m, int64_t w0t_base, cudaStream_t s);
+int launch_enc0_csr_fwd(const matcha_model_desc* m, int64_t w0t_base, const int64_t* x, const int32_t* perm,
+                        const int32_t* group_off, float* H0, DropCfg drop, cudaStream_t s);
+int launch_enc0_csr_wgrad(const matcha_model_desc* m, int64_t w0t_base, const int64_t* x, const int32_t* perm,
+                          const int32_t* group_off, const float* dH0pre, DropCfg drop, cudaStream_t s);
+
 // tcgen05 tile kernels (qkg_tiles.cu)
 int launch_split_wT(const float* W, void* out, cudaStream_t s);     // W [1536, 64] fp32 -> MN-major chunks for the dgrad
 int tc_qkg_forward_tiles(const uint8_t* xhat_tiles, const uint8_t* w_split, const float* bias, float* QKG, int64_t T,

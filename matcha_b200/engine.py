@@ -125,11 +125,20 @@ class Engine:
             desc.chrom_start[c], desc.chrom_end[c] = int(cr[c, 0]), int(cr[c, 1])
             desc.off_w0[c], desc.off_w1[c], desc.off_rw[c], desc.off_rb[c] = (pos[id(p)] for p in grp)
             emb = ne.embeddings[c]
-            if getattr(emb, "sparse", False):
-                raise MatchaError("CSR feature rows: use matcha_b200.encoder_csr for the encoder; the fused "
-                                  "Classifier path takes dense rows")
-            f = emb.embedding.to(dev, torch.float32)
             n_c = int(cr[c, 1] - cr[c, 0])
+            if getattr(emb, "sparse", False):
+                # CSR feature rows (Modules.py:58-65, sparse=True): uploaded as CSR, consumed by the SpMM encoder kernels
+                csr = emb.embedding.tocsr()
+                if csr.shape[0] != n_c:
+                    raise MatchaError(f"chromosome {c}: CSR feature table {csr.shape} does not match {n_c} bins")
+                indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(dev)
+                indices = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(dev)
+                values = torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float32)).to(dev)
+                self._keep += [indptr, indices, values]
+                desc.feat[c], desc.feat_ld[c] = None, 0
+                desc.feat_indptr[c], desc.feat_indices[c], desc.feat_values[c] = indptr.data_ptr(), indices.data_ptr(), values.data_ptr()
+                continue
+            f = emb.embedding.to(dev, torch.float32)
             if f.shape != (n_c, n_c) and f.shape[0] != n_c:
                 raise MatchaError(f"chromosome {c}: feature table {tuple(f.shape)} does not match {n_c} bins")
             ld = (f.shape[1] + 3) // 4 * 4        # 16-byte aligned rows for 128-bit loads

@@ -11,13 +11,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def model_from_golden(g, d=64):
+def model_from_golden(g, d=64, feats=None, sparse=False):
+    """feats / sparse: override the per-chromosome feature tables (e.g. scipy CSR matrices with sparse=True)."""
     from matcha_b200 import hyper_sagnn as M
     cr = g["chrom_range"]
     nums = [int(v) for v in g["nums"]]
-    feats = [g[f"feat/{c}"] for c in range(len(nums))]
+    if feats is None:
+        feats = [g[f"feat/{c}"] for c in range(len(nums))]
     torch.manual_seed(0)
-    ne = M.MultipleEmbedding(feats, d, False, np.cumsum(nums), cr, None)
+    ne = M.MultipleEmbedding(feats, d, sparse, np.cumsum(nums), cr, None)
     ne.inter_initial = M.SparseEmbedding(g["inter"], False)       # already z-scored by the reference
     model = M.Classifier(n_head=8, d_model=d, d_k=d, d_v=d, node_embedding=ne, diag_mask=True, bottle_neck=d,
                          attribute_dict=g["p/attribute_dict_embedding.weight"])

@@ -550,3 +550,47 @@ def test_pair_scorer_tensor_core_matches_simt(n, min_dis):
                                                    L.stream_ptr()), "tc")
             torch.cuda.synchronize()
             np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=5e-5)
+
+
+def test_csr_encoder_matches_dense_rows(golden, monkeypatch):
+    """SparseEmbedding(sparse=True) (Modules.py:58-65): the CSR SpMM encoder kernels (forward, weight gradient, feature
+    dropout on the nonzeros) vs the dense-row path on the SAME thresholded feature matrices: embeddings, eval logits, and
+    every gradient of a training step with dropout on."""
+    import scipy.sparse as sp
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([1]))
+    nchrom = len(golden["nums"])
+    dense = []
+    for c in range(nchrom):
+        f = np.array(golden[f"feat/{c}"], dtype=np.float32)
+        f[np.abs(f) < 0.35] = 0.0                      # genuinely sparse rows (some of them empty)
+        dense.append(f)
+    B, L = 400, 5
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(_random_hyperedges(golden, B, L, seed=99)).cuda()
+    y = torch.from_numpy((rng.random((B, 1)) < 0.3).astype("float32")).cuda()
+    w = torch.from_numpy(rng.uniform(0.5, 3, (B, 1)).astype("float32")).cuda()
+    res = {}
+    for kind in ("dense", "csr"):
+        feats = dense if kind == "dense" else [sp.csr_matrix(f) for f in dense]
+        model = model_from_golden(golden, feats=feats, sparse=(kind == "csr"))
+        model.eval()
+        N = int(golden["chrom_range"][-1][1]) - 1
+        with torch.no_grad():
+            emb = model.get_node_embeddings(torch.arange(1, N + 1, device="cuda").view(-1, 1)).cpu().numpy()
+            ev = model(x).cpu().numpy()
+        model.train()
+        eng = model._engine()
+        eng.seed_base = 55
+        eng.tape_id = 0
+        pred, rl = model(x, return_recon=True)
+        (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.1 * rl.sum()).backward()
+        res[kind] = (emb, ev, pred.detach().cpu().numpy(),
+                     {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None})
+    np.testing.assert_allclose(res["csr"][0], res["dense"][0], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(res["csr"][1], res["dense"][1], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(res["csr"][2], res["dense"][2], rtol=1e-4, atol=5e-5)
+    assert res["csr"][3].keys() == res["dense"][3].keys()
+    for k, g0 in res["dense"][3].items():
+        g1 = res["csr"][3][k]
+        scale = float(np.abs(g0).max())
+        assert float(np.abs(g1 - g0).max()) <= 5e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
