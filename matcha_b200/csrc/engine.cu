@@ -431,7 +431,7 @@ static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * kD, s), "memset E"))) return rc;
   if (model_uses_csr(m)) {
     const DropCfg fd = make_drop(seed, SITE_FEATURE, m->p_feature, training != 0);
-    if ((rc = PROF(P_ENC0, 1, launch_enc0_csr_fwd(m, derived_layout().total, x, w.perm, w.group_off, w.H0, fd, s)))) return rc;
+    if ((rc = PROF(P_ENC0, 1, launch_enc0_csr_fwd(m, derived_layout().total, x, T, w.perm, w.group_off, w.H0, fd, s)))) return rc;
   } else {
     GemmDesc d = gemm_base(FORM_NT, 0, kD, 0, nullptr, 0, nullptr, 0, w.H0, kD);
     d.perm = w.perm; d.a_ids = x; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, TAB_ENC0);
@@ -770,7 +770,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     if ((rc = run_gemm(e, s, P_D_ENC1))) return rc;
     if (model_uses_csr(m)) {
       if ((rc = check_cuda(cudaMemsetAsync(DG + l.total, 0, sizeof(float) * w0t_floats(m), s), "memset dW0T"))) return rc;
-      if ((rc = PROF(P_W_ENC0, 2, launch_enc0_csr_wgrad(m, l.total, x, w.perm, w.group_off, w.dH0pre,
+      if ((rc = PROF(P_W_ENC0, 2, launch_enc0_csr_wgrad(m, l.total, x, T, w.perm, w.group_off, w.dH0pre,
                                                         make_drop(seed, SITE_FEATURE, m->p_feature, true), s)))) return rc;
     } else {
       GemmDesc f = gemm_base(FORM_TN, kD, 0, 0, w.dH0pre, kD, nullptr, 0, nullptr, 0);

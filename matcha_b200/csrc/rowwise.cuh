@@ -120,9 +120,9 @@ int launch_wgrad_pair(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, c
 // offsets of derived_grad accumulate dW0T_c.
 bool model_uses_csr(const matcha_model_desc* m);
 int launch_csr_prepare(const matcha_model_desc* m, int64_t w0t_base, cudaStream_t s);
-int launch_enc0_csr_fwd(const matcha_model_desc* m, int64_t w0t_base, const int64_t* x, const int32_t* perm,
+int launch_enc0_csr_fwd(const matcha_model_desc* m, int64_t w0t_base, const int64_t* x, int64_t T, const int32_t* perm,
                         const int32_t* group_off, float* H0, DropCfg drop, cudaStream_t s);
-int launch_enc0_csr_wgrad(const matcha_model_desc* m, int64_t w0t_base, const int64_t* x, const int32_t* perm,
+int launch_enc0_csr_wgrad(const matcha_model_desc* m, int64_t w0t_base, const int64_t* x, int64_t T, const int32_t* perm,
                           const int32_t* group_off, const float* dH0pre, DropCfg drop, cudaStream_t s);
 
 // tcgen05 tile kernels (qkg_tiles.cu)
