@@ -15,8 +15,9 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmatcha_b200.so")
 SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+NVCC_COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                      "-Xcompiler", "-fPIC"]
+NVCC_LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
 MAX_CHROM = 64
 
 _lock = threading.Lock()
@@ -28,24 +29,47 @@ class MatchaError(RuntimeError):
 
 
 def _newest_source_mtime() -> float:
-    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "matcha_b200.h")]
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + [os.path.join(ROOT, "include", "matcha_b200.h")]
     return max(os.path.getmtime(p) for p in paths)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into matcha_b200/libmatcha_b200.so (nvcc cross-compiles
-    without a GPU).  Skips the build when the library is newer than all sources."""
+    without a GPU).  One object per source under matcha_b200/build/, compiled in parallel and only when
+    older than the source tree's headers / its own source; skips everything when the library is current."""
     if (not force) and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_mtime = max([os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] +
+                    [os.path.getmtime(os.path.join(ROOT, "include", "matcha_b200.h"))])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        path = os.path.join(CSRC, src)
+        if (not force) and os.path.exists(obj) and os.path.getmtime(obj) >= max(hdr_mtime, os.path.getmtime(path)):
+            return obj, None
+        cmd = [nvcc] + NVCC_COMPILE_FLAGS + ["-c", "-o", obj, path]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, (res.stdout + res.stderr) if res.returncode != 0 else None
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    errs = [e for _, e in results if e]
+    if errs:
+        raise MatchaError("nvcc failed:\n" + "\n".join(errs))
+    cmd = [nvcc] + NVCC_LINK_FLAGS + ["-o", LIB_PATH] + [o for o, _ in results]
     if verbose:
-        print(" ".join(cmd))
+        print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise MatchaError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise MatchaError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

@@ -6,8 +6,8 @@
 // the kernel from the FMA pipe to the HBM write roofline (4 bytes per pair).
 //   prepare : D, S, w -> PA / PB as pre-split bf16 hi | lo blocks of 128 nodes in the canonical UMMA layout, and u
 //   score   : persistent CTAs over the upper-triangular tile list; warp 0 bulk-copies operand blocks, warp 1 issues the
-//             MMAs, two epilogue warpgroups drain alternate TMEM stages, transpose 16-column chunks through shared
-//             memory so that every store instruction writes contiguous runs of the packed row-major pair order
+//             MMAs of the TRANSPOSED tile (TMEM lane = column node), two epilogue warpgroups drain alternate TMEM stages
+//             and store straight from registers: one store instruction = 128 contiguous bytes of a packed output row
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -20,10 +20,9 @@ constexpr int kPD = 64;
 // the accumulator already holds t = -log2(e) * logit and the epilogue is ex2 / add / rcp / store.
 constexpr int kPHi = 18 * 2048;
 constexpr int kPBlk = kPHi + 16 * 2048;      // 69632
-constexpr int kPThreads = 320;
-constexpr int kPStageRow = 20;               // floats per staged row (16 + 4 pad)
-constexpr int kPStageWarp = 32 * kPStageRow;
-constexpr int kPSmem = 3 * kPBlk + 8 * kPStageWarp * 4;      // A + 2 x B + staging = 229 376
+constexpr int kPStages = 4;                  // TMEM accumulator stages = epilogue warpgroups
+constexpr int kPThreads = 64 + kPStages * 128;
+constexpr int kPSmem = 3 * kPBlk;            // A + 2 x B = 208 896
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -120,14 +119,14 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sAop = smem;
   uint8_t* sBop = smem + kPBlk;
-  float* sStage = reinterpret_cast<float*>(smem + 3 * kPBlk);
-  __shared__ uint64_t a_full, a_empty, b_full[2], b_empty[2], acc_full[2], acc_empty[2];
+  __shared__ uint64_t a_full, a_empty, b_full[2], b_empty[2], acc_full[kPStages], acc_empty[kPStages];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) tmem_alloc(&tmem_base_s, kPStages * 128);
   if (tid == 32) {
     mbar_init(&a_full, 1); mbar_init(&a_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < kPStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -166,19 +165,19 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
       const uint32_t ah = smem_u32(sAop), al = ah + kPHi;
       for (int64_t f = f0, k = 0; f < f1; ++f, ++k) {
         if (ti != cur_ti) { mbar_wait_backoff(&a_full, (uint32_t)(na & 1)); cur_ti = ti; ++na; }
-        const int s = (int)(k & 1);
+        const int s = (int)(k & 1), as = (int)(k & (kPStages - 1));
         mbar_wait_backoff(&b_full[s], (uint32_t)((k >> 1) & 1));
-        mbar_wait_backoff(&acc_empty[s], (uint32_t)((k >> 1) & 1) ^ 1u);
+        mbar_wait_backoff(&acc_empty[as], (uint32_t)((k / kPStages) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t bh = smem_u32(sBop + s * kPBlk), bl = bh + kPHi;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          umma_x3s(tmem_base + s * 128, ah + ks * 4096, al + ks * 4096, bh + ks * 4096, bl + ks * 4096, 2048, 128, 2048, 128,
-                   idesc, ks == 0);
+          umma_x3s(tmem_base + as * 128, bh + ks * 4096, bl + ks * 4096, ah + ks * 4096, al + ks * 4096, 2048, 128, 2048, 128,
+                   idesc, ks == 0);      // D[j, i]: the column-node block is the M-side operand
         // k 128..143: the u / bias pieces (exact in bf16), hi * hi pass only
-        umma_bf16(tmem_base + s * 128, make_smem_desc(ah + 8 * 4096, 2048, 128), make_smem_desc(bh + 8 * 4096, 2048, 128), idesc, 1u);
+        umma_bf16(tmem_base + as * 128, make_smem_desc(bh + 8 * 4096, 2048, 128), make_smem_desc(ah + 8 * 4096, 2048, 128), idesc, 1u);
         umma_commit(&b_empty[s]);
-        umma_commit(&acc_full[s]);
+        umma_commit(&acc_full[as]);
         int64_t nti = ti, ntj = tj + 1;
         if (ntj >= a.nb) { ++nti; ntj = nti + a.bmd; }
         if (nti != ti || f + 1 >= f1) umma_commit(&a_empty);      // last tile that reads this A block
@@ -186,68 +185,87 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
       }
     }
   } else if (f0 < f1) {
+    // The accumulator is the TRANSPOSED tile: TMEM lane = column node j, TMEM column = row node i.  The thread that owns
+    // lane j therefore holds 32 consecutive rows i in its registers, and one store instruction of the warp (fixed register,
+    // 32 lanes) writes 32 consecutive j of one packed output row: a contiguous 128-byte run, straight from registers.
+    // Four epilogue warpgroups <-> four TMEM stages: while one group is held back by the HBM-bound store queue, another is
+    // reading TMEM and the tensor pipe runs ahead on the remaining stages.
     const int grp = (warp - 2) >> 2, q = warp & 3;          // epilogue warpgroup <-> TMEM stage; lane quarter
-    float* stage = sStage + (warp - 2) * kPStageWarp;
     int64_t ti, tj;
     flat_to_tile(f0, a.nb, a.bmd, ti, tj);
+    const int64_t full = a.n - a.md;
+    const int64_t plen = a.p_end - a.p_begin;
+    float* const out = a.out;
+    const bool sig = a.apply_sigmoid != 0;
     for (int64_t f = f0, k = 0; f < f1; ++f, ++k) {
-      if ((int)(k & 1) == grp) {
-        mbar_wait(&acc_full[grp], (uint32_t)((k >> 1) & 1));
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 128;
-        const int cc = lane & 15, half = lane >> 4;
-        const int64_t full = a.n - a.md;
-        const int64_t i_first = ti * 128 + q * 32, j_first = tj * 128;
-        // interior tile: every (i, j) of this warp's 32 x 128 slab is a valid pair inside [p_begin, p_end) -> no checks
-        const int64_t i_last = i_first + 31, j_last = j_first + 127;
-        const bool interior = i_last < a.n && j_last < a.n && j_first >= i_last + a.md &&
-                              tri_prefix(i_first, a.n, a.md) - (i_first + a.md) + j_first >= a.p_begin &&
+      if ((int)(k & (kPStages - 1)) == grp) {
+        const int64_t i_first = ti * 128, i_last = i_first + 127;
+        const int64_t j_first = tj * 128 + q * 32, j_last = j_first + 31, j = j_first + lane;
+        // p(i, j) = rowbase(i) + j,  rowbase(i + 1) - rowbase(i) = full - i - 1 for every row that holds pairs
+        const int64_t p00 = tri_prefix(i_first, a.n, a.md) - (i_first + a.md) - a.p_begin;
+        // interior slab: every (i, j) is a valid pair inside [p_begin, p_end) -> no per-element checks
+        const bool interior = i_last < a.n && j_last < a.n && j_first >= i_last + a.md && p00 + j_first >= 0 &&
                               tri_prefix(i_last, a.n, a.md) - (i_last + a.md) + j_last < a.p_end;
+        int64_t p = p00 + j;
+        int64_t stride = full - i_first - 1;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 128;
+        mbar_wait(&acc_full[grp], (uint32_t)((k / kPStages) & 1));
+        tc_fence_after();
+        auto emit = [&](const uint32_t (&cur)[32]) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float t = __uint_as_float(cur[c]);                      // -log2(e) * logit
+            out[p] = sig ? fast_rcp(1.0f + fast_ex2(t)) : -kLn2 * t;
+            p += stride;
+            --stride;
+          }
+        };
+        if (interior) {
+          uint32_t va[32], vb[32];
+          tmem_ld32_issue(taddr, va);
 #pragma unroll 1
-        for (int ch = 0; ch < 8; ++ch) {
-          float v[16];
-          tmem_ld16(taddr + ch * 16, v);
-#pragma unroll
-          for (int c4 = 0; c4 < 16; c4 += 4)
-            *reinterpret_cast<float4*>(stage + lane * kPStageRow + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);
-          __syncwarp();
-          const int64_t j = j_first + ch * 16 + cc;
-          if (interior) {
-            // p(i, j) = rowbase(i) + j with rowbase(i + 1) - rowbase(i) = full - i - 1: two rows per iteration
-            const int64_t i0 = i_first + half;
-            float* dst = a.out + (tri_prefix(i0, a.n, a.md) - (i0 + a.md) + j - a.p_begin);
-            int64_t stride = 2 * (full - i0) - 3;      // rowbase(i + 2) - rowbase(i), shrinking by 4 per iteration
-#pragma unroll
-            for (int it = 0; it < 16; ++it) {
-              const float t = stage[(it * 2 + half) * kPStageRow + cc];          // -log2(e) * logit
-              *dst = a.apply_sigmoid ? fast_rcp(1.0f + fast_ex2(t)) : -kLn2 * t;
-              dst += stride;
-              stride -= 4;
+          for (int half = 0; half < 2; ++half) {     // not unrolled: the fully unrolled epilogue overflowed the instruction cache
+            tmem_ld_wait(va);
+            tmem_ld32_issue(taddr + half * 64 + 32, vb);
+            emit(va);
+            tmem_ld_wait(vb);
+            if (half == 0) {
+              tmem_ld32_issue(taddr + 64, va);
+            } else {                    // the whole slab is in registers: hand the TMEM stage back before the last stores
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&acc_empty[grp]);
             }
-          } else {
-#pragma unroll 4
-            for (int it = 0; it < 16; ++it) {
-              const int rr = it * 2 + half;
-              const float t = stage[rr * kPStageRow + cc];
-              const int64_t i = i_first + rr;
-              if (i < a.n && j < a.n && j >= i + a.md) {
-                const int64_t p = tri_prefix(i, a.n, a.md) - (i + a.md) + j;
-                if (p >= a.p_begin && p < a.p_end) a.out[p - a.p_begin] = a.apply_sigmoid ? fast_rcp(1.0f + fast_ex2(t)) : -kLn2 * t;
-              }
+            emit(vb);
+          }
+        } else {
+          // diagonal / range-boundary slab: per-element checks, compact code (8 columns at a time)
+          const bool j_ok = j < a.n;
+#pragma unroll 1
+          for (int ch = 0; ch < 16; ++ch) {
+            uint32_t v[8];
+            tmem_ld8_issue(taddr + ch * 8, v);
+            tmem_ld_wait(v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int64_t i = i_first + ch * 8 + c;
+              const float t = __uint_as_float(v[c]);
+              if (j_ok && j >= i + a.md && (uint64_t)p < (uint64_t)plen) out[p] = sig ? fast_rcp(1.0f + fast_ex2(t)) : -kLn2 * t;
+              p += stride;
+              --stride;
             }
           }
+          tc_fence_before();
           __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[grp]);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[grp]);
       }
       if (++tj >= a.nb) { ++ti; tj = ti + a.bmd; }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, kPStages * 128);
 }
 
 }  // namespace
