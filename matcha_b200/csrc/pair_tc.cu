@@ -8,6 +8,8 @@
 //   score   : persistent CTAs over the upper-triangular tile list; warp 0 bulk-copies operand blocks, warp 1 issues the
 //             MMAs of the TRANSPOSED tile (TMEM lane = column node), two epilogue warpgroups drain alternate TMEM stages
 //             and store straight from registers: one store instruction = 128 contiguous bytes of a packed output row
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -106,6 +108,7 @@ struct PairArgs {
   int64_t p_begin, p_end;
   int apply_sigmoid;
   float* out;
+  int chunk;                                       // consecutive tiles per CTA visit (see pair_tc_kernel)
 };
 
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -133,55 +136,72 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  // contiguous share of the flat tile list (row-major, so the A block changes rarely)
-  const int64_t total = a.f_end - a.f_begin;
-  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
-  const int64_t f0 = a.f_begin + (int64_t)blockIdx.x * per;
-  const int64_t f1 = (f0 + per < a.f_end) ? f0 + per : a.f_end;
+  // Work distribution: the flat (row-major) tile list is cut into chunks of a.chunk consecutive tiles, dealt round-robin to
+  // the CTAs.  At any moment the whole grid therefore writes inside a window of gridDim.x * chunk tiles = a few tile rows
+  // (a few hundred output rows, each receiving long contiguous runs) instead of 148 x 128 unrelated output rows: the
+  // HBM write stream stays page-local.  The row block (A) is reloaded per chunk; the operand tables live in L2.
+  const int64_t G = a.chunk;
+  const int64_t nchunks = (a.f_end - a.f_begin + G - 1) / G;
+  const int64_t my_chunks = ((int64_t)blockIdx.x < nchunks) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t f0 = 0, f1 = my_chunks;          // (kept for the role guards below)
+  auto chunk_begin = [&](int64_t c) { return a.f_begin + ((int64_t)blockIdx.x + c * gridDim.x) * G; };
+  auto chunk_end = [&](int64_t c) { const int64_t e = chunk_begin(c) + G; return e < a.f_end ? e : a.f_end; };
 
   if (warp == 0) {
     if (lane == 0 && f0 < f1) {
-      int64_t ti, tj, cur_ti = -1, na = 0;
-      flat_to_tile(f0, a.nb, a.bmd, ti, tj);
-      for (int64_t f = f0, k = 0; f < f1; ++f, ++k) {
-        if (ti != cur_ti) {
-          mbar_wait_backoff(&a_empty, (uint32_t)(na & 1) ^ 1u);
-          mbar_expect_tx(&a_full, kPBlk);
-          bulk_g2s(sAop, a.PA + ti * (int64_t)kPBlk, kPBlk, &a_full);
-          cur_ti = ti; ++na;
+      int64_t ti, tj, cur_ti = -1, na = 0, k = 0;
+      for (int64_t c = 0; c < my_chunks; ++c) {
+        flat_to_tile(chunk_begin(c), a.nb, a.bmd, ti, tj);
+        cur_ti = -1;                                  // the row block is (re)loaded at every chunk start
+        for (int64_t f = chunk_begin(c); f < chunk_end(c); ++f, ++k) {
+          if (ti != cur_ti) {
+            mbar_wait_backoff(&a_empty, (uint32_t)(na & 1) ^ 1u);
+            mbar_expect_tx(&a_full, kPBlk);
+            bulk_g2s(sAop, a.PA + ti * (int64_t)kPBlk, kPBlk, &a_full);
+            cur_ti = ti; ++na;
+          }
+          const int s = (int)(k & 1);
+          mbar_wait_backoff(&b_empty[s], (uint32_t)((k >> 1) & 1) ^ 1u);
+          mbar_expect_tx(&b_full[s], kPBlk);
+          bulk_g2s(sBop + s * kPBlk, a.PB + tj * (int64_t)kPBlk, kPBlk, &b_full[s]);
+          if (++tj >= a.nb) { ++ti; tj = ti + a.bmd; }
         }
-        const int s = (int)(k & 1);
-        mbar_wait_backoff(&b_empty[s], (uint32_t)((k >> 1) & 1) ^ 1u);
-        mbar_expect_tx(&b_full[s], kPBlk);
-        bulk_g2s(sBop + s * kPBlk, a.PB + tj * (int64_t)kPBlk, kPBlk, &b_full[s]);
-        if (++tj >= a.nb) { ++ti; tj = ti + a.bmd; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && f0 < f1) {
       constexpr uint32_t idesc = make_idesc(128, 128, false, false);
-      int64_t ti, tj, cur_ti = -1, na = 0;
-      flat_to_tile(f0, a.nb, a.bmd, ti, tj);
-      const uint32_t ah = smem_u32(sAop), al = ah + kPHi;
-      for (int64_t f = f0, k = 0; f < f1; ++f, ++k) {
-        if (ti != cur_ti) { mbar_wait_backoff(&a_full, (uint32_t)(na & 1)); cur_ti = ti; ++na; }
-        const int s = (int)(k & 1), as = (int)(k & (kPStages - 1));
-        mbar_wait_backoff(&b_full[s], (uint32_t)((k >> 1) & 1));
-        mbar_wait_backoff(&acc_empty[as], (uint32_t)((k / kPStages) & 1) ^ 1u);
-        tc_fence_after();
-        const uint32_t bh = smem_u32(sBop + s * kPBlk), bl = bh + kPHi;
+      int64_t ti, tj, cur_ti = -1, na = 0, k = 0;
+      // descriptors are built once: advancing an operand by one k-step (4096 B) adds 256 to the 16-byte address field
+      const uint64_t dah = make_smem_desc(smem_u32(sAop), 2048, 128), dal = make_smem_desc(smem_u32(sAop) + kPHi, 2048, 128);
+      for (int64_t c = 0; c < my_chunks; ++c) {
+        flat_to_tile(chunk_begin(c), a.nb, a.bmd, ti, tj);
+        const int64_t fe = chunk_end(c);
+        for (int64_t f = chunk_begin(c); f < fe; ++f, ++k) {
+          if (ti != cur_ti) { mbar_wait(&a_full, (uint32_t)(na & 1)); cur_ti = ti; ++na; }
+          const int s = (int)(k & 1), as = (int)(k & (kPStages - 1));
+          mbar_wait(&b_full[s], (uint32_t)((k >> 1) & 1));
+          mbar_wait(&acc_empty[as], (uint32_t)((k / kPStages) & 1) ^ 1u);
+          tc_fence_after();
+          const uint64_t dbh = make_smem_desc(smem_u32(sBop + s * kPBlk), 2048, 128);
+          const uint64_t dbl = make_smem_desc(smem_u32(sBop + s * kPBlk) + kPHi, 2048, 128);
+          const uint32_t acc = tmem_base + as * 128;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_x3s(tmem_base + as * 128, bh + ks * 4096, bl + ks * 4096, ah + ks * 4096, al + ks * 4096, 2048, 128, 2048, 128,
-                   idesc, ks == 0);      // D[j, i]: the column-node block is the M-side operand
-        // k 128..143: the u / bias pieces (exact in bf16), hi * hi pass only
-        umma_bf16(tmem_base + as * 128, make_smem_desc(bh + 8 * 4096, 2048, 128), make_smem_desc(ah + 8 * 4096, 2048, 128), idesc, 1u);
-        umma_commit(&b_empty[s]);
-        umma_commit(&acc_full[as]);
-        int64_t nti = ti, ntj = tj + 1;
-        if (ntj >= a.nb) { ++nti; ntj = nti + a.bmd; }
-        if (nti != ti || f + 1 >= f1) umma_commit(&a_empty);      // last tile that reads this A block
-        ti = nti; tj = ntj;
+          for (int ks = 0; ks < 8; ++ks) {      // D[j, i]: the column-node block is the M-side operand; lo*hi + hi*lo + hi*hi
+            const uint64_t o = (uint64_t)(ks * 256);
+            umma_bf16(acc, dbl + o, dah + o, idesc, ks == 0 ? 0u : 1u);
+            umma_bf16(acc, dbh + o, dal + o, idesc, 1u);
+            umma_bf16(acc, dbh + o, dah + o, idesc, 1u);
+          }
+          // k 128..143: the u / bias pieces (exact in bf16), hi * hi pass only
+          umma_bf16(acc, dbh + 8 * 256, dah + 8 * 256, idesc, 1u);
+          umma_commit(&b_empty[s]);
+          umma_commit(&acc_full[as]);
+          int64_t nti = ti, ntj = tj + 1;
+          if (ntj >= a.nb) { ++nti; ntj = nti + a.bmd; }
+          if (nti != ti || f + 1 >= fe) { umma_commit(&a_empty); cur_ti = -1; }      // last tile of the chunk that reads this A block
+          ti = nti; tj = ntj;
+        }
       }
     }
   } else if (f0 < f1) {
@@ -191,13 +211,14 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
     // Four epilogue warpgroups <-> four TMEM stages: while one group is held back by the HBM-bound store queue, another is
     // reading TMEM and the tensor pipe runs ahead on the remaining stages.
     const int grp = (warp - 2) >> 2, q = warp & 3;          // epilogue warpgroup <-> TMEM stage; lane quarter
-    int64_t ti, tj;
-    flat_to_tile(f0, a.nb, a.bmd, ti, tj);
+    int64_t ti, tj, k = 0;
     const int64_t full = a.n - a.md;
     const int64_t plen = a.p_end - a.p_begin;
     float* const out = a.out;
     const bool sig = a.apply_sigmoid != 0;
-    for (int64_t f = f0, k = 0; f < f1; ++f, ++k) {
+    for (int64_t c = 0; c < my_chunks; ++c) {
+    flat_to_tile(chunk_begin(c), a.nb, a.bmd, ti, tj);
+    for (int64_t f = chunk_begin(c); f < chunk_end(c); ++f, ++k) {
       if ((int)(k & (kPStages - 1)) == grp) {
         const int64_t i_first = ti * 128, i_last = i_first + 127;
         const int64_t j_first = tj * 128 + q * 32, j_last = j_first + 31, j = j_first + lane;
@@ -262,6 +283,7 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
       }
       if (++tj >= a.nb) { ++ti; tj = ti + a.bmd; }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -318,6 +340,7 @@ int matcha_pair_tc_score_range(const void* workspace, int64_t lo, int64_t hi, in
   a.f_begin = tri_prefix(r0 / 128, nb, bmd);
   a.f_end = tri_prefix(r1 / 128 + 1, nb, bmd);
   a.p_begin = p_begin; a.p_end = p_end; a.apply_sigmoid = apply_sigmoid; a.out = out;
+  { const char* e = getenv("MATCHA_PAIR_CHUNK"); a.chunk = e ? atoi(e) : 4; if (a.chunk < 1) a.chunk = 1; }   // 4 measured best on B200 (sweep 1..130)
   if (a.f_end <= a.f_begin) return MATCHA_OK;
   static bool once = false;
   if (!once) {
