@@ -57,7 +57,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -288,7 +288,11 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        run(max(20, args.steps), False, 0)          # give nvidia-smi time to start sampling while the GPU is under the same load
     ms_dev, _ = timed(args.steps, False, warmup)                     # the reported value: no per-call-site events
+    if rank == 0:
+        run(max(20, args.steps), False, 0)
+        torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
     _, prof = timed(args.steps, False, warmup, profile=True)        # same steps again with CUDA events per call site
     run(2, True, 0)

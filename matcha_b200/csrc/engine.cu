@@ -281,7 +281,7 @@ __global__ void prep_bwd_g_kernel(const matcha_model_desc m) {
   __shared__ float sF[kD][kD + 1];    // fc1_h[o][mm]
   __shared__ float sV[kD][kD + 1];    // Wv_h[mm][c]
   __shared__ float sdb[kD], svb[kD], sfb[kD];  // db_dyn[o], (fc1_h^T db_dyn)[mm], (Wv_h b_v)[mm]
-  const int h = blockIdx.x, tid = threadIdx.x;
+  const int h = blockIdx.x >> 2, part = blockIdx.x & 3, tid = threadIdx.x;   // 4 blocks per head, 16 output rows each
   const float* dWg = m.derived_grad + l.wqkg + (int64_t)(2 * kH * kD + h * kD) * kD;
   for (int i = tid; i < kD * kD; i += blockDim.x) {
     const int a = i / kD, b = i % kD;
@@ -296,10 +296,10 @@ __global__ void prep_bwd_g_kernel(const matcha_model_desc m) {
     for (int o = 0; o < kD; ++o) s = fmaf(sF[o][tid], sdb[o], s);
     for (int c = 0; c < kD; ++c) s2 = fmaf(sV[tid][c], P[m.off_lnv_b + c], s2);
     svb[tid] = s; sfb[tid] = s2;
-    if (h == 0) atomicAdd(&G[m.off_fc1_b + tid], sdb[tid]);
+    if (blockIdx.x == 0) atomicAdd(&G[m.off_fc1_b + tid], sdb[tid]);
   }
   __syncthreads();
-  for (int i = tid; i < kD * kD; i += blockDim.x) {
+  for (int i = part * (kD * kD / 4) + tid; i < (part + 1) * (kD * kD / 4); i += blockDim.x) {
     const int a = i / kD, b = i % kD;
     // M_h[mm = a][c = b] = sum_o fc1_h[o][mm] dWg_h[o][c]
     float mh = 0.f;
@@ -784,7 +784,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   prof_begin(P_PREP_BWD, s);
   prep_bwd_qk_kernel<<<kD, 256, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_bwd_qk");
-  prep_bwd_g_kernel<<<kH, 256, 0, s>>>(*m);
+  prep_bwd_g_kernel<<<4 * kH, 256, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_bwd_g");
   prof_end(P_PREP_BWD, 2, s);
   if (active) {

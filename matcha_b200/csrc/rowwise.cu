@@ -97,18 +97,32 @@ __global__ void bucket_count_kernel(const int64_t* __restrict__ x, int64_t T, co
   for (int i = threadIdx.x; i <= cm.n; i += blockDim.x)
     if (h[i]) atomicAdd(&counts[i], h[i]);
 }
-__global__ void bucket_scan_kernel(const int32_t* counts, int n, int32_t* group_off, int32_t* cursor) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+// scan + scatter in one launch: every block derives the group offsets from the (complete) counts, histograms its own
+// contiguous token slice in shared memory, reserves one range per chromosome with a single global atomic, and places its
+// tokens with shared-memory atomics (82 k contended global atomics on ~23 cursors -> ~23 per block)
+__global__ void bucket_scatter_kernel(const int64_t* __restrict__ x, int64_t T, const ChromMeta cm, const int32_t* __restrict__ counts,
+                                      int32_t* __restrict__ group_off, int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+  __shared__ int32_t h[MATCHA_MAX_CHROM + 1], base[MATCHA_MAX_CHROM + 1];
+  for (int i = threadIdx.x; i <= cm.n; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const int64_t per = (T + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * per, t1 = (t0 + per < T) ? t0 + per : T;
+  for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) atomicAdd(&h[chrom_of(cm, x[t])], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
     int32_t acc = 0;
-    for (int c = 0; c < n; ++c) { group_off[c] = acc; cursor[c] = acc; acc += counts[c]; }
-    group_off[n] = acc;
+    for (int c = 0; c < cm.n; ++c) {
+      if (blockIdx.x == 0) group_off[c] = acc;
+      base[c] = h[c] ? acc + atomicAdd(&cursor[c], h[c]) : 0;       // cursor holds the per-chromosome fill (zeroed by the launcher)
+      h[c] = 0;
+      acc += counts[c];
+    }
+    if (blockIdx.x == 0) group_off[cm.n] = acc;
   }
-}
-__global__ void bucket_scatter_kernel(const int64_t* __restrict__ x, int64_t T, const ChromMeta cm, int32_t* cursor,
-                                      int32_t* perm) {
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
-    int c = chrom_of(cm, x[t]);
-    if (c < cm.n) perm[atomicAdd(&cursor[c], 1)] = (int32_t)t;
+  __syncthreads();
+  for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+    const int c = chrom_of(cm, x[t]);
+    if (c < cm.n) perm[base[c] + atomicAdd(&h[c], 1)] = (int32_t)t;
   }
 }
 __global__ void active_flags_kernel(const int32_t* counts, int n_chrom, int rchrom, int64_t T, int32_t* active) {
@@ -583,9 +597,8 @@ int launch_bucket(const int64_t* x, int64_t T, const ChromMeta& cm, int32_t* cou
   if (blocks > kSMs * 4) blocks = kSMs * 4;
   bucket_count_kernel<<<blocks, 256, 0, s>>>(x, T, cm, counts);
   MATCHA_CHECK_LAUNCH("bucket_count");
-  bucket_scan_kernel<<<1, 32, 0, s>>>(counts, cm.n, group_off, cursor);
-  MATCHA_CHECK_LAUNCH("bucket_scan");
-  bucket_scatter_kernel<<<blocks, 256, 0, s>>>(x, T, cm, cursor, perm);
+  if (int rc = check_cuda(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (cm.n + 1), s), "memset cursor")) return rc;
+  bucket_scatter_kernel<<<blocks, 256, 0, s>>>(x, T, cm, counts, group_off, cursor, perm);
   MATCHA_CHECK_LAUNCH("bucket_scatter");
   return MATCHA_OK;
 }
