@@ -76,7 +76,7 @@ static int gemm_impl() {
   }
   return g_gemm_impl;
 }
-static bool use_tiles(int64_t T) { return gemm_impl() == 1 && T >= kTilePathMinTokens; }
+static bool use_tiles(const matcha_model_desc* m, int64_t T) { return m->d == kD && gemm_impl() == 1 && T >= kTilePathMinTokens; }
 static int g_fused = -1;      // -1 = read MATCHA_FUSED on first use; 0 = decomposed pipeline; 1 = fused hyperedge-tile kernels
 static int fused_impl() {
   if (g_fused < 0) {
@@ -88,23 +88,23 @@ static int fused_impl() {
 // fused attention forward (eval and training) and backward: QKG and its gradient never leave the SM
 enum { CW_NEXT_K = 0, CW_NEXT_MN, CW_PFF0_K, CW_PFF0_MN, CW_PFF1_K, CW_PFF1_MN };
 static int g_chain = -1;      // row-chain kernels for the 64-wide layers (MATCHA_CHAIN=0 keeps the SIMT contractions)
-static bool use_fused(int64_t T, int L);
+static bool use_fused(const matcha_model_desc* m, int64_t T, int L);
 static bool use_chain(const matcha_model_desc* m, int64_t T, int L) {
   if (g_chain < 0) {
     const char* e = getenv("MATCHA_CHAIN");
     g_chain = (e && e[0] == '0') ? 0 : 1;
   }
-  return g_chain == 1 && use_fused(T, L) && m->attr_dim <= 32;
+  return g_chain == 1 && use_fused(m, T, L) && m->attr_dim <= 32;
 }
-static bool use_fused(int64_t T, int L) {
-  return fused_impl() == 1 && gemm_impl() == 1 && L >= 2 && L <= 6 && T >= kTilePathMinTokens;
+static bool use_fused(const matcha_model_desc* m, int64_t T, int L) {
+  return m->d == kD && fused_impl() == 1 && gemm_impl() == 1 && L >= 2 && L <= 6 && T >= kTilePathMinTokens;
 }
 
-static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
+static int run_gemm(const GemmDesc& d, cudaStream_t s, int label, bool allow_tc = true) {
   prof_begin(label, s);
   int rc = MATCHA_OK;
   bool handled = false;
-  if (gemm_impl() == 1) rc = launch_gemm_tc(d, s, &handled);
+  if (allow_tc && gemm_impl() == 1) rc = launch_gemm_tc(d, s, &handled);
   if (!rc && !handled) rc = launch_gemm_simt(d, s);
   prof_end(label, 1, s);
   return rc;
@@ -116,15 +116,16 @@ static int run_gemm(const GemmDesc& d, cudaStream_t s, int label) {
 struct DerivedLayout {
   int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, wheads, wpairs, wchain, tables, total;  // float offsets
 };
-static __host__ __device__ DerivedLayout derived_layout() {
+static __host__ __device__ DerivedLayout derived_layout(int D) {
   DerivedLayout l;
+  const int64_t QKG = 3 * kH * D;
   l.wqkg = 0;
-  l.bqkg = l.wqkg + (int64_t)kQKG * kD;
-  l.bdyn = l.bqkg + kQKG;
-  l.bdyn_part = l.bdyn + kD;        // per-head partial sums of b_dyn (summed in a fixed order: deterministic)
-  l.wsplit = (l.bdyn_part + kH * kD + 255) / 256 * 256;   // W_qkg pre-split to bf16 hi|lo chunks (same byte count)
-  l.wtsplit = l.wsplit + (int64_t)kQKG * kD;             // W_qkg^T pre-split, MN-major chunks (data-gradient B operand)
-  l.wheads = l.wtsplit + (int64_t)kQKG * kD;             // per-head [Q_h | K_h | G_h] chunks for the fused attention kernels
+  l.bqkg = l.wqkg + QKG * D;
+  l.bdyn = l.bqkg + QKG;
+  l.bdyn_part = l.bdyn + D;         // per-head partial sums of b_dyn (summed in a fixed order: deterministic)
+  l.wsplit = (l.bdyn_part + kH * D + 255) / 256 * 256;    // W_qkg pre-split to bf16 hi|lo chunks (same byte count)
+  l.wtsplit = l.wsplit + QKG * D;                        // W_qkg^T pre-split, MN-major chunks (data-gradient B operand)
+  l.wheads = l.wtsplit + QKG * D;                        // per-head [Q_h | K_h | G_h] chunks for the fused attention kernels
   l.wpairs = l.wheads + (int64_t)kH * kHeadWBytes / 4;   // per-head-pair G | K | Q piece pairs for the fused backward
   l.wchain = l.wpairs + (int64_t)4 * kPairWBytes / 4;    // next_w, pff_w0, pff_w1: K-major and MN-major pre-split copies
   l.tables = l.wchain + (int64_t)6 * kChainWBytes / 4;
@@ -134,8 +135,8 @@ static __host__ __device__ DerivedLayout derived_layout() {
   return l;
 }
 enum { TAB_ENC0 = 0, TAB_ENC1 = 1, TAB_GW1 = 2, TAB_GW0 = 3 };
-static __host__ __device__ const GemmGroup* table_ptr(const float* derived, int which) {
-  const DerivedLayout l = derived_layout();
+static __host__ __device__ const GemmGroup* table_ptr(const float* derived, int D, int which) {
+  const DerivedLayout l = derived_layout(D);
   const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
   return reinterpret_cast<const GemmGroup*>(derived + l.tables + which * table_floats);
 }
@@ -148,76 +149,75 @@ static __host__ __device__ const GemmGroup* table_ptr(const float* derived, int 
 //   b_dyn = fc1.bias + sum_h fc1_h Wv_h b_v        (softmax rows sum to 1)
 // ------------------------------------------------------------------------------------------
 __global__ void prep_qk_kernel(const matcha_model_desc m) {
-  const DerivedLayout l = derived_layout();
+  const int D = m.d;
+  const DerivedLayout l = derived_layout(D);
   const float* P = m.params;
   float* W = m.derived + l.wqkg;
   float* bq = m.derived + l.bqkg;
-  const float inv = rsqrtf((float)kD);
-  const int r = blockIdx.x;  // 0 .. 2*512-1
-  const int c = threadIdx.x; // 0 .. 63
-  if (r < kH * kD) {
-    const float w = P[m.off_wq + (int64_t)r * kD + c];
-    W[(int64_t)r * kD + c] = w * P[m.off_lnq_g + c] * inv;
+  const float inv = rsqrtf((float)D);
+  const int r = blockIdx.x;  // 0 .. 2*H*D-1
+  const int c = threadIdx.x; // 0 .. D-1
+  if (r < kH * D) {
+    const float w = P[m.off_wq + (int64_t)r * D + c];
+    W[(int64_t)r * D + c] = w * P[m.off_lnq_g + c] * inv;
     float part = w * P[m.off_lnq_b + c] * inv;
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    __shared__ float s2[2];
+    __shared__ float s2[4];
     if ((c & 31) == 0) s2[c >> 5] = part;
     __syncthreads();
-    if (c == 0) bq[r] = s2[0] + s2[1];
-  } else {
-    const int rk = r - kH * kD;
-    W[(int64_t)r * kD + c] = P[m.off_wk + (int64_t)rk * kD + c] * P[m.off_lnk_g + c];
+    if (c == 0) { float t = 0.f; for (int i = 0; i < D / 32; ++i) t += s2[i]; bq[r] = t; }
+  } else if (r < 2 * kH * D) {
+    const int rk = r - kH * D;
+    W[(int64_t)r * D + c] = P[m.off_wk + (int64_t)rk * D + c] * P[m.off_lnk_g + c];
     if (c == 0) bq[r] = 0.f;
+  } else {
+    // (Wv b_v)[h*D + mm], parked in the (otherwise zero) G part of the folded bias until prep_tables clears it
+    const int rv = r - 2 * kH * D;
+    float part = P[m.off_wv + (int64_t)rv * D + c] * P[m.off_lnv_b + c];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __shared__ float s3[4];
+    if ((c & 31) == 0) s3[c >> 5] = part;
+    __syncthreads();
+    if (c == 0) { float t = 0.f; for (int i = 0; i < D / 32; ++i) t += s3[i]; bq[r] = t; }
   }
 }
+// one thread per (head h, output row o, column c): Wg_h[o][c] = sum_mm fc1[o][h*D+mm] * Wv[h*D+mm][c] * g_v[c]; the
+// operands are tiny (L2 / L1 resident), a warp reads one fc1 value (broadcast) and one coalesced Wv row per step
 __global__ void prep_g_kernel(const matcha_model_desc m) {
-  // block = (head h), 64x64 output tile Wg_h[o][c] = sum_mm fc1[o][h*64+mm] * Wv[h*64+mm][c] * g_v[c]
-  const DerivedLayout l = derived_layout();
+  const int D = m.d;
+  const DerivedLayout l = derived_layout(D);
   const float* P = m.params;
-  __shared__ float sF[kD][kD + 1];   // fc1_h[o][mm]
-  __shared__ float sV[kD][kD + 1];   // Wv_h[mm][c]
-  __shared__ float sVb[kD];          // (Wv_h b_v)[mm]
-  const int h = blockIdx.x, tid = threadIdx.x;  // 256 threads
-  for (int i = tid; i < kD * kD; i += blockDim.x) {
-    const int a = i / kD, b = i % kD;
-    sF[a][b] = P[m.off_fc1_w + (int64_t)a * (kH * kD) + h * kD + b];
-    sV[a][b] = P[m.off_wv + (int64_t)(h * kD + a) * kD + b];
-  }
-  __syncthreads();
-  if (tid < kD) {
-    float s = 0.f;
-    for (int c = 0; c < kD; ++c) s = fmaf(sV[tid][c], P[m.off_lnv_b + c], s);
-    sVb[tid] = s;
-  }
-  __syncthreads();
-  float* W = m.derived + l.wqkg + (int64_t)(2 * kH * kD + h * kD) * kD;
-  for (int i = tid; i < kD * kD; i += blockDim.x) {
-    const int o = i / kD, c = i % kD;
-    float s = 0.f;
-#pragma unroll 8
-    for (int mm = 0; mm < kD; ++mm) s = fmaf(sF[o][mm], sV[mm][c], s);
-    W[(int64_t)o * kD + c] = s * P[m.off_lnv_g + c];
-  }
-  if (tid < kD) {
-    m.derived[l.bqkg + 2 * kH * kD + h * kD + tid] = 0.f;
-    float s = 0.f;
-    for (int mm = 0; mm < kD; ++mm) s = fmaf(sF[tid][mm], sVb[mm], s);
-    m.derived[l.bdyn_part + h * kD + tid] = s;
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= (int64_t)kH * D * D) return;
+  const int c = (int)(u % D), o = (int)((u / D) % D), h = (int)(u / ((int64_t)D * D));
+  const float* f = P + m.off_fc1_w + (int64_t)o * (kH * D) + h * D;
+  const float* v = P + m.off_wv + (int64_t)(h * D) * D;
+  float s = 0.f;
+  for (int mm = 0; mm < D; ++mm) s = fmaf(__ldg(f + mm), __ldg(v + (int64_t)mm * D + c), s);
+  m.derived[l.wqkg + (int64_t)(2 * kH * D + h * D + o) * D + c] = s * P[m.off_lnv_g + c];
+  if (c == 0) {
+    // b_dyn partial of head h, row o: sum_mm fc1_h[o][mm] * (Wv_h b_v)[mm]
+    const float* vb = m.derived + l.bqkg + 2 * kH * D + h * D;
+    float acc = 0.f;
+    for (int mm = 0; mm < D; ++mm) acc = fmaf(__ldg(f + mm), vb[mm], acc);
+    m.derived[l.bdyn_part + h * D + o] = acc;
   }
 }
 __global__ void prep_tables_kernel(const matcha_model_desc m) {
-  const int c = threadIdx.x;
-  if (c < kD) {   // b_dyn = fc1.bias + sum_h (fc1_h Wv_h b_v), heads added in a fixed order
-    const DerivedLayout l = derived_layout();
+  const int D = m.d;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {   // b_dyn = fc1.bias + sum_h (fc1_h Wv_h b_v), heads added in a fixed order
+    const DerivedLayout l = derived_layout(D);
     float s = m.params[m.off_fc1_b + c];
-    for (int h = 0; h < kH; ++h) s += m.derived[l.bdyn_part + h * kD + c];
+    for (int h = 0; h < kH; ++h) s += m.derived[l.bdyn_part + h * D + c];
     m.derived[l.bdyn + c] = s;
+    for (int h = 0; h < kH; ++h) m.derived[l.bqkg + 2 * kH * D + h * D + c] = 0.f;   // the G part of the folded bias is zero
   }
+  const int c = threadIdx.x;
   if (c >= m.n_chrom) return;
-  GemmGroup* t0 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_ENC0));
-  GemmGroup* t1 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_ENC1));
-  GemmGroup* t2 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_GW1));
-  GemmGroup* t3 = const_cast<GemmGroup*>(table_ptr(m.derived, TAB_GW0));
+  GemmGroup* t0 = const_cast<GemmGroup*>(table_ptr(m.derived, D, TAB_ENC0));
+  GemmGroup* t1 = const_cast<GemmGroup*>(table_ptr(m.derived, D, TAB_ENC1));
+  GemmGroup* t2 = const_cast<GemmGroup*>(table_ptr(m.derived, D, TAB_GW1));
+  GemmGroup* t3 = const_cast<GemmGroup*>(table_ptr(m.derived, D, TAB_GW0));
   const int32_t n_c = (int32_t)(m.chrom_end[c] - m.chrom_start[c]);
   GemmGroup g;
   g.pad = 0;
@@ -226,11 +226,11 @@ __global__ void prep_tables_kernel(const matcha_model_desc m) {
   g.B = m.params + m.off_w0[c]; g.ldb = n_c; g.C = nullptr; g.ldc = 0; g.dim = n_c;
   t0[c] = g;
   // enc1: E = H0 W1_c^T   (and, read as [K, N], dH0 = dE W1_c)
-  g.A = nullptr; g.lda = 0; g.a_id_off = 0; g.B = m.params + m.off_w1[c]; g.ldb = kD; g.dim = kD;
+  g.A = nullptr; g.lda = 0; g.a_id_off = 0; g.B = m.params + m.off_w1[c]; g.ldb = D; g.dim = D;
   t1[c] = g;
   if (m.grads) {
     // dW1_c += dE^T H0
-    g.A = nullptr; g.B = nullptr; g.ldb = 0; g.C = m.grads + m.off_w1[c]; g.ldc = kD; g.dim = kD;
+    g.A = nullptr; g.B = nullptr; g.ldb = 0; g.C = m.grads + m.off_w1[c]; g.ldc = D; g.dim = D;
     t2[c] = g;
     // dW0_c += dH0pre^T drop(F_c[id - start])
     g.B = m.feat[c]; g.ldb = m.feat_ld[c]; g.a_id_off = m.chrom_start[c];
@@ -241,22 +241,23 @@ __global__ void prep_tables_kernel(const matcha_model_desc m) {
 
 // derived-parameter gradients -> gradients of the reference's own parameters
 __global__ void prep_bwd_qk_kernel(const matcha_model_desc m) {
-  const DerivedLayout l = derived_layout();
+  const int D = m.d;
+  const DerivedLayout l = derived_layout(D);
   const float* P = m.params; float* G = m.grads;
   const float* dW = m.derived_grad + l.wqkg;
   const float* dbq = m.derived_grad + l.bqkg;
-  const float inv = rsqrtf((float)kD);
-  // one block per column c (64 blocks), threads stride over the 512 rows
+  const float inv = rsqrtf((float)D);
+  // one block per column c (D blocks), threads stride over the H*D rows
   const int c = blockIdx.x, tid = threadIdx.x;
   const float gq = P[m.off_lnq_g + c], bq = P[m.off_lnq_b + c], gk = P[m.off_lnk_g + c];
   float a_gq = 0.f, a_bq = 0.f, a_gk = 0.f;
-  for (int r = tid; r < kH * kD; r += blockDim.x) {
-    const float wq = P[m.off_wq + (int64_t)r * kD + c], dwq = dW[(int64_t)r * kD + c], dcq = dbq[r];
-    atomicAdd(&G[m.off_wq + (int64_t)r * kD + c], (dwq * gq + dcq * bq) * inv);
+  for (int r = tid; r < kH * D; r += blockDim.x) {
+    const float wq = P[m.off_wq + (int64_t)r * D + c], dwq = dW[(int64_t)r * D + c], dcq = dbq[r];
+    atomicAdd(&G[m.off_wq + (int64_t)r * D + c], (dwq * gq + dcq * bq) * inv);
     a_gq = fmaf(dwq, wq * inv, a_gq);
     a_bq = fmaf(dcq, wq * inv, a_bq);
-    const float wk = P[m.off_wk + (int64_t)r * kD + c], dwk = dW[(int64_t)(kH * kD + r) * kD + c];
-    atomicAdd(&G[m.off_wk + (int64_t)r * kD + c], dwk * gk);
+    const float wk = P[m.off_wk + (int64_t)r * D + c], dwk = dW[(int64_t)(kH * D + r) * D + c];
+    atomicAdd(&G[m.off_wk + (int64_t)r * D + c], dwk * gk);
     a_gk = fmaf(dwk, wk, a_gk);
   }
   __shared__ float red[3][32];
@@ -275,46 +276,40 @@ __global__ void prep_bwd_qk_kernel(const matcha_model_desc m) {
     atomicAdd(&G[m.off_lnk_g + c], s2);   // layer_norm2.bias (key side): exactly zero gradient
   }
 }
+// block = (head h, row a of the head): thread b.  With M_h = fc1_h^T dWg_h, u = fc1_h^T db_dyn, z = Wv_h b_v:
+//   dWv_h[a][b] += M_h[a][b] g_v[b] + u[a] b_v[b];   dg_v[b] += M_h[a][b] Wv_h[a][b];   db_v[b] += u[a] Wv_h[a][b]
+//   dfc1[a][h*D + b] += sum_c dWg_h[a][c] g_v[c] Wv_h[b][c] + db_dyn[a] z[b]
 __global__ void prep_bwd_g_kernel(const matcha_model_desc m) {
-  const DerivedLayout l = derived_layout();
+  const int D = m.d;
+  const DerivedLayout l = derived_layout(D);
   const float* P = m.params; float* G = m.grads;
-  __shared__ float sF[kD][kD + 1];    // fc1_h[o][mm]
-  __shared__ float sV[kD][kD + 1];    // Wv_h[mm][c]
-  __shared__ float sdb[kD], svb[kD], sfb[kD];  // db_dyn[o], (fc1_h^T db_dyn)[mm], (Wv_h b_v)[mm]
-  const int h = blockIdx.x >> 2, part = blockIdx.x & 3, tid = threadIdx.x;   // 4 blocks per head, 16 output rows each
-  const float* dWg = m.derived_grad + l.wqkg + (int64_t)(2 * kH * kD + h * kD) * kD;
-  for (int i = tid; i < kD * kD; i += blockDim.x) {
-    const int a = i / kD, b = i % kD;
-    sF[a][b] = P[m.off_fc1_w + (int64_t)a * (kH * kD) + h * kD + b];
-    sV[a][b] = P[m.off_wv + (int64_t)(h * kD + a) * kD + b];
-
-  }
-  if (tid < kD) sdb[tid] = m.derived_grad[l.bdyn + tid];
+  const int h = blockIdx.x / D, a = blockIdx.x % D, b = threadIdx.x;      // blockDim.x == D
+  const float* dWg = m.derived_grad + l.wqkg + (int64_t)(2 * kH * D + h * D) * D;
+  const float* F = P + m.off_fc1_w + h * D;                   // fc1_h[o][mm] = F[o * H*D + mm]
+  const float* V = P + m.off_wv + (int64_t)(h * D) * D;       // Wv_h[mm][c]
+  const float* dbd = m.derived_grad + l.bdyn;
+  __shared__ float s_dw[128], s_gv[128];                      // dWg_h[a][:], g_v
+  s_dw[b] = dWg[(int64_t)a * D + b];
+  s_gv[b] = P[m.off_lnv_g + b];
   __syncthreads();
-  if (tid < kD) {
-    float s = 0.f, s2 = 0.f;
-    for (int o = 0; o < kD; ++o) s = fmaf(sF[o][tid], sdb[o], s);
-    for (int c = 0; c < kD; ++c) s2 = fmaf(sV[tid][c], P[m.off_lnv_b + c], s2);
-    svb[tid] = s; sfb[tid] = s2;
-    if (blockIdx.x == 0) atomicAdd(&G[m.off_fc1_b + tid], sdb[tid]);
+  float mh = 0.f, u = 0.f;
+  for (int o = 0; o < D; ++o) {
+    const float f = __ldg(F + (int64_t)o * (kH * D) + a);
+    mh = fmaf(f, __ldg(dWg + (int64_t)o * D + b), mh);
+    u = fmaf(f, __ldg(dbd + o), u);
   }
-  __syncthreads();
-  for (int i = part * (kD * kD / 4) + tid; i < (part + 1) * (kD * kD / 4); i += blockDim.x) {
-    const int a = i / kD, b = i % kD;
-    // M_h[mm = a][c = b] = sum_o fc1_h[o][mm] dWg_h[o][c]
-    float mh = 0.f;
-#pragma unroll 8
-    for (int o = 0; o < kD; ++o) mh = fmaf(sF[o][a], __ldg(dWg + o * kD + b), mh);
-    const float gv = P[m.off_lnv_g + b], bv = P[m.off_lnv_b + b];
-    atomicAdd(&G[m.off_wv + (int64_t)(h * kD + a) * kD + b], mh * gv + svb[a] * bv);
-    atomicAdd(&G[m.off_lnv_g + b], mh * sV[a][b]);
-    atomicAdd(&G[m.off_lnv_b + b], svb[a] * sV[a][b]);
-    // dfc1[o = a][h*64 + mm = b] = sum_c dWg_h[o][c] Wv_h[mm][c] g_v[c] + db_dyn[o] (Wv_h b_v)[mm]
-    float df = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < kD; ++c) df = fmaf(__ldg(dWg + a * kD + c) * P[m.off_lnv_g + c], sV[b][c], df);
-    atomicAdd(&G[m.off_fc1_w + (int64_t)a * (kH * kD) + h * kD + b], df + sdb[a] * sfb[b]);
+  const float gv = s_gv[b], bv = P[m.off_lnv_b + b], vab = V[(int64_t)a * D + b];
+  atomicAdd(&G[m.off_wv + (int64_t)(h * D + a) * D + b], mh * gv + u * bv);
+  atomicAdd(&G[m.off_lnv_g + b], mh * vab);
+  atomicAdd(&G[m.off_lnv_b + b], u * vab);
+  float df = 0.f, z = 0.f;
+  for (int c = 0; c < D; ++c) {
+    const float vbc = __ldg(V + (int64_t)b * D + c);
+    df = fmaf(s_dw[c] * s_gv[c], vbc, df);
+    z = fmaf(vbc, P[m.off_lnv_b + c], z);
   }
+  atomicAdd(&G[m.off_fc1_w + (int64_t)a * (kH * D) + h * D + b], df + __ldg(dbd + a) * z);
+  if (blockIdx.x < D && b == 0) atomicAdd(&G[m.off_fc1_b + blockIdx.x], __ldg(dbd + blockIdx.x));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -340,6 +335,9 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
   Workspace w;
   memset(&w, 0, sizeof(w));
   const int64_t T = B * L;
+  const int D = m->d;
+  const int64_t QKG = 3 * (int64_t)kH * D;
+  const bool tc = D == kD;                       // tensor-core tile buffers exist only for embed_dim 64
   char* p = reinterpret_cast<char*>(base);
   int64_t off = 0;
   auto take = [&](int64_t nbytes) -> void* {
@@ -352,34 +350,35 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
   w.cursor = (int32_t*)take(sizeof(int32_t) * (MATCHA_MAX_CHROM + 2));
   w.perm = (int32_t*)take(sizeof(int32_t) * (T + 1));
   w.recon = (float*)take(sizeof(float) * 4);
-  const int64_t row = sizeof(float) * T * kD;
+  const int64_t row = sizeof(float) * T * D;
   w.H0 = (float*)take(row); w.E = (float*)take(row); w.V0 = (float*)take(row); w.X = (float*)take(row);
   w.xhat = (float*)take(row); w.rstd = (float*)take(sizeof(float) * (T + 1));
-  {
+  if (tc) {
     int64_t nt = num_token_tiles(T);
     if (L >= 2 && L <= 6 && num_atiles(T, L) > nt) nt = num_atiles(T, L);
     w.xhat_t = (uint8_t*)take(nt * (int64_t)kXTileBytes);
   }
-  w.QKG = (float*)take(sizeof(float) * T * kQKG);
+  w.QKG = (float*)take(sizeof(float) * T * QKG);
   w.U = (float*)take(row); w.H1d = (float*)take(row); w.H2 = (float*)take(row);
   w.pred_ld = m->inter ? (max_chrom_len(m) + 3) / 4 * 4 : 0;
   w.pred = (float*)take(sizeof(float) * T * (w.pred_ld > 0 ? w.pred_ld : 1));
   if (training) {
     w.dlogit = (float*)take(sizeof(float) * (B + 1));
     w.dH2 = (float*)take(row); w.dXs = (float*)take(row); w.dH1pre = (float*)take(row); w.dU = (float*)take(row);
-    w.dQKG = (float*)take(num_token_tiles(T) * (int64_t)kGChunks * kGTileBytes);   // >= T * 1536 * 4 bytes
+    w.dQKG = (float*)take(tc ? num_token_tiles(T) * (int64_t)kGChunks * kGTileBytes      // >= T * 1536 * 4 bytes
+                             : (int64_t)sizeof(float) * T * QKG);
     w.dqkg_t = reinterpret_cast<uint8_t*>(w.dQKG);
     w.dxhat = (float*)take(row); w.dP = (float*)take(row); w.dV0 = (float*)take(row); w.dtE = (float*)take(row);
     w.dE = (float*)take(row); w.dH0pre = (float*)take(row);
     w.probs = (float*)take(sizeof(float) * T * kH * 8);       // attention weights kept by the fused forward
-    if (L >= 2 && L <= 6) {
+    if (tc && L >= 2 && L <= 6) {
       const int64_t nat = num_atiles(T, L);
       w.v0_t = (uint8_t*)take(nat * 32768); w.u_t = (uint8_t*)take(nat * 32768); w.h1_t = (uint8_t*)take(nat * 32768);
       w.dh2_t = (uint8_t*)take(nat * 32768); w.dh1_t = (uint8_t*)take(nat * 32768); w.dp_t = (uint8_t*)take(nat * 32768);
       w.dv0_t = (uint8_t*)take(nat * 32768); w.attr_t = (uint8_t*)take(nat * 16384);
       w.wpair_scratch = (float*)take(sizeof(float) * wgrad_pair_scratch_floats());
     }
-    w.tc_scratch_floats = gemm_tc_scratch_floats(kQKG);
+    w.tc_scratch_floats = gemm_tc_scratch_floats(QKG);
     w.tc_scratch = (float*)take(sizeof(float) * w.tc_scratch_floats);
   }
   w.bytes = off;
@@ -388,14 +387,16 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
 
 static int validate(const matcha_model_desc* m) {
   MATCHA_REQUIRE(m != nullptr, "model descriptor is NULL");
-  if (m->d != kD || m->n_head != kH) {
-    set_error("this build supports embed_dim=%d n_head=%d (got %d, %d)", kD, kH, m->d, m->n_head);
+  if ((m->d != 64 && m->d != 128) || m->n_head != kH) {
+    set_error("this build supports embed_dim 64 (tensor-core path) or 128 (fp32 SIMT path) with n_head=%d (got %d, %d)", kH, m->d,
+              m->n_head);
     return MATCHA_ERR_UNSUPPORTED;
   }
   MATCHA_REQUIRE(m->n_chrom >= 1 && m->n_chrom <= MATCHA_MAX_CHROM, "n_chrom=%d out of range", m->n_chrom);
   MATCHA_REQUIRE(m->params && m->derived, "params / derived buffers missing");
   MATCHA_REQUIRE(m->attr_dim >= 1 && m->attr_table, "attribute table missing");
   const bool csr = model_uses_csr(m);
+  if (csr && m->d != kD) { set_error("CSR feature rows need embed_dim %d", kD); return MATCHA_ERR_UNSUPPORTED; }
   for (int c = 0; c < m->n_chrom; ++c) {
     const bool has_csr = m->feat_indptr[c] && m->feat_indices[c] && m->feat_values[c];
     if (csr ? (m->feat[c] || !has_csr) : !m->feat[c]) {
@@ -425,22 +426,25 @@ static ChromMeta chrom_meta(const matcha_model_desc* m) {
 // encoder: bucket tokens, two grouped contractions.  Outputs H0, E (zero rows for pads)
 static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, int training, uint64_t seed,
                        const Workspace& w, float* E_out, cudaStream_t s) {
+  const int Dm = m->d;
+  const int64_t QKGm = 3 * (int64_t)kH * Dm;
+  (void)QKGm;
   int rc;
   if ((rc = PROF(P_BUCKET, 3, launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s)))) return rc;
-  if ((rc = check_cuda(cudaMemsetAsync(w.H0, 0, sizeof(float) * T * kD, s), "memset H0"))) return rc;
-  if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * kD, s), "memset E"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(w.H0, 0, sizeof(float) * T * Dm, s), "memset H0"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * Dm, s), "memset E"))) return rc;
   if (model_uses_csr(m)) {
     const DropCfg fd = make_drop(seed, SITE_FEATURE, m->p_feature, training != 0);
-    if ((rc = PROF(P_ENC0, 1, launch_enc0_csr_fwd(m, derived_layout().total, x, T, w.perm, w.group_off, w.H0, fd, s)))) return rc;
+    if ((rc = PROF(P_ENC0, 1, launch_enc0_csr_fwd(m, derived_layout(m->d).total, x, T, w.perm, w.group_off, w.H0, fd, s)))) return rc;
   } else {
-    GemmDesc d = gemm_base(FORM_NT, 0, kD, 0, nullptr, 0, nullptr, 0, w.H0, kD);
-    d.perm = w.perm; d.a_ids = x; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, TAB_ENC0);
+    GemmDesc d = gemm_base(FORM_NT, 0, Dm, 0, nullptr, 0, nullptr, 0, w.H0, Dm);
+    d.perm = w.perm; d.a_ids = x; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, m->d, TAB_ENC0);
     d.group_off = w.group_off; d.total_rows = T; d.epi_act = 1;
     if (training && m->p_feature > 0.f) { d.drop_on = 1; d.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
     if ((rc = run_gemm(d, s, P_ENC0))) return rc;
   }
-  GemmDesc e = gemm_base(FORM_NT, 0, kD, kD, w.H0, kD, nullptr, 0, E_out, kD);
-  e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, TAB_ENC1);
+  GemmDesc e = gemm_base(FORM_NT, 0, Dm, Dm, w.H0, Dm, nullptr, 0, E_out, Dm);
+  e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, m->d, TAB_ENC1);
   e.group_off = w.group_off; e.total_rows = T;
   return run_gemm(e, s, P_ENC1);
 }
@@ -448,28 +452,31 @@ static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, 
 // X = tanh(next_w(E + attribute_nn(attr[id]))), xhat, rstd, QKG
 static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, const Workspace& w, cudaStream_t s,
                        int fused_L = 0, int training = 0) {
+  const int Dm = m->d;
+  const int64_t QKGm = 3 * (int64_t)kH * Dm;
+  (void)QKGm;
   int rc;
   const float* P = m->params;
-  const DerivedLayout l = derived_layout();
+  const DerivedLayout l = derived_layout(m->d);
   if (fused_L > 0 && use_chain(m, T, fused_L))     // attribute mix + next_w + LayerNorm statistics + tiles in one kernel
     return PROF(P_MIX, 1, launch_chain_mix_fwd(w.E, x, m->attr_table, m->attr_dim, P + m->off_attr_w, P + m->off_attr_b,
                                                m->derived + l.wchain + CW_NEXT_K * (kChainWBytes / 4), P + m->off_next_b, nullptr,
                                                w.X, w.xhat, w.rstd, w.xhat_t, training ? w.v0_t : nullptr, training ? w.attr_t : nullptr,
                                                T / fused_L, fused_L, s));
-  GemmDesc a = gemm_base(FORM_NT, T, kD, m->attr_dim, m->attr_table, m->attr_dim, P + m->off_attr_w, m->attr_dim, w.V0, kD);
-  a.a_ids = x; a.bias = P + m->off_attr_b; a.addend = w.E; a.ld_add = kD;
+  GemmDesc a = gemm_base(FORM_NT, T, Dm, m->attr_dim, m->attr_table, m->attr_dim, P + m->off_attr_w, m->attr_dim, w.V0, Dm);
+  a.a_ids = x; a.bias = P + m->off_attr_b; a.addend = w.E; a.ld_add = Dm;
   if ((rc = run_gemm(a, s, P_ATTR))) return rc;
-  GemmDesc b = gemm_base(FORM_NT, T, kD, kD, w.V0, kD, P + m->off_next_w, kD, w.X, kD);
+  GemmDesc b = gemm_base(FORM_NT, T, Dm, Dm, w.V0, Dm, P + m->off_next_w, Dm, w.X, Dm);
   b.bias = P + m->off_next_b; b.epi_act = 1;
   if ((rc = run_gemm(b, s, P_MIX))) return rc;
   if (fused_L > 0)   // fused attention: hyperedge-aligned tiles; the QKG projection happens inside the attention kernel
     return PROF(P_LN, 1, launch_ln_fwd_atiles(w.X, w.xhat, w.rstd, T, fused_L, w.xhat_t, s));
-  const bool tiles = use_tiles(T);
-  if ((rc = PROF(P_LN, 1, launch_ln_fwd(w.X, w.xhat, w.rstd, T, tiles ? w.xhat_t : nullptr, s)))) return rc;
+  const bool tiles = use_tiles(m, T);
+  if ((rc = PROF(P_LN, 1, launch_ln_fwd(m->d, w.X, w.xhat, w.rstd, T, tiles ? w.xhat_t : nullptr, s)))) return rc;
   if (tiles)
     return PROF(P_QKG, 1, tc_qkg_forward_tiles(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wsplit),
                                                m->derived + l.bqkg, w.QKG, T, s));
-  GemmDesc q = gemm_base(FORM_NT, T, kQKG, kD, w.xhat, kD, m->derived + l.wqkg, kD, w.QKG, kQKG);
+  GemmDesc q = gemm_base(FORM_NT, T, QKGm, Dm, w.xhat, Dm, m->derived + l.wqkg, Dm, w.QKG, QKGm);
   q.bias = m->derived + l.bqkg;
   q.b_split = reinterpret_cast<const uint8_t*>(m->derived + l.wsplit);
   return run_gemm(q, s, P_QKG);
@@ -477,14 +484,17 @@ static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, 
 
 // pff_n1 (two 1x1 convolutions with residual), input U, output H2 (pre-LayerNorm)
 static int run_pff(const matcha_model_desc* m, int64_t T, int training, uint64_t seed, const Workspace& w, cudaStream_t s) {
+  const int Dm = m->d;
+  const int64_t QKGm = 3 * (int64_t)kH * Dm;
+  (void)QKGm;
   int rc;
   const float* P = m->params;
-  GemmDesc a = gemm_base(FORM_NT, T, kD, kD, w.U, kD, P + m->off_pff_w0, kD, w.H1d, kD);
+  GemmDesc a = gemm_base(FORM_NT, T, Dm, Dm, w.U, Dm, P + m->off_pff_w0, Dm, w.H1d, Dm);
   a.bias = P + m->off_pff_b0; a.epi_act = 1;
   if (training && m->p_pff > 0.f) { a.epi_drop = 1; a.edrop = make_drop(seed, SITE_PFF, m->p_pff, true); }
   if ((rc = run_gemm(a, s, P_PFF0))) return rc;
-  GemmDesc b = gemm_base(FORM_NT, T, kD, kD, w.H1d, kD, P + m->off_pff_w1, kD, w.H2, kD);
-  b.bias = P + m->off_pff_b1; b.addend = w.U; b.ld_add = kD;
+  GemmDesc b = gemm_base(FORM_NT, T, Dm, Dm, w.H1d, Dm, P + m->off_pff_w1, Dm, w.H2, Dm);
+  b.bias = P + m->off_pff_b1; b.addend = w.U; b.ld_add = Dm;
   return run_gemm(b, s, P_PFF1);
 }
 
@@ -533,12 +543,15 @@ int matcha_version(void) { return 100; }
 
 // CSR models keep W0T_c [n_c, 64] (and, in derived_grad, its gradient) after the fixed-size part
 static int64_t w0t_floats(const matcha_model_desc* m) {
+  const int Dm = m->d;
+  const int64_t QKGm = 3 * (int64_t)kH * Dm;
+  (void)QKGm;
   if (!m || !model_uses_csr(m)) return 0;
   int64_t n = 0;
-  for (int c = 0; c < m->n_chrom; ++c) n += (m->chrom_end[c] - m->chrom_start[c]) * kD;
+  for (int c = 0; c < m->n_chrom; ++c) n += (m->chrom_end[c] - m->chrom_start[c]) * Dm;
   return n;
 }
-int64_t matcha_derived_elems(const matcha_model_desc* m) { return derived_layout().total + w0t_floats(m); }
+int64_t matcha_derived_elems(const matcha_model_desc* m) { return derived_layout(m->d).total + w0t_floats(m); }
 
 int64_t matcha_workspace_bytes(const matcha_model_desc* m, int64_t B, int32_t L, int32_t training) {
   if (!m || B < 0 || L < 1) return -1;
@@ -549,25 +562,27 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   int rc = validate(m);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  const DerivedLayout l = derived_layout();
+  const DerivedLayout l = derived_layout(m->d);
   (void)l;
   prof_begin(P_PREP, s);
-  prep_qk_kernel<<<2 * kH * kD, kD, 0, s>>>(*m);
+  prep_qk_kernel<<<3 * kH * m->d, m->d, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_qk");
-  prep_g_kernel<<<kH, 256, 0, s>>>(*m);
+  prep_g_kernel<<<(kH * m->d * m->d + 255) / 256, 256, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_g");
   prep_tables_kernel<<<1, MATCHA_MAX_CHROM, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_tables");
-  if ((rc = launch_split_weights_k64(m->derived + l.wqkg, kD, kQKG, m->derived + l.wsplit, s))) return rc;
-  if ((rc = launch_split_wT(m->derived + l.wqkg, m->derived + l.wtsplit, s))) return rc;
-  if ((rc = launch_split_w_heads(m->derived + l.wqkg, m->derived + l.wheads, s))) return rc;
-  if (m->grads && (rc = launch_split_w_pairs(m->derived + l.wqkg, m->derived + l.wpairs, s))) return rc;
-  {
-    float* wc = m->derived + l.wchain;
-    const int64_t st = kChainWBytes / 4;
-    if ((rc = launch_split_w64(m->params + m->off_next_w, wc + CW_NEXT_K * st, wc + CW_NEXT_MN * st, s))) return rc;
-    if ((rc = launch_split_w64(m->params + m->off_pff_w0, wc + CW_PFF0_K * st, wc + CW_PFF0_MN * st, s))) return rc;
-    if ((rc = launch_split_w64(m->params + m->off_pff_w1, wc + CW_PFF1_K * st, wc + CW_PFF1_MN * st, s))) return rc;
+  if (m->d == kD) {      // pre-split bf16 hi | lo operand copies for the tcgen05 kernels (embed_dim 64 only)
+    if ((rc = launch_split_weights_k64(m->derived + l.wqkg, kD, kQKG, m->derived + l.wsplit, s))) return rc;
+    if ((rc = launch_split_wT(m->derived + l.wqkg, m->derived + l.wtsplit, s))) return rc;
+    if ((rc = launch_split_w_heads(m->derived + l.wqkg, m->derived + l.wheads, s))) return rc;
+    if (m->grads && (rc = launch_split_w_pairs(m->derived + l.wqkg, m->derived + l.wpairs, s))) return rc;
+    {
+      float* wc = m->derived + l.wchain;
+      const int64_t st = kChainWBytes / 4;
+      if ((rc = launch_split_w64(m->params + m->off_next_w, wc + CW_NEXT_K * st, wc + CW_NEXT_MN * st, s))) return rc;
+      if ((rc = launch_split_w64(m->params + m->off_pff_w0, wc + CW_PFF0_K * st, wc + CW_PFF0_MN * st, s))) return rc;
+      if ((rc = launch_split_w64(m->params + m->off_pff_w1, wc + CW_PFF1_K * st, wc + CW_PFF1_MN * st, s))) return rc;
+    }
   }
   if (model_uses_csr(m) && (rc = launch_csr_prepare(m, l.total, s))) return rc;
   prof_end(P_PREP, 10, s);
@@ -577,6 +592,9 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
 int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int32_t L, int32_t training,
                    uint64_t seed, int32_t random_chrom, float* logits, float* recon, void* workspace,
                    int64_t workspace_bytes, void* stream) {
+  const int Dm = m->d;
+  const int64_t QKGm = 3 * (int64_t)kH * Dm;
+  (void)QKGm;
   int rc = validate(m);
   if (rc) return rc;
   MATCHA_REQUIRE(x && logits && workspace, "matcha_forward: NULL argument");
@@ -589,14 +607,14 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
   MATCHA_REQUIRE((int64_t)(base - (uintptr_t)workspace) + w.bytes <= workspace_bytes,
                  "workspace too small: need %lld bytes", (long long)(w.bytes + 256));
   const int64_t T = B * L;
-  const DerivedLayout l = derived_layout();
+  const DerivedLayout l = derived_layout(m->d);
 
   if ((rc = run_encoder(m, x, T, training, seed, w, w.E, s))) return rc;
   {
     if ((rc = check_cuda(cudaMemsetAsync(w.recon, 0, sizeof(float), s), "memset recon"))) return rc;
     if (random_chrom >= 0 && m->inter) {
       const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom];
-      GemmDesc p = gemm_base(FORM_NT, T, re - rs, kD, w.E, kD, m->params + m->off_rw[random_chrom], kD, w.pred, w.pred_ld);
+      GemmDesc p = gemm_base(FORM_NT, T, re - rs, Dm, w.E, Dm, m->params + m->off_rw[random_chrom], Dm, w.pred, w.pred_ld);
       p.a_act = 1; p.bias = m->params + m->off_rb[random_chrom];
       if ((rc = run_gemm(p, s, P_RECON_PRED))) return rc;
       if ((rc = PROF(P_RECON_DIFF, 1, launch_recon_diff(w.pred, w.pred_ld, x, T, m->inter, m->inter_ld, rs, re, w.counts, random_chrom,
@@ -605,7 +623,7 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
     if (recon && (rc = check_cuda(cudaMemcpyAsync(recon, w.recon, sizeof(float), cudaMemcpyDeviceToDevice, s), "copy recon")))
       return rc;
   }
-  const bool fused = use_fused(T, L);
+  const bool fused = use_fused(m, T, L);
   if ((rc = run_mix_qkg(m, x, T, w, s, fused ? L : 0, training))) return rc;
   DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, training != 0);
   if (fused) {
@@ -613,7 +631,7 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
                                                         m->derived + l.bqkg, m->derived + l.bdyn, x, w.U, training ? w.probs : nullptr, B, L,
                                                         dattn, s))))
       return rc;
-  } else if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fwd(w.QKG, x, m->derived + l.bdyn, w.U, B, L, dattn, s)))) return rc;
+  } else if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fwd(m->d, w.QKG, x, m->derived + l.bdyn, w.U, B, L, dattn, s)))) return rc;
   if (fused && use_chain(m, T, L)) {
     const float* wc = m->derived + l.wchain;
     return PROF(P_PFF0, 1, launch_chain_pff_fwd(w.U, w.xhat, x, wc + CW_PFF0_K * (kChainWBytes / 4), wc + CW_PFF1_K * (kChainWBytes / 4),
@@ -623,7 +641,7 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
                                                 training ? w.h1_t : nullptr, B, L, s));
   }
   if ((rc = run_pff(m, T, training, seed, w, s))) return rc;
-  return PROF(P_SCORE_FWD, 1, launch_score_fwd(w.H2, w.xhat, x, score_params(m), logits, B, L, s));
+  return PROF(P_SCORE_FWD, 1, launch_score_fwd(m->d, w.H2, w.xhat, x, score_params(m), logits, B, L, s));
 }
 
 int matcha_bce_loss(const float* logits, const float* y, const float* wgt, int64_t B, float alpha, float beta,
@@ -639,6 +657,9 @@ int matcha_bce_loss(const float* logits, const float* y, const float* wgt, int64
 int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int32_t L, uint64_t seed,
                     int32_t random_chrom, const float* dlogit, float beta, int32_t* active, void* workspace,
                     int64_t workspace_bytes, void* stream) {
+  const int Dm = m->d;
+  const int64_t QKGm = 3 * (int64_t)kH * Dm;
+  (void)QKGm;
   int rc = validate(m);
   if (rc) return rc;
   MATCHA_REQUIRE(m->grads && m->derived_grad, "matcha_backward: grads / derived_grad buffers missing");
@@ -651,7 +672,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   MATCHA_REQUIRE((int64_t)(base - (uintptr_t)workspace) + w.bytes <= workspace_bytes,
                  "workspace too small: need %lld bytes", (long long)(w.bytes + 256));
   const int64_t T = B * L;
-  const DerivedLayout l = derived_layout();
+  const DerivedLayout l = derived_layout(m->d);
   const float* P = m->params;
   float* G = m->grads;
   float* DG = m->derived_grad;
@@ -663,7 +684,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   ScoreGrads sg;
   sg.pff_g = G + m->off_pff_g; sg.pff_b = G + m->off_pff_b; sg.ln1_g = G + m->off_ln1_g; sg.ln1_b = G + m->off_ln1_b;
   sg.ln2_g = G + m->off_ln2_g; sg.ln2_b = G + m->off_ln2_b; sg.cls_w = G + m->off_cls_w; sg.cls_b = G + m->off_cls_b;
-  if ((rc = PROF(P_SCORE_BWD, 1, launch_score_bwd(w.H2, w.xhat, w.rstd, x, score_params(m), dlogit, w.dH2, w.dXs, sg, B, L, s)))) return rc;
+  if ((rc = PROF(P_SCORE_BWD, 1, launch_score_bwd(m->d, w.H2, w.xhat, w.rstd, x, score_params(m), dlogit, w.dH2, w.dXs, sg, B, L, s)))) return rc;
 
   // pff_n1 backward
   DropCfg dpff = make_drop(seed, SITE_PFF, m->p_pff, true);
@@ -677,104 +698,104 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     if ((rc = PROF(P_D_PFF1, 1, launch_chain_pff_bwd(w.dH2, w.H1d, x, wc + CW_PFF1_MN * (kChainWBytes / 4),
                                                      wc + CW_PFF0_MN * (kChainWBytes / 4), dpff, dattn, w.dU, w.dh2_t, w.dh1_t, B,
                                                      L, s)))) return rc;
-    if ((rc = PROF(P_W_PFF1, 2, launch_wgrad_pair(w.dh2_t, w.dh1_t, w.h1_t, w.u_t, 8, nat, w.wpair_scratch, G + m->off_pff_w1, kD,
-                                                  kD, G + m->off_pff_b1, G + m->off_pff_w0, kD, kD, G + m->off_pff_b0, s))))
+    if ((rc = PROF(P_W_PFF1, 2, launch_wgrad_pair(w.dh2_t, w.dh1_t, w.h1_t, w.u_t, 8, nat, w.wpair_scratch, G + m->off_pff_w1, Dm,
+                                                  Dm, G + m->off_pff_b1, G + m->off_pff_w0, Dm, Dm, G + m->off_pff_b0, s))))
       return rc;
   } else {
-    GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dH2, kD, w.H1d, kD, G + m->off_pff_w1, kD);
-    d.colsum = G + m->off_pff_b1; d.colsum_n = kD;
+    GemmDesc d = gemm_base(FORM_TN, Dm, Dm, T, w.dH2, Dm, w.H1d, Dm, G + m->off_pff_w1, Dm);
+    d.colsum = G + m->off_pff_b1; d.colsum_n = Dm;
     if ((rc = run_gemm(d, s, P_W_PFF1))) return rc;
-    GemmDesc e = gemm_base(FORM_NN, T, kD, kD, w.dH2, kD, P + m->off_pff_w1, kD, w.dH1pre, kD);
-    e.epi_act = 2; e.aux = w.H1d; e.ld_aux = kD;
+    GemmDesc e = gemm_base(FORM_NN, T, Dm, Dm, w.dH2, Dm, P + m->off_pff_w1, Dm, w.dH1pre, Dm);
+    e.epi_act = 2; e.aux = w.H1d; e.ld_aux = Dm;
     if (m->p_pff > 0.f) { e.epi_drop = 1; e.edrop = dpff; }
     if ((rc = run_gemm(e, s, P_D_PFF1))) return rc;
-    GemmDesc f = gemm_base(FORM_TN, kD, kD, T, w.dH1pre, kD, w.U, kD, G + m->off_pff_w0, kD);
-    f.colsum = G + m->off_pff_b0; f.colsum_n = kD;
+    GemmDesc f = gemm_base(FORM_TN, Dm, Dm, T, w.dH1pre, Dm, w.U, Dm, G + m->off_pff_w0, Dm);
+    f.colsum = G + m->off_pff_b0; f.colsum_n = Dm;
     if ((rc = run_gemm(f, s, P_W_PFF0))) return rc;
-    GemmDesc g = gemm_base(FORM_NN, T, kD, kD, w.dH1pre, kD, P + m->off_pff_w0, kD, w.dU, kD);
-    g.addend = w.dH2; g.ld_add = kD;
+    GemmDesc g = gemm_base(FORM_NN, T, Dm, Dm, w.dH1pre, Dm, P + m->off_pff_w0, Dm, w.dU, Dm);
+    g.addend = w.dH2; g.ld_add = Dm;
     if ((rc = run_gemm(g, s, P_D_PFF0))) return rc;
   }
   // attention backward
   int dx_parts = 1;
-  if (use_fused(T, L)) {
+  if (use_fused(m, T, L)) {
     // fused path: recompute + attention backward + data / weight gradients of the QKG projection in one kernel; the
     // per-head-pair dxhat partials live in the (otherwise unused) dQKG area
     dx_parts = 4;
     if ((rc = PROF(P_ATTN_BWD, 2, launch_attn_fused_bwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wpairs),
                                                         m->derived + l.bqkg, x, w.dU, w.probs, w.dQKG, w.tc_scratch,
                                                         DG + l.wqkg, DG + l.bqkg, DG + l.bdyn, B, L, dattn, chain ? 1 : 0, s)))) return rc;
-  } else if (use_tiles(T)) {
+  } else if (use_tiles(m, T)) {
     // tile path: the attention backward emits dQKG directly as bf16 hi|lo MMA tiles; rows of the last tile beyond T are zero
     const int64_t nt = num_token_tiles(T);
     if (T % kTileTok != 0 &&
         (rc = check_cuda(cudaMemsetAsync(w.dqkg_t + (nt - 1) * (int64_t)kGChunks * kGTileBytes, 0, (size_t)kGChunks * kGTileBytes, s),
                          "memset dQKG tail tile")))
       return rc;
-    if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_bwd(w.QKG, w.dU, x, nullptr, w.dqkg_t, DG + l.bdyn, B, L, dattn, s)))) return rc;
+    if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_bwd(m->d, w.QKG, w.dU, x, nullptr, w.dqkg_t, DG + l.bdyn, B, L, dattn, s)))) return rc;
     if ((rc = PROF(P_W_QKG, 2, tc_qkg_wgrad_tiles(w.dqkg_t, w.xhat_t, w.tc_scratch, w.tc_scratch_floats, DG + l.wqkg,
-                                                  DG + l.bqkg, kH * kD, T, s)))) return rc;
+                                                  DG + l.bqkg, kH * Dm, T, s)))) return rc;
     if ((rc = PROF(P_D_QKG, 1, tc_qkg_dgrad_tiles(w.dqkg_t, reinterpret_cast<const uint8_t*>(m->derived + l.wtsplit), w.dxhat,
                                                   T, s)))) return rc;
   } else {
-    if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_bwd(w.QKG, w.dU, x, w.dQKG, nullptr, DG + l.bdyn, B, L, dattn, s)))) return rc;
-    GemmDesc d = gemm_base(FORM_TN, kQKG, kD, T, w.dQKG, kQKG, w.xhat, kD, DG + l.wqkg, kD);
-    d.colsum = DG + l.bqkg; d.colsum_n = kH * kD;
+    if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_bwd(m->d, w.QKG, w.dU, x, w.dQKG, nullptr, DG + l.bdyn, B, L, dattn, s)))) return rc;
+    GemmDesc d = gemm_base(FORM_TN, QKGm, Dm, T, w.dQKG, QKGm, w.xhat, Dm, DG + l.wqkg, Dm);
+    d.colsum = DG + l.bqkg; d.colsum_n = kH * Dm;
     d.scratch = w.tc_scratch; d.scratch_floats = w.tc_scratch_floats;
     if ((rc = run_gemm(d, s, P_W_QKG))) return rc;
-    GemmDesc e = gemm_base(FORM_NN, T, kD, kQKG, w.dQKG, kQKG, m->derived + l.wqkg, kD, w.dxhat, kD);
+    GemmDesc e = gemm_base(FORM_NN, T, Dm, QKGm, w.dQKG, QKGm, m->derived + l.wqkg, Dm, w.dxhat, Dm);
     if ((rc = run_gemm(e, s, P_D_QKG))) return rc;
   }
   // reconstruction head backward (gdiff was left in w.pred by the forward pass, without the beta factor)
   const float* dtE = nullptr;
   if (recon_on) {
     const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom], nr = re - rs;
-    GemmDesc d = gemm_base(FORM_TN, nr, kD, T, w.pred, w.pred_ld, w.E, kD, G + m->off_rw[random_chrom], kD);
+    GemmDesc d = gemm_base(FORM_TN, nr, Dm, T, w.pred, w.pred_ld, w.E, Dm, G + m->off_rw[random_chrom], Dm);
     d.b_act = 1; d.out_scale = beta; d.colsum = G + m->off_rb[random_chrom]; d.colsum_n = nr;
     if ((rc = run_gemm(d, s, P_W_RECON))) return rc;
-    GemmDesc e = gemm_base(FORM_NN, T, kD, nr, w.pred, w.pred_ld, P + m->off_rw[random_chrom], kD, w.dtE, kD);
+    GemmDesc e = gemm_base(FORM_NN, T, Dm, nr, w.pred, w.pred_ld, P + m->off_rw[random_chrom], Dm, w.dtE, Dm);
     if ((rc = run_gemm(e, s, P_D_RECON))) return rc;
     dtE = w.dtE;
   }
   if (chain) {
     // LayerNorm / tanh / next_w backward and the encoder-gradient combine in one row-chain kernel; the next_w and
     // attribute_nn weight / bias gradients in one stacked tile kernel
-    if ((rc = PROF(P_LN_BWD, 1, launch_chain_mix_bwd(dx_parts > 1 ? w.dQKG : w.dxhat, dx_parts, T * kD, w.dXs, w.xhat, w.rstd, w.X,
+    if ((rc = PROF(P_LN_BWD, 1, launch_chain_mix_bwd(dx_parts > 1 ? w.dQKG : w.dxhat, dx_parts, T * Dm, w.dXs, w.xhat, w.rstd, w.X,
                                                      dtE, w.E, beta, wc + CW_NEXT_MN * (kChainWBytes / 4), w.dE, w.dp_t, w.dv0_t, B,
                                                      L, s)))) return rc;
-    if ((rc = PROF(P_W_NEXT, 2, launch_wgrad_pair(w.dp_t, w.dv0_t, w.v0_t, w.attr_t, 4, nat, w.wpair_scratch, G + m->off_next_w, kD,
-                                                  kD, G + m->off_next_b, G + m->off_attr_w, m->attr_dim, m->attr_dim,
+    if ((rc = PROF(P_W_NEXT, 2, launch_wgrad_pair(w.dp_t, w.dv0_t, w.v0_t, w.attr_t, 4, nat, w.wpair_scratch, G + m->off_next_w, Dm,
+                                                  Dm, G + m->off_next_b, G + m->off_attr_w, m->attr_dim, m->attr_dim,
                                                   G + m->off_attr_b, s)))) return rc;
   } else {
-    if ((rc = PROF(P_LN_BWD, 1, launch_ln_tanh_bwd(dx_parts > 1 ? w.dQKG : w.dxhat, dx_parts, T * kD, w.dXs, w.xhat, w.rstd, w.X,
+    if ((rc = PROF(P_LN_BWD, 1, launch_ln_tanh_bwd(m->d, dx_parts > 1 ? w.dQKG : w.dxhat, dx_parts, T * Dm, w.dXs, w.xhat, w.rstd, w.X,
                                                    w.dP, T, s)))) return rc;
-    GemmDesc d = gemm_base(FORM_TN, kD, kD, T, w.dP, kD, w.V0, kD, G + m->off_next_w, kD);
-    d.colsum = G + m->off_next_b; d.colsum_n = kD;
+    GemmDesc d = gemm_base(FORM_TN, Dm, Dm, T, w.dP, Dm, w.V0, Dm, G + m->off_next_w, Dm);
+    d.colsum = G + m->off_next_b; d.colsum_n = Dm;
     if ((rc = run_gemm(d, s, P_W_NEXT))) return rc;
-    GemmDesc e = gemm_base(FORM_NN, T, kD, kD, w.dP, kD, P + m->off_next_w, kD, w.dV0, kD);
+    GemmDesc e = gemm_base(FORM_NN, T, Dm, Dm, w.dP, Dm, P + m->off_next_w, Dm, w.dV0, Dm);
     if ((rc = run_gemm(e, s, P_D_NEXT))) return rc;
-    GemmDesc f = gemm_base(FORM_TN, kD, m->attr_dim, T, w.dV0, kD, m->attr_table, m->attr_dim, G + m->off_attr_w, m->attr_dim);
-    f.b_ids = x; f.colsum = G + m->off_attr_b; f.colsum_n = kD;
+    GemmDesc f = gemm_base(FORM_TN, Dm, m->attr_dim, T, w.dV0, Dm, m->attr_table, m->attr_dim, G + m->off_attr_w, m->attr_dim);
+    f.b_ids = x; f.colsum = G + m->off_attr_b; f.colsum_n = Dm;
     if ((rc = run_gemm(f, s, P_W_ATTR))) return rc;
-    if ((rc = PROF(P_ENC_COMBINE, 1, launch_enc_combine_bwd(w.dV0, dtE, w.E, beta, w.dE, T * kD, s)))) return rc;
+    if ((rc = PROF(P_ENC_COMBINE, 1, launch_enc_combine_bwd(w.dV0, dtE, w.E, beta, w.dE, T * Dm, s)))) return rc;
   }
   // encoder backward (grouped by chromosome; token lists from the forward pass are still in the workspace)
   {
-    GemmDesc d = gemm_base(FORM_TN, kD, kD, 0, w.dE, kD, w.H0, kD, nullptr, kD);
-    d.perm = w.perm; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, TAB_GW1); d.group_off = w.group_off;
-    d.total_rows = T; d.max_group_dim = kD;
+    GemmDesc d = gemm_base(FORM_TN, Dm, Dm, 0, w.dE, Dm, w.H0, Dm, nullptr, Dm);
+    d.perm = w.perm; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, m->d, TAB_GW1); d.group_off = w.group_off;
+    d.total_rows = T; d.max_group_dim = Dm;
     if ((rc = run_gemm(d, s, P_W_ENC1))) return rc;
-    GemmDesc e = gemm_base(FORM_NN, 0, kD, kD, w.dE, kD, nullptr, 0, w.dH0pre, kD);
-    e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, TAB_ENC1); e.group_off = w.group_off;
-    e.total_rows = T; e.epi_act = 2; e.aux = w.H0; e.ld_aux = kD;
+    GemmDesc e = gemm_base(FORM_NN, 0, Dm, Dm, w.dE, Dm, nullptr, 0, w.dH0pre, Dm);
+    e.perm = w.perm; e.ngroups = m->n_chrom; e.groups = table_ptr(m->derived, m->d, TAB_ENC1); e.group_off = w.group_off;
+    e.total_rows = T; e.epi_act = 2; e.aux = w.H0; e.ld_aux = Dm;
     if ((rc = run_gemm(e, s, P_D_ENC1))) return rc;
     if (model_uses_csr(m)) {
       if ((rc = check_cuda(cudaMemsetAsync(DG + l.total, 0, sizeof(float) * w0t_floats(m), s), "memset dW0T"))) return rc;
       if ((rc = PROF(P_W_ENC0, 2, launch_enc0_csr_wgrad(m, l.total, x, T, w.perm, w.group_off, w.dH0pre,
                                                         make_drop(seed, SITE_FEATURE, m->p_feature, true), s)))) return rc;
     } else {
-      GemmDesc f = gemm_base(FORM_TN, kD, 0, 0, w.dH0pre, kD, nullptr, 0, nullptr, 0);
-      f.perm = w.perm; f.b_ids = x; f.ngroups = m->n_chrom; f.groups = table_ptr(m->derived, TAB_GW0);
+      GemmDesc f = gemm_base(FORM_TN, Dm, 0, 0, w.dH0pre, Dm, nullptr, 0, nullptr, 0);
+      f.perm = w.perm; f.b_ids = x; f.ngroups = m->n_chrom; f.groups = table_ptr(m->derived, m->d, TAB_GW0);
       f.group_off = w.group_off; f.total_rows = T; f.max_group_dim = max_chrom_len(m);
       if (m->p_feature > 0.f) { f.drop_on = 2; f.drop = make_drop(seed, SITE_FEATURE, m->p_feature, true); }
       if ((rc = run_gemm(f, s, P_W_ENC0))) return rc;
@@ -782,9 +803,9 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   }
   // derived -> reference parameters
   prof_begin(P_PREP_BWD, s);
-  prep_bwd_qk_kernel<<<kD, 256, 0, s>>>(*m);
+  prep_bwd_qk_kernel<<<m->d, 256, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_bwd_qk");
-  prep_bwd_g_kernel<<<4 * kH, 256, 0, s>>>(*m);
+  prep_bwd_g_kernel<<<kH * m->d, m->d, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_bwd_g");
   prof_end(P_PREP_BWD, 2, s);
   if (active) {
@@ -808,6 +829,9 @@ int matcha_node_embeddings(const matcha_model_desc* m, const int64_t* ids, int64
 
 int matcha_pair_tables(const matcha_model_desc* m, float* D, float* S, void* workspace, int64_t workspace_bytes,
                        void* stream) {
+  const int Dm = m->d;
+  const int64_t QKGm = 3 * (int64_t)kH * Dm;
+  (void)QKGm;
   int rc = validate(m);
   if (rc) return rc;
   MATCHA_REQUIRE(D && S && workspace, "matcha_pair_tables: NULL argument");
@@ -821,12 +845,12 @@ int matcha_pair_tables(const matcha_model_desc* m, float* D, float* S, void* wor
   // run_mix_qkg, before run_pff overwrites H1d
   int64_t* ids = reinterpret_cast<int64_t*>(w.H1d);
   if ((rc = PROF(P_MISC, 1, launch_iota_i64(ids, T, s)))) return rc;
-  const DerivedLayout l = derived_layout();
+  const DerivedLayout l = derived_layout(m->d);
   if ((rc = run_encoder(m, ids, T, 0, 0, w, w.E, s))) return rc;
   if ((rc = run_mix_qkg(m, ids, T, w, s))) return rc;
-  if ((rc = PROF(P_MISC, 1, launch_pair_u(w.QKG, m->derived + l.bdyn, w.U, T, s)))) return rc;
+  if ((rc = PROF(P_MISC, 1, launch_pair_u(m->d, w.QKG, m->derived + l.bdyn, w.U, T, s)))) return rc;
   if ((rc = run_pff(m, T, 0, 0, w, s))) return rc;
-  return PROF(P_MISC, 1, launch_pair_ds(w.H2, w.xhat, score_params(m), D, S, T, s));
+  return PROF(P_MISC, 1, launch_pair_ds(m->d, w.H2, w.xhat, score_params(m), D, S, T, s));
 }
 
 int64_t matcha_gemm_scratch_floats(int64_t M) { return gemm_tc_scratch_floats(M); }

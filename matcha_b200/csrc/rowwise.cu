@@ -11,7 +11,10 @@ namespace {
 constexpr int kBlock = 256;
 constexpr float kLnEps = 1e-5f;
 
-__device__ __forceinline__ float red16(float v) {
+// sum over the D / 4 lanes that share one row (16 lanes for d = 64: a half-warp; 32 for d = 128: the warp)
+template <int D>
+__device__ __forceinline__ float redrow(float v) {
+  if (D == 128) v += __shfl_xor_sync(0xffffffffu, v, 16);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -32,47 +35,52 @@ __device__ __forceinline__ float4 fma4(float s, float4 a, float4 c) {
 }
 
 struct LnOut { float4 xh; float rstd; };
-// LayerNorm statistics of one 64-wide row spread over 16 lanes (biased variance, eps 1e-5)
+// LayerNorm statistics of one D-wide row spread over D / 4 lanes (biased variance, eps 1e-5)
+template <int D>
 __device__ __forceinline__ LnOut ln_norm(float4 v) {
-  const float mean = red16(sum4(v)) * (1.0f / kD);
+  const float mean = redrow<D>(sum4(v)) * (1.0f / D);
   const float4 c = v - f4(mean);
-  const float var = red16(dot4(c, c)) * (1.0f / kD);
+  const float var = redrow<D>(dot4(c, c)) * (1.0f / D);
   LnOut o;
   o.rstd = 1.0f / sqrtf(var + kLnEps);
   o.xh = c * o.rstd;
   return o;
 }
 // dx of y = LN(x) given gy = dy * gamma, normalised row xh and rstd
+template <int D>
 __device__ __forceinline__ float4 ln_bwd(float4 gy, float4 xh, float rstd) {
-  const float m1 = red16(sum4(gy)) * (1.0f / kD);
-  const float m2 = red16(dot4(gy, xh)) * (1.0f / kD);
+  const float m1 = redrow<D>(sum4(gy)) * (1.0f / D);
+  const float m2 = redrow<D>(dot4(gy, xh)) * (1.0f / D);
   return (gy - f4(m1) - xh * m2) * rstd;
 }
 
-// block-level column reduction: every thread holds a float4 for columns [4*hl, 4*hl+4); add to dst[64]
-__device__ __forceinline__ void block_colsum_atomic(float4 v, float* smem64, float* dst) {
-  const int lane = threadIdx.x & 31, hl = threadIdx.x & 15;
-  v.x += __shfl_xor_sync(0xffffffffu, v.x, 16);
-  v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
-  v.z += __shfl_xor_sync(0xffffffffu, v.z, 16);
-  v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
-  if (threadIdx.x < kD) smem64[threadIdx.x] = 0.f;
+// block-level column reduction: every thread holds a float4 for columns [4*hl, 4*hl+4); add to dst[D]
+template <int D>
+__device__ __forceinline__ void block_colsum_atomic(float4 v, float* smemD, float* dst) {
+  const int lane = threadIdx.x & 31, hl = threadIdx.x & (D / 4 - 1);
+  if (D == 64) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, 16);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, 16);
+    v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
+  }
+  if (threadIdx.x < D) smemD[threadIdx.x] = 0.f;
   __syncthreads();
-  if (lane < 16) {
-    atomicAdd(&smem64[hl * 4 + 0], v.x);
-    atomicAdd(&smem64[hl * 4 + 1], v.y);
-    atomicAdd(&smem64[hl * 4 + 2], v.z);
-    atomicAdd(&smem64[hl * 4 + 3], v.w);
+  if (lane < D / 4) {
+    atomicAdd(&smemD[hl * 4 + 0], v.x);
+    atomicAdd(&smemD[hl * 4 + 1], v.y);
+    atomicAdd(&smemD[hl * 4 + 2], v.z);
+    atomicAdd(&smemD[hl * 4 + 3], v.w);
   }
   __syncthreads();
-  if (threadIdx.x < kD && dst) atomicAdd(dst + threadIdx.x, smem64[threadIdx.x]);
+  if (threadIdx.x < D && dst) atomicAdd(dst + threadIdx.x, smemD[threadIdx.x]);
   __syncthreads();
 }
 
 __device__ __forceinline__ int64_t num_token_tiles_dev(int64_t T) { return (T + kTileTok - 1) / kTileTok; }
 
-inline int grid_for_halfwarps(int64_t n, int cap_blocks) {
-  int64_t blocks = (n * 16 + kBlock - 1) / kBlock;
+inline int grid_for_rows(int64_t n, int d, int cap_blocks) {       // d / 4 lanes per row
+  int64_t blocks = (n * (d / 4) + kBlock - 1) / kBlock;
   if (blocks < 1) blocks = 1;
   if (blocks > cap_blocks) blocks = cap_blocks;
   return (int)blocks;
@@ -155,19 +163,20 @@ __device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
 // byte offset, inside a tile half, of columns [4*hl, 4*hl+4) of token `tok` (0..127)
 __device__ __forceinline__ int tile_off(int hl, int tok) { return (hl >> 1) * kPlaneBytes + tok * 16 + (hl & 1) * 8; }
 
+template <int D>
 __global__ void __launch_bounds__(kBlock) ln_fwd_kernel(const float* __restrict__ X, float* __restrict__ xhat,
                                                          float* __restrict__ rstd, int64_t T, uint8_t* __restrict__ xt) {
-  const int hl = threadIdx.x & 15;
-  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int hl = threadIdx.x & (D / 4 - 1);
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (D / 4), nhw = ((int64_t)gridDim.x * blockDim.x) / (D / 4);
   const int64_t Tp = xt ? num_token_tiles_dev(T) * kTileTok : T;     // tile path: also zero the tail rows of the last tile
   const int64_t iters = (Tp + nhw - 1) / nhw;
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t t = hw0 + it * nhw;
     const bool valid = t < T;
     const int64_t tt = valid ? t : T - 1;
-    LnOut o = ln_norm(ldg4(X + tt * kD + hl * 4));
+    LnOut o = ln_norm<D>(ldg4(X + tt * D + hl * 4));
     if (valid) {
-      st4(xhat + t * kD + hl * 4, o.xh);
+      st4(xhat + t * D + hl * 4, o.xh);
       if (hl == 0) rstd[t] = o.rstd;
     }
     if (xt && t < Tp) {
@@ -207,19 +216,19 @@ __device__ __forceinline__ void softmax_offdiag(float (&A)[L][L]) {
   }
 }
 
-template <int L>
+template <int D, int L>
 __global__ void __launch_bounds__(kBlock) attn_fwd_kernel(const float* __restrict__ QKG, const int64_t* __restrict__ x,
                                                            const float* __restrict__ b_dyn, float* __restrict__ U,
                                                            int64_t B, const DropCfg drop) {
-  const int hl = threadIdx.x & 15;
-  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int hl = threadIdx.x & (D / 4 - 1);
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (D / 4), nhw = ((int64_t)gridDim.x * blockDim.x) / (D / 4);
   const int64_t iters = (B + nhw - 1) / nhw;
   const float4 bd = ldg4(b_dyn + hl * 4);
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t b = hw0 + it * nhw;
     const bool valid = b < B;
     const int64_t bb = valid ? b : B - 1;
-    const float* base = QKG + bb * L * kQKG + hl * 4;
+    const float* base = QKG + bb * L * (3 * kH * D) + hl * 4;
     float4 o[L];
 #pragma unroll
     for (int i = 0; i < L; ++i) o[i] = bd;
@@ -228,18 +237,18 @@ __global__ void __launch_bounds__(kBlock) attn_fwd_kernel(const float* __restric
       float4 q[L], k[L];
 #pragma unroll
       for (int i = 0; i < L; ++i) {
-        q[i] = ldg4(base + i * kQKG + h * kD);
-        k[i] = ldg4(base + i * kQKG + kH * kD + h * kD);
+        q[i] = ldg4(base + i * (3 * kH * D) + h * D);
+        k[i] = ldg4(base + i * (3 * kH * D) + kH * D + h * D);
       }
       float A[L][L];
 #pragma unroll
       for (int i = 0; i < L; ++i)
 #pragma unroll
-        for (int j = 0; j < L; ++j) A[i][j] = (i != j) ? red16(dot4(q[i], k[j])) : 0.f;
+        for (int j = 0; j < L; ++j) A[i][j] = (i != j) ? redrow<D>(dot4(q[i], k[j])) : 0.f;
       softmax_offdiag<L>(A);
 #pragma unroll
       for (int j = 0; j < L; ++j) {
-        const float4 g = ldg4(base + j * kQKG + 2 * kH * kD + h * kD);
+        const float4 g = ldg4(base + j * (3 * kH * D) + 2 * kH * D + h * D);
 #pragma unroll
         for (int i = 0; i < L; ++i) if (i != j) o[i] = fma4(A[i][j], g, o[i]);
       }
@@ -250,17 +259,17 @@ __global__ void __launch_bounds__(kBlock) attn_fwd_kernel(const float* __restric
         const int64_t t = b * L + i;
         const float m = x[t] != 0 ? 1.f : 0.f;                       // non_pad_mask (Modules.py:614)
         float4 v = drop_apply4(drop, (uint64_t)t, (uint32_t)(hl * 4), o[i]);   // dropout after fc1 (:572)
-        st4(U + t * kD + hl * 4, v * m);
+        st4(U + t * D + hl * 4, v * m);
       }
     }
   }
 }
 
 // store 4 consecutive gradient columns of token t: fp32 row-major, or pre-split tile (chunk fc, columns 4*hl..)
-template <bool SPLIT>
+template <int D, bool SPLIT>
 __device__ __forceinline__ void store_dqkg(float* dQKG, uint8_t* gt, int64_t t, int fc, int hl, float4 v) {
   if (!SPLIT) {
-    st4(dQKG + t * kQKG + fc * kD + hl * 4, v);
+    st4(dQKG + t * (3 * kH * D) + fc * D + hl * 4, v);
   } else {
     uint2 hi, lo;
     split4(v, hi, lo);
@@ -271,27 +280,27 @@ __device__ __forceinline__ void store_dqkg(float* dQKG, uint8_t* gt, int64_t t, 
   }
 }
 
-template <int L, bool SPLIT>
+template <int D, int L, bool SPLIT>
 __global__ void __launch_bounds__(kBlock) attn_bwd_kernel(const float* __restrict__ QKG, const float* __restrict__ dU,
                                                            const int64_t* __restrict__ x, float* __restrict__ dQKG,
                                                            uint8_t* __restrict__ gt, float* __restrict__ db_dyn, int64_t B,
                                                            const DropCfg drop) {
-  __shared__ float red[kD];
-  const int hl = threadIdx.x & 15;
-  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  __shared__ float red[D];
+  const int hl = threadIdx.x & (D / 4 - 1);
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (D / 4), nhw = ((int64_t)gridDim.x * blockDim.x) / (D / 4);
   const int64_t iters = (B + nhw - 1) / nhw;
   float4 acc_b = f4(0.f);
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t b = hw0 + it * nhw;
     const bool valid = b < B;
     const int64_t bb = valid ? b : B - 1;
-    const float* base = QKG + bb * L * kQKG + hl * 4;
+    const float* base = QKG + bb * L * (3 * kH * D) + hl * 4;
     float4 dd[L];
 #pragma unroll
     for (int i = 0; i < L; ++i) {
       const int64_t t = bb * L + i;
       const float m = x[t] != 0 ? 1.f : 0.f;
-      dd[i] = ldg4(dU + t * kD + hl * 4) * drop_factor4(drop, (uint64_t)t, (uint32_t)(hl * 4)) * m;
+      dd[i] = ldg4(dU + t * D + hl * 4) * drop_factor4(drop, (uint64_t)t, (uint32_t)(hl * 4)) * m;
       if (valid) acc_b = acc_b + dd[i];
     }
 #pragma unroll 1
@@ -299,17 +308,17 @@ __global__ void __launch_bounds__(kBlock) attn_bwd_kernel(const float* __restric
       float4 q[L], k[L], g[L];
 #pragma unroll
       for (int i = 0; i < L; ++i) {
-        q[i] = ldg4(base + i * kQKG + h * kD);
-        k[i] = ldg4(base + i * kQKG + kH * kD + h * kD);
-        g[i] = ldg4(base + i * kQKG + 2 * kH * kD + h * kD);
+        q[i] = ldg4(base + i * (3 * kH * D) + h * D);
+        k[i] = ldg4(base + i * (3 * kH * D) + kH * D + h * D);
+        g[i] = ldg4(base + i * (3 * kH * D) + 2 * kH * D + h * D);
       }
       float A[L][L], dA[L][L];
 #pragma unroll
       for (int i = 0; i < L; ++i)
 #pragma unroll
         for (int j = 0; j < L; ++j) {
-          A[i][j] = (i != j) ? red16(dot4(q[i], k[j])) : 0.f;
-          dA[i][j] = (i != j) ? red16(dot4(dd[i], g[j])) : 0.f;
+          A[i][j] = (i != j) ? redrow<D>(dot4(q[i], k[j])) : 0.f;
+          dA[i][j] = (i != j) ? redrow<D>(dot4(dd[i], g[j])) : 0.f;
         }
       softmax_offdiag<L>(A);
       // dG_h[j] = sum_i A[i][j] * ddyn_i
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(kBlock) attn_bwd_kernel(const float* __restric
         float4 dg = f4(0.f);
 #pragma unroll
         for (int i = 0; i < L; ++i) if (i != j) dg = fma4(A[i][j], dd[i], dg);
-        if (valid) store_dqkg<SPLIT>(dQKG, gt, bb * L + j, 2 * kH + h, hl, dg);
+        if (valid) store_dqkg<D, SPLIT>(dQKG, gt, bb * L + j, 2 * kH + h, hl, dg);
       }
       // softmax backward -> dS (stored in dA)
 #pragma unroll
@@ -335,13 +344,13 @@ __global__ void __launch_bounds__(kBlock) attn_bwd_kernel(const float* __restric
 #pragma unroll
         for (int j = 0; j < L; ++j) if (j != i) { dq = fma4(dA[i][j], k[j], dq); dk = fma4(dA[j][i], q[j], dk); }
         if (valid) {
-          store_dqkg<SPLIT>(dQKG, gt, bb * L + i, h, hl, dq);
-          store_dqkg<SPLIT>(dQKG, gt, bb * L + i, kH + h, hl, dk);
+          store_dqkg<D, SPLIT>(dQKG, gt, bb * L + i, h, hl, dq);
+          store_dqkg<D, SPLIT>(dQKG, gt, bb * L + i, kH + h, hl, dk);
         }
       }
     }
   }
-  block_colsum_atomic(acc_b, red, db_dyn);
+  block_colsum_atomic<D>(acc_b, red, db_dyn);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -358,12 +367,12 @@ __device__ __forceinline__ ScoreVec load_score_params(const ScoreParams& p, int 
   return v;
 }
 
-template <int L>
+template <int D, int L>
 __global__ void __launch_bounds__(kBlock) score_fwd_kernel(const float* __restrict__ H2, const float* __restrict__ xhat,
                                                             const int64_t* __restrict__ x, const ScoreParams p,
                                                             float* __restrict__ logits, int64_t B) {
-  const int hl = threadIdx.x & 15;
-  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int hl = threadIdx.x & (D / 4 - 1);
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (D / 4), nhw = ((int64_t)gridDim.x * blockDim.x) / (D / 4);
   const int64_t iters = (B + nhw - 1) / nhw;
   const ScoreVec sv = load_score_params(p, hl);
   for (int64_t it = 0; it < iters; ++it) {
@@ -375,13 +384,13 @@ __global__ void __launch_bounds__(kBlock) score_fwd_kernel(const float* __restri
     for (int i = 0; i < L; ++i) {
       const int64_t t = bb * L + i;
       const float m = x[t] != 0 ? 1.f : 0.f;
-      LnOut a = ln_norm(ldg4(H2 + t * kD + hl * 4));
+      LnOut a = ln_norm<D>(ldg4(H2 + t * D + hl * 4));
       const float4 dyn2 = (a.xh * sv.gp + sv.bp) * m;
-      LnOut c = ln_norm(dyn2);
-      const float4 D = c.xh * sv.g1 + sv.b1;
-      const float4 S = ldg4(xhat + t * kD + hl * 4) * sv.g2 + sv.b2;
-      const float4 df = D - S;
-      const float z = red16(dot4(df * df, sv.w)) + sv.cb;
+      LnOut c = ln_norm<D>(dyn2);
+      const float4 Dv = c.xh * sv.g1 + sv.b1;
+      const float4 S = ldg4(xhat + t * D + hl * 4) * sv.g2 + sv.b2;
+      const float4 df = Dv - S;
+      const float z = redrow<D>(dot4(df * df, sv.w)) + sv.cb;
       zsum += z * m;
       msum += m;
     }
@@ -389,15 +398,15 @@ __global__ void __launch_bounds__(kBlock) score_fwd_kernel(const float* __restri
   }
 }
 
-template <int L>
+template <int D, int L>
 __global__ void __launch_bounds__(kBlock) score_bwd_kernel(const float* __restrict__ H2, const float* __restrict__ xhat,
                                                             const float* __restrict__ rstd_x, const int64_t* __restrict__ x,
                                                             const ScoreParams p, const float* __restrict__ dlogit,
                                                             float* __restrict__ dH2, float* __restrict__ dXs,
                                                             const ScoreGrads g, int64_t B) {
-  __shared__ float red[kD];
-  const int hl = threadIdx.x & 15;
-  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  __shared__ float red[D];
+  const int hl = threadIdx.x & (D / 4 - 1);
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (D / 4), nhw = ((int64_t)gridDim.x * blockDim.x) / (D / 4);
   const int64_t iters = (B + nhw - 1) / nhw;
   const ScoreVec sv = load_score_params(p, hl);
   float4 a_gp = f4(0.f), a_bp = f4(0.f), a_g1 = f4(0.f), a_b1 = f4(0.f), a_g2 = f4(0.f), a_b2 = f4(0.f), a_w = f4(0.f);
@@ -415,33 +424,33 @@ __global__ void __launch_bounds__(kBlock) score_bwd_kernel(const float* __restri
       const int64_t t = bb * L + i;
       const float m = x[t] != 0 ? 1.f : 0.f;
       const float dz = dl * m;
-      LnOut a = ln_norm(ldg4(H2 + t * kD + hl * 4));
+      LnOut a = ln_norm<D>(ldg4(H2 + t * D + hl * 4));
       const float4 dyn2 = (a.xh * sv.gp + sv.bp) * m;
-      LnOut c = ln_norm(dyn2);
-      const float4 D = c.xh * sv.g1 + sv.b1;
-      const float4 xh = ldg4(xhat + t * kD + hl * 4);
+      LnOut c = ln_norm<D>(dyn2);
+      const float4 Dv = c.xh * sv.g1 + sv.b1;
+      const float4 xh = ldg4(xhat + t * D + hl * 4);
       const float4 S = xh * sv.g2 + sv.b2;
-      const float4 df = D - S;
+      const float4 df = Dv - S;
       if (hl == 0) a_cb += dz;
       a_w = a_w + df * df * dz;
       const float4 dD = df * sv.w * (2.f * dz);
       // Classifier.layer_norm1 backward
       a_g1 = a_g1 + dD * c.xh; a_b1 = a_b1 + dD;
-      float4 ddyn2 = ln_bwd(dD * sv.g1, c.xh, c.rstd) * m;
+      float4 ddyn2 = ln_bwd<D>(dD * sv.g1, c.xh, c.rstd) * m;
       // pff_n1.layer_norm backward
       a_gp = a_gp + ddyn2 * a.xh; a_bp = a_bp + ddyn2;
-      const float4 dh2 = ln_bwd(ddyn2 * sv.gp, a.xh, a.rstd);
+      const float4 dh2 = ln_bwd<D>(ddyn2 * sv.gp, a.xh, a.rstd);
       // Classifier.layer_norm2 (static branch) backward, directly w.r.t. X
       const float4 dS = f4(0.f) - dD;
       a_g2 = a_g2 + dS * xh; a_b2 = a_b2 + dS;
-      const float4 dxs = ln_bwd(dS * sv.g2, xh, rstd_x[t]);
-      if (valid) { st4(dH2 + t * kD + hl * 4, dh2); st4(dXs + t * kD + hl * 4, dxs); }
+      const float4 dxs = ln_bwd<D>(dS * sv.g2, xh, rstd_x[t]);
+      if (valid) { st4(dH2 + t * D + hl * 4, dh2); st4(dXs + t * D + hl * 4, dxs); }
     }
   }
-  block_colsum_atomic(a_gp, red, g.pff_g); block_colsum_atomic(a_bp, red, g.pff_b);
-  block_colsum_atomic(a_g1, red, g.ln1_g); block_colsum_atomic(a_b1, red, g.ln1_b);
-  block_colsum_atomic(a_g2, red, g.ln2_g); block_colsum_atomic(a_b2, red, g.ln2_b);
-  block_colsum_atomic(a_w, red, g.cls_w);
+  block_colsum_atomic<D>(a_gp, red, g.pff_g); block_colsum_atomic<D>(a_bp, red, g.pff_b);
+  block_colsum_atomic<D>(a_g1, red, g.ln1_g); block_colsum_atomic<D>(a_b1, red, g.ln1_b);
+  block_colsum_atomic<D>(a_g2, red, g.ln2_g); block_colsum_atomic<D>(a_b2, red, g.ln2_b);
+  block_colsum_atomic<D>(a_w, red, g.cls_w);
   // scalar bias gradient
   float s = a_cb;
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -513,24 +522,25 @@ __global__ void __launch_bounds__(kBlock) recon_diff_kernel(float* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // small backward helpers
 // ------------------------------------------------------------------------------------------
+template <int D>
 __global__ void __launch_bounds__(kBlock) ln_tanh_bwd_kernel(const float* __restrict__ dxhat, int nparts, int64_t part_stride,
                                                               const float* __restrict__ dXs,
                                                               const float* __restrict__ xhat, const float* __restrict__ rstd,
                                                               const float* __restrict__ X, float* __restrict__ dP, int64_t T) {
-  const int hl = threadIdx.x & 15;
-  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int hl = threadIdx.x & (D / 4 - 1);
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (D / 4), nhw = ((int64_t)gridDim.x * blockDim.x) / (D / 4);
   const int64_t iters = (T + nhw - 1) / nhw;
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t t = hw0 + it * nhw;
     const bool valid = t < T;
     const int64_t tt = valid ? t : T - 1;
-    const float4 xh = ldg4(xhat + tt * kD + hl * 4);
-    float4 gy = ldg4(dxhat + tt * kD + hl * 4);
-    for (int p = 1; p < nparts; ++p) gy = gy + ldg4(dxhat + p * part_stride + tt * kD + hl * 4);
-    float4 dx = ln_bwd(gy, xh, rstd[tt]) + ldg4(dXs + tt * kD + hl * 4);
-    const float4 xv = ldg4(X + tt * kD + hl * 4);
+    const float4 xh = ldg4(xhat + tt * D + hl * 4);
+    float4 gy = ldg4(dxhat + tt * D + hl * 4);
+    for (int p = 1; p < nparts; ++p) gy = gy + ldg4(dxhat + p * part_stride + tt * D + hl * 4);
+    float4 dx = ln_bwd<D>(gy, xh, rstd[tt]) + ldg4(dXs + tt * D + hl * 4);
+    const float4 xv = ldg4(X + tt * D + hl * 4);
     dx = dx * (f4(1.f) - xv * xv);                      // X = tanh(P)  (Modules.py:270)
-    if (valid) st4(dP + t * kD + hl * 4, dx);
+    if (valid) st4(dP + t * D + hl * 4, dx);
   }
 }
 __global__ void enc_combine_bwd_kernel(const float4* __restrict__ dV0, const float4* __restrict__ dtE,
@@ -549,33 +559,35 @@ __global__ void enc_combine_bwd_kernel(const float4* __restrict__ dV0, const flo
 // ------------------------------------------------------------------------------------------
 // k = 2 closed-form tables
 // ------------------------------------------------------------------------------------------
+template <int D>
 __global__ void __launch_bounds__(kBlock) pair_u_kernel(const float* __restrict__ QKG, const float* __restrict__ b_dyn,
                                                          float* __restrict__ U, int64_t T) {
-  const int hl = threadIdx.x & 15;
-  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int hl = threadIdx.x & (D / 4 - 1);
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (D / 4), nhw = ((int64_t)gridDim.x * blockDim.x) / (D / 4);
   for (int64_t t = hw0; t < T; t += nhw) {
     float4 o = ldg4(b_dyn + hl * 4);
 #pragma unroll
-    for (int h = 0; h < kH; ++h) o = o + ldg4(QKG + t * kQKG + 2 * kH * kD + h * kD + hl * 4);
-    st4(U + t * kD + hl * 4, o);
+    for (int h = 0; h < kH; ++h) o = o + ldg4(QKG + t * (3 * kH * D) + 2 * kH * D + h * D + hl * 4);
+    st4(U + t * D + hl * 4, o);
   }
 }
+template <int D>
 __global__ void __launch_bounds__(kBlock) pair_ds_kernel(const float* __restrict__ H2, const float* __restrict__ xhat,
-                                                          const ScoreParams p, float* __restrict__ D, float* __restrict__ S,
+                                                          const ScoreParams p, float* __restrict__ Dt, float* __restrict__ St,
                                                           int64_t T) {
-  const int hl = threadIdx.x & 15;
-  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int hl = threadIdx.x & (D / 4 - 1);
+  const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (D / 4), nhw = ((int64_t)gridDim.x * blockDim.x) / (D / 4);
   const int64_t iters = (T + nhw - 1) / nhw;
   const ScoreVec sv = load_score_params(p, hl);
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t t = hw0 + it * nhw;
     const bool valid = t < T;
     const int64_t tt = valid ? t : T - 1;
-    LnOut a = ln_norm(ldg4(H2 + tt * kD + hl * 4));
-    LnOut c = ln_norm(a.xh * sv.gp + sv.bp);
+    LnOut a = ln_norm<D>(ldg4(H2 + tt * D + hl * 4));
+    LnOut c = ln_norm<D>(a.xh * sv.gp + sv.bp);
     if (valid) {
-      st4(D + t * kD + hl * 4, c.xh * sv.g1 + sv.b1);
-      st4(S + t * kD + hl * 4, ldg4(xhat + t * kD + hl * 4) * sv.g2 + sv.b2);
+      st4(Dt + t * D + hl * 4, c.xh * sv.g1 + sv.b1);
+      st4(St + t * D + hl * 4, ldg4(xhat + t * D + hl * 4) * sv.g2 + sv.b2);
     }
   }
 }
@@ -609,13 +621,11 @@ int launch_active_flags(const int32_t* counts, int n_chrom, int rchrom, int64_t 
   return MATCHA_OK;
 }
 
-int launch_ln_fwd(const float* X, float* xhat, float* rstd, int64_t T, uint8_t* xhat_tiles, cudaStream_t s) {
-  if (T <= 0) return MATCHA_OK;
-  ln_fwd_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(X, xhat, rstd, T, xhat_tiles);
-  MATCHA_CHECK_LAUNCH("ln_fwd");
-  return MATCHA_OK;
-}
 
+#define MATCHA_DISPATCH_D(d, CALL)                                              \
+  if ((d) == 64) { constexpr int DD = 64; CALL; }                               \
+  else if ((d) == 128) { constexpr int DD = 128; CALL; }                        \
+  else { set_error("embed_dim %d unsupported (64, 128)", (int)(d)); return MATCHA_ERR_UNSUPPORTED; }
 #define MATCHA_DISPATCH_L(L, CALL)                                              \
   switch (L) {                                                                  \
     case 2: { constexpr int LL = 2; CALL; } break;                              \
@@ -628,39 +638,48 @@ int launch_ln_fwd(const float* X, float* xhat, float* rstd, int64_t T, uint8_t* 
       return MATCHA_ERR_UNSUPPORTED;                                            \
   }
 
-int launch_attn_fwd(const float* QKG, const int64_t* x, const float* b_dyn, float* U, int64_t B, int L, DropCfg drop,
+int launch_ln_fwd(int d, const float* X, float* xhat, float* rstd, int64_t T, uint8_t* xhat_tiles, cudaStream_t s) {
+  if (T <= 0) return MATCHA_OK;
+  if (xhat_tiles && d != 64) { set_error("ln_fwd: pre-split tiles need embed_dim 64"); return MATCHA_ERR_UNSUPPORTED; }
+  MATCHA_DISPATCH_D(d, (ln_fwd_kernel<DD><<<grid_for_rows(T, d, kSMs * 16), kBlock, 0, s>>>(X, xhat, rstd, T, xhat_tiles)));
+  MATCHA_CHECK_LAUNCH("ln_fwd");
+  return MATCHA_OK;
+}
+
+int launch_attn_fwd(int d, const float* QKG, const int64_t* x, const float* b_dyn, float* U, int64_t B, int L, DropCfg drop,
                     cudaStream_t s) {
   if (B <= 0) return MATCHA_OK;
-  const int grid = grid_for_halfwarps(B, kSMs * 8);
-  MATCHA_DISPATCH_L(L, (attn_fwd_kernel<LL><<<grid, kBlock, 0, s>>>(QKG, x, b_dyn, U, B, drop)));
+  const int grid = grid_for_rows(B, d, kSMs * 8);
+  MATCHA_DISPATCH_D(d, MATCHA_DISPATCH_L(L, (attn_fwd_kernel<DD, LL><<<grid, kBlock, 0, s>>>(QKG, x, b_dyn, U, B, drop))));
   MATCHA_CHECK_LAUNCH("attn_fwd");
   return MATCHA_OK;
 }
-int launch_attn_bwd(const float* QKG, const float* dU, const int64_t* x, float* dQKG, uint8_t* dqkg_tiles, float* db_dyn,
+int launch_attn_bwd(int d, const float* QKG, const float* dU, const int64_t* x, float* dQKG, uint8_t* dqkg_tiles, float* db_dyn,
                     int64_t B, int L, DropCfg drop, cudaStream_t s) {
   if (B <= 0) return MATCHA_OK;
-  const int grid = grid_for_halfwarps(B, kSMs * 4);
+  const int grid = grid_for_rows(B, d, kSMs * 4);
   if (dqkg_tiles) {
-    MATCHA_DISPATCH_L(L, (attn_bwd_kernel<LL, true><<<grid, kBlock, 0, s>>>(QKG, dU, x, dQKG, dqkg_tiles, db_dyn, B, drop)));
+    if (d != 64) { set_error("attn_bwd: pre-split tiles need embed_dim 64"); return MATCHA_ERR_UNSUPPORTED; }
+    MATCHA_DISPATCH_L(L, (attn_bwd_kernel<64, LL, true><<<grid, kBlock, 0, s>>>(QKG, dU, x, dQKG, dqkg_tiles, db_dyn, B, drop)));
   } else {
-    MATCHA_DISPATCH_L(L, (attn_bwd_kernel<LL, false><<<grid, kBlock, 0, s>>>(QKG, dU, x, dQKG, dqkg_tiles, db_dyn, B, drop)));
+    MATCHA_DISPATCH_D(d, MATCHA_DISPATCH_L(L, (attn_bwd_kernel<DD, LL, false><<<grid, kBlock, 0, s>>>(QKG, dU, x, dQKG, dqkg_tiles, db_dyn, B, drop))));
   }
   MATCHA_CHECK_LAUNCH("attn_bwd");
   return MATCHA_OK;
 }
-int launch_score_fwd(const float* H2, const float* xhat, const int64_t* x, ScoreParams p, float* logits, int64_t B, int L,
+int launch_score_fwd(int d, const float* H2, const float* xhat, const int64_t* x, ScoreParams p, float* logits, int64_t B, int L,
                      cudaStream_t s) {
   if (B <= 0) return MATCHA_OK;
-  const int grid = grid_for_halfwarps(B, kSMs * 8);
-  MATCHA_DISPATCH_L(L, (score_fwd_kernel<LL><<<grid, kBlock, 0, s>>>(H2, xhat, x, p, logits, B)));
+  const int grid = grid_for_rows(B, d, kSMs * 8);
+  MATCHA_DISPATCH_D(d, MATCHA_DISPATCH_L(L, (score_fwd_kernel<DD, LL><<<grid, kBlock, 0, s>>>(H2, xhat, x, p, logits, B))));
   MATCHA_CHECK_LAUNCH("score_fwd");
   return MATCHA_OK;
 }
-int launch_score_bwd(const float* H2, const float* xhat, const float* rstd_x, const int64_t* x, ScoreParams p,
+int launch_score_bwd(int d, const float* H2, const float* xhat, const float* rstd_x, const int64_t* x, ScoreParams p,
                      const float* dlogit, float* dH2, float* dXs, ScoreGrads g, int64_t B, int L, cudaStream_t s) {
   if (B <= 0) return MATCHA_OK;
-  const int grid = grid_for_halfwarps(B, kSMs * 4);
-  MATCHA_DISPATCH_L(L, (score_bwd_kernel<LL><<<grid, kBlock, 0, s>>>(H2, xhat, rstd_x, x, p, dlogit, dH2, dXs, g, B)));
+  const int grid = grid_for_rows(B, d, kSMs * 4);
+  MATCHA_DISPATCH_D(d, MATCHA_DISPATCH_L(L, (score_bwd_kernel<DD, LL><<<grid, kBlock, 0, s>>>(H2, xhat, rstd_x, x, p, dlogit, dH2, dXs, g, B))));
   MATCHA_CHECK_LAUNCH("score_bwd");
   return MATCHA_OK;
 }
@@ -689,10 +708,10 @@ int launch_recon_diff(float* pred, int64_t ld, const int64_t* x, int64_t T, cons
   MATCHA_CHECK_LAUNCH("recon_diff");
   return MATCHA_OK;
 }
-int launch_ln_tanh_bwd(const float* dxhat, int nparts, int64_t part_stride, const float* dXs, const float* xhat,
+int launch_ln_tanh_bwd(int d, const float* dxhat, int nparts, int64_t part_stride, const float* dXs, const float* xhat,
                        const float* rstd, const float* X, float* dP, int64_t T, cudaStream_t s) {
   if (T <= 0) return MATCHA_OK;
-  ln_tanh_bwd_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(dxhat, nparts, part_stride, dXs, xhat, rstd, X, dP, T);
+  MATCHA_DISPATCH_D(d, (ln_tanh_bwd_kernel<DD><<<grid_for_rows(T, d, kSMs * 16), kBlock, 0, s>>>(dxhat, nparts, part_stride, dXs, xhat, rstd, X, dP, T)));
   MATCHA_CHECK_LAUNCH("ln_tanh_bwd");
   return MATCHA_OK;
 }
@@ -717,15 +736,15 @@ int launch_iota_i64(int64_t* out, int64_t n, cudaStream_t s) {
   MATCHA_CHECK_LAUNCH("iota_i64");
   return MATCHA_OK;
 }
-int launch_pair_u(const float* QKG, const float* b_dyn, float* U, int64_t T, cudaStream_t s) {
+int launch_pair_u(int d, const float* QKG, const float* b_dyn, float* U, int64_t T, cudaStream_t s) {
   if (T <= 0) return MATCHA_OK;
-  pair_u_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(QKG, b_dyn, U, T);
+  MATCHA_DISPATCH_D(d, (pair_u_kernel<DD><<<grid_for_rows(T, d, kSMs * 16), kBlock, 0, s>>>(QKG, b_dyn, U, T)));
   MATCHA_CHECK_LAUNCH("pair_u");
   return MATCHA_OK;
 }
-int launch_pair_ds(const float* H2, const float* xhat, ScoreParams p, float* D, float* S, int64_t T, cudaStream_t s) {
+int launch_pair_ds(int d, const float* H2, const float* xhat, ScoreParams p, float* D, float* S, int64_t T, cudaStream_t s) {
   if (T <= 0) return MATCHA_OK;
-  pair_ds_kernel<<<grid_for_halfwarps(T, kSMs * 16), kBlock, 0, s>>>(H2, xhat, p, D, S, T);
+  MATCHA_DISPATCH_D(d, (pair_ds_kernel<DD><<<grid_for_rows(T, d, kSMs * 16), kBlock, 0, s>>>(H2, xhat, p, D, S, T)));
   MATCHA_CHECK_LAUNCH("pair_ds");
   return MATCHA_OK;
 }

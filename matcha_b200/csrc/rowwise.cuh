@@ -41,13 +41,13 @@ int launch_bucket(const int64_t* x, int64_t T, const ChromMeta& cm, int32_t* cou
                   int32_t* cursor, int32_t* perm, cudaStream_t s);
 
 // xhat_tiles (optional): also emit the pre-split tiles (num_token_tiles(T) * kXTileBytes bytes, tail rows zeroed)
-int launch_ln_fwd(const float* X, float* xhat, float* rstd, int64_t T, uint8_t* xhat_tiles, cudaStream_t s);
-int launch_attn_fwd(const float* QKG, const int64_t* x, const float* b_dyn, float* U, int64_t B, int L,
+int launch_ln_fwd(int d, const float* X, float* xhat, float* rstd, int64_t T, uint8_t* xhat_tiles, cudaStream_t s);
+int launch_attn_fwd(int d, const float* QKG, const int64_t* x, const float* b_dyn, float* U, int64_t B, int L,
                     DropCfg drop, cudaStream_t s);
 struct ScoreParams {
   const float *pff_g, *pff_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b, *cls_w, *cls_b;
 };
-int launch_score_fwd(const float* H2, const float* xhat, const int64_t* x, ScoreParams p, float* logits,
+int launch_score_fwd(int d, const float* H2, const float* xhat, const int64_t* x, ScoreParams p, float* logits,
                      int64_t B, int L, cudaStream_t s);
 int launch_bce(const float* logits, const float* y, const float* w, float alpha, float* dlogit, float* loss_out,
                int64_t B, cudaStream_t s);
@@ -60,11 +60,11 @@ int launch_recon_diff(float* pred, int64_t ld, const int64_t* x, int64_t T, cons
 struct ScoreGrads {
   float *pff_g, *pff_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b, *cls_w, *cls_b;
 };
-int launch_score_bwd(const float* H2, const float* xhat, const float* rstd_x, const int64_t* x, ScoreParams p,
+int launch_score_bwd(int d, const float* H2, const float* xhat, const float* rstd_x, const int64_t* x, ScoreParams p,
                      const float* dlogit, float* dH2, float* dXs, ScoreGrads g, int64_t B, int L, cudaStream_t s);
 // dQKG is written as fp32 [T, 1536], or -- when dqkg_tiles != NULL -- only as pre-split tiles
 // [token tile][24 chunks][kGTileBytes] (the caller zeroes the tail rows of the last tile)
-int launch_attn_bwd(const float* QKG, const float* dU, const int64_t* x, float* dQKG, uint8_t* dqkg_tiles, float* db_dyn,
+int launch_attn_bwd(int d, const float* QKG, const float* dU, const int64_t* x, float* dQKG, uint8_t* dqkg_tiles, float* db_dyn,
                     int64_t B, int L, DropCfg drop, cudaStream_t s);
 
 // fused attention kernels (attn_fused.cu)
@@ -133,7 +133,7 @@ int tc_qkg_dgrad_tiles(const uint8_t* dqkg_tiles, const uint8_t* wT_split, float
 int tc_qkg_wgrad_tiles(const uint8_t* dqkg_tiles, const uint8_t* xhat_tiles, float* scratch, int64_t scratch_floats,
                        float* dW, float* dbias, int64_t dbias_n, int64_t T, cudaStream_t s);
 // dP = (LNbwd(sum of nparts dxhat partials, part_stride floats apart) + dXs) * (1 - X^2)
-int launch_ln_tanh_bwd(const float* dxhat, int nparts, int64_t part_stride, const float* dXs, const float* xhat,
+int launch_ln_tanh_bwd(int d, const float* dxhat, int nparts, int64_t part_stride, const float* dXs, const float* xhat,
                        const float* rstd, const float* X, float* dP, int64_t T, cudaStream_t s);
 // dE = dV0 + beta * dtE * (1 - tanh(E)^2)   (dtE may be NULL)
 int launch_enc_combine_bwd(const float* dV0, const float* dtE, const float* E, float beta, float* dE, int64_t n,
@@ -141,9 +141,9 @@ int launch_enc_combine_bwd(const float* dV0, const float* dtE, const float* E, f
 // active[c] = counts[c] > 0 ; active[C + c] = (c == rchrom && eligible > 0)
 int launch_active_flags(const int32_t* counts, int n_chrom, int rchrom, int64_t T, int32_t* active, cudaStream_t s);
 // per-node tables for the k = 2 closed form: U[n] = sum_h G_h[n] + b_dyn (the other token's attention output)
-int launch_pair_u(const float* QKG, const float* b_dyn, float* U, int64_t T, cudaStream_t s);
+int launch_pair_u(int d, const float* QKG, const float* b_dyn, float* U, int64_t T, cudaStream_t s);
 // D = LN1(LN_pff(H2)), S = LN2 affine of xhat
-int launch_pair_ds(const float* H2, const float* xhat, ScoreParams p, float* D, float* S, int64_t T, cudaStream_t s);
+int launch_pair_ds(int d, const float* H2, const float* xhat, ScoreParams p, float* D, float* S, int64_t T, cudaStream_t s);
 
 int launch_iota_i64(int64_t* out, int64_t n, cudaStream_t s);
 

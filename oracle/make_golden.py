@@ -1,6 +1,6 @@
 """Generate golden vectors by EXECUTING THE UNMODIFIED REFERENCE (authoring container only).
 
-    python oracle/make_golden.py            # writes tests/golden/ref_small.npz
+    python oracle/make_golden.py            # writes tests/golden/ref_small.npz and ref_small_d128.npz (embed_dim 128)
 
 Imports /root/reference/Code/Modules.py untouched (only a stub `pybloom_live` package is put on
 sys.path because the real one is not installed; it is needed solely by `utils.py:9`'s import).  The
@@ -77,9 +77,9 @@ def make_inputs(rng, N, L, B):
     return x
 
 
-def main(out=os.path.join(HERE, "..", "tests", "golden", "ref_small.npz")):
+def main(out=os.path.join(HERE, "..", "tests", "golden", "ref_small.npz"), d=64, widths=(2, 3, 4, 5), full_grads=(3, 5), full_grad_max_elems=None):
     nums = [40, 28, 33]
-    model, feats, chrom_range, N = build_reference(nums)
+    model, feats, chrom_range, N = build_reference(nums, d=d)
     C = len(nums)
     sd = model.state_dict()
     arrays = {"chrom_range": chrom_range, "nums": np.asarray(nums)}
@@ -92,7 +92,7 @@ def main(out=os.path.join(HERE, "..", "tests", "golden", "ref_small.npz")):
     rng = np.random.default_rng(5)
     real_choice = np.random.choice
     try:
-        for L in (2, 3, 4, 5):
+        for L in widths:
             x = make_inputs(rng, N, L, 16)
             xt = torch.from_numpy(x)
             arrays[f"x/L{L}"] = x
@@ -127,8 +127,8 @@ def main(out=os.path.join(HERE, "..", "tests", "golden", "ref_small.npz")):
             live = []
             for k, p in model.named_parameters():
                 if p.grad is not None:
-                    if L in (3, 5):                     # full gradient sets for two widths keep the fixture small
-                        arrays[f"grad/L{L}/{k}"] = p.grad.numpy().copy()
+                    if L in full_grads and (full_grad_max_elems is None or p.numel() <= full_grad_max_elems):
+                        arrays[f"grad/L{L}/{k}"] = p.grad.numpy().copy()     # full gradients for some widths / tensors keep the fixture small
                     else:
                         arrays[f"gradnorm/L{L}/{k}"] = np.asarray([p.grad.double().norm().item()])
                     live.append(k)
@@ -153,7 +153,7 @@ def main(out=os.path.join(HERE, "..", "tests", "golden", "ref_small.npz")):
     dead = {}
     live_all = set(sum(grads_any.values(), []))
     for k, v in sd.items():
-        if k in live_all or k.startswith("attribute_dict"):
+        if k in live_all or k.startswith("attribute_dict") or "Embedding_recon" in k:   # recon heads feed the eval recon loss
             arrays[f"p/{k}"] = v.numpy()             # values only for tensors that influence outputs
         else:
             dead[k] = list(v.shape)
@@ -170,3 +170,5 @@ def main(out=os.path.join(HERE, "..", "tests", "golden", "ref_small.npz")):
 
 if __name__ == "__main__":
     main()
+    # embed_dim 128 (BASELINE.json configs[4]): a smaller fixture, widths 3 and 5, full gradients of the tensors up to 20 000 elements (norms for the rest) at width 5
+    main(out=os.path.join(HERE, "..", "tests", "golden", "ref_small_d128.npz"), d=128, widths=(3, 5), full_grads=(5,), full_grad_max_elems=20000)

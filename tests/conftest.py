@@ -31,3 +31,10 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "ref_small.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden128():
+    """embed_dim 128 (BASELINE.json configs[4]) vectors of the unmodified reference: widths 3 and 5."""
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "ref_small_d128.npz"), allow_pickle=False)

@@ -594,3 +594,99 @@ def test_csr_encoder_matches_dense_rows(golden, monkeypatch):
         g1 = res["csr"][3][k]
         scale = float(np.abs(g0).max())
         assert float(np.abs(g1 - g0).max()) <= 5e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
+
+
+# ------------------------------------------------------------------------------------------
+# embed_dim 128 (BASELINE.json configs[4]): fp32 SIMT path, same bar as embed_dim 64
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [3, 5])
+def test_d128_eval_matches_reference_golden(golden128, L, monkeypatch):
+    model = model_from_golden(golden128, d=128)
+    model.eval()
+    x = torch.from_numpy(golden128[f"x/L{L}"]).cuda()
+    with torch.no_grad():
+        got = model(x)
+    np.testing.assert_allclose(got.cpu().numpy(), golden128[f"logits_eval/L{L}"], rtol=1e-4, atol=5e-5)
+    for r in range(len(golden128["nums"])):
+        monkeypatch.setattr(np.random, "choice", lambda a, size=None, r=r: np.asarray([r]))
+        with torch.no_grad():
+            _, rl = model(x, return_recon=True)
+        np.testing.assert_allclose(rl.cpu().numpy(), golden128[f"recon_eval/L{L}/r{r}"], rtol=1e-4)
+    N = golden128["embeddings"].shape[0]
+    with torch.no_grad():
+        e = model.get_node_embeddings(torch.arange(1, N + 1).view(-1, 1).cuda())
+    assert e.shape == (N, 1, 128)
+    np.testing.assert_allclose(e[:, 0, :].cpu().numpy(), golden128["embeddings"], rtol=1e-4, atol=2e-6)
+
+
+def test_d128_gradients_match_reference_golden(golden128, monkeypatch):
+    L = 5
+    model = model_from_golden(golden128, d=128)
+    model.train()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    r = int(golden128[f"train_rchrom/L{L}"][0])
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([r]))
+    x = torch.from_numpy(golden128[f"x/L{L}"]).cuda()
+    y, w = torch.from_numpy(golden128[f"y/L{L}"]).cuda(), torch.from_numpy(golden128[f"w/L{L}"]).cuda()
+    model.zero_grad(set_to_none=True)
+    pred, rl = model(x, return_recon=True)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w)
+    (bce * 1.0 + rl * 0.5).backward()
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), golden128[f"train_logits/L{L}"], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(rl.detach().cpu().numpy(), golden128[f"train_recon/L{L}"], rtol=1e-4)
+    meta = json.loads(str(golden128["meta"]))
+    live = set(meta["live_keys_by_L"][str(L)])
+    got_live = set()
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        got_live.add(k)
+        g = p.grad.cpu().numpy()
+        if f"grad/L{L}/{k}" in golden128.files:
+            ref = golden128[f"grad/L{L}/{k}"]
+            scale = float(np.abs(ref).max())
+            err = float(np.abs(g - ref).max())
+            assert err <= 3e-4 * scale + 2e-7, (k, err, scale)
+        else:       # large tensors: Frobenius norm only in the fixture
+            ref = float(golden128[f"gradnorm/L{L}/{k}"][0])
+            assert abs(float(np.linalg.norm(g.astype(np.float64))) - ref) <= 3e-4 * ref + 1e-9, k
+    assert got_live == live
+
+
+@pytest.mark.parametrize("L,B", [(3, 16), (5, 600)])
+def test_d128_train_step_with_dropout_matches_oracle(golden128, L, B, monkeypatch):
+    """Dropout ON at embed_dim 128, every gradient element against the oracle's fp64 autograd (B = 600 exercises the
+    multi-block grids)."""
+    model = model_from_golden(golden128, d=128)
+    model.train()
+    eng = model._engine()
+    r = L % 3
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([r]))
+    rng = np.random.default_rng(11)
+    N = int(golden128["embeddings"].shape[0])
+    xs = np.zeros((B, L), dtype=np.int64)
+    for b in range(B):
+        k = L if b % 2 == 0 else int(rng.integers(2, L + 1))
+        xs[b, :k] = np.sort(rng.choice(np.arange(1, N + 1), size=k, replace=False))
+    x = torch.from_numpy(xs).cuda()
+    y = torch.from_numpy((rng.random((B, 1)) < 0.4).astype("float32")).cuda()
+    w = torch.from_numpy(rng.uniform(0.5, 3.0, size=(B, 1)).astype("float32")).cuda()
+    pred, rl = model(x, return_recon=True)
+    (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.25 * rl.sum()).backward()
+    om = oracle_from_model(model).to(torch.float64)
+    out = O.loss_and_grads(om, x.cpu(), y.cpu().double(), w.cpu().double(), 1.0, 0.25, random_chrom=r, train=True,
+                           seed=step_seed(eng))
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), out["logits"].numpy(), rtol=2e-4, atol=1e-4)
+    np.testing.assert_allclose(rl.detach().cpu().numpy(), out["recon"].numpy(), rtol=1e-4)
+    sd = dict(model.named_parameters())
+    for k, gref in out["grads"].items():
+        p = sd[k]
+        gref = gref.numpy()
+        if p.grad is None:
+            assert np.abs(gref).max() == 0.0, k
+            continue
+        scale = float(np.abs(gref).max())
+        err = float(np.abs(p.grad.cpu().numpy() - gref).max())
+        assert err <= 5e-4 * scale + 2e-7, (k, err, scale)

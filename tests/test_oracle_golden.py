@@ -97,3 +97,46 @@ def test_counter_rng_vector_matches_scalar():
             assert bool(keep[ri, j]) == (v >= O.dropout_threshold16(0.3))
     big = O.dropout_keep_mask(7, O.SITE_PFF, np.arange(4000), 64, 0.4)
     assert abs(big.mean() - 0.6) < 0.01
+
+
+# ---- embed_dim 128 (BASELINE.json configs[4]) --------------------------------------------------------------
+@pytest.mark.parametrize("L", [3, 5])
+def test_d128_eval_logits_and_recon_match_reference(golden128, L):
+    m = O.model_from_npz(golden128)
+    x = torch.from_numpy(golden128[f"x/L{L}"])
+    got, _ = O.forward(m, x)
+    np.testing.assert_allclose(got.numpy(), golden128[f"logits_eval/L{L}"], rtol=1e-4, atol=2e-5)
+    for r in range(len(golden128["nums"])):
+        _, rl = O.forward(m, x, random_chrom=r)
+        np.testing.assert_allclose(rl.numpy(), golden128[f"recon_eval/L{L}/r{r}"], rtol=1e-5)
+    N = golden128["embeddings"].shape[0]
+    emb = O.node_embeddings(m, torch.arange(1, N + 1))
+    assert emb.shape[1] == 128
+    np.testing.assert_allclose(emb.numpy(), golden128["embeddings"], rtol=1e-4, atol=1e-6)
+
+
+def test_d128_gradients_match_reference(golden128):
+    L = 5
+    m = O.model_from_npz(golden128, dtype=torch.float64)
+    x = torch.from_numpy(golden128[f"x/L{L}"])
+    y = torch.from_numpy(golden128[f"y/L{L}"]).double()
+    w = torch.from_numpy(golden128[f"w/L{L}"]).double()
+    r = int(golden128[f"train_rchrom/L{L}"][0])
+    m.p_feature = m.p_attn = m.p_pff = 0.0
+    out = O.loss_and_grads(m, x, y, w, alpha=1.0, beta=0.5, random_chrom=r, train=True)
+    np.testing.assert_allclose(out["logits"].numpy(), golden128[f"train_logits/L{L}"], rtol=1e-4, atol=2e-5)
+    meta = json.loads(str(golden128["meta"]))
+    live_ref = set(meta["live_keys_by_L"][str(L)])
+    checked = 0
+    for k, g in out["grads"].items():
+        if k not in live_ref:
+            assert float(g.abs().max()) == 0.0, k
+        elif f"grad/L{L}/{k}" in golden128.files:        # full gradient kept for the tensors up to 20 000 elements
+            ref = golden128[f"grad/L{L}/{k}"]
+            assert np.abs(g.numpy() - ref).max() <= 2e-4 * float(np.abs(ref).max()) + 1e-7, k
+            checked += 1
+        else:                                            # Frobenius norm for the large ones
+            ref = float(golden128[f"gradnorm/L{L}/{k}"][0])
+            assert abs(float(g.double().norm()) - ref) <= 2e-4 * ref + 1e-9, k
+            checked += 1
+    assert checked == len(live_ref)
