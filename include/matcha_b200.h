@@ -50,6 +50,9 @@ void matcha_set_fused(int32_t on);
 /* 1 (default) = the 64-wide layers around the attention block run as tcgen05 row-chain kernels (needs the fused
  * path), 0 = SIMT fp32 contractions; also MATCHA_CHAIN=0 */
 void matcha_set_chain(int32_t on);
+/* 1 (default) = the reconstruction head (Modules.py:192-199) and its backward run as one fused tcgen05 kernel per pass
+ * (needs the fused path), 0 = four SIMT launches through a [T, n_r] buffer; also MATCHA_RECON_TC=0 */
+void matcha_set_recon_tc(int32_t on);
 
 /* ---------------------------------------------------------------------------------------------
  * Model description: where every live tensor of Modules.Classifier sits.

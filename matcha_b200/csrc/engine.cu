@@ -100,6 +100,15 @@ static bool use_fused(const matcha_model_desc* m, int64_t T, int L) {
   return m->d == kD && fused_impl() == 1 && gemm_impl() == 1 && L >= 2 && L <= 6 && T >= kTilePathMinTokens;
 }
 
+static int g_recon_tc = -1;   // fused tensor-core reconstruction head (MATCHA_RECON_TC=0 keeps the four SIMT launches)
+static bool use_recon_tc(const matcha_model_desc* m, int64_t T, int L) {
+  if (g_recon_tc < 0) {
+    const char* e = getenv("MATCHA_RECON_TC");
+    g_recon_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_recon_tc == 1 && use_fused(m, T, L);
+}
+
 static int run_gemm(const GemmDesc& d, cudaStream_t s, int label, bool allow_tc = true) {
   prof_begin(label, s);
   int rc = MATCHA_OK;
@@ -539,6 +548,7 @@ int matcha_profile_read(float* ms, int64_t* calls, int64_t* kernels, int32_t n) 
 void matcha_set_gemm_impl(int32_t impl) { g_gemm_impl = impl; }
 void matcha_set_fused(int32_t on) { g_fused = on != 0; }
 void matcha_set_chain(int32_t on) { g_chain = on != 0; }
+void matcha_set_recon_tc(int32_t on) { g_recon_tc = on != 0; }
 int matcha_version(void) { return 100; }
 
 // CSR models keep W0T_c [n_c, 64] (and, in derived_grad, its gradient) after the fixed-size part
@@ -614,11 +624,17 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
     if ((rc = check_cuda(cudaMemsetAsync(w.recon, 0, sizeof(float), s), "memset recon"))) return rc;
     if (random_chrom >= 0 && m->inter) {
       const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom];
-      GemmDesc p = gemm_base(FORM_NT, T, re - rs, Dm, w.E, Dm, m->params + m->off_rw[random_chrom], Dm, w.pred, w.pred_ld);
-      p.a_act = 1; p.bias = m->params + m->off_rb[random_chrom];
-      if ((rc = run_gemm(p, s, P_RECON_PRED))) return rc;
-      if ((rc = PROF(P_RECON_DIFF, 1, launch_recon_diff(w.pred, w.pred_ld, x, T, m->inter, m->inter_ld, rs, re, w.counts, random_chrom,
-                                  m->n_chrom, w.recon, s)))) return rc;
+      if (use_recon_tc(m, T, L)) {
+        if ((rc = PROF(P_RECON_PRED, 1, launch_recon_tc(w.E, x, T, m->inter, m->inter_ld, rs, re, m->params + m->off_rw[random_chrom],
+                                                        m->params + m->off_rb[random_chrom], w.counts, random_chrom, m->n_chrom,
+                                                        w.recon, nullptr, nullptr, nullptr, 0.f, 0, s)))) return rc;
+      } else {
+        GemmDesc p = gemm_base(FORM_NT, T, re - rs, Dm, w.E, Dm, m->params + m->off_rw[random_chrom], Dm, w.pred, w.pred_ld);
+        p.a_act = 1; p.bias = m->params + m->off_rb[random_chrom];
+        if ((rc = run_gemm(p, s, P_RECON_PRED))) return rc;
+        if ((rc = PROF(P_RECON_DIFF, 1, launch_recon_diff(w.pred, w.pred_ld, x, T, m->inter, m->inter_ld, rs, re, w.counts, random_chrom,
+                                    m->n_chrom, w.recon, s)))) return rc;
+      }
     }
     if (recon && (rc = check_cuda(cudaMemcpyAsync(recon, w.recon, sizeof(float), cudaMemcpyDeviceToDevice, s), "copy recon")))
       return rc;
@@ -750,11 +766,20 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   const float* dtE = nullptr;
   if (recon_on) {
     const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom], nr = re - rs;
-    GemmDesc d = gemm_base(FORM_TN, nr, Dm, T, w.pred, w.pred_ld, w.E, Dm, G + m->off_rw[random_chrom], Dm);
-    d.b_act = 1; d.out_scale = beta; d.colsum = G + m->off_rb[random_chrom]; d.colsum_n = nr;
-    if ((rc = run_gemm(d, s, P_W_RECON))) return rc;
-    GemmDesc e = gemm_base(FORM_NN, T, Dm, nr, w.pred, w.pred_ld, P + m->off_rw[random_chrom], Dm, w.dtE, Dm);
-    if ((rc = run_gemm(e, s, P_D_RECON))) return rc;
+    if (use_recon_tc(m, T, L)) {
+      // recompute pred / gdiff on chip; weight, bias and data gradients in the same kernel
+      if ((rc = check_cuda(cudaMemsetAsync(w.dtE, 0, sizeof(float) * T * Dm, s), "memset dtE"))) return rc;
+      if ((rc = PROF(P_W_RECON, 1, launch_recon_tc(w.E, x, T, m->inter, m->inter_ld, rs, re, P + m->off_rw[random_chrom],
+                                                   P + m->off_rb[random_chrom], w.counts, random_chrom, m->n_chrom, nullptr,
+                                                   G + m->off_rw[random_chrom], G + m->off_rb[random_chrom], w.dtE, beta, 1, s))))
+        return rc;
+    } else {
+      GemmDesc d = gemm_base(FORM_TN, nr, Dm, T, w.pred, w.pred_ld, w.E, Dm, G + m->off_rw[random_chrom], Dm);
+      d.b_act = 1; d.out_scale = beta; d.colsum = G + m->off_rb[random_chrom]; d.colsum_n = nr;
+      if ((rc = run_gemm(d, s, P_W_RECON))) return rc;
+      GemmDesc e = gemm_base(FORM_NN, T, Dm, nr, w.pred, w.pred_ld, P + m->off_rw[random_chrom], Dm, w.dtE, Dm);
+      if ((rc = run_gemm(e, s, P_D_RECON))) return rc;
+    }
     dtE = w.dtE;
   }
   if (chain) {

@@ -12,7 +12,7 @@ namespace matcha {
 
 namespace {
 constexpr int TM = 64, TN = 64, TK = 16, NTHREADS = 256, PAD = 4;
-constexpr int KC_GROUPED = 512;  // tokens per CTA in grouped TN (weight-gradient) launches
+constexpr int KC_GROUPED = 512;  // most tokens per CTA in grouped TN (weight-gradient) launches
 
 __device__ __forceinline__ float4 ld4_guard(const float* __restrict__ p, int64_t i, int64_t n) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_simt_kernel(const GemmDesc d, c
   int64_t a_id_off = d.a_id_off, b_id_off = d.b_id_off;
   int64_t tok_off = 0, m0, n0 = (int64_t)blockIdx.x * TN, k_begin = 0, k_end;
   if (d.ngroups > 0) {
-    const int64_t unit = tn ? KC_GROUPED : TM;
+    const int64_t unit = tn ? kc : TM;
     int64_t tile = tn ? blockIdx.z : blockIdx.y, before = 0;
     int g = 0, cnt = 0;
     for (; g < d.ngroups; ++g) {
@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_simt_kernel(const GemmDesc d, c
       Kg = cnt; Ng = gr.dim; C = gr.C; ldc = gr.ldc;
       if (gr.B) { B = gr.B; ldb = gr.ldb; b_id_off = gr.a_id_off; }
       m0 = (int64_t)blockIdx.y * TM;
-      k_begin = (tile - before) * KC_GROUPED;
-      k_end = min((int64_t)cnt, k_begin + KC_GROUPED);
+      k_begin = (tile - before) * kc;
+      k_end = min((int64_t)cnt, k_begin + kc);
       if (n0 >= Ng) return;
     } else {
       Mg = cnt; Kg = gr.dim;
@@ -241,7 +241,11 @@ int launch_gemm_simt(const GemmDesc& d, cudaStream_t stream) {
     if (tn) {
       grid.x = (unsigned)((d.max_group_dim + TN - 1) / TN);
       grid.y = (unsigned)((d.M + TM - 1) / TM);
-      grid.z = (unsigned)((d.total_rows + KC_GROUPED - 1) / KC_GROUPED + d.ngroups);
+      // tokens per CTA: aim at >= 4 CTAs per SM, between 128 and KC_GROUPED tokens each
+      const int64_t xy = (int64_t)grid.x * grid.y;
+      kc = d.total_rows * xy / (4 * kSMs);
+      kc = kc < 128 ? 128 : (kc > KC_GROUPED ? KC_GROUPED : kc / TK * TK);
+      grid.z = (unsigned)((d.total_rows + kc - 1) / kc + d.ngroups);
     } else {
       grid.x = (unsigned)((d.N + TN - 1) / TN);
       grid.y = (unsigned)((d.total_rows + TM - 1) / TM + d.ngroups);

@@ -1,0 +1,309 @@
+// Fused reconstruction head (Modules.py:192-199 and its backward) on tensor cores:
+//   pred = tanh(E) . Rw^T + rb  ->  diff vs the z-scored inter-chromosomal target rows  ->  loss,
+//   and in the backward pass also  dRw += beta * gdiff^T . tanh(E),  drb += beta * sum_t gdiff,  dtE = gdiff . Rw
+// in ONE kernel per pass: pred / gdiff [T, n_r] never touch HBM (the decomposed path writes and re-reads them three
+// times through four SIMT launches).
+//
+// One CTA = 128 threads = 128 consecutive tokens (thread r owns token row r = TMEM lane r) x one block of 128 target
+// columns.  Per token tile:
+//   stage   tanh(E) rows -> bf16 hi | lo tile sA [feature/8][token][8]  (+ a ones column: plane 8, zeros: plane 9)
+//   MMA1    P[128 tok, 128 col] = sA . sW^T                      (K = 64; sW = Rw block, K-major)
+//   SIMT    thread = token: gdiff row = (P + rb - target) * gscale on eligible tokens; loss partial; -> sG tile
+//   MMA2    dtE[128 tok, 64]   = sG . sW          (K = 128 columns; sW read MN-major)
+//   MMA3    dRw[128 col, 80]  += sG^T . sA        (K = 128 tokens; both MN-major; column 64 = ones -> bias gradient)
+// dRw stays resident in TMEM across all tiles of the CTA.  bf16x3 split, fp32 accumulation (tc_common.cuh).
+#include "rowwise.cuh"
+#include "tc_common.cuh"
+
+namespace matcha {
+namespace {
+
+constexpr int kRThreads = 128;
+constexpr int kRA = 2 * 10 * 2048;            // sA: hi 10 planes | lo 10 planes                      40 960
+constexpr int kRAHalf = 10 * 2048;
+constexpr int kRW = 32768;                    // sW: 128 rows x 64 k, hi 16 KB | lo 16 KB
+constexpr int kRG = 65536;                    // sG: 128 tokens x 128 columns, hi 32 KB | lo 32 KB
+constexpr int kRStageRow = 68;                // row staging (coalesced row I/O), floats per row
+constexpr int kRStage = 4 * 32 * kRStageRow * 4;   // 34 816
+constexpr int kRTgtRow = 33;                  // target staging: 32 x 32 block per warp, padded
+constexpr int kRSmem = kRA + kRW + kRG + kRStage;  // 174 080
+constexpr uint32_t kColP = 0, kColDT = 128, kColDW = 192;
+
+struct ReconArgs {
+  const float* E; const int64_t* x; int64_t T;
+  const float* inter; int64_t inter_ld;
+  int64_t rs, re;                 // node-id range of the drawn chromosome
+  const float* Rw; const float* rb;
+  const int32_t* counts; int rchrom, n_chrom;
+  float* recon_out;               // mode 0: += 100 * mean((pred - target)^2)
+  float* dRw; float* drb; float* dtE; float beta;     // mode 1
+  int mode;
+};
+
+// a warp's 32 consecutive token rows <-> registers through a padded staging area (coalesced 128-bit global accesses)
+__device__ __forceinline__ void rows_in(const float* __restrict__ g, int nrows, float* stage, int lane, float (&v)[64]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 4, c4 = idx & 15;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nrows) e = __ldg(reinterpret_cast<const float4*>(g) + idx);
+    *reinterpret_cast<float4*>(stage + row * kRStageRow + c4 * 4) = e;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float4 e = *reinterpret_cast<const float4*>(stage + lane * kRStageRow + k * 4);
+    v[4 * k] = e.x; v[4 * k + 1] = e.y; v[4 * k + 2] = e.z; v[4 * k + 3] = e.w;
+  }
+  __syncwarp();
+}
+// rows -> global with atomic adds (several column blocks contribute to the same dtE row), coalesced
+__device__ __forceinline__ void rows_red(float* __restrict__ g, int nrows, float* stage, int lane, const float (&v)[64]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    *reinterpret_cast<float4*>(stage + lane * kRStageRow + k * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  __syncwarp();
+#pragma unroll 4
+  for (int k = 0; k < 64; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 6, c = idx & 63;
+    if (row < nrows) atomicAdd(g + idx, stage[row * kRStageRow + c]);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void put_planes(uint8_t* hi_base, int lo_off, int r, const float (&v)[64]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 hi, lo;
+    split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+           make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+    sts16(hi_base + j * 2048 + r * 16, hi);
+    sts16(hi_base + lo_off + j * 2048 + r * 16, lo);
+  }
+}
+
+__global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + kRA;
+  // loss-only pass (mode 0): no gdiff tile, the staging area follows sW directly (106 KB per CTA)
+  uint8_t* sG = smem + kRA + kRW;
+  float* sStage = reinterpret_cast<float*>(smem + kRA + kRW + (a.mode == 1 ? kRG : 0));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_rb[128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid;
+  const int cb = blockIdx.y;                                   // column block: target columns [cb * 128, cb * 128 + 128)
+  const int64_t n_r = a.re - a.rs;
+  const int64_t ntiles = (a.T + 127) / 128;
+  const int S = gridDim.x;
+  const int64_t elig = a.T - a.counts[a.n_chrom] - a.counts[a.rchrom];
+  const float gscale = elig > 0 ? 200.0f / ((float)elig * (float)n_r) : 0.f;
+
+  const uint32_t tmem_cols = a.mode == 1 ? 512u : 128u;      // loss-only pass: P alone -> two CTAs per SM
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {   // Rw block -> sW (row = target column), zero rows beyond n_r; bias slice
+    const int64_t col = (int64_t)cb * 128 + r;
+    float v[64];
+    if (col < n_r) {
+      const float* src = a.Rw + col * 64;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(src) + k);
+        v[4 * k] = e.x; v[4 * k + 1] = e.y; v[4 * k + 2] = e.z; v[4 * k + 3] = e.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 64; ++c) v[c] = 0.f;
+    }
+    put_planes(sW, 16384, r, v);
+    s_rb[r] = col < n_r ? __ldg(a.rb + col) : 0.f;
+    // ones / zero planes of sA never change
+    sts16(sA + 8 * 2048 + r * 16, make_uint4(0x00003F80u, 0u, 0u, 0u));          // bf16(1.0) in column 64
+    sts16(sA + 9 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
+    sts16(sA + kRAHalf + 8 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
+    sts16(sA + kRAHalf + 9 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t idescP = make_idesc(128, 128, false, false);
+  constexpr uint32_t idescD = make_idesc(128, 64, false, true);
+  constexpr uint32_t idescW = make_idesc(128, 80, true, true);
+  const uint32_t ah = smem_u32(sA), al = ah + kRAHalf;
+  const uint32_t wh = smem_u32(sW), wl = wh + 16384;
+  const uint32_t gh = smem_u32(sG), gl = gh + 32768;
+  float* stage = sStage + warp * (32 * kRStageRow);
+  uint32_t phase = 0;
+  float loss = 0.f;
+  bool first = true;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += S) {
+    const int64_t t0 = tile * 128 + warp * 32, t = t0 + lane;
+    const int nrows = (a.T - t0) <= 0 ? 0 : ((a.T - t0) < 32 ? (int)(a.T - t0) : 32);
+    const int64_t id = t < a.T ? a.x[t] : 0;
+    const bool ok = id != 0 && (id < a.rs || id >= a.re);
+    // ---- stage tanh(E) ----
+    {
+      float v[64];
+      rows_in(a.E + t0 * 64, nrows, stage, lane, v);
+#pragma unroll
+      for (int c = 0; c < 64; ++c) v[c] = tanhf(v[c]);
+      put_planes(sA, kRAHalf, r, v);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_x3s(tmem_base + kColP, ah + ks * 4096, al + ks * 4096, wh + ks * 4096, wl + ks * 4096, 2048, 128, 2048, 128, idescP,
+                 ks == 0);
+      umma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- gdiff rows: thread = token, 4 chunks of 32 target columns ----
+    float* tstage = stage;                                   // 32 x 33 floats of the warp's staging area
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      const int64_t c0 = (int64_t)cb * 128 + ch * 32;          // first target column of the chunk
+      // target block [32 tokens x 32 columns]: row k of the warp is read by all lanes (coalesced), kept transposed
+      {
+        float tv[32];
+        const float* tbase = a.inter + (a.rs - 1) + c0 + lane;
+        const bool col_ok = c0 + lane < n_r;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {                         // 32 independent loads in flight per lane
+          const int64_t idk = __shfl_sync(0xffffffffu, id, k);
+          const bool okk = __shfl_sync(0xffffffffu, ok ? 1 : 0, k) != 0;
+          tv[k] = (okk && col_ok) ? __ldg(tbase + (idk - 1) * a.inter_ld) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) tstage[k * kRTgtRow + lane] = tv[k];
+      }
+      __syncwarp();
+      uint32_t pv[32];
+      tmem_ld32_issue(tlane + kColP + ch * 32, pv);
+      tmem_ld_wait(pv);
+      float g[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float dv = 0.f;
+        if (ok && c0 + i < n_r) dv = __uint_as_float(pv[i]) + s_rb[ch * 32 + i] - tstage[lane * kRTgtRow + i];
+        loss = fmaf(dv, dv, loss);
+        g[i] = dv * gscale;
+      }
+      __syncwarp();
+      if (a.mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 hi, lo;
+          split8(make_float4(g[8 * j], g[8 * j + 1], g[8 * j + 2], g[8 * j + 3]),
+                 make_float4(g[8 * j + 4], g[8 * j + 5], g[8 * j + 6], g[8 * j + 7]), hi, lo);
+          sts16(sG + (ch * 4 + j) * 2048 + r * 16, hi);
+          sts16(sG + 32768 + (ch * 4 + j) * 2048 + r * 16, lo);
+        }
+      }
+    }
+    tc_fence_before();
+    if (a.mode == 1) {
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)      // dtE[128 tok, 64] = gdiff[128 tok, 128 col] . Rw[128 col, 64]   (B MN-major)
+          umma_x3s(tmem_base + kColDT, gh + ks * 4096, gl + ks * 4096, wh + ks * 256, wl + ks * 256, 2048, 128, 128, 2048, idescD,
+                   ks == 0);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)      // dRw[128 col, 80] += gdiff^T[128 col, 128 tok] . [tanh(E) | 1][128 tok, 80]
+          umma_x3s(tmem_base + kColDW, gh + ks * 256, gl + ks * 256, ah + ks * 256, al + ks * 256, 128, 2048, 128, 2048, idescW,
+                   first && ks == 0);
+        umma_commit(&bar);
+      }
+      first = false;
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      {
+        uint32_t d0[32], d1[32];
+        tmem_ld32_issue(tlane + kColDT, d0);
+        tmem_ld32_issue(tlane + kColDT + 32, d1);
+        tmem_ld_wait(d0);
+        tmem_ld_wait(d1);
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(d0[i]); v[32 + i] = __uint_as_float(d1[i]); }
+        rows_red(a.dtE + t0 * 64, nrows, stage, lane, v);
+      }
+      tc_fence_before();
+    }
+    __syncthreads();       // sA / sG / staging are rewritten by the next tile
+  }
+
+  if (a.mode == 0) {
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if (lane == 0 && elig > 0 && loss != 0.f) atomicAdd(a.recon_out, loss * 100.0f / ((float)elig * (float)n_r));
+  } else if (!first) {
+    // weight / bias gradient slice of this CTA: TMEM lane = target column
+    tc_fence_after();
+    const int64_t col = (int64_t)cb * 128 + r;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32_issue(tlane + kColDW + c * 32, v);
+      tmem_ld_wait(v);
+      if (col < n_r) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(a.dRw + col * 64 + c * 32 + i, __uint_as_float(v[i]) * a.beta);
+      }
+    }
+    uint32_t b8[8];
+    tmem_ld8_issue(tlane + kColDW + 64, b8);
+    tmem_ld_wait(b8);
+    if (col < n_r) atomicAdd(a.drb + col, __uint_as_float(b8[0]) * a.beta);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+// mode 0: recon_out[0] += loss (forward / eval);  mode 1: dRw, drb += beta * ..., dtE += gdiff . Rw (dtE zeroed by the caller)
+int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* inter, int64_t inter_ld, int64_t rs, int64_t re,
+                    const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, float* recon_out,
+                    float* dRw, float* drb, float* dtE, float beta, int mode, cudaStream_t s) {
+  if (T <= 0 || re <= rs) return MATCHA_OK;
+  static bool once = false;
+  if (!once) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmem),
+                            "cudaFuncSetAttribute"))
+      return rc;
+    once = true;
+  }
+  ReconArgs a;
+  a.E = E; a.x = x; a.T = T; a.inter = inter; a.inter_ld = inter_ld; a.rs = rs; a.re = re; a.Rw = Rw; a.rb = rb;
+  a.counts = counts; a.rchrom = rchrom; a.n_chrom = n_chrom; a.recon_out = recon_out; a.dRw = dRw; a.drb = drb; a.dtE = dtE;
+  a.beta = beta; a.mode = mode;
+  const int ncb = (int)((re - rs + 127) / 128);
+  const int64_t ntiles = (T + 127) / 128;
+  const int per_sm = mode == 1 ? 1 : 2;                      // 174 KB (gradient pass) or 106 KB (loss pass) of shared memory per CTA
+  int64_t S = (per_sm * kSMs + ncb - 1) / ncb;
+  if (S > ntiles) S = ntiles;
+  if (S < 1) S = 1;
+  recon_tc_kernel<<<dim3((unsigned)S, (unsigned)ncb), kRThreads, mode == 1 ? kRSmem : kRSmem - kRG, s>>>(a);
+  MATCHA_CHECK_LAUNCH("recon_tc");
+  return MATCHA_OK;
+}
+
+}  // namespace matcha

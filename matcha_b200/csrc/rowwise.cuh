@@ -115,6 +115,12 @@ int launch_wgrad_pair(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, c
                       float* scratch, float* w1, int ld1, int n1, float* bias1, float* w2, int ld2, int n2, float* bias2,
                       cudaStream_t s);
 
+// fused reconstruction head on tensor cores (recon_tc.cu): mode 0 adds the loss to recon_out[0]; mode 1 adds beta * the
+// weight / bias gradients to dRw [n_r, 64] / drb [n_r] and gdiff . Rw to dtE [T, 64] (zeroed by the caller)
+int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* inter, int64_t inter_ld, int64_t rs, int64_t re,
+                    const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, float* recon_out,
+                    float* dRw, float* drb, float* dtE, float beta, int mode, cudaStream_t s);
+
 // CSR first encoder layer (csr_encoder.cu): feature rows given as CSR (feat[c] == NULL, feat_indptr/indices/values set).
 // W0T_c [n_c, 64] copies live in the derived buffer from float offset w0t_base (chromosome after chromosome); the same
 // offsets of derived_grad accumulate dW0T_c.

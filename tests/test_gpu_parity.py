@@ -690,3 +690,48 @@ def test_d128_train_step_with_dropout_matches_oracle(golden128, L, B, monkeypatc
         scale = float(np.abs(gref).max())
         err = float(np.abs(p.grad.cpu().numpy() - gref).max())
         assert err <= 5e-4 * scale + 2e-7, (k, err, scale)
+
+
+# ------------------------------------------------------------------------------------------
+# fused tensor-core reconstruction head vs the SIMT launches (chromosomes wider than one 128-column block)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,B,rchrom", [(5, 700, 0), (3, 450, 1), (4, 1031, 0)])
+def test_recon_head_tensor_core_matches_simt(monkeypatch, L, B, rchrom):
+    from matcha_b200.synthetic import build_model, make_dataset
+    lib = _lib().load()
+    ds = make_dataset("cfg1", kmers_per_size=3000, seed=3)            # chr1 + chr2 at 1 Mb: 250 and 244 bins -> two column blocks
+    N = int(ds["chrom_range"][-1][1]) - 1
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([rchrom]))
+    rng = np.random.default_rng(100 + B)
+    xs = np.zeros((B, L), dtype=np.int64)
+    for b in range(B):
+        k = L if b % 3 else int(rng.integers(2, L + 1))
+        xs[b, :k] = np.sort(rng.choice(np.arange(1, N + 1), size=k, replace=False))
+    x = torch.from_numpy(xs).cuda()
+    y = torch.from_numpy((rng.random((B, 1)) < 0.3).astype("float32")).cuda()
+    w = torch.from_numpy(rng.uniform(0.5, 3, (B, 1)).astype("float32")).cuda()
+    res = {}
+    try:
+        for tc in (0, 1):
+            lib.matcha_set_recon_tc(tc)
+            model = build_model(ds, seed=1)
+            model.train()
+            model._engine().seed_base = 17
+            pred, rl = model(x, return_recon=True)
+            (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.7 * rl.sum()).backward()
+            res[tc] = ({k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None},
+                       pred.detach().cpu().numpy(), float(rl.sum()))
+            model.eval()
+            with torch.no_grad():
+                res[tc] += (float(model(x, return_recon=True)[1].sum()),)
+    finally:
+        lib.matcha_set_recon_tc(1)
+    assert res[0][2] > 0
+    assert abs(res[1][2] - res[0][2]) <= 2e-5 * abs(res[0][2])          # training-mode recon loss
+    assert abs(res[1][3] - res[0][3]) <= 2e-5 * abs(res[0][3])          # eval-mode recon loss
+    np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-5, atol=1e-6)
+    assert res[0][0].keys() == res[1][0].keys()
+    for k, g0 in res[0][0].items():
+        g1 = res[1][0][k]
+        scale = float(np.abs(g0).max())
+        assert float(np.abs(g1 - g0).max()) <= 3e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
