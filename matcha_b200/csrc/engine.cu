@@ -100,6 +100,15 @@ static bool use_fused(const matcha_model_desc* m, int64_t T, int L) {
   return m->d == kD && fused_impl() == 1 && gemm_impl() == 1 && L >= 2 && L <= 6 && T >= kTilePathMinTokens;
 }
 
+static int g_enc_tc = -1;     // tensor-core node encoder forward (MATCHA_ENC_TC=0 keeps the two grouped SIMT launches)
+static bool enc_tc_eligible(const matcha_model_desc* m) { return m->d == kD && !model_uses_csr(m); }
+static bool use_enc_tc(const matcha_model_desc* m, int64_t T) {
+  if (g_enc_tc < 0) {
+    const char* e = getenv("MATCHA_ENC_TC");
+    g_enc_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_enc_tc == 1 && enc_tc_eligible(m) && gemm_impl() == 1 && T >= kTilePathMinTokens;
+}
 static int g_recon_tc = -1;   // fused tensor-core reconstruction head (MATCHA_RECON_TC=0 keeps the four SIMT launches)
 static bool use_recon_tc(const matcha_model_desc* m, int64_t T, int L) {
   if (g_recon_tc < 0) {
@@ -442,6 +451,10 @@ static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   if ((rc = PROF(P_BUCKET, 3, launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s)))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(w.H0, 0, sizeof(float) * T * Dm, s), "memset H0"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * Dm, s), "memset E"))) return rc;
+  if (use_enc_tc(m, T)) {    // both encoder layers in one tcgen05 kernel over the bucketed token list
+    const DropCfg fd = make_drop(seed, SITE_FEATURE, m->p_feature, training != 0);
+    return PROF(P_ENC0, 1, launch_enc_tc_fwd(m, derived_layout(m->d).total, x, T, w.perm, w.group_off, w.H0, E_out, fd, s));
+  }
   if (model_uses_csr(m)) {
     const DropCfg fd = make_drop(seed, SITE_FEATURE, m->p_feature, training != 0);
     if ((rc = PROF(P_ENC0, 1, launch_enc0_csr_fwd(m, derived_layout(m->d).total, x, T, w.perm, w.group_off, w.H0, fd, s)))) return rc;
@@ -549,6 +562,7 @@ void matcha_set_gemm_impl(int32_t impl) { g_gemm_impl = impl; }
 void matcha_set_fused(int32_t on) { g_fused = on != 0; }
 void matcha_set_chain(int32_t on) { g_chain = on != 0; }
 void matcha_set_recon_tc(int32_t on) { g_recon_tc = on != 0; }
+void matcha_set_enc_tc(int32_t on) { g_enc_tc = on != 0; }
 int matcha_version(void) { return 100; }
 
 // CSR models keep W0T_c [n_c, 64] (and, in derived_grad, its gradient) after the fixed-size part
@@ -561,7 +575,10 @@ static int64_t w0t_floats(const matcha_model_desc* m) {
   for (int c = 0; c < m->n_chrom; ++c) n += (m->chrom_end[c] - m->chrom_start[c]) * Dm;
   return n;
 }
-int64_t matcha_derived_elems(const matcha_model_desc* m) { return derived_layout(m->d).total + w0t_floats(m); }
+// after the fixed-size part: W0T copies (CSR models) or the pre-split encoder weight chunks (dense rows, embed_dim 64)
+int64_t matcha_derived_elems(const matcha_model_desc* m) {
+  return derived_layout(m->d).total + w0t_floats(m) + (enc_tc_eligible(m) ? enc_tc_split_floats(m) : 0);
+}
 
 int64_t matcha_workspace_bytes(const matcha_model_desc* m, int64_t B, int32_t L, int32_t training) {
   if (!m || B < 0 || L < 1) return -1;
@@ -595,6 +612,7 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
     }
   }
   if (model_uses_csr(m) && (rc = launch_csr_prepare(m, l.total, s))) return rc;
+  if (enc_tc_eligible(m) && (rc = launch_enc_tc_prepare(m, l.total, s))) return rc;
   prof_end(P_PREP, 10, s);
   return MATCHA_OK;
 }

@@ -121,6 +121,13 @@ int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* in
                     const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, float* recon_out,
                     float* dRw, float* drb, float* dtE, float beta, int mode, cudaStream_t s);
 
+// node encoder forward on tensor cores (enc_tc.cu): dense feature rows, embed_dim 64.  The pre-split weight chunks live in
+// the derived buffer from float offset split_base (enc_tc_split_floats(m) floats, rebuilt by launch_enc_tc_prepare)
+int64_t enc_tc_split_floats(const matcha_model_desc* m);
+int launch_enc_tc_prepare(const matcha_model_desc* m, int64_t split_base, cudaStream_t s);
+int launch_enc_tc_fwd(const matcha_model_desc* m, int64_t split_base, const int64_t* x, int64_t T, const int32_t* perm,
+                      const int32_t* group_off, float* H0, float* E, DropCfg drop, cudaStream_t s);
+
 // CSR first encoder layer (csr_encoder.cu): feature rows given as CSR (feat[c] == NULL, feat_indptr/indices/values set).
 // W0T_c [n_c, 64] copies live in the derived buffer from float offset w0t_base (chromosome after chromosome); the same
 // offsets of derived_grad accumulate dW0T_c.

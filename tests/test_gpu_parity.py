@@ -735,3 +735,54 @@ def test_recon_head_tensor_core_matches_simt(monkeypatch, L, B, rchrom):
         g1 = res[1][0][k]
         scale = float(np.abs(g0).max())
         assert float(np.abs(g1 - g0).max()) <= 3e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
+
+
+# ------------------------------------------------------------------------------------------
+# tensor-core node encoder forward vs the grouped SIMT launches (chromosomes of 250 / 244 bins: 4 weight chunks, ragged)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,B,train", [(5, 700, True), (3, 450, False), (4, 1031, True)])
+def test_encoder_tensor_core_matches_simt(monkeypatch, L, B, train):
+    from matcha_b200.synthetic import build_model, make_dataset
+    lib = _lib().load()
+    ds = make_dataset("cfg1", kmers_per_size=3000, seed=3)
+    N = int(ds["chrom_range"][-1][1]) - 1
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([1]))
+    rng = np.random.default_rng(200 + B)
+    xs = np.zeros((B, L), dtype=np.int64)
+    for b in range(B):
+        k = L if b % 3 else int(rng.integers(2, L + 1))
+        xs[b, :k] = np.sort(rng.choice(np.arange(1, N + 1), size=k, replace=False))
+    x = torch.from_numpy(xs).cuda()
+    y = torch.from_numpy((rng.random((B, 1)) < 0.3).astype("float32")).cuda()
+    w = torch.from_numpy(rng.uniform(0.5, 3, (B, 1)).astype("float32")).cuda()
+    res = {}
+    try:
+        for tc in (0, 1):
+            lib.matcha_set_enc_tc(tc)
+            model = build_model(ds, seed=1)
+            model._engine().seed_base = 23
+            if train:
+                model.train()
+                pred, rl = model(x, return_recon=True)
+                (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.7 * rl.sum()).backward()
+                grads = {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
+            else:
+                model.eval()
+                with torch.no_grad():
+                    pred, rl = model(x, return_recon=True)
+                grads = {}
+            with torch.no_grad():
+                model.eval()
+                emb = model.get_node_embeddings(torch.arange(0, 3 * N + 3).remainder(N + 1).view(-1, 1).cuda())[:, 0, :].cpu().numpy()
+            res[tc] = (grads, pred.detach().cpu().numpy(), float(rl.sum()), emb)
+    finally:
+        lib.matcha_set_enc_tc(1)
+    np.testing.assert_allclose(res[1][3], res[0][3], rtol=1e-4, atol=2e-6)          # embeddings.npy rows (eval, ids incl. 0)
+    assert float(np.abs(res[1][3][0]).max()) == 0.0                                  # id 0 -> zero row
+    np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-4, atol=5e-5)
+    assert abs(res[1][2] - res[0][2]) <= 1e-4 * abs(res[0][2])
+    assert res[0][0].keys() == res[1][0].keys()
+    for k, g0 in res[0][0].items():
+        g1 = res[1][0][k]
+        scale = float(np.abs(g0).max())
+        assert float(np.abs(g1 - g0).max()) <= 5e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
