@@ -340,6 +340,7 @@ struct Workspace {
   uint8_t *v0_t, *attr_t, *u_t, *h1_t, *dh2_t, *dh1_t, *dp_t, *dv0_t;   // row-chain tiles kept for the weight-gradient kernel
   float* wpair_scratch;
   float *dlogit, *dH2, *dXs, *dH1pre, *dU, *dQKG, *dxhat, *dP, *dV0, *dtE, *dE, *dH0pre, *tc_scratch;
+  float* recon_stash;      // unscaled dRw [n_r, 64] | drb [n_r] left by the training forward of the fused recon head
   int64_t tc_scratch_floats;
   int64_t pred_ld;
   int64_t bytes;
@@ -396,6 +397,7 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
       w.dv0_t = (uint8_t*)take(nat * 32768); w.attr_t = (uint8_t*)take(nat * 16384);
       w.wpair_scratch = (float*)take(sizeof(float) * wgrad_pair_scratch_floats());
     }
+    if (m->inter) w.recon_stash = (float*)take(sizeof(float) * max_chrom_len(m) * (D + 1));
     w.tc_scratch_floats = gemm_tc_scratch_floats(QKG);
     w.tc_scratch = (float*)take(sizeof(float) * w.tc_scratch_floats);
   }
@@ -643,9 +645,16 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
     if (random_chrom >= 0 && m->inter) {
       const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom];
       if (use_recon_tc(m, T, L)) {
+        // training: loss AND the (unscaled) gradients in one pass -- the backward pass only applies d loss / d recon
+        float* st = training ? w.recon_stash : nullptr;
+        if (training) {
+          if ((rc = check_cuda(cudaMemsetAsync(st, 0, sizeof(float) * (re - rs) * (Dm + 1), s), "memset recon stash"))) return rc;
+          if ((rc = check_cuda(cudaMemsetAsync(w.dtE, 0, sizeof(float) * T * Dm, s), "memset dtE"))) return rc;
+        }
         if ((rc = PROF(P_RECON_PRED, 1, launch_recon_tc(w.E, x, T, m->inter, m->inter_ld, rs, re, m->params + m->off_rw[random_chrom],
                                                         m->params + m->off_rb[random_chrom], w.counts, random_chrom, m->n_chrom,
-                                                        w.recon, nullptr, nullptr, nullptr, 0.f, 0, s)))) return rc;
+                                                        w.recon, st, training ? st + (re - rs) * Dm : nullptr,
+                                                        training ? w.dtE : nullptr, 1.f, training ? 1 : 0, s)))) return rc;
       } else {
         GemmDesc p = gemm_base(FORM_NT, T, re - rs, Dm, w.E, Dm, m->params + m->off_rw[random_chrom], Dm, w.pred, w.pred_ld);
         p.a_act = 1; p.bias = m->params + m->off_rb[random_chrom];
@@ -785,12 +794,9 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
   if (recon_on) {
     const int64_t rs = m->chrom_start[random_chrom], re = m->chrom_end[random_chrom], nr = re - rs;
     if (use_recon_tc(m, T, L)) {
-      // recompute pred / gdiff on chip; weight, bias and data gradients in the same kernel
-      if ((rc = check_cuda(cudaMemsetAsync(w.dtE, 0, sizeof(float) * T * Dm, s), "memset dtE"))) return rc;
-      if ((rc = PROF(P_W_RECON, 1, launch_recon_tc(w.E, x, T, m->inter, m->inter_ld, rs, re, P + m->off_rw[random_chrom],
-                                                   P + m->off_rb[random_chrom], w.counts, random_chrom, m->n_chrom, nullptr,
-                                                   G + m->off_rw[random_chrom], G + m->off_rb[random_chrom], w.dtE, beta, 1, s))))
-        return rc;
+      // the training forward left gdiff . Rw in w.dtE and the unscaled weight / bias gradients in the stash
+      if ((rc = PROF(P_W_RECON, 2, launch_axpy(w.recon_stash, beta, G + m->off_rw[random_chrom], nr * Dm, s)))) return rc;
+      if ((rc = launch_axpy(w.recon_stash + nr * Dm, beta, G + m->off_rb[random_chrom], nr, s))) return rc;
     } else {
       GemmDesc d = gemm_base(FORM_TN, nr, Dm, T, w.pred, w.pred_ld, w.E, Dm, G + m->off_rw[random_chrom], Dm);
       d.b_act = 1; d.out_scale = beta; d.colsum = G + m->off_rb[random_chrom]; d.colsum_n = nr;

@@ -35,7 +35,7 @@ struct ReconArgs {
   int64_t rs, re;                 // node-id range of the drawn chromosome
   const float* Rw; const float* rb;
   const int32_t* counts; int rchrom, n_chrom;
-  float* recon_out;               // mode 0: += 100 * mean((pred - target)^2)
+  float* recon_out;               // (optional) += 100 * mean((pred - target)^2)
   float* dRw; float* drb; float* dtE; float beta;     // mode 1
   int mode;
 };
@@ -250,10 +250,11 @@ __global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs 
     __syncthreads();       // sA / sG / staging are rewritten by the next tile
   }
 
-  if (a.mode == 0) {
+  if (a.recon_out != nullptr) {
     for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
     if (lane == 0 && elig > 0 && loss != 0.f) atomicAdd(a.recon_out, loss * 100.0f / ((float)elig * (float)n_r));
-  } else if (!first) {
+  }
+  if (a.mode == 1 && !first) {
     // weight / bias gradient slice of this CTA: TMEM lane = target column
     tc_fence_after();
     const int64_t col = (int64_t)cb * 128 + r;
@@ -277,9 +278,22 @@ __global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs 
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// out[i] += scale * in[i]  (the training forward leaves the unscaled weight / bias gradients in the workspace; the backward
+// pass applies d loss / d recon)
+__global__ void axpy_kernel(const float* __restrict__ in, float scale, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] += scale * in[i];
+}
 }  // namespace
-
-// mode 0: recon_out[0] += loss (forward / eval);  mode 1: dRw, drb += beta * ..., dtE += gdiff . Rw (dtE zeroed by the caller)
+int launch_axpy(const float* in, float scale, float* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return MATCHA_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kSMs * 4) blocks = kSMs * 4;
+  axpy_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, scale, out, n);
+  MATCHA_CHECK_LAUNCH("axpy");
+  return MATCHA_OK;
+}
+// mode 0: loss only (eval);  mode 1: also dRw, drb += beta * ..., dtE += gdiff . Rw (dtE zeroed by the caller).  recon_out
+// (optional) receives the loss in either mode
 int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* inter, int64_t inter_ld, int64_t rs, int64_t re,
                     const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, float* recon_out,
                     float* dRw, float* drb, float* dtE, float beta, int mode, cudaStream_t s) {

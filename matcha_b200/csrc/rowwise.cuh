@@ -115,11 +115,13 @@ int launch_wgrad_pair(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, c
                       float* scratch, float* w1, int ld1, int n1, float* bias1, float* w2, int ld2, int n2, float* bias2,
                       cudaStream_t s);
 
-// fused reconstruction head on tensor cores (recon_tc.cu): mode 0 adds the loss to recon_out[0]; mode 1 adds beta * the
-// weight / bias gradients to dRw [n_r, 64] / drb [n_r] and gdiff . Rw to dtE [T, 64] (zeroed by the caller)
+// fused reconstruction head on tensor cores (recon_tc.cu): the loss is added to recon_out[0] (if given); mode 1 also adds
+// beta * the weight / bias gradients to dRw [n_r, 64] / drb [n_r] and gdiff . Rw to dtE [T, 64] (zeroed by the caller)
 int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* inter, int64_t inter_ld, int64_t rs, int64_t re,
                     const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, float* recon_out,
                     float* dRw, float* drb, float* dtE, float beta, int mode, cudaStream_t s);
+
+int launch_axpy(const float* in, float scale, float* out, int64_t n, cudaStream_t s);      // out += scale * in
 
 // node encoder forward on tensor cores (enc_tc.cu): dense feature rows, embed_dim 64.  The pre-split weight chunks live in
 // the derived buffer from float offset split_base (enc_tc_split_floats(m) floats, rebuilt by launch_enc_tc_prepare)
