@@ -4,8 +4,8 @@
 // in ONE kernel per pass: pred / gdiff [T, n_r] never touch HBM (the decomposed path writes and re-reads them three
 // times through four SIMT launches).
 //
-// One CTA = 128 threads = 128 consecutive tokens (thread r owns token row r = TMEM lane r) x one block of 128 target
-// columns.  Per token tile:
+// One CTA = 256 threads = 128 consecutive tokens x one block of 128 target columns: thread (r, h) owns token row r (= TMEM
+// lane r) and half h of the features / of the target columns.  Per token tile:
 //   stage   tanh(E) rows -> bf16 hi | lo tile sA [feature/8][token][8]  (+ a ones column: plane 8, zeros: plane 9)
 //   MMA1    P[128 tok, 128 col] = sA . sW^T                      (K = 64; sW = Rw block, K-major)
 //   SIMT    thread = token: gdiff row = (P + rb - target) * gscale on eligible tokens; loss partial; -> sG tile
@@ -18,15 +18,14 @@
 namespace matcha {
 namespace {
 
-constexpr int kRThreads = 128;
+constexpr int kRThreads = 256;                // two warpgroups: thread = (token row r = tid & 127, half h = tid >> 7)
 constexpr int kRA = 2 * 10 * 2048;            // sA: hi 10 planes | lo 10 planes                      40 960
 constexpr int kRAHalf = 10 * 2048;
 constexpr int kRW = 32768;                    // sW: 128 rows x 64 k, hi 16 KB | lo 16 KB
 constexpr int kRG = 65536;                    // sG: 128 tokens x 128 columns, hi 32 KB | lo 32 KB
-constexpr int kRStageRow = 68;                // row staging (coalesced row I/O), floats per row
-constexpr int kRStage = 4 * 32 * kRStageRow * 4;   // 34 816
-constexpr int kRTgtRow = 33;                  // target staging: 32 x 32 block per warp, padded
-constexpr int kRSmem = kRA + kRW + kRG + kRStage;  // 174 080
+constexpr int kRStageRow = 36;                // staging row: 32 floats + pad (coalesced half-row I/O, 32 x 32 target blocks)
+constexpr int kRStage = 8 * 32 * kRStageRow * 4;   // 36 864
+constexpr int kRSmem = kRA + kRW + kRG + kRStage;  // 176 128 (gradient pass); 110 592 without sG (loss pass: 2 CTAs / SM)
 constexpr uint32_t kColP = 0, kColDT = 128, kColDW = 192;
 
 struct ReconArgs {
@@ -40,58 +39,59 @@ struct ReconArgs {
   int mode;
 };
 
-// a warp's 32 consecutive token rows <-> registers through a padded staging area (coalesced 128-bit global accesses)
-__device__ __forceinline__ void rows_in(const float* __restrict__ g, int nrows, float* stage, int lane, float (&v)[64]) {
+// 32 consecutive token rows x 32 floats (columns [col0, col0 + 32) of a 64-float row) <-> registers through the warp's
+// padded staging area: coalesced 128-bit global accesses, four rows per instruction
+__device__ __forceinline__ void half_rows_in(const float* __restrict__ g, int nrows, float* stage, int lane, float (&v)[32]) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int idx = k * 32 + lane, row = idx >> 4, c4 = idx & 15;
+  for (int k = 0; k < 8; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 3, c4 = idx & 7;
     float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < nrows) e = __ldg(reinterpret_cast<const float4*>(g) + idx);
+    if (row < nrows) e = __ldg(reinterpret_cast<const float4*>(g + row * 64) + c4);
     *reinterpret_cast<float4*>(stage + row * kRStageRow + c4 * 4) = e;
   }
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
+  for (int k = 0; k < 8; ++k) {
     const float4 e = *reinterpret_cast<const float4*>(stage + lane * kRStageRow + k * 4);
     v[4 * k] = e.x; v[4 * k + 1] = e.y; v[4 * k + 2] = e.z; v[4 * k + 3] = e.w;
   }
   __syncwarp();
 }
-// rows -> global with atomic adds (several column blocks contribute to the same dtE row), coalesced
-__device__ __forceinline__ void rows_red(float* __restrict__ g, int nrows, float* stage, int lane, const float (&v)[64]) {
+// half rows -> global with atomic adds (several column blocks contribute to the same dtE row), coalesced
+__device__ __forceinline__ void half_rows_red(float* __restrict__ g, int nrows, float* stage, int lane, const float (&v)[32]) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k)
+  for (int k = 0; k < 8; ++k)
     *reinterpret_cast<float4*>(stage + lane * kRStageRow + k * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
   __syncwarp();
 #pragma unroll 4
-  for (int k = 0; k < 64; ++k) {
-    const int idx = k * 32 + lane, row = idx >> 6, c = idx & 63;
-    if (row < nrows) atomicAdd(g + idx, stage[row * kRStageRow + c]);
-  }
+  for (int row = 0; row < 32; ++row)
+    if (row < nrows) atomicAdd(g + row * 64 + lane, stage[row * kRStageRow + lane]);
   __syncwarp();
 }
-__device__ __forceinline__ void put_planes(uint8_t* hi_base, int lo_off, int r, const float (&v)[64]) {
+// 32 floats of row r -> planes p0 .. p0 + 3 of a K-major bf16 hi | lo tile
+__device__ __forceinline__ void put_planes4(uint8_t* hi_base, int lo_off, int p0, int r, const float (&v)[32]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     uint4 hi, lo;
     split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
            make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
-    sts16(hi_base + j * 2048 + r * 16, hi);
-    sts16(hi_base + lo_off + j * 2048 + r * 16, lo);
+    sts16(hi_base + (p0 + j) * 2048 + r * 16, hi);
+    sts16(hi_base + lo_off + (p0 + j) * 2048 + r * 16, lo);
   }
 }
 
-__global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs a) {
+__global__ void __launch_bounds__(kRThreads, 2) recon_tc_kernel(const ReconArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kRA;
-  // loss-only pass (mode 0): no gdiff tile, the staging area follows sW directly (106 KB per CTA)
+  // loss-only pass (mode 0): no gdiff tile, the staging area follows sW directly (108 KB per CTA)
   uint8_t* sG = smem + kRA + kRW;
   float* sStage = reinterpret_cast<float*>(smem + kRA + kRW + (a.mode == 1 ? kRG : 0));
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_rb[128];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & 127, h = tid >> 7, wq = warp & 3;         // token row, half, TMEM lane quarter
   const int cb = blockIdx.y;                                   // column block: target columns [cb * 128, cb * 128 + 128)
   const int64_t n_r = a.re - a.rs;
   const int64_t ntiles = (a.T + 127) / 128;
@@ -105,34 +105,36 @@ __global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs 
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  {   // Rw block -> sW (row = target column), zero rows beyond n_r; bias slice
+  {   // Rw block -> sW (row = target column; this thread: features [32 h, 32 h + 32)), zero rows beyond n_r; bias slice
     const int64_t col = (int64_t)cb * 128 + r;
-    float v[64];
+    float v[32];
     if (col < n_r) {
-      const float* src = a.Rw + col * 64;
+      const float* src = a.Rw + col * 64 + h * 32;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
+      for (int k = 0; k < 8; ++k) {
         const float4 e = __ldg(reinterpret_cast<const float4*>(src) + k);
         v[4 * k] = e.x; v[4 * k + 1] = e.y; v[4 * k + 2] = e.z; v[4 * k + 3] = e.w;
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) v[c] = 0.f;
+      for (int c = 0; c < 32; ++c) v[c] = 0.f;
     }
-    put_planes(sW, 16384, r, v);
-    s_rb[r] = col < n_r ? __ldg(a.rb + col) : 0.f;
-    // ones / zero planes of sA never change
-    sts16(sA + 8 * 2048 + r * 16, make_uint4(0x00003F80u, 0u, 0u, 0u));          // bf16(1.0) in column 64
-    sts16(sA + 9 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
-    sts16(sA + kRAHalf + 8 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
-    sts16(sA + kRAHalf + 9 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
+    put_planes4(sW, 16384, h * 4, r, v);
+    if (h == 0) {
+      s_rb[r] = col < n_r ? __ldg(a.rb + col) : 0.f;
+      // ones / zero planes of sA never change
+      sts16(sA + 8 * 2048 + r * 16, make_uint4(0x00003F80u, 0u, 0u, 0u));          // bf16(1.0) in column 64
+      sts16(sA + 9 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
+      sts16(sA + kRAHalf + 8 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
+      sts16(sA + kRAHalf + 9 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
+    }
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
   constexpr uint32_t idescP = make_idesc(128, 128, false, false);
   constexpr uint32_t idescD = make_idesc(128, 64, false, true);
   constexpr uint32_t idescW = make_idesc(128, 80, true, true);
@@ -145,17 +147,17 @@ __global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs 
   bool first = true;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += S) {
-    const int64_t t0 = tile * 128 + warp * 32, t = t0 + lane;
+    const int64_t t0 = tile * 128 + wq * 32, t = t0 + lane;
     const int nrows = (a.T - t0) <= 0 ? 0 : ((a.T - t0) < 32 ? (int)(a.T - t0) : 32);
     const int64_t id = t < a.T ? a.x[t] : 0;
     const bool ok = id != 0 && (id < a.rs || id >= a.re);
-    // ---- stage tanh(E) ----
+    // ---- stage tanh(E): this thread's 32 features ----
     {
-      float v[64];
-      rows_in(a.E + t0 * 64, nrows, stage, lane, v);
+      float v[32];
+      half_rows_in(a.E + t0 * 64 + h * 32, nrows, stage, lane, v);
 #pragma unroll
-      for (int c = 0; c < 64; ++c) v[c] = tanhf(v[c]);
-      put_planes(sA, kRAHalf, r, v);
+      for (int c = 0; c < 32; ++c) v[c] = tanhf(v[c]);
+      put_planes4(sA, kRAHalf, h * 4, r, v);
     }
     fence_async_smem();
     tc_fence_before();
@@ -171,10 +173,10 @@ __global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs 
     mbar_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- gdiff rows: thread = token, 4 chunks of 32 target columns ----
-    float* tstage = stage;                                   // 32 x 33 floats of the warp's staging area
+    // ---- gdiff rows: thread = (token, half): 2 chunks of 32 target columns ----
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int ch = h * 2 + c2;                               // chunk of the 128-column block
       const int64_t c0 = (int64_t)cb * 128 + ch * 32;          // first target column of the chunk
       // target block [32 tokens x 32 columns]: row k of the warp is read by all lanes (coalesced), kept transposed
       {
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs 
           tv[k] = (okk && col_ok) ? __ldg(tbase + (idk - 1) * a.inter_ld) : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < 32; ++k) tstage[k * kRTgtRow + lane] = tv[k];
+        for (int k = 0; k < 32; ++k) stage[k * kRStageRow + lane] = tv[k];
       }
       __syncwarp();
       uint32_t pv[32];
@@ -198,21 +200,12 @@ __global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs 
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float dv = 0.f;
-        if (ok && c0 + i < n_r) dv = __uint_as_float(pv[i]) + s_rb[ch * 32 + i] - tstage[lane * kRTgtRow + i];
+        if (ok && c0 + i < n_r) dv = __uint_as_float(pv[i]) + s_rb[ch * 32 + i] - stage[lane * kRStageRow + i];
         loss = fmaf(dv, dv, loss);
         g[i] = dv * gscale;
       }
       __syncwarp();
-      if (a.mode == 1) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 hi, lo;
-          split8(make_float4(g[8 * j], g[8 * j + 1], g[8 * j + 2], g[8 * j + 3]),
-                 make_float4(g[8 * j + 4], g[8 * j + 5], g[8 * j + 6], g[8 * j + 7]), hi, lo);
-          sts16(sG + (ch * 4 + j) * 2048 + r * 16, hi);
-          sts16(sG + 32768 + (ch * 4 + j) * 2048 + r * 16, lo);
-        }
-      }
+      if (a.mode == 1) put_planes4(sG, 32768, ch * 4, r, g);
     }
     tc_fence_before();
     if (a.mode == 1) {
@@ -235,15 +228,13 @@ __global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs 
       phase ^= 1;
       tc_fence_after();
       {
-        uint32_t d0[32], d1[32];
-        tmem_ld32_issue(tlane + kColDT, d0);
-        tmem_ld32_issue(tlane + kColDT + 32, d1);
+        uint32_t d0[32];
+        tmem_ld32_issue(tlane + kColDT + h * 32, d0);
         tmem_ld_wait(d0);
-        tmem_ld_wait(d1);
-        float v[64];
+        float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(d0[i]); v[32 + i] = __uint_as_float(d1[i]); }
-        rows_red(a.dtE + t0 * 64, nrows, stage, lane, v);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(d0[i]);
+        half_rows_red(a.dtE + t0 * 64 + h * 32, nrows, stage, lane, v);
       }
       tc_fence_before();
     }
@@ -255,23 +246,22 @@ __global__ void __launch_bounds__(kRThreads, 1) recon_tc_kernel(const ReconArgs 
     if (lane == 0 && elig > 0 && loss != 0.f) atomicAdd(a.recon_out, loss * 100.0f / ((float)elig * (float)n_r));
   }
   if (a.mode == 1 && !first) {
-    // weight / bias gradient slice of this CTA: TMEM lane = target column
+    // weight / bias gradient slice of this CTA: TMEM lane = target column, this thread: features [32 h, 32 h + 32)
     tc_fence_after();
     const int64_t col = (int64_t)cb * 128 + r;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32_issue(tlane + kColDW + c * 32, v);
-      tmem_ld_wait(v);
-      if (col < n_r) {
+    uint32_t v[32];
+    tmem_ld32_issue(tlane + kColDW + h * 32, v);
+    tmem_ld_wait(v);
+    if (col < n_r) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(a.dRw + col * 64 + c * 32 + i, __uint_as_float(v[i]) * a.beta);
-      }
+      for (int i = 0; i < 32; ++i) atomicAdd(a.dRw + col * 64 + h * 32 + i, __uint_as_float(v[i]) * a.beta);
     }
-    uint32_t b8[8];
-    tmem_ld8_issue(tlane + kColDW + 64, b8);
-    tmem_ld_wait(b8);
-    if (col < n_r) atomicAdd(a.drb + col, __uint_as_float(b8[0]) * a.beta);
+    if (h == 1) {
+      uint32_t b8[8];
+      tmem_ld8_issue(tlane + kColDW + 64, b8);
+      tmem_ld_wait(b8);
+      if (col < n_r) atomicAdd(a.drb + col, __uint_as_float(b8[0]) * a.beta);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -311,7 +301,7 @@ int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* in
   a.beta = beta; a.mode = mode;
   const int ncb = (int)((re - rs + 127) / 128);
   const int64_t ntiles = (T + 127) / 128;
-  const int per_sm = mode == 1 ? 1 : 2;                      // 174 KB (gradient pass) or 106 KB (loss pass) of shared memory per CTA
+  const int per_sm = mode == 1 ? 1 : 2;                      // 172 KB (gradient pass) or 108 KB (loss pass) of shared memory per CTA
   int64_t S = (per_sm * kSMs + ncb - 1) / ncb;
   if (S > ntiles) S = ntiles;
   if (S < 1) S = 1;
