@@ -247,6 +247,230 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
   if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
+// ==========================================================================================
+// backward:  dH0pre = (dE . W1_c) * (1 - H0^2),   dW1_c += dE^T . H0,   dW0_c += dH0pre^T . dropout(F_c rows)
+// One CTA = 256 threads: thread (r, h) owns token row r (TMEM lane r) and half h of every 64-wide row.  The two weight
+// gradients share ONE M = 128 contraction per operand tile: the stacked tile sS = [dE | dH0pre] (128 feature rows, K =
+// tokens, MN-major view) against sB = H0 and then each feature chunk; lanes 0..63 of the H0 columns are dW1_c, lanes
+// 64..127 of the chunk columns are dW0_c (the other two blocks of the 2 x 2 product are ignored).  Accumulators stay in
+// TMEM while the CTA stays inside one chromosome (CTAs own contiguous tile ranges) and are flushed with atomics.
+// ==========================================================================================
+constexpr int kBThreads = 256;
+constexpr int kBS = 65536;                      // sS: 16 planes, hi 32 KB | lo 32 KB
+constexpr int kBB = 32768;                      // sB: 8 planes, hi 16 KB | lo 16 KB
+constexpr int kBStageRow = 36;
+constexpr int kBStage = 8 * 32 * kBStageRow * 4;            // 36 864
+constexpr int kBSmem = kBS + kBB + kEChunk + kBStage;       // 151 552
+constexpr int kBMaxChunks = 6;                  // TMEM: dH0 64 | dW1 64 | 6 x 64 chunk columns = 512
+constexpr uint32_t kColDH = 0, kColW1 = 64, kColW0 = 128;
+
+// 32 scattered rows x 32 floats (row pointer incl. column offset held by the owning lane, NULL = zero row): four rows per
+// instruction, 8 lanes x float4 each; transposed through the warp's staging area
+__device__ __forceinline__ void gather_half_rows(const float* rowp, bool col_ok_base, int64_t k_first, int64_t klimit, float* stage,
+                                                 int lane, float (&v)[32]) {
+  (void)col_ok_base;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int row = 4 * k + (lane >> 3), c4 = lane & 7;
+    const float* p = shfl_ptr(rowp, row);
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p != nullptr && k_first + c4 * 4 < klimit) e = __ldg(reinterpret_cast<const float4*>(p) + c4);
+    *reinterpret_cast<float4*>(stage + row * kBStageRow + c4 * 4) = e;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 e = *reinterpret_cast<const float4*>(stage + lane * kBStageRow + k * 4);
+    v[4 * k] = e.x; v[4 * k + 1] = e.y; v[4 * k + 2] = e.z; v[4 * k + 3] = e.w;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void put4(uint8_t* hi_base, int lo_off, int p0, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 hi, lo;
+    split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+           make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+    sts16(hi_base + (p0 + j) * 2048 + r * 16, hi);
+    sts16(hi_base + lo_off + (p0 + j) * 2048 + r * 16, lo);
+  }
+}
+
+__global__ void __launch_bounds__(kBThreads, 1)
+enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const int64_t* __restrict__ x,
+                  const int32_t* __restrict__ perm, const int32_t* __restrict__ group_off, const float* __restrict__ dE,
+                  const float* __restrict__ H0, float* __restrict__ grads, const DropCfg drop) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sS = smem;
+  uint8_t* sB = smem + kBS;
+  uint8_t* sW1 = smem + kBS + kBB;
+  float* sStage = reinterpret_cast<float*>(smem + kBS + kBB + kEChunk);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & 127, h = tid >> 7, wq = warp & 3;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+  constexpr uint32_t idescD = make_idesc(128, 64, false, true);     // dH0 = dE . W1          (B MN-major)
+  constexpr uint32_t idescW = make_idesc(128, 64, true, true);      // [dE | dH0pre]^T . tile  (both MN-major)
+  const uint32_t sh = smem_u32(sS), sl = sh + 32768;
+  const uint32_t bh = smem_u32(sB), bl = bh + 16384;
+  const uint32_t vh = smem_u32(sW1), vl = vh + 8192;
+  float* stage = sStage + warp * (32 * kBStageRow);
+  uint32_t phase = 0;
+
+  // this CTA's contiguous range of the tile list (chromosome c contributes ceil(count_c / 128) tiles)
+  int64_t total = 0;
+  for (int c = 0; c < em.n; ++c) total += (group_off[c + 1] - group_off[c] + 127) / 128;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t ti0 = (int64_t)blockIdx.x * per, ti1 = (ti0 + per < total) ? ti0 + per : total;
+
+  auto flush = [&](int c, int nchunk) {   // TMEM -> atomics on the weight gradients of chromosome c
+    tc_fence_after();
+    if (r < 64) {                          // lanes 0..63: dW1_c[o = r][k], this thread: k in [32 h, 32 h + 32)
+      uint32_t v[32];
+      tmem_ld32_issue(tlane + kColW1 + h * 32, v);
+      tmem_ld_wait(v);
+      float* dst = grads + em.off_w1[c] + (int64_t)r * 64 + h * 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+    } else {                               // lanes 64..127: dW0_c[f = r - 64][k]
+      const int nc = em.nc[c];
+      float* dst = grads + em.off_w0[c] + (int64_t)(r - 64) * nc;
+      for (int kc = 0; kc < nchunk; ++kc) {
+        uint32_t v[32];
+        tmem_ld32_issue(tlane + kColW0 + kc * 64 + h * 32, v);
+        tmem_ld_wait(v);
+        const int k0 = kc * 64 + h * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (k0 + i < nc) atomicAdd(dst + k0 + i, __uint_as_float(v[i]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  };
+
+  int c = 0, cur_c = -1, cur_nchunk = 0;
+  int64_t before = 0;
+  bool fresh = true;                       // no tile accumulated yet for cur_c
+  for (int64_t ti = ti0; ti < ti1; ++ti) {
+    int cnt = 0;
+    for (; c < em.n; ++c) {
+      cnt = group_off[c + 1] - group_off[c];
+      const int64_t nt = (cnt + 127) / 128;
+      if (ti < before + nt) break;
+      before += nt;
+    }
+    if (c >= em.n) break;
+    const int nchunk = (em.nc[c] + 63) / 64;
+    if (c != cur_c) {
+      if (cur_c >= 0 && !fresh) flush(cur_c, cur_nchunk);
+      __syncthreads();
+      {   // W1_c chunk (K-major for the forward; read MN-major here)
+        const uint4* s4 = reinterpret_cast<const uint4*>(wsplit + em.woff[c] + (int64_t)nchunk * kEChunk);
+        uint4* d4 = reinterpret_cast<uint4*>(sW1);
+#pragma unroll
+        for (int i = 0; i < kEChunk / 16 / kBThreads; ++i) d4[tid + i * kBThreads] = __ldg(s4 + tid + i * kBThreads);
+      }
+      cur_c = c; cur_nchunk = nchunk; fresh = true;
+    }
+    const int off = (int)(ti - before) * 128;
+    const int nrows_cta = cnt - off < 128 ? cnt - off : 128;
+    const bool live = r < nrows_cta;
+    const int64_t t = live ? perm[group_off[c] + off + r] : 0;
+    // ---- dE rows -> planes 0..7 of sS ----
+    {
+      float v[32];
+      gather_half_rows(live ? dE + t * 64 + h * 32 : nullptr, true, 0, 64, stage, lane, v);
+      put4(sS, 32768, h * 4, r, v);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)       // dH0[128 tok, 64] = dE[128 tok, 64 o] . W1[64 o, 64 k]
+        umma_x3s(tmem_base + kColDH, sh + ks * 4096, sl + ks * 4096, vh + ks * 256, vl + ks * 256, 2048, 128, 128, 1024, idescD, ks == 0);
+      umma_commit(&bar);
+    }
+    // H0 rows while the MMA runs
+    float hv[32];
+    gather_half_rows(live ? H0 + t * 64 + h * 32 : nullptr, true, 0, 64, stage, lane, hv);
+    put4(sB, 16384, h * 4, r, hv);
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t d0[32];
+      tmem_ld32_issue(tlane + kColDH + h * 32, d0);
+      tmem_ld_wait(d0);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = live ? __uint_as_float(d0[i]) * (1.f - hv[i] * hv[i]) : 0.f;     // tanh'
+      put4(sS, 32768, 8 + h * 4, r, v);
+    }
+    tc_fence_before();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)       // [dE | dH0pre]^T[128 feat, 128 tok] . H0[128 tok, 64]: lanes 0..63 = dW1_c
+        umma_x3s(tmem_base + kColW1, sh + ks * 256, sl + ks * 256, bh + ks * 256, bl + ks * 256, 128, 2048, 128, 2048, idescW,
+                 fresh && ks == 0);
+      umma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);                // sB is rewritten by the feature chunks
+    phase ^= 1;
+    tc_fence_after();
+    const float* frow = live ? em.feat[c] + (x[t] - em.start[c]) * em.ld[c] : nullptr;
+    for (int kc = 0; kc < nchunk; ++kc) {
+      float v[32];
+      const int64_t kf = (int64_t)kc * 64 + h * 32;
+      gather_half_rows(frow ? frow + kf : nullptr, true, kf, em.ld[c], stage, lane, v);
+      if (drop.thr != 0u && live) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 d = drop_apply4(drop, (uint64_t)t, (uint32_t)(kf + 4 * j), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          v[4 * j] = d.x; v[4 * j + 1] = d.y; v[4 * j + 2] = d.z; v[4 * j + 3] = d.w;
+        }
+      }
+      put4(sB, 16384, h * 4, r, v);
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)     // lanes 64..127 = dW0_c[:, chunk kc]
+          umma_x3s(tmem_base + kColW0 + kc * 64, sh + ks * 256, sl + ks * 256, bh + ks * 256, bl + ks * 256, 128, 2048, 128, 2048,
+                   idescW, fresh && ks == 0);
+        umma_commit(&bar);
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+    }
+    fresh = false;
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (cur_c >= 0 && !fresh) flush(cur_c, cur_nchunk);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 EncMeta make_meta(const matcha_model_desc* m, int64_t* total_bytes) {
   EncMeta em;
   memset(&em, 0, sizeof(em));
@@ -301,6 +525,34 @@ int launch_enc_tc_fwd(const matcha_model_desc* m, int64_t split_base, const int6
   enc_tc_fwd_kernel<<<grid, kEThreads, kESmem, s>>>(em, reinterpret_cast<const uint8_t*>(m->derived + split_base), x, perm,
                                                     group_off, H0, E, drop);
   MATCHA_CHECK_LAUNCH("enc_tc_fwd");
+  return MATCHA_OK;
+}
+
+
+// feature chunks per chromosome the backward kernel keeps resident in TMEM (wider chromosomes use the SIMT launches)
+bool enc_tc_bwd_fits(const matcha_model_desc* m) {
+  for (int c = 0; c < m->n_chrom; ++c)
+    if ((m->chrom_end[c] - m->chrom_start[c] + 63) / 64 > kBMaxChunks) return false;
+  return true;
+}
+
+// grads (flat, same layout as params): dW1_c += dE^T H0, dW0_c += ((dE W1_c) * (1 - H0^2))^T dropout(F_c rows)
+int launch_enc_tc_bwd(const matcha_model_desc* m, int64_t split_base, const int64_t* x, int64_t T, const int32_t* perm,
+                      const int32_t* group_off, const float* dE, const float* H0, DropCfg drop, cudaStream_t s) {
+  if (T <= 0) return MATCHA_OK;
+  static bool once = false;
+  if (!once) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(enc_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem),
+                            "cudaFuncSetAttribute"))
+      return rc;
+    once = true;
+  }
+  const EncMeta em = make_meta(m, nullptr);
+  const int64_t tiles = (T + 127) / 128 + m->n_chrom;
+  const unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
+  enc_tc_bwd_kernel<<<grid, kBThreads, kBSmem, s>>>(em, reinterpret_cast<const uint8_t*>(m->derived + split_base), x, perm,
+                                                    group_off, dE, H0, m->grads, drop);
+  MATCHA_CHECK_LAUNCH("enc_tc_bwd");
   return MATCHA_OK;
 }
 

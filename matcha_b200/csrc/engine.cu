@@ -829,7 +829,11 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     if ((rc = PROF(P_ENC_COMBINE, 1, launch_enc_combine_bwd(w.dV0, dtE, w.E, beta, w.dE, T * Dm, s)))) return rc;
   }
   // encoder backward (grouped by chromosome; token lists from the forward pass are still in the workspace)
-  {
+  if (use_enc_tc(m, T) && enc_tc_bwd_fits(m)) {
+    // dH0pre and both weight gradients in one tcgen05 kernel (dH0pre never leaves the SM)
+    if ((rc = PROF(P_W_ENC0, 1, launch_enc_tc_bwd(m, l.total, x, T, w.perm, w.group_off, w.dE, w.H0,
+                                                  make_drop(seed, SITE_FEATURE, m->p_feature, true), s)))) return rc;
+  } else {
     GemmDesc d = gemm_base(FORM_TN, Dm, Dm, 0, w.dE, Dm, w.H0, Dm, nullptr, Dm);
     d.perm = w.perm; d.ngroups = m->n_chrom; d.groups = table_ptr(m->derived, m->d, TAB_GW1); d.group_off = w.group_off;
     d.total_rows = T; d.max_group_dim = Dm;

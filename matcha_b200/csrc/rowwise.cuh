@@ -130,6 +130,12 @@ int launch_enc_tc_prepare(const matcha_model_desc* m, int64_t split_base, cudaSt
 int launch_enc_tc_fwd(const matcha_model_desc* m, int64_t split_base, const int64_t* x, int64_t T, const int32_t* perm,
                       const int32_t* group_off, float* H0, float* E, DropCfg drop, cudaStream_t s);
 
+// backward of the same two layers: dW1_c and dW0_c accumulated into m->grads (chromosomes up to 384 bins: 6 feature
+// chunks resident in TMEM; enc_tc_bwd_fits says whether the model qualifies)
+bool enc_tc_bwd_fits(const matcha_model_desc* m);
+int launch_enc_tc_bwd(const matcha_model_desc* m, int64_t split_base, const int64_t* x, int64_t T, const int32_t* perm,
+                      const int32_t* group_off, const float* dE, const float* H0, DropCfg drop, cudaStream_t s);
+
 // CSR first encoder layer (csr_encoder.cu): feature rows given as CSR (feat[c] == NULL, feat_indptr/indices/values set).
 // W0T_c [n_c, 64] copies live in the derived buffer from float offset w0t_base (chromosome after chromosome); the same
 // offsets of derived_grad accumulate dW0T_c.
