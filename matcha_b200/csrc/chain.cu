@@ -21,8 +21,12 @@ constexpr float kLnEpsC = 1e-5f;
 // parameter preparation: W [64][64] row-major -> (a) K-major [k/8][n][8] for Y = X W^T, (b) the layout of W read as
 // B[N = column, K = row] MN-major ([row/8][col/8][row%8][8 cols]) for dX = dY W.  LBO 1024 / SBO 128 in both.
 // ------------------------------------------------------------------------------------------
-__global__ void split_w64_kernel(const float* __restrict__ W, uint8_t* __restrict__ out_k, uint8_t* __restrict__ out_mn) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;       // unit = (row r, group g of 8 columns)
+struct SplitW3 { const float* W[3]; uint8_t* out_k[3]; uint8_t* out_mn[3]; };
+__global__ void split_w64_kernel(const SplitW3 a) {          // grid = 2 blocks per weight
+  const float* __restrict__ W = a.W[blockIdx.x >> 1];
+  uint8_t* __restrict__ out_k = a.out_k[blockIdx.x >> 1];
+  uint8_t* __restrict__ out_mn = a.out_mn[blockIdx.x >> 1];
+  const int u = (blockIdx.x & 1) * blockDim.x + threadIdx.x;       // unit = (row r, group g of 8 columns)
   if (u >= 64 * 8) return;
   const int g = u & 7, r = u >> 3;
   const float* src = W + r * 64 + g * 8;
@@ -791,8 +795,13 @@ int launch_chain_mix_bwd(const float* dxhat, int nparts, int64_t part_stride, co
   }
 }
 
-int launch_split_w64(const float* W, void* out_k, void* out_mn, cudaStream_t s) {
-  split_w64_kernel<<<2, 256, 0, s>>>(W, reinterpret_cast<uint8_t*>(out_k), reinterpret_cast<uint8_t*>(out_mn));
+int launch_split_w64x3(const float* W0, const float* W1, const float* W2, void* k0, void* mn0, void* k1, void* mn1, void* k2,
+                       void* mn2, cudaStream_t s) {
+  SplitW3 a;
+  a.W[0] = W0; a.W[1] = W1; a.W[2] = W2;
+  a.out_k[0] = reinterpret_cast<uint8_t*>(k0); a.out_k[1] = reinterpret_cast<uint8_t*>(k1); a.out_k[2] = reinterpret_cast<uint8_t*>(k2);
+  a.out_mn[0] = reinterpret_cast<uint8_t*>(mn0); a.out_mn[1] = reinterpret_cast<uint8_t*>(mn1); a.out_mn[2] = reinterpret_cast<uint8_t*>(mn2);
+  split_w64_kernel<<<6, 256, 0, s>>>(a);
   MATCHA_CHECK_LAUNCH("split_w64");
   return MATCHA_OK;
 }

@@ -430,12 +430,9 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
                  fresh && ks == 0);
       umma_commit(&bar);
     }
-    mbar_wait(&bar, phase);                // sB is rewritten by the feature chunks
-    phase ^= 1;
-    tc_fence_after();
     const float* frow = live ? em.feat[c] + (x[t] - em.start[c]) * em.ld[c] : nullptr;
-    for (int kc = 0; kc < nchunk; ++kc) {
-      float v[32];
+    // feature chunk kc + 1 is gathered (global loads, dropout) while the tensor pipe works on chunk kc
+    auto gather_chunk = [&](int kc, float (&v)[32]) {
       const int64_t kf = (int64_t)kc * 64 + h * 32;
       gather_half_rows(frow ? frow + kf : nullptr, true, kf, em.ld[c], stage, lane, v);
       if (drop.thr != 0u && live) {
@@ -445,7 +442,14 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
           v[4 * j] = d.x; v[4 * j + 1] = d.y; v[4 * j + 2] = d.z; v[4 * j + 3] = d.w;
         }
       }
-      put4(sB, 16384, h * 4, r, v);
+    };
+    float fv[32];
+    gather_chunk(0, fv);
+    mbar_wait(&bar, phase);                // dW1 contraction done: sB may be rewritten
+    phase ^= 1;
+    tc_fence_after();
+    for (int kc = 0; kc < nchunk; ++kc) {
+      put4(sB, 16384, h * 4, r, fv);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -457,6 +461,7 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
                    idescW, fresh && ks == 0);
         umma_commit(&bar);
       }
+      if (kc + 1 < nchunk) gather_chunk(kc + 1, fv);
       mbar_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();

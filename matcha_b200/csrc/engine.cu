@@ -496,6 +496,8 @@ static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   if (fused_L > 0)   // fused attention: hyperedge-aligned tiles; the QKG projection happens inside the attention kernel
     return PROF(P_LN, 1, launch_ln_fwd_atiles(w.X, w.xhat, w.rstd, T, fused_L, w.xhat_t, s));
   const bool tiles = use_tiles(m, T);
+  if (m->d == kD && gemm_impl() == 1 &&
+      (rc = launch_split_weights_k64(m->derived + l.wqkg, kD, kQKG, m->derived + l.wsplit, s))) return rc;   // decomposed pipeline only
   if ((rc = PROF(P_LN, 1, launch_ln_fwd(m->d, w.X, w.xhat, w.rstd, T, tiles ? w.xhat_t : nullptr, s)))) return rc;
   if (tiles)
     return PROF(P_QKG, 1, tc_qkg_forward_tiles(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wsplit),
@@ -601,16 +603,15 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   prep_tables_kernel<<<1, MATCHA_MAX_CHROM, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_tables");
   if (m->d == kD) {      // pre-split bf16 hi | lo operand copies for the tcgen05 kernels (embed_dim 64 only)
-    if ((rc = launch_split_weights_k64(m->derived + l.wqkg, kD, kQKG, m->derived + l.wsplit, s))) return rc;
-    if ((rc = launch_split_wT(m->derived + l.wqkg, m->derived + l.wtsplit, s))) return rc;
+    // (the K-major / MN-major copies of the whole W_qkg are only read by the decomposed pipeline: built there, on demand)
     if ((rc = launch_split_w_heads(m->derived + l.wqkg, m->derived + l.wheads, s))) return rc;
     if (m->grads && (rc = launch_split_w_pairs(m->derived + l.wqkg, m->derived + l.wpairs, s))) return rc;
     {
       float* wc = m->derived + l.wchain;
       const int64_t st = kChainWBytes / 4;
-      if ((rc = launch_split_w64(m->params + m->off_next_w, wc + CW_NEXT_K * st, wc + CW_NEXT_MN * st, s))) return rc;
-      if ((rc = launch_split_w64(m->params + m->off_pff_w0, wc + CW_PFF0_K * st, wc + CW_PFF0_MN * st, s))) return rc;
-      if ((rc = launch_split_w64(m->params + m->off_pff_w1, wc + CW_PFF1_K * st, wc + CW_PFF1_MN * st, s))) return rc;
+      if ((rc = launch_split_w64x3(m->params + m->off_next_w, m->params + m->off_pff_w0, m->params + m->off_pff_w1, wc + CW_NEXT_K * st,
+                                 wc + CW_NEXT_MN * st, wc + CW_PFF0_K * st, wc + CW_PFF0_MN * st, wc + CW_PFF1_K * st,
+                                 wc + CW_PFF1_MN * st, s))) return rc;
     }
   }
   if (model_uses_csr(m) && (rc = launch_csr_prepare(m, l.total, s))) return rc;
@@ -778,6 +779,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_bwd(m->d, w.QKG, w.dU, x, nullptr, w.dqkg_t, DG + l.bdyn, B, L, dattn, s)))) return rc;
     if ((rc = PROF(P_W_QKG, 2, tc_qkg_wgrad_tiles(w.dqkg_t, w.xhat_t, w.tc_scratch, w.tc_scratch_floats, DG + l.wqkg,
                                                   DG + l.bqkg, kH * Dm, T, s)))) return rc;
+    if ((rc = launch_split_wT(m->derived + l.wqkg, m->derived + l.wtsplit, s))) return rc;
     if ((rc = PROF(P_D_QKG, 1, tc_qkg_dgrad_tiles(w.dqkg_t, reinterpret_cast<const uint8_t*>(m->derived + l.wtsplit), w.dxhat,
                                                   T, s)))) return rc;
   } else {

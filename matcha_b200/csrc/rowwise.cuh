@@ -89,7 +89,9 @@ constexpr int kPairWBytes = 3 * 32768;                 // per head pair: G | K |
 
 // row-chain kernels (chain.cu): the 64-wide layers around the attention block on tensor cores, thread = tile row
 constexpr int kChainWBytes = 16384;                    // one 64x64 weight, bf16 hi 8 KB | lo 8 KB
-int launch_split_w64(const float* W, void* out_k, void* out_mn, cudaStream_t s);
+// next_w, pff_w0, pff_w1 [64, 64] -> K-major and MN-major bf16 hi | lo copies, one launch
+int launch_split_w64x3(const float* W0, const float* W1, const float* W2, void* k0, void* mn0, void* k1, void* mn1, void* k2,
+                       void* mn2, cudaStream_t s);
 // V0 = E + attribute_nn(attr[id]); X = tanh(next_w V0 + b); xhat / rstd; hyperedge-aligned xhat tiles
 // (optional: V0, V0 tiles and attribute-row tiles for the backward pass)
 int launch_chain_mix_fwd(const float* E, const int64_t* x, const float* attr_table, int attr_dim, const float* attr_w,
