@@ -603,13 +603,20 @@ __global__ void iota_i64_kernel(int64_t* out, int64_t n) {
 // ==========================================================================================
 int launch_bucket(const int64_t* x, int64_t T, const ChromMeta& cm, int32_t* counts, int32_t* group_off,
                   int32_t* cursor, int32_t* perm, cudaStream_t s) {
-  if (int rc = check_cuda(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (cm.n + 1), s), "memset counts")) return rc;
+  // counts and cursor start at zero; when they sit in one small span of the workspace (group_off between them is rewritten
+  // by the scatter kernel anyway) a single memset covers both
+  const ptrdiff_t span = reinterpret_cast<char*>(cursor + cm.n + 1) - reinterpret_cast<char*>(counts);
+  if (cursor > counts && group_off > counts && group_off < cursor && span <= 4096) {
+    if (int rc = check_cuda(cudaMemsetAsync(counts, 0, (size_t)span, s), "memset counts..cursor")) return rc;
+  } else {
+    if (int rc = check_cuda(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (cm.n + 1), s), "memset counts")) return rc;
+    if (int rc = check_cuda(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (cm.n + 1), s), "memset cursor")) return rc;
+  }
   int blocks = (int)((T + 1023) / 1024);
   if (blocks < 1) blocks = 1;
   if (blocks > kSMs * 4) blocks = kSMs * 4;
   bucket_count_kernel<<<blocks, 256, 0, s>>>(x, T, cm, counts);
   MATCHA_CHECK_LAUNCH("bucket_count");
-  if (int rc = check_cuda(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (cm.n + 1), s), "memset cursor")) return rc;
   bucket_scatter_kernel<<<blocks, 256, 0, s>>>(x, T, cm, counts, group_off, cursor, perm);
   MATCHA_CHECK_LAUNCH("bucket_scatter");
   return MATCHA_OK;
