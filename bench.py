@@ -284,15 +284,16 @@ def main():
         del out
         return total, ms
 
-    run(warmup, False, 0)
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
-        run(max(20, args.steps), False, 0)          # give nvidia-smi time to start sampling while the GPU is under the same load
+        clocks.start()                               # started before the warm-up: nvidia-smi takes a while to produce samples
+    run(warmup, False, 0)
+    # every rank runs the same steps (the step holds a collective when world > 1); the extra untimed steps on both sides
+    # give nvidia-smi time to sample the clocks while the GPU is under the same load
+    run(max(20, args.steps), False, 0)
     ms_dev, _ = timed(args.steps, False, warmup)                     # the reported value: no per-call-site events
-    if rank == 0:
-        run(max(20, args.steps), False, 0)
-        torch.cuda.synchronize()
+    run(max(20, args.steps), False, 0)
+    torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
     _, prof = timed(args.steps, False, warmup, profile=True)        # same steps again with CUDA events per call site
     run(2, True, 0)

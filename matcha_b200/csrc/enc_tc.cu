@@ -13,12 +13,12 @@
 namespace matcha {
 namespace {
 
-constexpr int kEThreads = 128;
+constexpr int kFThreads = 256;                 // forward kernel: two warpgroups split every 64-wide row
+constexpr int kHStageRow = 36;                 // half-row staging: 32 floats + pad
 constexpr int kEChunk = 16384;                 // one 64 x 64 weight chunk: K-major [k/8][row][8], hi 8 KB | lo 8 KB
 constexpr int kEA = 32768;                     // A tile: 128 tokens x 64 k, hi 16 KB | lo 16 KB
-constexpr int kEStageRow = 68;
-constexpr int kEStage = 4 * 32 * kEStageRow * 4;     // 34 816
-constexpr int kESmem = kEA + 2 * kEChunk + kEStage;  // 100 352 -> two CTAs per SM
+constexpr int kEStage = 8 * 32 * kHStageRow * 4;     // 36 864
+constexpr int kESmem = kEA + 2 * kEChunk + kEStage;  // 102 400 -> two CTAs per SM
 
 struct EncMeta {
   int32_t n;
@@ -72,57 +72,53 @@ __device__ __forceinline__ float* shfl_ptr(float* p, int src) {
   return const_cast<float*>(shfl_ptr(const_cast<const float*>(p), src));
 }
 
-// gather 64 consecutive floats of 32 scattered rows (row pointer held by the lane that owns the row, NULL = zero row):
-// two rows per instruction, 16 lanes x float4 each (256 B contiguous per row), transposed through the staging area
-__device__ __forceinline__ void gather_rows(const float* rowp, int64_t k0, int64_t klimit, float* stage, int lane, float (&v)[64]) {
+
+// 32 scattered rows x 32 floats (row pointer incl. column offset held by the owning lane, NULL = zero row): four rows per
+// instruction, 8 lanes x float4 each; transposed through the warp's staging area
+__device__ __forceinline__ void gather_half_rows(const float* rowp, int64_t k_first, int64_t klimit, float* stage, int lane,
+                                                 float (&v)[32]) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int row = 2 * k + (lane >> 4), c4 = lane & 15;
+  for (int k = 0; k < 8; ++k) {
+    const int row = 4 * k + (lane >> 3), c4 = lane & 7;
     const float* p = shfl_ptr(rowp, row);
     float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p != nullptr && k0 + c4 * 4 < klimit) e = __ldg(reinterpret_cast<const float4*>(p + k0) + c4);
-    *reinterpret_cast<float4*>(stage + row * kEStageRow + c4 * 4) = e;
+    if (p != nullptr && k_first + c4 * 4 < klimit) e = __ldg(reinterpret_cast<const float4*>(p) + c4);
+    *reinterpret_cast<float4*>(stage + row * kHStageRow + c4 * 4) = e;
   }
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const float4 e = *reinterpret_cast<const float4*>(stage + lane * kEStageRow + k * 4);
+  for (int k = 0; k < 8; ++k) {
+    const float4 e = *reinterpret_cast<const float4*>(stage + lane * kHStageRow + k * 4);
     v[4 * k] = e.x; v[4 * k + 1] = e.y; v[4 * k + 2] = e.z; v[4 * k + 3] = e.w;
   }
   __syncwarp();
 }
-// scatter 32 rows of 64 floats to their (scattered) destinations, same access pattern
-__device__ __forceinline__ void scatter_rows(float* rowp, float* stage, int lane, const float (&v)[64]) {
+__device__ __forceinline__ void scatter_half_rows(float* rowp, float* stage, int lane, const float (&v)[32]) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k)
-    *reinterpret_cast<float4*>(stage + lane * kEStageRow + k * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  for (int k = 0; k < 8; ++k)
+    *reinterpret_cast<float4*>(stage + lane * kHStageRow + k * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int row = 2 * k + (lane >> 4), c4 = lane & 15;
+  for (int k = 0; k < 8; ++k) {
+    const int row = 4 * k + (lane >> 3), c4 = lane & 7;
     float* p = shfl_ptr(rowp, row);
-    if (p != nullptr) reinterpret_cast<float4*>(p)[c4] = *reinterpret_cast<const float4*>(stage + row * kEStageRow + c4 * 4);
+    if (p != nullptr) reinterpret_cast<float4*>(p)[c4] = *reinterpret_cast<const float4*>(stage + row * kHStageRow + c4 * 4);
   }
   __syncwarp();
 }
-__device__ __forceinline__ void put_tile(uint8_t* sA, int r, const float (&v)[64]) {
+__device__ __forceinline__ void put4(uint8_t* hi_base, int lo_off, int p0, int r, const float (&v)[32]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     uint4 hi, lo;
     split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
            make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
-    sts16(sA + j * 2048 + r * 16, hi);
-    sts16(sA + 16384 + j * 2048 + r * 16, lo);
+    sts16(hi_base + (p0 + j) * 2048 + r * 16, hi);
+    sts16(hi_base + lo_off + (p0 + j) * 2048 + r * 16, lo);
   }
 }
-__device__ __forceinline__ void load_chunk(uint8_t* dst, const uint8_t* src) {   // 16 KB, all 128 threads
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int i = 0; i < kEChunk / 16 / kEThreads; ++i) d[threadIdx.x + i * kEThreads] = __ldg(s + threadIdx.x + i * kEThreads);
-}
 
-__global__ void __launch_bounds__(kEThreads, 2)
+// One CTA = 256 threads: thread (r, h) owns token row r (TMEM lane r) and half h of every 64-wide row / chunk
+__global__ void __launch_bounds__(kFThreads, 2)
 enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const int64_t* __restrict__ x,
                   const int32_t* __restrict__ perm, const int32_t* __restrict__ group_off, float* __restrict__ H0,
                   float* __restrict__ E, const DropCfg drop) {
@@ -133,7 +129,8 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
   float* sStage = reinterpret_cast<float*>(smem + kEA + 2 * kEChunk);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & 127, h = tid >> 7, wq = warp & 3;
   if (warp == 0) tmem_alloc(&tmem_base_s, 64);
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -143,14 +140,20 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
   constexpr uint32_t idesc = make_idesc(128, 64, false, false);
   const uint32_t ah = smem_u32(sA), al = ah + 16384;
   const uint32_t wh = smem_u32(sW), wl = wh + 8192;
   const uint32_t vh = smem_u32(sW1), vl = vh + 8192;
-  float* stage = sStage + warp * (32 * kEStageRow);
+  float* stage = sStage + warp * (32 * kHStageRow);
   uint32_t phase = 0;
   int cur_c = -1;
+  auto copy_chunk = [&](uint8_t* dst, const uint8_t* src) {     // 16 KB, all 256 threads
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < kEChunk / 16 / kFThreads; ++i) d4[tid + i * kFThreads] = __ldg(s4 + tid + i * kFThreads);
+  };
 
   // tile list: chromosome c contributes ceil(count_c / 128) tiles of its bucket (pads live in bucket em.n: skipped)
   int c = 0;
@@ -169,25 +172,31 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
     const bool live = r < nrows_cta;
     const int64_t t = live ? perm[group_off[c] + off + r] : 0;
     const float* frow = live ? em.feat[c] + (x[t] - em.start[c]) * em.ld[c] : nullptr;
+    const int64_t ld = em.ld[c];
     const int nchunk = (em.nc[c] + 63) / 64;
     const uint8_t* wbase = wsplit + em.woff[c];
     if (c != cur_c) {                       // W1_c stays resident while the CTA works on this chromosome
       __syncthreads();
-      load_chunk(sW1, wbase + (int64_t)nchunk * kEChunk);
+      copy_chunk(sW1, wbase + (int64_t)nchunk * kEChunk);
       cur_c = c;
     }
-    for (int kc = 0; kc < nchunk; ++kc) {
-      float v[64];
-      gather_rows(frow, (int64_t)kc * 64, em.ld[c], stage, lane, v);
+    // feature chunk kc + 1 is gathered (global loads, dropout) while the tensor pipe works on chunk kc
+    auto gather_chunk = [&](int kc, float (&v)[32]) {
+      const int64_t kf = (int64_t)kc * 64 + h * 32;
+      gather_half_rows(frow ? frow + kf : nullptr, kf, ld, stage, lane, v);
       if (drop.thr != 0u && live) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 d = drop_apply4(drop, (uint64_t)t, (uint32_t)(kc * 64 + 4 * j), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        for (int j = 0; j < 8; ++j) {
+          const float4 d = drop_apply4(drop, (uint64_t)t, (uint32_t)(kf + 4 * j), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
           v[4 * j] = d.x; v[4 * j + 1] = d.y; v[4 * j + 2] = d.z; v[4 * j + 3] = d.w;
         }
       }
-      put_tile(sA, r, v);
-      load_chunk(sW, wbase + (int64_t)kc * kEChunk);
+    };
+    float fv[32];
+    gather_chunk(0, fv);
+    for (int kc = 0; kc < nchunk; ++kc) {
+      put4(sA, 16384, h * 4, r, fv);
+      copy_chunk(sW, wbase + (int64_t)kc * kEChunk);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -199,24 +208,22 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
                    kc == 0 && ks == 0);
         umma_commit(&bar);
       }
+      if (kc + 1 < nchunk) gather_chunk(kc + 1, fv);
       mbar_wait(&bar, phase);               // the A tile and the weight chunk are rewritten by the next chunk
       phase ^= 1;
       tc_fence_after();
     }
     // ---- H0 = tanh(acc): kept for the backward pass, and the A operand of the second contraction ----
-    float h[64];
+    float hv[32];
     {
-      uint32_t d0[32], d1[32];
-      tmem_ld32_issue(tlane, d0);
-      tmem_ld32_issue(tlane + 32, d1);
+      uint32_t d0[32];
+      tmem_ld32_issue(tlane + h * 32, d0);
       tmem_ld_wait(d0);
-      tmem_ld_wait(d1);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { h[i] = live ? tanhf(__uint_as_float(d0[i])) : 0.f; h[32 + i] = live ? tanhf(__uint_as_float(d1[i])) : 0.f; }
+      for (int i = 0; i < 32; ++i) hv[i] = live ? tanhf(__uint_as_float(d0[i])) : 0.f;
     }
     tc_fence_before();
-    scatter_rows(live ? H0 + t * 64 : nullptr, stage, lane, h);
-    put_tile(sA, r, h);
+    put4(sA, 16384, h * 4, r, hv);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -226,20 +233,19 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
         umma_x3s(tmem_base, ah + ks * 4096, al + ks * 4096, vh + ks * 2048, vl + ks * 2048, 2048, 128, 1024, 128, idesc, ks == 0);
       umma_commit(&bar);
     }
+    scatter_half_rows(live ? H0 + t * 64 + h * 32 : nullptr, stage, lane, hv);      // under the second contraction
     mbar_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
     {
-      uint32_t d0[32], d1[32];
-      tmem_ld32_issue(tlane, d0);
-      tmem_ld32_issue(tlane + 32, d1);
+      uint32_t d0[32];
+      tmem_ld32_issue(tlane + h * 32, d0);
       tmem_ld_wait(d0);
-      tmem_ld_wait(d1);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { h[i] = __uint_as_float(d0[i]); h[32 + i] = __uint_as_float(d1[i]); }
+      for (int i = 0; i < 32; ++i) hv[i] = __uint_as_float(d0[i]);
     }
     tc_fence_before();
-    scatter_rows(live ? E + t * 64 : nullptr, stage, lane, h);
+    scatter_half_rows(live ? E + t * 64 + h * 32 : nullptr, stage, lane, hv);
     __syncthreads();
   }
   tc_fence_before();
@@ -258,43 +264,10 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
 constexpr int kBThreads = 256;
 constexpr int kBS = 65536;                      // sS: 16 planes, hi 32 KB | lo 32 KB
 constexpr int kBB = 32768;                      // sB: 8 planes, hi 16 KB | lo 16 KB
-constexpr int kBStageRow = 36;
-constexpr int kBStage = 8 * 32 * kBStageRow * 4;            // 36 864
+constexpr int kBStage = 8 * 32 * kHStageRow * 4;            // 36 864
 constexpr int kBSmem = kBS + kBB + kEChunk + kBStage;       // 151 552
 constexpr int kBMaxChunks = 6;                  // TMEM: dH0 64 | dW1 64 | 6 x 64 chunk columns = 512
 constexpr uint32_t kColDH = 0, kColW1 = 64, kColW0 = 128;
-
-// 32 scattered rows x 32 floats (row pointer incl. column offset held by the owning lane, NULL = zero row): four rows per
-// instruction, 8 lanes x float4 each; transposed through the warp's staging area
-__device__ __forceinline__ void gather_half_rows(const float* rowp, bool col_ok_base, int64_t k_first, int64_t klimit, float* stage,
-                                                 int lane, float (&v)[32]) {
-  (void)col_ok_base;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int row = 4 * k + (lane >> 3), c4 = lane & 7;
-    const float* p = shfl_ptr(rowp, row);
-    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p != nullptr && k_first + c4 * 4 < klimit) e = __ldg(reinterpret_cast<const float4*>(p) + c4);
-    *reinterpret_cast<float4*>(stage + row * kBStageRow + c4 * 4) = e;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float4 e = *reinterpret_cast<const float4*>(stage + lane * kBStageRow + k * 4);
-    v[4 * k] = e.x; v[4 * k + 1] = e.y; v[4 * k + 2] = e.z; v[4 * k + 3] = e.w;
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void put4(uint8_t* hi_base, int lo_off, int p0, int r, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 hi, lo;
-    split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
-           make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
-    sts16(hi_base + (p0 + j) * 2048 + r * 16, hi);
-    sts16(hi_base + lo_off + (p0 + j) * 2048 + r * 16, lo);
-  }
-}
 
 __global__ void __launch_bounds__(kBThreads, 1)
 enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const int64_t* __restrict__ x,
@@ -324,7 +297,7 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
   const uint32_t sh = smem_u32(sS), sl = sh + 32768;
   const uint32_t bh = smem_u32(sB), bl = bh + 16384;
   const uint32_t vh = smem_u32(sW1), vl = vh + 8192;
-  float* stage = sStage + warp * (32 * kBStageRow);
+  float* stage = sStage + warp * (32 * kHStageRow);
   uint32_t phase = 0;
 
   // this CTA's contiguous range of the tile list (chromosome c contributes ceil(count_c / 128) tiles)
@@ -390,7 +363,7 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
     // ---- dE rows -> planes 0..7 of sS ----
     {
       float v[32];
-      gather_half_rows(live ? dE + t * 64 + h * 32 : nullptr, true, 0, 64, stage, lane, v);
+      gather_half_rows(live ? dE + t * 64 + h * 32 : nullptr, 0, 64, stage, lane, v);
       put4(sS, 32768, h * 4, r, v);
     }
     fence_async_smem();
@@ -405,7 +378,7 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
     }
     // H0 rows while the MMA runs
     float hv[32];
-    gather_half_rows(live ? H0 + t * 64 + h * 32 : nullptr, true, 0, 64, stage, lane, hv);
+    gather_half_rows(live ? H0 + t * 64 + h * 32 : nullptr, 0, 64, stage, lane, hv);
     put4(sB, 16384, h * 4, r, hv);
     mbar_wait(&bar, phase);
     phase ^= 1;
@@ -434,7 +407,7 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
     // feature chunk kc + 1 is gathered (global loads, dropout) while the tensor pipe works on chunk kc
     auto gather_chunk = [&](int kc, float (&v)[32]) {
       const int64_t kf = (int64_t)kc * 64 + h * 32;
-      gather_half_rows(frow ? frow + kf : nullptr, true, kf, em.ld[c], stage, lane, v);
+      gather_half_rows(frow ? frow + kf : nullptr, kf, em.ld[c], stage, lane, v);
       if (drop.thr != 0u && live) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -527,7 +500,7 @@ int launch_enc_tc_fwd(const matcha_model_desc* m, int64_t split_base, const int6
   const EncMeta em = make_meta(m, nullptr);
   int64_t tiles = (T + 127) / 128 + m->n_chrom;            // upper bound; the kernel stops at the real tile count
   const unsigned grid = (unsigned)(tiles < 2 * kSMs ? tiles : 2 * kSMs);
-  enc_tc_fwd_kernel<<<grid, kEThreads, kESmem, s>>>(em, reinterpret_cast<const uint8_t*>(m->derived + split_base), x, perm,
+  enc_tc_fwd_kernel<<<grid, kFThreads, kESmem, s>>>(em, reinterpret_cast<const uint8_t*>(m->derived + split_base), x, perm,
                                                     group_off, H0, E, drop);
   MATCHA_CHECK_LAUNCH("enc_tc_fwd");
   return MATCHA_OK;

@@ -46,7 +46,8 @@ class PairScorer:
 
     def refresh(self):
         """Recompute the per-node tables (call after the weights change)."""
-        self.D, self.S = self.engine.pair_tables()
+        self.engine.ensure_bound()
+        self.D, self.S = self.engine.pair_tables() if self.engine.d == 64 else (None, None)
         m = self.model
         self.cls_w = m.pff_classifier.PWF_Conv0.weight.data.reshape(-1)
         self.cls_b = m.pff_classifier.PWF_Conv0.bias.data.reshape(-1)
@@ -75,6 +76,8 @@ class PairScorer:
         eng = self.engine
         if out is None:
             out = torch.empty(p_end - p_begin, dtype=torch.float32, device=eng.dev)
+        if eng.d != 64:
+            return self._score_range_generic(lo, hi, min_dis, p_begin, p_end, sigmoid, out)
         if impl == "tc":
             ws = self._pack(lo, hi)
             check(eng.lib.matcha_pair_tc_score_range(ptr(ws), int(lo), int(hi), int(min_dis), int(p_begin),
@@ -84,6 +87,27 @@ class PairScorer:
             check(eng.lib.matcha_pair_score_range(ptr(self.D), ptr(self.S), ptr(self.cls_w), ptr(self.cls_b), eng.d,
                                                   int(lo), int(hi), int(min_dis), int(p_begin), int(p_end),
                                                   1 if sigmoid else 0, ptr(out), stream_ptr()), "matcha_pair_score_range")
+        return out
+
+    def _score_range_generic(self, lo, hi, min_dis, p_begin, p_end, sigmoid, out, batch=1 << 18):
+        """embed_dim != 64: the closed-form kernels are specialised for 64, so pairs go through Classifier.forward as width-2
+        tuples (exactly what denoise_contact.py:76-88 does), generated on the device in batches."""
+        model = self.model
+        model.eval()
+        n, full = hi - lo, hi - lo - min_dis
+        with torch.no_grad():
+            for b in range(p_begin, p_end, batch):
+                e = min(b + batch, p_end)
+                p = torch.arange(b, e, device=self.engine.dev, dtype=torch.float64)
+                r = torch.floor(((2 * full + 1) - torch.sqrt((2 * full + 1) ** 2 - 8.0 * p)) / 2).to(torch.int64)
+                p = p.to(torch.int64)
+                for _ in range(2):                       # exact integer correction of the float row estimate
+                    r = torch.where(r * full - r * (r - 1) // 2 > p, r - 1, r)
+                    r = torch.where((r + 1) * full - (r + 1) * r // 2 <= p, r + 1, r)
+                pref = r * full - r * (r - 1) // 2
+                x = torch.stack([lo + r, lo + r + min_dis + (p - pref)], dim=1)
+                o = model(x).view(-1)
+                out[b - p_begin:e - p_begin] = torch.sigmoid(o) if sigmoid else o
         return out
 
     def score_chromosome(self, chrom_id, min_dis=0, sigmoid=False, rank=0, world=1):

@@ -786,3 +786,18 @@ def test_encoder_tensor_core_matches_simt(monkeypatch, L, B, train):
         g1 = res[1][0][k]
         scale = float(np.abs(g0).max())
         assert float(np.abs(g1 - g0).max()) <= 5e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
+
+
+def test_d128_pair_scorer_falls_back_to_generic_path(golden128):
+    """embed_dim 128: all-pairs scoring goes through Classifier.forward on device-generated width-2 tuples."""
+    from matcha_b200.scorer import PairScorer, pair_count, pair_index_to_ij
+    model = model_from_golden(golden128, d=128)
+    model.eval()
+    lo, hi = (int(v) for v in golden128["chrom_range"][1])
+    sc = PairScorer(model)
+    total = pair_count(lo, hi, 1)
+    got = sc.score_range(lo, hi, min_dis=1, p_begin=5, p_end=total - 3).cpu().numpy()
+    i, j = pair_index_to_ij(np.arange(5, total - 3), lo, hi, 1)
+    with torch.no_grad():
+        want = model(torch.from_numpy(np.stack([i, j], 1)).cuda()).view(-1).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
