@@ -224,3 +224,19 @@ def test_two_rank_gloo_allreduce_of_gradients_and_flags():
         assert res[r][4] == 0.5
     assert res[0][5] == [0, 2, 4, 6, 8] and res[1][5] == [1, 3, 5, 7, 9]
     assert res[0][6] == (0, 50) and res[1][6] == (50, 101)
+
+
+def test_bench_steps_are_rank_symmetric():
+    """Every rank must execute the same training steps: a step holds an NCCL all-reduce when world > 1, so a step that only
+    rank 0 runs deadlocks the job (regression guard for bench.py's clock-sampling warm-up)."""
+    import re
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    body = src[src.index("def main():"):]
+    lines = body.split("\n")
+    for i, ln in enumerate(lines):
+        if re.match(r"\s*if rank == 0:", ln):
+            indent = len(ln) - len(ln.lstrip())
+            j = i + 1
+            while j < len(lines) and (not lines[j].strip() or len(lines[j]) - len(lines[j].lstrip()) > indent):
+                assert not re.search(r"\b(run|timed|trainer\.step)\(", lines[j]), f"rank-0-only step at bench.py main() line {j}: {lines[j].strip()}"
+                j += 1
