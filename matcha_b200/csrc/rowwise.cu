@@ -117,15 +117,15 @@ __global__ void bucket_scatter_kernel(const int64_t* __restrict__ x, int64_t T, 
   const int64_t t0 = (int64_t)blockIdx.x * per, t1 = (t0 + per < T) ? t0 + per : T;
   for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) atomicAdd(&h[chrom_of(cm, x[t])], 1);
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x <= cm.n) {          // one thread per chromosome: the range reservations (global atomics with a return value)
+    const int c = threadIdx.x;        // go out in parallel instead of as a serial chain of ~23 round trips
     int32_t acc = 0;
-    for (int c = 0; c < cm.n; ++c) {
-      if (blockIdx.x == 0) group_off[c] = acc;
+    for (int cc = 0; cc < c; ++cc) acc += counts[cc];
+    if (blockIdx.x == 0) group_off[c] = acc;
+    if (c < cm.n) {
       base[c] = h[c] ? acc + atomicAdd(&cursor[c], h[c]) : 0;       // cursor holds the per-chromosome fill (zeroed by the launcher)
       h[c] = 0;
-      acc += counts[c];
     }
-    if (blockIdx.x == 0) group_off[cm.n] = acc;
   }
   __syncthreads();
   for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
@@ -685,7 +685,7 @@ int launch_score_fwd(int d, const float* H2, const float* xhat, const int64_t* x
 int launch_score_bwd(int d, const float* H2, const float* xhat, const float* rstd_x, const int64_t* x, ScoreParams p,
                      const float* dlogit, float* dH2, float* dXs, ScoreGrads g, int64_t B, int L, cudaStream_t s) {
   if (B <= 0) return MATCHA_OK;
-  const int grid = grid_for_rows(B, d, kSMs * 4);
+  const int grid = grid_for_rows(B, d, kSMs * 2);      // fewer blocks: fewer contended parameter-gradient atomics
   MATCHA_DISPATCH_D(d, MATCHA_DISPATCH_L(L, (score_bwd_kernel<DD, LL><<<grid, kBlock, 0, s>>>(H2, xhat, rstd_x, x, p, dlogit, dH2, dXs, g, B))));
   MATCHA_CHECK_LAUNCH("score_bwd");
   return MATCHA_OK;
