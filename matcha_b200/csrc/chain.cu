@@ -670,9 +670,12 @@ struct WgradPairOut {
   float* w1; int ld1; int n1; float* bias1;       // rows 0..63,  columns [0, n1)
   float* w2; int ld2; int n2; float* bias2;       // rows 64..127, columns [64, 64 + n2)
 };
+// 8 lanes per output element: each sums every 8th split-K partial (8 independent load streams instead of one serial
+// chain of ~148 dependent adds), then a fixed xor-shuffle tree -> deterministic
 __global__ void wgrad_pair_reduce_kernel(const float* __restrict__ part, int nparts, int N, int ones_col, const WgradPairOut o) {
   const int total = 128 * N;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  const int sub = threadIdx.x & 7;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < total; i += (gridDim.x * blockDim.x) >> 3) {   // warp-uniform trip count
     const int row = i / N, col = i - row * N;
     float* dst = nullptr;
     if (row < 64) {
@@ -682,10 +685,13 @@ __global__ void wgrad_pair_reduce_kernel(const float* __restrict__ part, int npa
       if (col >= 64 && col < 64 + o.n2) dst = o.w2 + (row - 64) * o.ld2 + (col - 64);
       else if (col == ones_col) dst = o.bias2 + (row - 64);
     }
-    if (!dst) continue;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * total + i];
-    *dst += s;
+    if (dst)
+      for (int p = sub; p < nparts; p += 8) s += part[(int64_t)p * total + i];
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (dst && sub == 0) *dst += s;
   }
 }
 
@@ -758,7 +764,7 @@ int launch_wgrad_pair(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, c
   wgrad_pair_kernel<<<grid, kWThreadsP, smem, s>>>(a);
   MATCHA_CHECK_LAUNCH("wgrad_pair");
   WgradPairOut o{w1, ld1, n1, bias1, w2, ld2, n2, bias2};
-  wgrad_pair_reduce_kernel<<<(128 * N + 255) / 256, 256, 0, s>>>(scratch, (int)grid, N, (8 + b2_planes) * 8, o);
+  wgrad_pair_reduce_kernel<<<(128 * N * 8 + 255) / 256, 256, 0, s>>>(scratch, (int)grid, N, (8 + b2_planes) * 8, o);
   MATCHA_CHECK_LAUNCH("wgrad_pair_reduce");
   return MATCHA_OK;
 }
