@@ -259,7 +259,10 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
 // gradients share ONE M = 128 contraction per operand tile: the stacked tile sS = [dE | dH0pre] (128 feature rows, K =
 // tokens, MN-major view) against sB = H0 and then each feature chunk; lanes 0..63 of the H0 columns are dW1_c, lanes
 // 64..127 of the chunk columns are dW0_c (the other two blocks of the 2 x 2 product are ignored).  Accumulators stay in
-// TMEM while the CTA stays inside one chromosome (CTAs own contiguous tile ranges) and are flushed with atomics.
+// TMEM while the CTA stays inside one (chromosome, column group) and are flushed with atomics.  A column group is
+// kBMaxChunks feature chunks (384 bins: what fits in TMEM next to dH0 and dW1); a chromosome wider than that contributes
+// its token tiles once per column group (work item = (chromosome, group, tile), group major), re-deriving dH0pre per item
+// -- 512 B per token next to the 1.5 KB of feature columns the item gathers.  CTAs own contiguous item ranges.
 // ==========================================================================================
 constexpr int kBThreads = 256;
 constexpr int kBS = 65536;                      // sS: 16 planes, hi 32 KB | lo 32 KB
@@ -300,27 +303,30 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
   float* stage = sStage + warp * (32 * kHStageRow);
   uint32_t phase = 0;
 
-  // this CTA's contiguous range of the tile list (chromosome c contributes ceil(count_c / 128) tiles)
+  // this CTA's contiguous range of the item list (chromosome c contributes groups_c * ceil(count_c / 128) items)
+  auto n_groups = [&](int cc) { return ((em.nc[cc] + 63) / 64 + kBMaxChunks - 1) / kBMaxChunks; };
   int64_t total = 0;
-  for (int c = 0; c < em.n; ++c) total += (group_off[c + 1] - group_off[c] + 127) / 128;
+  for (int c = 0; c < em.n; ++c) total += (int64_t)((group_off[c + 1] - group_off[c] + 127) / 128) * n_groups(c);
   const int64_t per = (total + gridDim.x - 1) / gridDim.x;
   const int64_t ti0 = (int64_t)blockIdx.x * per, ti1 = (ti0 + per < total) ? ti0 + per : total;
 
-  auto flush = [&](int c, int nchunk) {   // TMEM -> atomics on the weight gradients of chromosome c
+  auto flush = [&](int c, int kc0, int kc1) {   // TMEM -> atomics on the weight gradients of chromosome c, chunks [kc0, kc1)
     tc_fence_after();
     if (r < 64) {                          // lanes 0..63: dW1_c[o = r][k], this thread: k in [32 h, 32 h + 32)
-      uint32_t v[32];
-      tmem_ld32_issue(tlane + kColW1 + h * 32, v);
-      tmem_ld_wait(v);
-      float* dst = grads + em.off_w1[c] + (int64_t)r * 64 + h * 32;
+      if (kc0 == 0) {                      // every column group accumulates dW1_c; the first one publishes it
+        uint32_t v[32];
+        tmem_ld32_issue(tlane + kColW1 + h * 32, v);
+        tmem_ld_wait(v);
+        float* dst = grads + em.off_w1[c] + (int64_t)r * 64 + h * 32;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+      }
     } else {                               // lanes 64..127: dW0_c[f = r - 64][k]
       const int nc = em.nc[c];
       float* dst = grads + em.off_w0[c] + (int64_t)(r - 64) * nc;
-      for (int kc = 0; kc < nchunk; ++kc) {
+      for (int kc = kc0; kc < kc1; ++kc) {
         uint32_t v[32];
-        tmem_ld32_issue(tlane + kColW0 + kc * 64 + h * 32, v);
+        tmem_ld32_issue(tlane + kColW0 + (kc - kc0) * 64 + h * 32, v);
         tmem_ld_wait(v);
         const int k0 = kc * 64 + h * 32;
 #pragma unroll
@@ -332,31 +338,35 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
     __syncthreads();
   };
 
-  int c = 0, cur_c = -1, cur_nchunk = 0;
+  int c = 0, cur_c = -1, cur_kc0 = 0, cur_kc1 = 0;
   int64_t before = 0;
-  bool fresh = true;                       // no tile accumulated yet for cur_c
+  bool fresh = true;                       // no tile accumulated yet for (cur_c, cur_kc0)
   for (int64_t ti = ti0; ti < ti1; ++ti) {
     int cnt = 0;
+    int64_t nt = 0;
     for (; c < em.n; ++c) {
       cnt = group_off[c + 1] - group_off[c];
-      const int64_t nt = (cnt + 127) / 128;
-      if (ti < before + nt) break;
-      before += nt;
+      nt = (cnt + 127) / 128;
+      const int64_t ni = nt * n_groups(c);
+      if (ti < before + ni) break;
+      before += ni;
     }
     if (c >= em.n) break;
     const int nchunk = (em.nc[c] + 63) / 64;
-    if (c != cur_c) {
-      if (cur_c >= 0 && !fresh) flush(cur_c, cur_nchunk);
+    const int grp = (int)((ti - before) / nt);
+    const int kc0 = grp * kBMaxChunks, kc1 = kc0 + kBMaxChunks < nchunk ? kc0 + kBMaxChunks : nchunk;
+    if (c != cur_c || kc0 != cur_kc0) {
+      if (cur_c >= 0 && !fresh) flush(cur_c, cur_kc0, cur_kc1);
       __syncthreads();
-      {   // W1_c chunk (K-major for the forward; read MN-major here)
+      if (c != cur_c) {   // W1_c chunk (K-major for the forward; read MN-major here)
         const uint4* s4 = reinterpret_cast<const uint4*>(wsplit + em.woff[c] + (int64_t)nchunk * kEChunk);
         uint4* d4 = reinterpret_cast<uint4*>(sW1);
 #pragma unroll
         for (int i = 0; i < kEChunk / 16 / kBThreads; ++i) d4[tid + i * kBThreads] = __ldg(s4 + tid + i * kBThreads);
       }
-      cur_c = c; cur_nchunk = nchunk; fresh = true;
+      cur_c = c; cur_kc0 = kc0; cur_kc1 = kc1; fresh = true;
     }
-    const int off = (int)(ti - before) * 128;
+    const int off = (int)((ti - before) - (int64_t)grp * nt) * 128;
     const int nrows_cta = cnt - off < 128 ? cnt - off : 128;
     const bool live = r < nrows_cta;
     const int64_t t = live ? perm[group_off[c] + off + r] : 0;
@@ -417,11 +427,11 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
       }
     };
     float fv[32];
-    gather_chunk(0, fv);
+    gather_chunk(kc0, fv);
     mbar_wait(&bar, phase);                // dW1 contraction done: sB may be rewritten
     phase ^= 1;
     tc_fence_after();
-    for (int kc = 0; kc < nchunk; ++kc) {
+    for (int kc = kc0; kc < kc1; ++kc) {
       put4(sB, 16384, h * 4, r, fv);
       fence_async_smem();
       tc_fence_before();
@@ -430,11 +440,11 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)     // lanes 64..127 = dW0_c[:, chunk kc]
-          umma_x3s(tmem_base + kColW0 + kc * 64, sh + ks * 256, sl + ks * 256, bh + ks * 256, bl + ks * 256, 128, 2048, 128, 2048,
-                   idescW, fresh && ks == 0);
+          umma_x3s(tmem_base + kColW0 + (kc - kc0) * 64, sh + ks * 256, sl + ks * 256, bh + ks * 256, bl + ks * 256, 128, 2048, 128,
+                   2048, idescW, fresh && ks == 0);
         umma_commit(&bar);
       }
-      if (kc + 1 < nchunk) gather_chunk(kc + 1, fv);
+      if (kc + 1 < kc1) gather_chunk(kc + 1, fv);
       mbar_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
@@ -443,7 +453,7 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
     tc_fence_before();
     __syncthreads();
   }
-  if (cur_c >= 0 && !fresh) flush(cur_c, cur_nchunk);
+  if (cur_c >= 0 && !fresh) flush(cur_c, cur_kc0, cur_kc1);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
@@ -507,11 +517,16 @@ int launch_enc_tc_fwd(const matcha_model_desc* m, int64_t split_base, const int6
 }
 
 
-// feature chunks per chromosome the backward kernel keeps resident in TMEM (wider chromosomes use the SIMT launches)
-bool enc_tc_bwd_fits(const matcha_model_desc* m) {
-  for (int c = 0; c < m->n_chrom; ++c)
-    if ((m->chrom_end[c] - m->chrom_start[c] + 63) / 64 > kBMaxChunks) return false;
-  return true;
+// the backward kernel keeps kBMaxChunks feature chunks resident in TMEM and walks wider chromosomes in column groups
+bool enc_tc_bwd_fits(const matcha_model_desc*) { return true; }
+static int64_t max_col_groups(const matcha_model_desc* m) {
+  int64_t g = 1;
+  for (int c = 0; c < m->n_chrom; ++c) {
+    const int64_t nchunk = (m->chrom_end[c] - m->chrom_start[c] + 63) / 64;
+    const int64_t gc = (nchunk + kBMaxChunks - 1) / kBMaxChunks;
+    if (gc > g) g = gc;
+  }
+  return g;
 }
 
 // grads (flat, same layout as params): dW1_c += dE^T H0, dW0_c += ((dE W1_c) * (1 - H0^2))^T dropout(F_c rows)
@@ -526,7 +541,7 @@ int launch_enc_tc_bwd(const matcha_model_desc* m, int64_t split_base, const int6
     once = true;
   }
   const EncMeta em = make_meta(m, nullptr);
-  const int64_t tiles = (T + 127) / 128 + m->n_chrom;
+  const int64_t tiles = ((T + 127) / 128 + m->n_chrom) * max_col_groups(m);     // upper bound of the item count
   const unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
   enc_tc_bwd_kernel<<<grid, kBThreads, kBSmem, s>>>(em, reinterpret_cast<const uint8_t*>(m->derived + split_base), x, perm,
                                                     group_off, dE, H0, m->grads, drop);

@@ -739,12 +739,18 @@ def test_recon_head_tensor_core_matches_simt(monkeypatch, L, B, rchrom):
 
 # ------------------------------------------------------------------------------------------
 # tensor-core node encoder forward vs the grouped SIMT launches (chromosomes of 250 / 244 bins: 4 weight chunks, ragged)
+# and, for the backward kernel's column groups, chromosomes wider than the 384 bins one TMEM-resident group holds
+# (chr21 / chr22 at 50 kb: 936 / 1018 bins = 15 / 16 chunks = 3 groups each, the last one ragged)
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("L,B,train", [(5, 700, True), (3, 450, False), (4, 1031, True)])
-def test_encoder_tensor_core_matches_simt(monkeypatch, L, B, train):
+WIDE = (["chr21", "chr22"], 50_000, 64)
+
+
+@pytest.mark.parametrize("cfg,L,B,train", [("cfg1", 5, 700, True), ("cfg1", 3, 450, False), ("cfg1", 4, 1031, True),
+                                           (WIDE, 5, 700, True), (WIDE, 3, 900, True)])
+def test_encoder_tensor_core_matches_simt(monkeypatch, cfg, L, B, train):
     from matcha_b200.synthetic import build_model, make_dataset
     lib = _lib().load()
-    ds = make_dataset("cfg1", kmers_per_size=3000, seed=3)
+    ds = make_dataset(cfg, kmers_per_size=3000, seed=3)
     N = int(ds["chrom_range"][-1][1]) - 1
     monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([1]))
     rng = np.random.default_rng(200 + B)
@@ -786,6 +792,45 @@ def test_encoder_tensor_core_matches_simt(monkeypatch, L, B, train):
         g1 = res[1][0][k]
         scale = float(np.abs(g0).max())
         assert float(np.abs(g1 - g0).max()) <= 5e-4 * scale + 1e-7, (k, float(np.abs(g1 - g0).max()), scale)
+
+
+def test_wide_chromosome_train_step_matches_oracle(monkeypatch):
+    """Chromosomes of ~1000 bins (the cfg3 / cfg5 regime: several column groups in the encoder backward, a 16-chunk
+    contraction in the forward, a ~1000-column reconstruction head): one training step with dropout ON against the
+    oracle's fp64 autograd on the kernels' own dropout masks."""
+    from matcha_b200.synthetic import build_model, make_dataset
+    ds = make_dataset(WIDE, kmers_per_size=3000, seed=5)
+    N = int(ds["chrom_range"][-1][1]) - 1
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([0]))
+    rng = np.random.default_rng(77)
+    B, L = 320, 5
+    xs = np.zeros((B, L), dtype=np.int64)
+    for b in range(B):
+        k = L if b % 2 == 0 else int(rng.integers(2, L + 1))
+        xs[b, :k] = np.sort(rng.choice(np.arange(1, N + 1), size=k, replace=False))
+    x = torch.from_numpy(xs).cuda()
+    y = torch.from_numpy((rng.random((B, 1)) < 0.4).astype("float32")).cuda()
+    w = torch.from_numpy(rng.uniform(0.5, 3.0, size=(B, 1)).astype("float32")).cuda()
+    model = build_model(ds, seed=1)
+    model.train()
+    eng = model._engine()
+    eng.ensure_bound()
+    pred, recon = model(x, return_recon=True)
+    (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.5 * recon.sum()).backward()
+    om = oracle_from_model(model)
+    out = O.loss_and_grads(om.to(torch.float64), x.cpu(), y.cpu().double(), w.cpu().double(), 1.0, 0.5, random_chrom=0,
+                           train=True, seed=step_seed(eng))
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), out["logits"].numpy(), rtol=1e-4, atol=2e-4)
+    assert abs(float(recon.sum()) - float(out["recon"])) <= 1e-4 * abs(float(out["recon"]))
+    n_checked = 0
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        ref = out["grads"][k].numpy()
+        scale = max(1e-12, float(np.abs(ref).max()))
+        assert float(np.abs(p.grad.cpu().numpy() - ref).max()) <= 2e-3 * scale, (k, scale)
+        n_checked += 1
+    assert n_checked >= 30
 
 
 def test_d128_pair_scorer_falls_back_to_generic_path(golden128):
