@@ -29,7 +29,14 @@ sys.path.insert(0, ROOT)
 
 METRIC = "hyperedges_per_s_trained"
 UNIT = "hyperedges/s"
-WORKLOAD = "cfg2: synthetic SPRITE-like clusters, whole-genome 1 Mb (3067 bins, 23 chromosomes), k=2..5 mixed, embed_dim 64"
+WORKLOADS = {
+    # BASELINE.json configs[1] -- the single-GPU configuration the metric is quoted on (the default)
+    "cfg2": "cfg2: synthetic SPRITE-like clusters, whole-genome 1 Mb (3067 bins, 23 chromosomes), k=2..5 mixed, embed_dim 64",
+    # configs[0] (the reference's CPU-runnable case) and configs[2] (the 8-GPU training configuration; per-GPU work is
+    # the same at any N, so `--workload cfg3 --gpus 1` measures one rank of it): parity cases, selectable here
+    "cfg1": "cfg1: synthetic SPRITE-like clusters, chr1+chr2 at 1 Mb (494 bins), k=2..5 mixed, embed_dim 64",
+    "cfg3": "cfg3: synthetic SPRITE-like clusters, whole-genome 100 kb (30344 bins, 23 chromosomes), k=2..5 mixed, embed_dim 64",
+}
 POS_PER_STEP = 4096          # positives per GPU per step; x3 negatives -> 16384 hyperedges / GPU / step
 NEG_NUM = 3
 KMERS_PER_SIZE = 400_000
@@ -143,13 +150,15 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-impl", type=int, default=-1, help="-1 library default, 0 SIMT, 1 tcgen05")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-pairs", action="store_true", help="skip the all-pairs scorer measurement")
     args = ap.parse_args()
     warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": WORKLOAD, "hyperedges_per_gpu_per_step": args.pos_per_step * (1 + NEG_NUM),
+    config = {"workload": WORKLOADS[args.workload], "hyperedges_per_gpu_per_step": args.pos_per_step * (1 + NEG_NUM),
               "positives_per_gpu_per_step": args.pos_per_step, "neg_num": NEG_NUM, "padded_width": 5,
               "kmers_per_size": args.kmers_per_size, "parallelism": f"dp{world}",
               "l2": "per-step activation stream (~1.4 GB) exceeds the 126 MB L2; no explicit flush"}
@@ -158,7 +167,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ds = make_dataset("cfg2", kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
+        ds = make_dataset(args.workload, kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
         r = cpu_reference_arm(ds, max(1, args.steps), max(1, args.warmup))
         cfg = dict(config, hyperedges_per_gpu_per_step=384, positives_per_gpu_per_step=96,
                    note="CPU oracle port of the reference path at the reference's batch size; the unmodified reference is "
@@ -187,7 +196,7 @@ def main():
     if args.gemm_impl >= 0:
         lib.matcha_set_gemm_impl(args.gemm_impl)
 
-    ds = make_dataset("cfg2", kmers_per_size=args.kmers_per_size, seed=0)      # same data on every rank
+    ds = make_dataset(args.workload, kmers_per_size=args.kmers_per_size, seed=0)      # same data on every rank
     model = build_model(ds, seed=1)
     hs = KmerHashSet(len(ds["dict"]), width=5).insert(ds["dict"])
     sampler = NegativeSampler(hs, ds["chrom_range"], min_dis=0, neg_num=NEG_NUM, seed=2 + rank)
@@ -209,18 +218,16 @@ def main():
         torch.cuda.synchronize()
 
     def run(n_steps, host_io, start):
-        loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+        if host_io:
+            # the package's own host-fed loop (matcha_b200/trainer.py): per step one H2D copy of the batch from pinned
+            # memory (prefetched one step ahead on a copy stream) and one D2H read of the step's losses (asynchronous,
+            # all n_steps rows are on the host when it returns)
+            losses, _, _ = trainer.run_host_batches(pos_host, w_host, P, n_steps, start)
+            assert bool(torch.isfinite(losses).all())
+            return
         for i in range(n_steps):
             b = (start + i) % nb
-            if host_io:
-                x = pos_host[b * P:(b + 1) * P].cuda(non_blocking=True)
-                w = w_host[b * P:(b + 1) * P].cuda(non_blocking=True)
-            else:
-                x, w = pos_dev[b * P:(b + 1) * P], w_dev[b * P:(b + 1) * P]
-            trainer.step(x, w)
-            if host_io:
-                loss_host.copy_(trainer.loss_out, non_blocking=True)
-                torch.cuda.current_stream().synchronize()      # the caller reads the step's loss, as main.py:187-188 does
+            trainer.step(pos_dev[b * P:(b + 1) * P], w_dev[b * P:(b + 1) * P])
 
     def timed(n_steps, host_io, start, profile=False):
         barrier()
@@ -299,7 +306,7 @@ def main():
     run(2, True, 0)
     ms_e2e, _ = timed(args.steps, True, warmup + args.steps)
     losses = trainer.mean_losses()
-    pair_total, pair_ms = pair_scorer_bench()
+    pair_total, pair_ms = (0, 1.0) if args.no_pairs else pair_scorer_bench()
 
     if rank != 0:
         if world > 1:
@@ -323,6 +330,18 @@ def main():
             "qkg_gemm": ("tensor", 2.0 * T * qkg * d), "qkg_wgrad": ("tensor", 2.0 * T * qkg * d), "qkg_dgrad": ("tensor", 2.0 * T * qkg * d),
             "attn_fwd": ("hbm", T * (qkg + d) * 4.0), "attn_bwd": ("hbm", T * (2 * qkg + d) * 4.0),
         }
+    # node encoder (HBM-bound once the feature tables exceed L2): every real token reads its 4 * n_c byte feature row;
+    # forward also writes H0 and E (512 B), backward reads dE and H0 (512 B).  Re-reads by the backward kernel's column
+    # groups are implementation cost.  n_c is averaged over the real tokens of the positives pool (negatives stay on the
+    # positive's chromosomes)
+    node_nc = np.zeros(ds["N"] + 1, dtype=np.float64)
+    for (cs, ce) in ds["chrom_range"]:
+        node_nc[int(cs):int(ce)] = float(ce - cs)
+    real = ds["positives"] != 0
+    row_bytes = 4.0 * float(node_nc[ds["positives"][real]].mean())
+    real_tokens = P * (1 + NEG_NUM) * float(real.sum()) / len(ds["positives"])
+    alg["enc0_gather_gemm"] = ("hbm", real_tokens * (row_bytes + 512.0))
+    alg["enc0_wgrad"] = ("hbm", real_tokens * (row_bytes + 512.0))
     top = max(prof.items(), key=lambda kv: kv[1][0])
     tot_ms = sum(v[0] for v in prof.values())
     name, (tms, calls, _) = top
@@ -350,7 +369,7 @@ def main():
             roof["traffic"] = ent["dram_read_bytes"] + ent["dram_write_bytes"]
     except Exception:
         pass
-    roof.update({"kernel": ("fused_" + name) if fused and name in alg else name, "ms_per_launch": per_launch_ms,
+    roof.update({"kernel": ("fused_" + name) if fused and name.startswith("attn_") else name, "ms_per_launch": per_launch_ms,
                  "share_of_step": tms / tot_ms, "peak_source": peaks["src"],
                  "contractions": "tcgen05 bf16x3 split, fp32 accumulate" if impl_used == 1 else "fp32 SIMT"})
     pair_rate = pair_total / (pair_ms * 1e-3)
@@ -365,7 +384,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        small = make_dataset("cfg2", kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
+        small = make_dataset(args.workload, kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
         r = cpu_reference_arm(small, args.cpu_baseline_steps, 3)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
@@ -374,7 +393,12 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": config, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(P * 5 * 8 + P * 4), "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clk, "kernel_ms_per_step": breakdown, "losses": losses, "pair_scores": pair}
+            "gpu_launches": launches, "clocks": clk, "kernel_ms_per_step": breakdown, "losses": losses,
+            "pair_scores": None if args.no_pairs else pair}
+    # achieved HBM GB/s of the node-encoder kernels (the north star's evidence for the sparse-row encoder)
+    line["encoder_hbm"] = {k: {"GB/s": alg[k][1] / (prof[k][0] / prof[k][1] * 1e-3) / 1e9, "ms_per_launch": prof[k][0] / prof[k][1],
+                               "frac_of_peak": alg[k][1] / (prof[k][0] / prof[k][1] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                           for k in ("enc0_gather_gemm", "enc0_wgrad") if k in prof}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -257,6 +257,30 @@ __global__ void prep_tables_kernel(const matcha_model_desc m) {
   }
 }
 
+// Side stream of the backward pass: the fold of the derived-weight gradients back onto the reference's parameters only
+// needs the attention backward, so it runs under the row-chain / encoder backward kernels that follow (fork after the
+// attention backward, join before matcha_backward returns: stream-ordered on the caller's stream as before).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+};
+static int side_stream(SideStream** out) {
+  static SideStream g[16];
+  int dev = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (dev < 0 || dev >= 16) { set_error("side_stream: device index %d out of range", dev); return MATCHA_ERR_ARG; }
+  SideStream& ss = g[dev];
+  if (ss.stream == nullptr) {
+    if (int rc = check_cuda(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return rc;
+    if (int rc = check_cuda(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    if (int rc = check_cuda(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    ss.device = dev;
+  }
+  *out = &ss;
+  return MATCHA_OK;
+}
+
 // derived-parameter gradients -> gradients of the reference's own parameters
 __global__ void prep_bwd_qk_kernel(const matcha_model_desc m) {
   const int D = m.d;
@@ -791,6 +815,18 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     GemmDesc e = gemm_base(FORM_NN, T, Dm, QKGm, w.dQKG, QKGm, m->derived + l.wqkg, Dm, w.dxhat, Dm);
     if ((rc = run_gemm(e, s, P_D_QKG))) return rc;
   }
+  // derived -> reference parameters (weights / LayerNorm affine / fc1 of the attention block), on the side stream
+  SideStream* side = nullptr;
+  if ((rc = side_stream(&side))) return rc;
+  if ((rc = check_cuda(cudaEventRecord(side->fork, s), "cudaEventRecord"))) return rc;
+  if ((rc = check_cuda(cudaStreamWaitEvent(side->stream, side->fork, 0), "cudaStreamWaitEvent"))) return rc;
+  prof_begin(P_PREP_BWD, side->stream);
+  prep_bwd_qk_kernel<<<m->d, 256, 0, side->stream>>>(*m);
+  MATCHA_CHECK_LAUNCH("prep_bwd_qk");
+  prep_bwd_g_kernel<<<kH * m->d, m->d, 0, side->stream>>>(*m);
+  MATCHA_CHECK_LAUNCH("prep_bwd_g");
+  prof_end(P_PREP_BWD, 2, side->stream);
+  if ((rc = check_cuda(cudaEventRecord(side->join, side->stream), "cudaEventRecord"))) return rc;
   // reconstruction head backward (gdiff was left in w.pred by the forward pass, without the beta factor)
   const float* dtE = nullptr;
   if (recon_on) {
@@ -856,13 +892,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
       if ((rc = run_gemm(f, s, P_W_ENC0))) return rc;
     }
   }
-  // derived -> reference parameters
-  prof_begin(P_PREP_BWD, s);
-  prep_bwd_qk_kernel<<<m->d, 256, 0, s>>>(*m);
-  MATCHA_CHECK_LAUNCH("prep_bwd_qk");
-  prep_bwd_g_kernel<<<kH * m->d, m->d, 0, s>>>(*m);
-  MATCHA_CHECK_LAUNCH("prep_bwd_g");
-  prof_end(P_PREP_BWD, 2, s);
+  if ((rc = check_cuda(cudaStreamWaitEvent(s, side->join, 0), "cudaStreamWaitEvent"))) return rc;     // join
   if (active) {
     if ((rc = PROF(P_MISC, 1, launch_active_flags(w.counts, m->n_chrom, recon_on ? random_chrom : -1, T, active, s)))) return rc;
   }

@@ -39,6 +39,10 @@ class Trainer:
         self.loss_sum = torch.zeros(3, dtype=torch.float32, device=self.e.dev)
         self.steps = 0
         self._buf_P = -1
+        # the derived-weight folds of matcha_prepare depend on the weights only: they run on a side stream under the
+        # batch assembly + negative sampling of the same step (both are small launches that leave most SMs idle)
+        self._side = torch.cuda.Stream(device=self.e.dev)
+        self._copy = None
 
     def _buffers(self, P, L):
         if self._buf_P == (P, L):
@@ -61,13 +65,17 @@ class Trainer:
         P, L = pos.shape
         self._buffers(P, L)
         n = P * (1 + self.neg_num)
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)               # the previous step's AdamW (weights) and backward (derived buffers)
+        with torch.cuda.stream(self._side):
+            e.prepare()
         self.x[:P].copy_(pos)
         self.w[:P].copy_(pos_w)
         self.sampler.sample(pos, out=self.x[P:], valid=self.valid)
         self.w[P:].copy_(self.valid)               # exhausted rows (emitted as the positive itself) get weight 0
         rchrom = int(self.recon_rng.randint(0, e.C)) if (self.beta != 0.0 and e.desc.inter) else -1
         seed = e.next_seed()
-        e.prepare()
+        main.wait_stream(self._side)
         e.run_forward(self.x, True, seed, rchrom, logits=self.logits, recon=self.recon)
         check(lib.matcha_bce_loss(ptr(self.logits), ptr(self.y), ptr(self.w), n, self.alpha, self.beta, ptr(self.recon),
                                   ptr(self.dlogit), ptr(self.loss_out), stream_ptr()), "matcha_bce_loss")
@@ -79,6 +87,45 @@ class Trainer:
         self.loss_sum += self.loss_out
         self.steps += 1
         return n
+
+    def run_host_batches(self, pos_host, w_host, P, n_steps, start=0):
+        """Steps over positives held in PINNED HOST memory (int64 [n, L], fp32 [n]): every step copies its own batch
+        host -> device (issued one step ahead on a copy stream, two device slots) and reads its {bce, recon, loss}
+        back device -> host (asynchronously into a pinned [n_steps, 3] array, complete when this returns), so the host
+        never blocks on the step it has just launched.  Batch i is rows [b * P, (b + 1) * P), b = (start + i) mod
+        (n // P).  Returns (losses fp32 [n_steps, 3] pinned, h2d bytes per step, d2h bytes per step)."""
+        dev = self.e.dev
+        main = torch.cuda.current_stream()
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(device=dev)
+        L = pos_host.shape[1]
+        nb = len(pos_host) // P
+        xs = [torch.empty(P, L, dtype=torch.int64, device=dev) for _ in range(2)]
+        ws = [torch.empty(P, dtype=torch.float32, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        out = torch.empty(n_steps, 3, dtype=torch.float32).pin_memory()
+
+        def issue(i):
+            slot, b = i & 1, (start + i) % nb
+            self._copy.wait_event(consumed[slot])          # the step that last used this slot has finished (no-op at first)
+            with torch.cuda.stream(self._copy):
+                xs[slot].copy_(pos_host[b * P:(b + 1) * P], non_blocking=True)
+                ws[slot].copy_(w_host[b * P:(b + 1) * P], non_blocking=True)
+                ready[slot].record(self._copy)
+
+        self._copy.wait_stream(main)
+        issue(0)
+        for i in range(n_steps):
+            if i + 1 < n_steps:
+                issue(i + 1)
+            slot = i & 1
+            main.wait_event(ready[slot])
+            self.step(xs[slot], ws[slot])
+            consumed[slot].record(main)
+            out[i].copy_(self.loss_out, non_blocking=True)
+        main.synchronize()
+        return out, P * L * 8 + P * 4, 12
 
     def mean_losses(self):
         """Host read of the running means (one sync; call once per epoch, as main.py:197 does)."""
