@@ -422,8 +422,84 @@ struct PffBwdArgs {
   int64_t T;
 };
 
+// ---- half-row helpers for the 256-thread kernels: thread (r, h) owns token row r (= TMEM lane r) and columns [32 h, 32 h + 32)
+constexpr int kHalfStageRow = 36;                          // 32 floats + pad: conflict free for both access patterns
+constexpr int kHalfStageBytes = 8 * 32 * kHalfStageRow * 4;   // 36 864: one 32 x 32 staging block per warp
+// 32 consecutive token rows x 32 floats (this warp's column half of a [*, 64] fp32 array) <-> registers, coalesced
+__device__ __forceinline__ void half_rows_load(const float* __restrict__ g, int nrows, float* stage, int lane, float (&v)[32]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 3, c4 = idx & 7;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nrows) e = __ldg(reinterpret_cast<const float4*>(g + row * 64) + c4);
+    *reinterpret_cast<float4*>(stage + row * kHalfStageRow + c4 * 4) = e;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 e = *reinterpret_cast<const float4*>(stage + lane * kHalfStageRow + k * 4);
+    v[4 * k] = e.x; v[4 * k + 1] = e.y; v[4 * k + 2] = e.z; v[4 * k + 3] = e.w;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void half_rows_store(float* __restrict__ g, int nrows, float* stage, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    *reinterpret_cast<float4*>(stage + lane * kHalfStageRow + k * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int idx = k * 32 + lane, row = idx >> 3, c4 = idx & 7;
+    if (row < nrows) reinterpret_cast<float4*>(g + row * 64)[c4] = *reinterpret_cast<const float4*>(stage + row * kHalfStageRow + c4 * 4);
+  }
+  __syncwarp();
+}
+// 32 floats of row r -> planes p0 .. p0 + 3 of the shared A tile and (optionally) the same tile in global memory
+__device__ __forceinline__ void put_half_row(uint8_t* sA, uint8_t* gT, int p0, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 hi, lo;
+    split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+           make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+    sts16(sA + (p0 + j) * 2048 + r * 16, hi);
+    sts16(sA + 16384 + (p0 + j) * 2048 + r * 16, lo);
+    if (gT) {
+      *reinterpret_cast<uint4*>(gT + (p0 + j) * 2048 + r * 16) = hi;
+      *reinterpret_cast<uint4*>(gT + 16384 + (p0 + j) * 2048 + r * 16) = lo;
+    }
+  }
+}
+// the 256-thread form of run_stage: every thread reads back its 32 columns of the output row
+__device__ __forceinline__ void run_stage_half(ChainCtx& c, uint32_t w_hi, uint32_t idesc, int h, float (&out)[32]) {
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    const uint32_t ah = smem_u32(c.sA), al = ah + 16384;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      umma_x3s(c.tmem, ah + ks * 4096, al + ks * 4096, w_hi + ks * 2048, w_hi + 8192 + ks * 2048, 2048, 128, 1024, 128, idesc,
+               ks == 0);
+    umma_commit(c.bar);
+  }
+  mbar_wait(c.bar, c.phase);
+  c.phase ^= 1;
+  tc_fence_after();
+  const uint32_t taddr = c.tmem + ((uint32_t)((c.r >> 5) * 32) << 16) + h * 32;
+  uint32_t a[32];
+  tmem_ld32_issue_c(taddr, a);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(a[i]));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) out[i] = __uint_as_float(a[i]);
+  tc_fence_before();
+}
+constexpr int kC2Threads = 256;
+
 template <int L>
-__global__ void __launch_bounds__(kCThreads) chain_pff_bwd_kernel(const PffBwdArgs a) {
+__global__ void __launch_bounds__(kC2Threads, 2) chain_pff_bwd_kernel(const PffBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW1 = smem + kCTile;
@@ -433,50 +509,54 @@ __global__ void __launch_bounds__(kCThreads) chain_pff_bwd_kernel(const PffBwdAr
   __shared__ uint32_t tmem_base_s;
   constexpr int RPW = (32 / L) * L;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & 127, h = tid >> 7, wq = warp & 3, c0 = h * 32;
   const int64_t ntiles = (a.T + 4 * RPW - 1) / (4 * RPW);
   if (warp == 0) tmem_alloc(&tmem_base_s, 64);
   if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  load_weight(sW1, a.w1mn);
-  load_weight(sW0, a.w0mn);
+  for (int i = tid; i < kCW / 16; i += kC2Threads) {
+    reinterpret_cast<uint4*>(sW1)[i] = __ldg(reinterpret_cast<const uint4*>(a.w1mn) + i);
+    reinterpret_cast<uint4*>(sW0)[i] = __ldg(reinterpret_cast<const uint4*>(a.w0mn) + i);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
+  ChainCtx c{sA, &bar, tmem_base_s, 0u, r};
   constexpr uint32_t idesc = make_idesc(128, 64, false, true);      // B = W read as [N = column, K = row], MN-major
   const uint32_t w1_hi = smem_u32(sW1), w0_hi = smem_u32(sW0);
-  float* stage = sStage + warp * kStageWarp;
+  float* stage = sStage + warp * (32 * kHalfStageRow);
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t t0 = (tile * 4 + warp) * RPW, t = t0 + lane;
+    const int64_t t0 = (tile * 4 + wq) * RPW, t = t0 + lane;
     const int nrows = warp_rows(t0, RPW, a.T);
     const bool live = lane < nrows;
-    float g[64];
-    warp_load_rows(a.dH2 + t0 * 64, nrows, stage, lane, g);
-    put_row(sA, a.dh2t + tile * (int64_t)kCTile, tid, g);
-    float o[64];
-    run_stage(c, w1_hi, idesc, o);
-    warp_load_rows(a.H1d + t0 * 64, nrows, stage, lane, g);
+    float g[32];
+    half_rows_load(a.dH2 + t0 * 64 + c0, nrows, stage, lane, g);
+    put_half_row(sA, a.dh2t + tile * (int64_t)kCTile, h * 4, r, g);
+    float o[32];
+    run_stage_half(c, w1_hi, idesc, h, o);
+    half_rows_load(a.H1d + t0 * 64 + c0, nrows, stage, lane, g);
     // gradient through H1d = dropout(tanh(.)): dy * f * (1 - (y / f)^2), f = keep * scale
 #pragma unroll
-    for (int cc = 0; cc < 64; cc += 4) {
-      const float4 f = drop_factor4(a.dpff, (uint64_t)t, (uint32_t)cc);
+    for (int cc = 0; cc < 32; cc += 4) {
+      const float4 f = drop_factor4(a.dpff, (uint64_t)t, (uint32_t)(c0 + cc));
       const float ff[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float h = ff[j] > 0.f ? g[cc + j] / ff[j] : 0.f;
-        o[cc + j] = live ? o[cc + j] * ff[j] * (1.f - h * h) : 0.f;
+        const float hh = ff[j] > 0.f ? g[cc + j] / ff[j] : 0.f;
+        o[cc + j] = live ? o[cc + j] * ff[j] * (1.f - hh * hh) : 0.f;
       }
     }
-    put_row(sA, a.dh1t + tile * (int64_t)kCTile, tid, o);
-    run_stage(c, w0_hi, idesc, o);
-    warp_add_rows(a.dH2 + t0 * 64, nrows, stage, lane, o);            // residual branch (second read: L2 hit)
+    put_half_row(sA, a.dh1t + tile * (int64_t)kCTile, h * 4, r, o);
+    run_stage_half(c, w0_hi, idesc, h, o);
+    half_rows_load(a.dH2 + t0 * 64 + c0, nrows, stage, lane, g);      // residual branch (second read: L2 hit)
     const float m = (live && a.x[t] != 0) ? 1.f : 0.f;
 #pragma unroll
-    for (int cc = 0; cc < 64; cc += 4) {
-      const float4 f = drop_factor4(a.dattn, (uint64_t)t, (uint32_t)cc);
-      o[cc] *= f.x * m; o[cc + 1] *= f.y * m; o[cc + 2] *= f.z * m; o[cc + 3] *= f.w * m;
+    for (int cc = 0; cc < 32; cc += 4) {
+      const float4 f = drop_factor4(a.dattn, (uint64_t)t, (uint32_t)(c0 + cc));
+      o[cc] = (o[cc] + g[cc]) * (f.x * m); o[cc + 1] = (o[cc + 1] + g[cc + 1]) * (f.y * m);
+      o[cc + 2] = (o[cc + 2] + g[cc + 2]) * (f.z * m); o[cc + 3] = (o[cc + 3] + g[cc + 3]) * (f.w * m);
     }
-    warp_store_rows(a.dd + t0 * 64, nrows, stage, lane, o);
+    half_rows_store(a.dd + t0 * 64 + c0, nrows, stage, lane, o);
   }
   tc_fence_before();
   __syncthreads();
@@ -729,10 +809,10 @@ int launch_pff_L(const PffArgs& a, cudaStream_t s) {
 
 template <int L>
 int launch_pff_bwd_L(const PffBwdArgs& a, cudaStream_t s) {
-  constexpr int smem = kCTile + 2 * kCW + kStageBytes;
+  constexpr int smem = kCTile + 2 * kCW + kHalfStageBytes;
   static bool once = false;
   if (!once) { if (int rc = set_smem_attr_c(chain_pff_bwd_kernel<L>, smem)) return rc; once = true; }
-  chain_pff_bwd_kernel<L><<<chain_grid(chain_pff_bwd_kernel<L>, smem, num_atiles(a.T, L)), kCThreads, smem, s>>>(a);
+  chain_pff_bwd_kernel<L><<<chain_grid(chain_pff_bwd_kernel<L>, smem, num_atiles(a.T, L)), kC2Threads, smem, s>>>(a);
   MATCHA_CHECK_LAUNCH("chain_pff_bwd");
   return MATCHA_OK;
 }
