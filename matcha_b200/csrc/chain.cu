@@ -1,8 +1,11 @@
 // "Row-chain" kernels: the 64-wide position-wise layers around the attention block (Modules.py:263-270 attribute mix,
 // :353-376 pff_n1, :290-311 scorer) as chains of tcgen05 contractions whose activations stay in registers.
 //
-// One CTA = 128 threads = the 128 rows of one hyperedge-aligned tile (rowwise.cuh); thread r owns tile row r, which is
-// also TMEM lane r.  A stage = { the thread splits its fp32 row into bf16 hi | lo and stores it into the shared A tile
+// One CTA = the 128 rows of one hyperedge-aligned tile (rowwise.cuh).  The forward kernels and the pff backward run 256
+// threads: thread (r, h) owns half h (32 columns) of tile row r = TMEM lane r, so 16 warps per SM (at 128 registers) hide
+// the load -> MMA -> read-out latency chain; row statistics meet through a 64-thread named barrier per warp pair.  The
+// LayerNorm / next_w backward, which is bound by its nine row streams rather than by latency, keeps 128 threads (thread r
+// owns the whole row r).  A stage = { the thread splits its fp32 row into bf16 hi | lo and stores it into the shared A tile
 // (and, when a consumer needs it, into the same tile in global memory) -> one thread issues the bf16x3 MMAs against a
 // pre-split 64x64 weight resident in shared memory -> every thread reads its output row back with tcgen05.ld }.
 // Several CTAs per SM (<= 64 KB shared memory, 64 TMEM columns each) overlap each other's load / MMA / store phases.
@@ -13,6 +16,7 @@ namespace matcha {
 namespace {
 
 constexpr int kCThreads = 128;
+constexpr int kC2Threads = 256;               // half a row per thread: 16 warps per SM at 128 registers
 constexpr int kCTile = 32768;                 // A tile: hi 16 KB (8 planes x 128 rows x 16 B) | lo 16 KB
 constexpr int kCW = kChainWBytes;             // one 64x64 weight: hi 8 KB | lo 8 KB
 constexpr float kLnEpsC = 1e-5f;
@@ -185,243 +189,6 @@ __device__ __forceinline__ void load_weight(uint8_t* dst, const uint8_t* src) { 
   for (int i = 0; i < kCW / 16 / kCThreads; ++i) d[threadIdx.x + i * kCThreads] = __ldg(s + threadIdx.x + i * kCThreads);
 }
 
-// LayerNorm statistics of a row held by one thread (biased variance, eps 1e-5); v <- normalised row
-__device__ __forceinline__ float ln_row(float (&v)[64]) {
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < 64; ++c) s += v[c];
-  const float mean = s * (1.0f / 64);
-  float q = 0.f;
-#pragma unroll
-  for (int c = 0; c < 64; ++c) { v[c] -= mean; q = fmaf(v[c], v[c], q); }
-  const float rstd = 1.0f / sqrtf(q * (1.0f / 64) + kLnEpsC);
-#pragma unroll
-  for (int c = 0; c < 64; ++c) v[c] *= rstd;
-  return rstd;
-}
-
-// ==========================================================================================
-// F1: V0 = E + attribute_nn(attr[id]);  X = tanh(next_w V0 + b);  xhat, rstd = LayerNorm statistics of X
-// ==========================================================================================
-struct MixArgs {
-  const float* E; const int64_t* x; const float* attr_table; int attr_dim; const float* attr_w; const float* attr_b;
-  const uint8_t* w_next; const float* next_b;
-  float* V0; float* X; float* xhat; float* rstd;
-  uint8_t* xt;       // hyperedge-aligned xhat tiles (kXTileBytes each)
-  uint8_t* v0t;      // V0 tiles (32 KB each: hi 16 KB | lo 16 KB) for the weight-gradient kernel, or NULL
-  uint8_t* attrt;    // attribute-row tiles [128 x 32] hi 8 KB | lo 8 KB, or NULL
-  int64_t T;
-};
-
-template <int L>
-__global__ void __launch_bounds__(kCThreads) chain_mix_fwd_kernel(const MixArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sW = smem + kCTile;
-  float* sStage = reinterpret_cast<float*>(smem + kCTile + kCW);
-  float* sWt = reinterpret_cast<float*>(smem + kCTile + kCW + kStageBytes);     // attribute_nn.weight^T [attr_dim][64]
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ float sNb[64], sAb[64];
-  constexpr int RPW = (32 / L) * L;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t ntiles = (a.T + 4 * RPW - 1) / (4 * RPW);
-  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
-  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  load_weight(sW, a.w_next);
-  for (int i = tid; i < a.attr_dim * 64; i += kCThreads) sWt[i] = __ldg(a.attr_w + (i & 63) * a.attr_dim + (i >> 6));
-  if (tid < 64) { sNb[tid] = __ldg(a.next_b + tid); sAb[tid] = __ldg(a.attr_b + tid); }
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
-  constexpr uint32_t idesc = make_idesc(128, 64, false, false);
-  const uint32_t w_hi = smem_u32(sW);
-  float* stage = sStage + warp * kStageWarp;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t t0 = (tile * 4 + warp) * RPW, t = t0 + lane;
-    const int nrows = warp_rows(t0, RPW, a.T);
-    const bool live = lane < nrows;
-    float v[64];
-    warp_load_rows(a.E + t0 * 64, nrows, stage, lane, v);
-    float av[32];
-    {
-      const int64_t id = live ? a.x[t] : 0;
-      const float* arow = a.attr_table + id * a.attr_dim;
-#pragma unroll
-      for (int k = 0; k < 32; ++k) av[k] = (live && k < a.attr_dim) ? __ldg(arow + k) : 0.f;
-    }
-    if (a.attrt) {       // attribute rows for the attribute_nn weight gradient: 4 planes of 8 columns (zeros for dead rows)
-      uint8_t* gt = a.attrt + tile * 16384;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 hi, lo;
-        split8(make_float4(av[8 * j], av[8 * j + 1], av[8 * j + 2], av[8 * j + 3]),
-               make_float4(av[8 * j + 4], av[8 * j + 5], av[8 * j + 6], av[8 * j + 7]), hi, lo);
-        *reinterpret_cast<uint4*>(gt + j * 2048 + tid * 16) = hi;
-        *reinterpret_cast<uint4*>(gt + 8192 + j * 2048 + tid * 16) = lo;
-      }
-    }
-    if (live) {
-#pragma unroll
-      for (int cc = 0; cc < 64; ++cc) v[cc] += sAb[cc];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {        // attribute rows are one-hot + one scalar (main.py:497-512): skip the zeros
-        if (k < a.attr_dim && av[k] != 0.f) {
-          const float* wt = sWt + k * 64;
-#pragma unroll
-          for (int cc = 0; cc < 64; ++cc) v[cc] = fmaf(av[k], wt[cc], v[cc]);
-        }
-      }
-    }
-    if (a.V0) warp_store_rows(a.V0 + t0 * 64, nrows, stage, lane, v);
-    put_row(sA, a.v0t ? a.v0t + tile * (int64_t)kCTile : nullptr, tid, v);
-    float o[64];
-    run_stage(c, w_hi, idesc, o);
-    if (live) {
-#pragma unroll
-      for (int cc = 0; cc < 64; ++cc) o[cc] = tanhf(o[cc] + sNb[cc]);
-    } else {
-#pragma unroll
-      for (int cc = 0; cc < 64; ++cc) o[cc] = 0.f;
-    }
-    warp_store_rows(a.X + t0 * 64, nrows, stage, lane, o);
-    const float rs = ln_row(o);
-    if (live) {
-      a.rstd[t] = rs;
-    } else {
-#pragma unroll
-      for (int cc = 0; cc < 64; ++cc) o[cc] = 0.f;
-    }
-    warp_store_rows(a.xhat + t0 * 64, nrows, stage, lane, o);
-    put_row_global(a.xt + tile * (int64_t)kXTileBytes, kXHalfBytes, tid, o);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base_s, 64);
-}
-
-// ==========================================================================================
-// F3: pff_n1 (two 1x1 convolutions, tanh, dropout, residual) + scorer (LayerNorms, (dyn - static)^2, masked mean)
-// ==========================================================================================
-struct PffArgs {
-  const float* U; const float* xhat; const int64_t* x;
-  const uint8_t* w0; const uint8_t* w1; const float* b0; const float* b1;
-  ScoreParams p; DropCfg drop;
-  float* H1d; float* H2; float* logits;
-  uint8_t* ut; uint8_t* h1t;       // U / H1d tiles for the weight-gradient kernel (training) or NULL
-  int64_t T;
-};
-
-template <int L>
-__global__ void __launch_bounds__(kCThreads) chain_pff_fwd_kernel(const PffArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sW0 = smem + kCTile;
-  uint8_t* sW1 = smem + kCTile + kCW;
-  float* sStage = reinterpret_cast<float*>(smem + kCTile + 2 * kCW);
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ float sP[9][64];        // b0, b1, pff_g, pff_b, ln1_g, ln1_b, ln2_g, ln2_b, cls_w
-  __shared__ float sCb;
-  constexpr int RPW = (32 / L) * L;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t ntiles = (a.T + 4 * RPW - 1) / (4 * RPW);
-  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
-  if (tid == 0) { mbar_init(&bar, 1); sCb = __ldg(a.p.cls_b); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  load_weight(sW0, a.w0);
-  load_weight(sW1, a.w1);
-  if (tid < 64) {
-    sP[0][tid] = __ldg(a.b0 + tid); sP[1][tid] = __ldg(a.b1 + tid);
-    sP[2][tid] = __ldg(a.p.pff_g + tid); sP[3][tid] = __ldg(a.p.pff_b + tid);
-    sP[4][tid] = __ldg(a.p.ln1_g + tid); sP[5][tid] = __ldg(a.p.ln1_b + tid);
-    sP[6][tid] = __ldg(a.p.ln2_g + tid); sP[7][tid] = __ldg(a.p.ln2_b + tid);
-    sP[8][tid] = __ldg(a.p.cls_w + tid);
-  }
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  ChainCtx c{sA, &bar, tmem_base_s, 0u, tid};
-  constexpr uint32_t idesc = make_idesc(128, 64, false, false);
-  const uint32_t w0_hi = smem_u32(sW0), w1_hi = smem_u32(sW1);
-  float* stage = sStage + warp * kStageWarp;
-  const bool live_lane = lane < RPW;
-  const int g = lane / L, pos = lane - g * L;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t t0 = (tile * 4 + warp) * RPW, t = t0 + lane;
-    const int nrows = warp_rows(t0, RPW, a.T);
-    const bool live = lane < nrows;
-    float u[64];
-    warp_load_rows(a.U + t0 * 64, nrows, stage, lane, u);
-    put_row(sA, a.ut ? a.ut + tile * (int64_t)kCTile : nullptr, tid, u);
-    float h[64];
-    run_stage(c, w0_hi, idesc, h);
-    if (live) {
-#pragma unroll
-      for (int cc = 0; cc < 64; cc += 4) {
-        float4 v = make_float4(tanhf(h[cc] + sP[0][cc]), tanhf(h[cc + 1] + sP[0][cc + 1]), tanhf(h[cc + 2] + sP[0][cc + 2]),
-                               tanhf(h[cc + 3] + sP[0][cc + 3]));
-        v = drop_apply4(a.drop, (uint64_t)t, (uint32_t)cc, v);          // dropout inside pff_n1 (Modules.py:359-360)
-        h[cc] = v.x; h[cc + 1] = v.y; h[cc + 2] = v.z; h[cc + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int cc = 0; cc < 64; ++cc) h[cc] = 0.f;
-    }
-    if (a.H1d) warp_store_rows(a.H1d + t0 * 64, nrows, stage, lane, h);
-    put_row(sA, a.h1t ? a.h1t + tile * (int64_t)kCTile : nullptr, tid, h);
-    float o[64];
-    run_stage(c, w1_hi, idesc, o);
-#pragma unroll
-    for (int cc = 0; cc < 64; ++cc) o[cc] = o[cc] + sP[1][cc] + u[cc];      // residual (Modules.py:371-372)
-    if (a.H2) warp_store_rows(a.H2 + t0 * 64, nrows, stage, lane, o);
-    warp_load_rows(a.xhat + t0 * 64, nrows, stage, lane, u);                // u now holds the normalised layer input
-    float z = 0.f, m = 0.f;
-    if (live) {
-      m = a.x[t] != 0 ? 1.f : 0.f;
-      ln_row(o);                                                            // pff_n1.layer_norm
-#pragma unroll
-      for (int cc = 0; cc < 64; ++cc) o[cc] = fmaf(o[cc], sP[2][cc], sP[3][cc]) * m;
-      ln_row(o);                                                            // Classifier.layer_norm1
-#pragma unroll
-      for (int cc = 0; cc < 64; ++cc) {
-        const float D = fmaf(o[cc], sP[4][cc], sP[5][cc]);
-        const float S = fmaf(u[cc], sP[6][cc], sP[7][cc]);                  // Classifier.layer_norm2 of the layer input
-        const float df = D - S;
-        z = fmaf(df * df, sP[8][cc], z);
-      }
-      z += sCb;
-    }
-    // masked mean over the L tokens of the hyperedge (all inside this warp)
-    float zs = z * m, ms = m;
-#pragma unroll
-    for (int s = 1; s < L; ++s) {
-      const int src = live_lane ? g * L + (pos + s) % L : lane;
-      zs += __shfl_sync(0xffffffffu, z * m, src);
-      ms += __shfl_sync(0xffffffffu, m, src);
-    }
-    if (live && pos == 0) a.logits[t / L] = zs / (ms + 1e-15f);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base_s, 64);
-}
-
-// ==========================================================================================
-// B1: pff_n1 backward.  dH2 -> dH1pre = (dH2 W1) * tanh' * dropout -> dU = dH1pre W0 + dH2 -> masked / dropout-scaled
-// gradient of the attention output.  The dH2 and dH1pre tiles go to global memory for the weight-gradient kernel.
-// ==========================================================================================
-struct PffBwdArgs {
-  const float* dH2; const float* H1d; const int64_t* x;
-  const uint8_t* w1mn; const uint8_t* w0mn;
-  DropCfg dpff, dattn;
-  float* dd;                      // out [T, 64]
-  uint8_t* dh2t; uint8_t* dh1t;   // out tiles (32 KB each)
-  int64_t T;
-};
-
 // ---- half-row helpers for the 256-thread kernels: thread (r, h) owns token row r (= TMEM lane r) and columns [32 h, 32 h + 32)
 constexpr int kHalfStageRow = 36;                          // 32 floats + pad: conflict free for both access patterns
 constexpr int kHalfStageBytes = 8 * 32 * kHalfStageRow * 4;   // 36 864: one 32 x 32 staging block per warp
@@ -496,7 +263,273 @@ __device__ __forceinline__ void run_stage_half(ChainCtx& c, uint32_t w_hi, uint3
   for (int i = 0; i < 32; ++i) out[i] = __uint_as_float(a[i]);
   tc_fence_before();
 }
-constexpr int kC2Threads = 256;
+
+// sums across the two threads that share a token row (warps w and w + 4 of the 256-thread kernels): one 64-thread named
+// barrier per exchange; every exchange of a tile uses its own slot array, and a slot is rewritten one tile later, behind
+// the CTA-wide barriers of the tile's contraction stages.  Fixed order (half 0 + half 1): both threads get the same bits.
+__device__ __forceinline__ float pair_sum(float v, float* slot, int r, int h, int bar_id) {
+  slot[h * 128 + r] = v;
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  return slot[r] + slot[128 + r];
+}
+// LayerNorm statistics of a row split over two threads (biased variance, eps 1e-5); v <- normalised half row
+__device__ __forceinline__ float ln_half_row(float (&v)[32], float* slot_mean, float* slot_var, int r, int h, int bar_id) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) s += v[c];
+  const float mean = pair_sum(s, slot_mean, r, h, bar_id) * (1.0f / 64);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) { v[c] -= mean; q = fmaf(v[c], v[c], q); }
+  const float rstd = 1.0f / sqrtf(pair_sum(q, slot_var, r, h, bar_id) * (1.0f / 64) + kLnEpsC);
+#pragma unroll
+  for (int c = 0; c < 32; ++c) v[c] *= rstd;
+  return rstd;
+}
+// only the global copy of a half row (tiles that feed a later kernel but no MMA of this one)
+__device__ __forceinline__ void put_half_row_global(uint8_t* gT, int half_bytes, int p0, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 hi, lo;
+    split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+           make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+    *reinterpret_cast<uint4*>(gT + (p0 + j) * 2048 + r * 16) = hi;
+    *reinterpret_cast<uint4*>(gT + half_bytes + (p0 + j) * 2048 + r * 16) = lo;
+  }
+}
+__device__ __forceinline__ void load_weight2(uint8_t* dst, const uint8_t* src) {   // 16 KB, all 256 threads
+  for (int i = threadIdx.x; i < kCW / 16; i += kC2Threads) reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+}
+
+// ==========================================================================================
+// F1: V0 = E + attribute_nn(attr[id]);  X = tanh(next_w V0 + b);  xhat, rstd = LayerNorm statistics of X
+// ==========================================================================================
+struct MixArgs {
+  const float* E; const int64_t* x; const float* attr_table; int attr_dim; const float* attr_w; const float* attr_b;
+  const uint8_t* w_next; const float* next_b;
+  float* V0; float* X; float* xhat; float* rstd;
+  uint8_t* xt;       // hyperedge-aligned xhat tiles (kXTileBytes each)
+  uint8_t* v0t;      // V0 tiles (32 KB each: hi 16 KB | lo 16 KB) for the weight-gradient kernel, or NULL
+  uint8_t* attrt;    // attribute-row tiles [128 x 32] hi 8 KB | lo 8 KB, or NULL
+  int64_t T;
+};
+
+template <int L>
+__global__ void __launch_bounds__(kC2Threads, 2) chain_mix_fwd_kernel(const MixArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + kCTile;
+  float* sStage = reinterpret_cast<float*>(smem + kCTile + kCW);
+  float* sWt = reinterpret_cast<float*>(smem + kCTile + kCW + kHalfStageBytes);     // attribute_nn.weight^T [attr_dim][64]
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sNb[64], sAb[64];
+  __shared__ float sX[2][256];
+  constexpr int RPW = (32 / L) * L;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & 127, h = tid >> 7, wq = warp & 3, c0 = h * 32, pbar = 1 + wq;
+  const int64_t ntiles = (a.T + 4 * RPW - 1) / (4 * RPW);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  load_weight2(sW, a.w_next);
+  for (int i = tid; i < a.attr_dim * 64; i += kC2Threads) sWt[i] = __ldg(a.attr_w + (i & 63) * a.attr_dim + (i >> 6));
+  if (tid < 64) { sNb[tid] = __ldg(a.next_b + tid); sAb[tid] = __ldg(a.attr_b + tid); }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  ChainCtx c{sA, &bar, tmem_base_s, 0u, r};
+  constexpr uint32_t idesc = make_idesc(128, 64, false, false);
+  const uint32_t w_hi = smem_u32(sW);
+  float* stage = sStage + warp * (32 * kHalfStageRow);
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t t0 = (tile * 4 + wq) * RPW, t = t0 + lane;
+    const int nrows = warp_rows(t0, RPW, a.T);
+    const bool live = lane < nrows;
+    float v[32];
+    half_rows_load(a.E + t0 * 64 + c0, nrows, stage, lane, v);
+    float av[32];
+    {
+      const int64_t id = live ? a.x[t] : 0;
+      const float* arow = a.attr_table + id * a.attr_dim;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) av[k] = (live && k < a.attr_dim) ? __ldg(arow + k) : 0.f;
+    }
+    if (a.attrt) {       // attribute rows for the attribute_nn weight gradient: 4 planes of 8 columns, two per half
+      uint8_t* gt = a.attrt + tile * 16384;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * h + jj;
+        uint4 hi, lo;
+        // (selects keep the indices static)
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = h == 0 ? av[8 * jj + i] : av[16 + 8 * jj + i];
+        split8(make_float4(e[0], e[1], e[2], e[3]), make_float4(e[4], e[5], e[6], e[7]), hi, lo);
+        *reinterpret_cast<uint4*>(gt + j * 2048 + r * 16) = hi;
+        *reinterpret_cast<uint4*>(gt + 8192 + j * 2048 + r * 16) = lo;
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < 32; ++cc) v[cc] += sAb[c0 + cc];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {        // attribute rows are one-hot + one scalar (main.py:497-512): skip the zeros
+        if (k < a.attr_dim && av[k] != 0.f) {
+          const float* wt = sWt + k * 64 + c0;
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) v[cc] = fmaf(av[k], wt[cc], v[cc]);
+        }
+      }
+    }
+    if (a.V0) half_rows_store(a.V0 + t0 * 64 + c0, nrows, stage, lane, v);
+    put_half_row(sA, a.v0t ? a.v0t + tile * (int64_t)kCTile : nullptr, h * 4, r, v);
+    float o[32];
+    run_stage_half(c, w_hi, idesc, h, o);
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < 32; ++cc) o[cc] = tanhf(o[cc] + sNb[c0 + cc]);
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 32; ++cc) o[cc] = 0.f;
+    }
+    half_rows_store(a.X + t0 * 64 + c0, nrows, stage, lane, o);
+    const float rs = ln_half_row(o, sX[0], sX[1], r, h, pbar);
+    if (live) {
+      if (h == 0) a.rstd[t] = rs;
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 32; ++cc) o[cc] = 0.f;
+    }
+    half_rows_store(a.xhat + t0 * 64 + c0, nrows, stage, lane, o);
+    put_half_row_global(a.xt + tile * (int64_t)kXTileBytes, kXHalfBytes, h * 4, r, o);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 64);
+}
+
+// ==========================================================================================
+// F3: pff_n1 (two 1x1 convolutions, tanh, dropout, residual) + scorer (LayerNorms, (dyn - static)^2, masked mean)
+// ==========================================================================================
+struct PffArgs {
+  const float* U; const float* xhat; const int64_t* x;
+  const uint8_t* w0; const uint8_t* w1; const float* b0; const float* b1;
+  ScoreParams p; DropCfg drop;
+  float* H1d; float* H2; float* logits;
+  uint8_t* ut; uint8_t* h1t;       // U / H1d tiles for the weight-gradient kernel (training) or NULL
+  int64_t T;
+};
+
+template <int L>
+__global__ void __launch_bounds__(kC2Threads, 2) chain_pff_fwd_kernel(const PffArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW0 = smem + kCTile;
+  uint8_t* sW1 = smem + kCTile + kCW;
+  float* sStage = reinterpret_cast<float*>(smem + kCTile + 2 * kCW);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sP[9][64];        // b0, b1, pff_g, pff_b, ln1_g, ln1_b, ln2_g, ln2_b, cls_w
+  __shared__ float sCb;
+  __shared__ float sX[5][256];
+  constexpr int RPW = (32 / L) * L;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & 127, h = tid >> 7, wq = warp & 3, c0 = h * 32, pbar = 1 + wq;
+  const int64_t ntiles = (a.T + 4 * RPW - 1) / (4 * RPW);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  if (tid == 0) { mbar_init(&bar, 1); sCb = __ldg(a.p.cls_b); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  load_weight2(sW0, a.w0);
+  load_weight2(sW1, a.w1);
+  if (tid < 64) {
+    sP[0][tid] = __ldg(a.b0 + tid); sP[1][tid] = __ldg(a.b1 + tid);
+    sP[2][tid] = __ldg(a.p.pff_g + tid); sP[3][tid] = __ldg(a.p.pff_b + tid);
+    sP[4][tid] = __ldg(a.p.ln1_g + tid); sP[5][tid] = __ldg(a.p.ln1_b + tid);
+    sP[6][tid] = __ldg(a.p.ln2_g + tid); sP[7][tid] = __ldg(a.p.ln2_b + tid);
+    sP[8][tid] = __ldg(a.p.cls_w + tid);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  ChainCtx c{sA, &bar, tmem_base_s, 0u, r};
+  constexpr uint32_t idesc = make_idesc(128, 64, false, false);
+  const uint32_t w0_hi = smem_u32(sW0), w1_hi = smem_u32(sW1);
+  float* stage = sStage + warp * (32 * kHalfStageRow);
+  const bool live_lane = lane < RPW;
+  const int g = lane / L, pos = lane - g * L;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t t0 = (tile * 4 + wq) * RPW, t = t0 + lane;
+    const int nrows = warp_rows(t0, RPW, a.T);
+    const bool live = lane < nrows;
+    float u[32];
+    half_rows_load(a.U + t0 * 64 + c0, nrows, stage, lane, u);
+    put_half_row(sA, a.ut ? a.ut + tile * (int64_t)kCTile : nullptr, h * 4, r, u);
+    float hh[32];
+    run_stage_half(c, w0_hi, idesc, h, hh);
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < 32; cc += 4) {
+        float4 v = make_float4(tanhf(hh[cc] + sP[0][c0 + cc]), tanhf(hh[cc + 1] + sP[0][c0 + cc + 1]),
+                               tanhf(hh[cc + 2] + sP[0][c0 + cc + 2]), tanhf(hh[cc + 3] + sP[0][c0 + cc + 3]));
+        v = drop_apply4(a.drop, (uint64_t)t, (uint32_t)(c0 + cc), v);    // dropout inside pff_n1 (Modules.py:359-360)
+        hh[cc] = v.x; hh[cc + 1] = v.y; hh[cc + 2] = v.z; hh[cc + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 32; ++cc) hh[cc] = 0.f;
+    }
+    if (a.H1d) half_rows_store(a.H1d + t0 * 64 + c0, nrows, stage, lane, hh);
+    put_half_row(sA, a.h1t ? a.h1t + tile * (int64_t)kCTile : nullptr, h * 4, r, hh);
+    float o[32];
+    run_stage_half(c, w1_hi, idesc, h, o);
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) o[cc] = o[cc] + sP[1][c0 + cc] + u[cc];      // residual (Modules.py:371-372)
+    if (a.H2) half_rows_store(a.H2 + t0 * 64 + c0, nrows, stage, lane, o);
+    half_rows_load(a.xhat + t0 * 64 + c0, nrows, stage, lane, u);                // u now holds the normalised layer input
+    // dead rows run the same exchanges on zeros (the named barriers need both warps of a row)
+    const float m = (live && a.x[t] != 0) ? 1.f : 0.f;
+    ln_half_row(o, sX[0], sX[1], r, h, pbar);                                    // pff_n1.layer_norm
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) o[cc] = fmaf(o[cc], sP[2][c0 + cc], sP[3][c0 + cc]) * m;
+    ln_half_row(o, sX[2], sX[3], r, h, pbar);                                    // Classifier.layer_norm1
+    float zp = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) {
+      const float D = fmaf(o[cc], sP[4][c0 + cc], sP[5][c0 + cc]);
+      const float S = fmaf(u[cc], sP[6][c0 + cc], sP[7][c0 + cc]);               // Classifier.layer_norm2 of the layer input
+      const float df = D - S;
+      zp = fmaf(df * df, sP[8][c0 + cc], zp);
+    }
+    float z = pair_sum(zp, sX[4], r, h, pbar);
+    z = live ? z + sCb : 0.f;
+    // masked mean over the L tokens of the hyperedge (all inside this warp)
+    float zs = z * m, ms = m;
+#pragma unroll
+    for (int s = 1; s < L; ++s) {
+      const int src = live_lane ? g * L + (pos + s) % L : lane;
+      zs += __shfl_sync(0xffffffffu, z * m, src);
+      ms += __shfl_sync(0xffffffffu, m, src);
+    }
+    if (live && pos == 0 && h == 0) a.logits[t / L] = zs / (ms + 1e-15f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 64);
+}
+
+// ==========================================================================================
+// B1: pff_n1 backward.  dH2 -> dH1pre = (dH2 W1) * tanh' * dropout -> dU = dH1pre W0 + dH2 -> masked / dropout-scaled
+// gradient of the attention output.  The dH2 and dH1pre tiles go to global memory for the weight-gradient kernel.
+// ==========================================================================================
+struct PffBwdArgs {
+  const float* dH2; const float* H1d; const int64_t* x;
+  const uint8_t* w1mn; const uint8_t* w0mn;
+  DropCfg dpff, dattn;
+  float* dd;                      // out [T, 64]
+  uint8_t* dh2t; uint8_t* dh1t;   // out tiles (32 KB each)
+  int64_t T;
+};
 
 template <int L>
 __global__ void __launch_bounds__(kC2Threads, 2) chain_pff_bwd_kernel(const PffBwdArgs a) {
@@ -789,19 +822,19 @@ unsigned chain_grid(K, int, int64_t ntiles) {
 
 template <int L>
 int launch_mix_L(const MixArgs& a, cudaStream_t s) {
-  const int smem = kCTile + kCW + kStageBytes + a.attr_dim * 64 * 4;
+  const int smem = kCTile + kCW + kHalfStageBytes + a.attr_dim * 64 * 4;
   static int set_for = 0;
   if (set_for < smem) { if (int rc = set_smem_attr_c(chain_mix_fwd_kernel<L>, smem)) return rc; set_for = smem; }
-  chain_mix_fwd_kernel<L><<<chain_grid(chain_mix_fwd_kernel<L>, smem, num_atiles(a.T, L)), kCThreads, smem, s>>>(a);
+  chain_mix_fwd_kernel<L><<<chain_grid(chain_mix_fwd_kernel<L>, smem, num_atiles(a.T, L)), kC2Threads, smem, s>>>(a);
   MATCHA_CHECK_LAUNCH("chain_mix_fwd");
   return MATCHA_OK;
 }
 template <int L>
 int launch_pff_L(const PffArgs& a, cudaStream_t s) {
-  constexpr int smem = kCTile + 2 * kCW + kStageBytes;
+  constexpr int smem = kCTile + 2 * kCW + kHalfStageBytes;
   static bool once = false;
   if (!once) { if (int rc = set_smem_attr_c(chain_pff_fwd_kernel<L>, smem)) return rc; once = true; }
-  chain_pff_fwd_kernel<L><<<chain_grid(chain_pff_fwd_kernel<L>, smem, num_atiles(a.T, L)), kCThreads, smem, s>>>(a);
+  chain_pff_fwd_kernel<L><<<chain_grid(chain_pff_fwd_kernel<L>, smem, num_atiles(a.T, L)), kC2Threads, smem, s>>>(a);
   MATCHA_CHECK_LAUNCH("chain_pff_fwd");
   return MATCHA_OK;
 }

@@ -678,7 +678,7 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
         }
         if ((rc = PROF(P_RECON_PRED, 1, launch_recon_tc(w.E, x, T, m->inter, m->inter_ld, rs, re, m->params + m->off_rw[random_chrom],
                                                         m->params + m->off_rb[random_chrom], w.counts, random_chrom, m->n_chrom,
-                                                        w.recon, st, training ? st + (re - rs) * Dm : nullptr,
+                                                        w.perm, w.group_off, w.recon, st, training ? st + (re - rs) * Dm : nullptr,
                                                         training ? w.dtE : nullptr, 1.f, training ? 1 : 0, s)))) return rc;
       } else {
         GemmDesc p = gemm_base(FORM_NT, T, re - rs, Dm, w.E, Dm, m->params + m->off_rw[random_chrom], Dm, w.pred, w.pred_ld);

@@ -4,8 +4,10 @@
 // in ONE kernel per pass: pred / gdiff [T, n_r] never touch HBM (the decomposed path writes and re-reads them three
 // times through four SIMT launches).
 //
-// One CTA = 256 threads = 128 consecutive tokens x one block of 128 target columns: thread (r, h) owns token row r (= TMEM
-// lane r) and half h of the features / of the target columns.  Per token tile:
+// One CTA = 256 threads = 128 ELIGIBLE tokens x one block of 128 target columns: thread (r, h) owns token row r (= TMEM
+// lane r) and half h of the features / of the target columns.  Eligible = real tokens outside the drawn chromosome; they
+// are taken from the chromosome-bucketed token list the encoder already built (every bucket but the drawn one and the pad
+// bucket), so the ~1/3 of the rows that are padding or in-chromosome never enter a tile.  Per token tile:
 //   stage   tanh(E) rows -> bf16 hi | lo tile sA [feature/8][token][8]  (+ a ones column: plane 8, zeros: plane 9)
 //   MMA1    P[128 tok, 128 col] = sA . sW^T                      (K = 64; sW = Rw block, K-major)
 //   SIMT    thread = token: gdiff row = (P + rb - target) * gscale on eligible tokens; loss partial; -> sG tile
@@ -34,19 +36,27 @@ struct ReconArgs {
   int64_t rs, re;                 // node-id range of the drawn chromosome
   const float* Rw; const float* rb;
   const int32_t* counts; int rchrom, n_chrom;
+  const int32_t* perm; const int32_t* group_off;      // chromosome-bucketed token list (rowwise.cu: launch_bucket)
   float* recon_out;               // (optional) += 100 * mean((pred - target)^2)
   float* dRw; float* drb; float* dtE; float beta;     // mode 1
   int mode;
 };
 
-// 32 consecutive token rows x 32 floats (columns [col0, col0 + 32) of a 64-float row) <-> registers through the warp's
-// padded staging area: coalesced 128-bit global accesses, four rows per instruction
-__device__ __forceinline__ void half_rows_in(const float* __restrict__ g, int nrows, float* stage, int lane, float (&v)[32]) {
+// 64-bit pointer broadcast from lane `src`
+__device__ __forceinline__ const float* bcast_ptr(const float* p, int src) {
+  const unsigned long long v = reinterpret_cast<unsigned long long>(p);
+  const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return reinterpret_cast<const float*>(((unsigned long long)hi << 32) | lo);
+}
+// 32 scattered rows x 32 floats (row pointer incl. column offset held by the owning lane, NULL = zero row) -> registers:
+// four rows per instruction, 8 lanes x float4 each, transposed through the warp's staging area
+__device__ __forceinline__ void half_rows_gather(const float* rowp, float* stage, int lane, float (&v)[32]) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int idx = k * 32 + lane, row = idx >> 3, c4 = idx & 7;
+    const int row = 4 * k + (lane >> 3), c4 = lane & 7;
+    const float* p = bcast_ptr(rowp, row);
     float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < nrows) e = __ldg(reinterpret_cast<const float4*>(g + row * 64) + c4);
+    if (p != nullptr) e = __ldg(reinterpret_cast<const float4*>(p) + c4);
     *reinterpret_cast<float4*>(stage + row * kRStageRow + c4 * 4) = e;
   }
   __syncwarp();
@@ -57,15 +67,18 @@ __device__ __forceinline__ void half_rows_in(const float* __restrict__ g, int nr
   }
   __syncwarp();
 }
-// half rows -> global with atomic adds (several column blocks contribute to the same dtE row), coalesced
-__device__ __forceinline__ void half_rows_red(float* __restrict__ g, int nrows, float* stage, int lane, const float (&v)[32]) {
+// half rows -> scattered global rows with atomic adds (several column blocks contribute to the same dtE row); one row of
+// 32 consecutive floats per instruction
+__device__ __forceinline__ void half_rows_scatter_red(float* rowp, float* stage, int lane, const float (&v)[32]) {
 #pragma unroll
   for (int k = 0; k < 8; ++k)
     *reinterpret_cast<float4*>(stage + lane * kRStageRow + k * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
   __syncwarp();
 #pragma unroll 4
-  for (int row = 0; row < 32; ++row)
-    if (row < nrows) atomicAdd(g + row * 64 + lane, stage[row * kRStageRow + lane]);
+  for (int row = 0; row < 32; ++row) {
+    float* p = const_cast<float*>(bcast_ptr(rowp, row));
+    if (p != nullptr) atomicAdd(p + lane, stage[row * kRStageRow + lane]);
+  }
   __syncwarp();
 }
 // 32 floats of row r -> planes p0 .. p0 + 3 of a K-major bf16 hi | lo tile
@@ -94,9 +107,11 @@ __global__ void __launch_bounds__(kRThreads, 2) recon_tc_kernel(const ReconArgs 
   const int r = tid & 127, h = tid >> 7, wq = warp & 3;         // token row, half, TMEM lane quarter
   const int cb = blockIdx.y;                                   // column block: target columns [cb * 128, cb * 128 + 128)
   const int64_t n_r = a.re - a.rs;
-  const int64_t ntiles = (a.T + 127) / 128;
   const int S = gridDim.x;
-  const int64_t elig = a.T - a.counts[a.n_chrom] - a.counts[a.rchrom];
+  // eligible tokens = bucketed list minus the drawn chromosome's bucket: list positions [0, lo_n) and [lo_n + skip, ...)
+  const int64_t lo_n = a.group_off[a.rchrom], skip = a.counts[a.rchrom];
+  const int64_t elig = (int64_t)a.group_off[a.n_chrom] - skip;
+  const int64_t ntiles = (elig + 127) / 128;
   const float gscale = elig > 0 ? 200.0f / ((float)elig * (float)n_r) : 0.f;
 
   const uint32_t tmem_cols = a.mode == 1 ? 512u : 128u;      // loss-only pass: P alone -> two CTAs per SM
@@ -147,14 +162,14 @@ __global__ void __launch_bounds__(kRThreads, 2) recon_tc_kernel(const ReconArgs 
   bool first = true;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += S) {
-    const int64_t t0 = tile * 128 + wq * 32, t = t0 + lane;
-    const int nrows = (a.T - t0) <= 0 ? 0 : ((a.T - t0) < 32 ? (int)(a.T - t0) : 32);
-    const int64_t id = t < a.T ? a.x[t] : 0;
-    const bool ok = id != 0 && (id < a.rs || id >= a.re);
+    const int64_t e = tile * 128 + wq * 32 + lane;           // position in the eligible list
+    const bool ok = e < elig;
+    const int64_t t = ok ? a.perm[e < lo_n ? e : e + skip] : 0;
+    const int64_t id = ok ? a.x[t] : 0;
     // ---- stage tanh(E): this thread's 32 features ----
     {
       float v[32];
-      half_rows_in(a.E + t0 * 64 + h * 32, nrows, stage, lane, v);
+      half_rows_gather(ok ? a.E + t * 64 + h * 32 : nullptr, stage, lane, v);
 #pragma unroll
       for (int c = 0; c < 32; ++c) v[c] = tanhf(v[c]);
       put_planes4(sA, kRAHalf, h * 4, r, v);
@@ -234,7 +249,7 @@ __global__ void __launch_bounds__(kRThreads, 2) recon_tc_kernel(const ReconArgs 
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(d0[i]);
-        half_rows_red(a.dtE + t0 * 64 + h * 32, nrows, stage, lane, v);
+        half_rows_scatter_red(ok ? a.dtE + t * 64 + h * 32 : nullptr, stage, lane, v);
       }
       tc_fence_before();
     }
@@ -285,8 +300,9 @@ int launch_axpy(const float* in, float scale, float* out, int64_t n, cudaStream_
 // mode 0: loss only (eval);  mode 1: also dRw, drb += beta * ..., dtE += gdiff . Rw (dtE zeroed by the caller).  recon_out
 // (optional) receives the loss in either mode
 int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* inter, int64_t inter_ld, int64_t rs, int64_t re,
-                    const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, float* recon_out,
-                    float* dRw, float* drb, float* dtE, float beta, int mode, cudaStream_t s) {
+                    const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, const int32_t* perm,
+                    const int32_t* group_off, float* recon_out, float* dRw, float* drb, float* dtE, float beta, int mode,
+                    cudaStream_t s) {
   if (T <= 0 || re <= rs) return MATCHA_OK;
   static bool once = false;
   if (!once) {
@@ -297,7 +313,7 @@ int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* in
   }
   ReconArgs a;
   a.E = E; a.x = x; a.T = T; a.inter = inter; a.inter_ld = inter_ld; a.rs = rs; a.re = re; a.Rw = Rw; a.rb = rb;
-  a.counts = counts; a.rchrom = rchrom; a.n_chrom = n_chrom; a.recon_out = recon_out; a.dRw = dRw; a.drb = drb; a.dtE = dtE;
+  a.counts = counts; a.rchrom = rchrom; a.n_chrom = n_chrom; a.perm = perm; a.group_off = group_off; a.recon_out = recon_out; a.dRw = dRw; a.drb = drb; a.dtE = dtE;
   a.beta = beta; a.mode = mode;
   const int ncb = (int)((re - rs + 127) / 128);
   const int64_t ntiles = (T + 127) / 128;

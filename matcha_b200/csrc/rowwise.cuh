@@ -118,10 +118,12 @@ int launch_wgrad_pair(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, c
                       cudaStream_t s);
 
 // fused reconstruction head on tensor cores (recon_tc.cu): the loss is added to recon_out[0] (if given); mode 1 also adds
-// beta * the weight / bias gradients to dRw [n_r, 64] / drb [n_r] and gdiff . Rw to dtE [T, 64] (zeroed by the caller)
+// beta * the weight / bias gradients to dRw [n_r, 64] / drb [n_r] and gdiff . Rw to dtE [T, 64] (zeroed by the caller).
+// perm / group_off / counts: the chromosome-bucketed token list of launch_bucket (the kernel walks the eligible tokens only)
 int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* inter, int64_t inter_ld, int64_t rs, int64_t re,
-                    const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, float* recon_out,
-                    float* dRw, float* drb, float* dtE, float beta, int mode, cudaStream_t s);
+                    const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, const int32_t* perm,
+                    const int32_t* group_off, float* recon_out, float* dRw, float* drb, float* dtE, float beta, int mode,
+                    cudaStream_t s);
 
 int launch_axpy(const float* in, float scale, float* out, int64_t n, cudaStream_t s);      // out += scale * in
 
