@@ -226,8 +226,11 @@ def main():
             assert bool(torch.isfinite(losses).all())
             return
         for i in range(n_steps):
-            b = (start + i) % nb
-            trainer.step(pos_dev[b * P:(b + 1) * P], w_dev[b * P:(b + 1) * P])
+            b, b2 = (start + i) % nb, (start + i + 1) % nb
+            if i + 1 < n_steps:      # the next batch's positives: its negatives are sampled under this step
+                trainer.step(pos_dev[b * P:(b + 1) * P], w_dev[b * P:(b + 1) * P], pos_dev[b2 * P:(b2 + 1) * P], w_dev[b2 * P:(b2 + 1) * P])
+            else:
+                trainer.step(pos_dev[b * P:(b + 1) * P], w_dev[b * P:(b + 1) * P])
 
     def timed(n_steps, host_io, start, profile=False):
         barrier()

@@ -111,7 +111,11 @@ int64_t matcha_workspace_bytes(const matcha_model_desc* m, int64_t B, int32_t L,
 
 /* Fold LayerNorm affine / temperature / fc1 into the effective projection weights.  Call after every
  * parameter update and before forward.  Replaces nothing in the reference (a B200-side re-association
- * of Modules.py:519-529,572); exact in real arithmetic. */
+ * of Modules.py:519-529,572); exact in real arithmetic.
+ * Stream contract: it may be queued on a DIFFERENT stream than the pass that follows (it reads the weights only, so a
+ * trainer can run it beside batch assembly).  matcha_forward / matcha_node_embeddings / matcha_pair_tables wait, on
+ * their own stream and after their weight-free token bucketing, for the most recent matcha_prepare queued on this
+ * device.  The caller orders matcha_prepare after the weight update and after the previous backward pass. */
 int matcha_prepare(const matcha_model_desc* m, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -281,6 +281,20 @@ static int side_stream(SideStream** out) {
   return MATCHA_OK;
 }
 
+// matcha_prepare may be issued on a different stream than the passes that consume the derived weights (it depends on the
+// weights only, so the trainer runs it beside batch assembly): it records this event when its last kernel is queued,
+// and the encoder -- the first consumer in every pass -- waits for it AFTER the token bucketing, which needs no weights.
+static int prepare_event(cudaEvent_t* out) {
+  static cudaEvent_t g[16] = {};
+  int dev = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (dev < 0 || dev >= 16) { set_error("prepare_event: device index %d out of range", dev); return MATCHA_ERR_ARG; }
+  if (g[dev] == nullptr)
+    if (int rc = check_cuda(cudaEventCreateWithFlags(&g[dev], cudaEventDisableTiming), "cudaEventCreate")) return rc;
+  *out = g[dev];
+  return MATCHA_OK;
+}
+
 // derived-parameter gradients -> gradients of the reference's own parameters
 __global__ void prep_bwd_qk_kernel(const matcha_model_desc m) {
   const int D = m.d;
@@ -475,6 +489,11 @@ static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   (void)QKGm;
   int rc;
   if ((rc = PROF(P_BUCKET, 3, launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s)))) return rc;
+  {   // the derived weights of the most recent matcha_prepare (possibly queued on another stream)
+    cudaEvent_t ev;
+    if ((rc = prepare_event(&ev))) return rc;
+    if ((rc = check_cuda(cudaStreamWaitEvent(s, ev, 0), "cudaStreamWaitEvent"))) return rc;
+  }
   if ((rc = check_cuda(cudaMemsetAsync(w.H0, 0, sizeof(float) * T * Dm, s), "memset H0"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * Dm, s), "memset E"))) return rc;
   if (use_enc_tc(m, T)) {    // both encoder layers in one tcgen05 kernel over the bucketed token list
@@ -641,7 +660,9 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   if (model_uses_csr(m) && (rc = launch_csr_prepare(m, l.total, s))) return rc;
   if (enc_tc_eligible(m) && (rc = launch_enc_tc_prepare(m, l.total, s))) return rc;
   prof_end(P_PREP, 10, s);
-  return MATCHA_OK;
+  cudaEvent_t ev;
+  if ((rc = prepare_event(&ev))) return rc;
+  return check_cuda(cudaEventRecord(ev, s), "cudaEventRecord");
 }
 
 int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int32_t L, int32_t training,

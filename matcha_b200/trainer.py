@@ -42,25 +42,44 @@ class Trainer:
         # the derived-weight folds of matcha_prepare depend on the weights only: they run on a side stream under the
         # batch assembly + negative sampling of the same step (both are small launches that leave most SMs idle)
         self._side = torch.cuda.Stream(device=self.e.dev)
+        self._side2 = torch.cuda.Stream(device=self.e.dev)     # assembles the next step's batch (see step())
         self._copy = None
 
     def _buffers(self, P, L):
         if self._buf_P == (P, L):
             return
         dev, n = self.e.dev, P * (1 + self.neg_num)
-        self.x = torch.zeros(n, L, dtype=torch.int64, device=dev)
+        # two batch slots: while step i computes on one, the batch of step i + 1 is assembled in the other
+        self.xb = [torch.zeros(n, L, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.wb = [torch.ones(n, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.vb = [torch.empty(n - P, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.y = torch.zeros(n, dtype=torch.float32, device=dev)
         self.y[:P] = 1.0
-        self.w = torch.ones(n, dtype=torch.float32, device=dev)
-        self.valid = torch.empty(n - P, dtype=torch.uint8, device=dev)
         self.logits = torch.empty(n, dtype=torch.float32, device=dev)
         self.dlogit = torch.empty(n, dtype=torch.float32, device=dev)
         self.recon = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._assembled = [torch.cuda.Event() for _ in range(2)]
+        self._released = [torch.cuda.Event() for _ in range(2)]
+        self._slot, self._pending = 0, None
         self._buf_P = (P, L)
 
-    def step(self, pos, pos_w):
+    def _assemble(self, slot, pos, pos_w):
+        """x = [pos; negatives], w = [pos_w; valid] into batch slot `slot`, on the current stream."""
+        P = pos.shape[0]
+        x, w, valid = self.xb[slot], self.wb[slot], self.vb[slot]
+        x[:P].copy_(pos)
+        w[:P].copy_(pos_w)
+        self.sampler.sample(pos, out=x[P:], valid=valid)
+        w[P:].copy_(valid)                         # exhausted rows (emitted as the positive itself) get weight 0
+
+    def step(self, pos, pos_w, next_pos=None, next_w=None, next_ready=None):
         """pos int64 [P, L] (device, rows sorted, zero padded), pos_w fp32 [P] (device).  Returns nothing:
-        running losses accumulate on the device in `loss_sum` ({bce, recon, total})."""
+        running losses accumulate on the device in `loss_sum` ({bce, recon, total}).
+
+        next_pos / next_w (optional): the positives of the FOLLOWING step.  Their negatives are sampled and the batch is
+        assembled on a side stream while this step computes (the sampler depends on the positives and the hash set only),
+        so the next call -- which must pass exactly these tensors as pos / pos_w -- finds its batch ready.  next_ready: a
+        CUDA event after which next_pos / next_w hold their data (e.g. the H2D copy of a host-fed loop)."""
         e, lib = self.e, self.e.lib
         P, L = pos.shape
         self._buffers(P, L)
@@ -69,23 +88,42 @@ class Trainer:
         self._side.wait_stream(main)               # the previous step's AdamW (weights) and backward (derived buffers)
         with torch.cuda.stream(self._side):
             e.prepare()
-        self.x[:P].copy_(pos)
-        self.w[:P].copy_(pos_w)
-        self.sampler.sample(pos, out=self.x[P:], valid=self.valid)
-        self.w[P:].copy_(self.valid)               # exhausted rows (emitted as the positive itself) get weight 0
+        slot = self._slot
+        hit = False
+        if self._pending is not None:
+            main.wait_event(self._assembled[slot])  # assembled under the previous step
+            hit = self._pending == (pos.data_ptr(), pos_w.data_ptr(), P, L)
+            self._pending = None
+        if not hit:
+            self._assemble(slot, pos, pos_w)
+        x, w = self.xb[slot], self.wb[slot]
         rchrom = int(self.recon_rng.randint(0, e.C)) if (self.beta != 0.0 and e.desc.inter) else -1
         seed = e.next_seed()
-        main.wait_stream(self._side)
-        e.run_forward(self.x, True, seed, rchrom, logits=self.logits, recon=self.recon)
-        check(lib.matcha_bce_loss(ptr(self.logits), ptr(self.y), ptr(self.w), n, self.alpha, self.beta, ptr(self.recon),
+        # no main.wait_stream(side) here: matcha_forward itself waits for the prepare it depends on, after the token
+        # bucketing (which needs no weights) has been queued, so bucketing and prepare overlap too
+        e.run_forward(x, True, seed, rchrom, logits=self.logits, recon=self.recon)
+        if next_pos is not None and tuple(next_pos.shape) == (P, L):
+            other = slot ^ 1
+            self._side2.wait_event(self._released[other])      # the step that last read that slot (no-op at first)
+            if next_ready is not None:
+                self._side2.wait_event(next_ready)
+            else:
+                self._side2.wait_stream(main)
+            with torch.cuda.stream(self._side2):
+                self._assemble(other, next_pos, next_w)
+                self._assembled[other].record(self._side2)
+            self._pending = (next_pos.data_ptr(), next_w.data_ptr(), P, L)
+        check(lib.matcha_bce_loss(ptr(self.logits), ptr(self.y), ptr(w), n, self.alpha, self.beta, ptr(self.recon),
                                   ptr(self.dlogit), ptr(self.loss_out), stream_ptr()), "matcha_bce_loss")
         e.gflat.zero_()
-        e.run_backward(self.x, seed, rchrom, self.dlogit, self.beta)
+        e.run_backward(x, seed, rchrom, self.dlogit, self.beta)
+        self._released[slot].record(main)
         # one collective per step: gradients + activity flags (no-op when world == 1)
         scale = allreduce_grads_and_flags(e.gflat, e.n_flat, e.active, self.world)
         self.opt.step(grad_scale=scale)
         self.loss_sum += self.loss_out
         self.steps += 1
+        self._slot = slot ^ 1 if self._pending is not None else slot
         return n
 
     def run_host_batches(self, pos_host, w_host, P, n_steps, start=0):
@@ -121,7 +159,10 @@ class Trainer:
                 issue(i + 1)
             slot = i & 1
             main.wait_event(ready[slot])
-            self.step(xs[slot], ws[slot])
+            if i + 1 < n_steps:
+                self.step(xs[slot], ws[slot], xs[slot ^ 1], ws[slot ^ 1], ready[slot ^ 1])
+            else:
+                self.step(xs[slot], ws[slot])
             consumed[slot].record(main)
             out[i].copy_(self.loss_out, non_blocking=True)
         main.synchronize()

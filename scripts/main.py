@@ -119,9 +119,14 @@ def train(model, trainer, sampler, training_data, validation_data, epochs, batch
         trainer.loss_sum.zero_(); trainer.steps = 0
         nb = len(e_part) // batch
         e_dev, w_dev = torch.from_numpy(e_part).to(device), torch.from_numpy(w_part).to(device)
-        for i in range(nb):
+        def rank_batch(i):      # this rank's rows of global batch i
             sl = slice(i * batch, (i + 1) * batch)
-            trainer.step(e_dev[sl][shard_rows(batch, rank, world)].contiguous(), w_dev[sl][shard_rows(batch, rank, world)].contiguous())
+            return (e_dev[sl][shard_rows(batch, rank, world)].contiguous(), w_dev[sl][shard_rows(batch, rank, world)].contiguous())
+        cur = rank_batch(0) if nb > 0 else None
+        for i in range(nb):
+            nxt = rank_batch(i + 1) if i + 1 < nb else (None, None)      # sampled under step i (Trainer.step)
+            trainer.step(cur[0], cur[1], nxt[0], nxt[1])
+            cur = nxt
         losses = trainer.mean_losses()
         print("  - (Training)   bce: %7.4f, recon: %7.4f, steps: %d, elapse: %3.3f s" %
               (losses["bce"], losses["recon"], nb, time.time() - start))

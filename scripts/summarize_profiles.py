@@ -17,7 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum"]
 
 
@@ -88,6 +90,11 @@ def ncu_reports(tag):
                                              "tokens": 81920, "source": f"profiles/{tag}_ncu_{name}.md"}
         open(os.path.join(ROOT, "profiles", f"{tag}_ncu_{name}.md"), "w").write("\n".join(out) + "\n")
     if traffic:
+        path = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+        if os.path.exists(path):
+            old = json.load(open(path))
+            old.update(traffic)
+            traffic = old
         json.dump(traffic, open(os.path.join(ROOT, "profiles", "top_kernel_traffic.json"), "w"), indent=1)
 
 

@@ -846,3 +846,160 @@ def test_d128_pair_scorer_falls_back_to_generic_path(golden128):
     with torch.no_grad():
         want = model(torch.from_numpy(np.stack([i, j], 1)).cuda()).view(-1).cpu().numpy()
     np.testing.assert_array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json's FULL sizes, through size-independent properties (the oracle does not finish these in seconds)
+# ------------------------------------------------------------------------------------------
+def test_cfg4_full_size_all_pairs_properties():
+    """configs[3]: chr1 at 10 kb, 24,897 bins, n(n+1)/2 = 3.1e8 pairs (denoise_contact.py:67-88 with min_distance 0).
+    (i) the 8 contiguous rank shards of `score_chromosome` concatenate bit-exactly to the single-GPU pass (no-communication
+    sharding); (ii) 200k sampled pairs equal the fp64 closed form of SURVEY 8a evaluated on the host from the
+    same tables; (iii) pair order is generate_pair_wise's: the first n outputs are row i = lo; (iv) sigmoid(logit) = prob."""
+    L = _lib()
+    lib = L.load()
+    n, lo = 24897, 1
+    g = torch.Generator(device="cuda").manual_seed(4)
+    D = torch.randn(lo + n, 64, device="cuda", generator=g) * 0.5
+    S = torch.randn(lo + n, 64, device="cuda", generator=g) * 0.5
+    w = (torch.rand(64, device="cuda", generator=g) - 0.3) * 0.1
+    b = torch.full((1,), -0.2, device="cuda")
+    total = int(lib.matcha_pair_count(lo, lo + n, 0))
+    assert total == n * (n + 1) // 2 == 309942753
+    nbytes = int(lib.matcha_pair_tc_workspace_bytes(lo, lo + n))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    L.check(lib.matcha_pair_tc_prepare(L.ptr(D), L.ptr(S), L.ptr(w), L.ptr(b), 64, lo, lo + n, L.ptr(ws), nbytes, L.stream_ptr()), "prep")
+    full = torch.empty(total, dtype=torch.float32, device="cuda")
+    L.check(lib.matcha_pair_tc_score_range(L.ptr(ws), lo, lo + n, 0, 0, total, 0, L.ptr(full), L.stream_ptr()), "full")
+    world = 8
+    for rank in range(world):
+        pb, pe = total * rank // world, total * (rank + 1) // world
+        part = torch.full((pe - pb,), float("nan"), device="cuda")
+        L.check(lib.matcha_pair_tc_score_range(L.ptr(ws), lo, lo + n, 0, pb, pe, 0, L.ptr(part), L.stream_ptr()), "shard")
+        assert torch.equal(part, full[pb:pe]), rank
+        del part
+    assert bool(torch.isfinite(full).all())
+    # sampled pairs vs the closed form in fp64: logit(i, j) = 1/2 [sum_c w_c (D_jc - S_ic)^2 + sum_c w_c (D_ic - S_jc)^2] + b
+    from matcha_b200.scorer import pair_index_to_ij
+    rng = np.random.default_rng(0)
+    p = np.unique(np.concatenate([rng.integers(0, total, 200_000), [0, n - 1, n, total - 1]]))
+    i, j = pair_index_to_ij(p, lo, lo + n, 0)
+    assert i[0] == lo and j[0] == lo and i[-1] == lo + n - 1 and j[-1] == lo + n - 1
+    assert (i[p < n] == lo).all()                                     # row i = lo comes first, j ascending
+    Dh, Sh, wh = D.double().cpu().numpy(), S.double().cpu().numpy(), w.double().cpu().numpy()
+    want = 0.5 * (((Dh[j] - Sh[i]) ** 2) @ wh + ((Dh[i] - Sh[j]) ** 2) @ wh) + float(b)
+    got = full[torch.from_numpy(p).cuda()].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    prob = torch.empty(1 << 20, dtype=torch.float32, device="cuda")
+    L.check(lib.matcha_pair_tc_score_range(L.ptr(ws), lo, lo + n, 0, 12345, 12345 + (1 << 20), 1, L.ptr(prob), L.stream_ptr()), "sig")
+    np.testing.assert_allclose(prob.cpu().numpy(), torch.sigmoid(full[12345:12345 + (1 << 20)]).cpu().numpy(), rtol=2e-6, atol=1e-7)
+
+
+def test_cfg3_full_size_model_properties(monkeypatch):
+    """configs[2] bins: whole genome at 100 kb, 30,344 bins, chromosomes of up to 2,491 bins (39 encoder weight chunks, 7
+    column groups in the encoder backward, 20 column blocks in the reconstruction head).  Properties that do not need the
+    oracle: the tensor-core path agrees with the independent fp32 SIMT path on one training step (logits, recon loss, every
+    gradient) and on eval logits; hyperedges are order-invariant; the k = 2 closed form equals the generic forward on pairs
+    across the genome; id 0 embeds to zero."""
+    from matcha_b200.scorer import PairScorer
+    from matcha_b200.synthetic import build_model, make_dataset
+    lib = _lib().load()
+    ds = make_dataset("cfg3", kmers_per_size=20000, seed=11)
+    N = ds["N"]
+    assert N == 30344 and max(ds["nums"]) == 2491
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([0]))     # recon on chr1 (2,491 columns)
+    rng = np.random.default_rng(5)
+    B, L = 600, 5
+    pos = ds["positives"]
+    xs = pos[rng.choice(len(pos), B, replace=False)].copy()
+    x = torch.from_numpy(xs).cuda()
+    y = torch.from_numpy((rng.random((B, 1)) < 0.4).astype("float32")).cuda()
+    w = torch.from_numpy(rng.uniform(0.5, 3.0, size=(B, 1)).astype("float32")).cuda()
+    model = build_model(ds, seed=1)
+    res = {}
+    try:
+        for impl in (0, 1):
+            lib.matcha_set_gemm_impl(impl)
+            model.zero_grad(set_to_none=True)
+            model.train()
+            model._engine().seed_base, model._engine().tape_id = 23, 0
+            pred, rl = model(x, return_recon=True)
+            (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.5 * rl.sum()).backward()
+            grads = {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
+            model.eval()
+            with torch.no_grad():
+                ev = model(x).cpu().numpy()
+            res[impl] = (pred.detach().cpu().numpy(), float(rl.detach().sum()), grads, ev)
+    finally:
+        lib.matcha_set_gemm_impl(1)
+    np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(res[1][3], res[0][3], rtol=1e-4, atol=1e-4)
+    assert abs(res[1][1] - res[0][1]) <= 1e-4 * abs(res[0][1])
+    assert res[0][2].keys() == res[1][2].keys() and len(res[1][2]) >= 30
+    for k, g0 in res[0][2].items():
+        scale = float(np.abs(g0).max())
+        assert float(np.abs(res[1][2][k] - g0).max()) <= 1e-3 * scale + 1e-7, (k, scale)
+    # order invariance within a hyperedge (full-width rows: no padding moves)
+    model.eval()
+    full_rows = xs[(xs != 0).all(1)][:200]
+    with torch.no_grad():
+        a = model(torch.from_numpy(full_rows).cuda()).cpu().numpy()
+        bperm = model(torch.from_numpy(np.ascontiguousarray(full_rows[:, ::-1])).cuda()).cpu().numpy()
+    np.testing.assert_allclose(bperm, a, rtol=1e-4, atol=1e-4)
+    # k = 2 closed form vs the generic forward, pairs inside chr1 (ids 1..2491) and inside the last chromosome
+    sc = PairScorer(model)
+    for (lo, hi) in (tuple(int(v) for v in ds["chrom_range"][0]), tuple(int(v) for v in ds["chrom_range"][-1])):
+        total = int(lib.matcha_pair_count(lo, hi, 0))
+        pb = total // 2
+        got = sc.score_range(lo, hi, 0, pb, pb + 4096).cpu().numpy()
+        from matcha_b200.scorer import pair_index_to_ij
+        i, j = pair_index_to_ij(np.arange(pb, pb + 4096), lo, hi, 0)
+        with torch.no_grad():
+            want = model(torch.from_numpy(np.stack([i, j], 1)).cuda()).view(-1).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    with torch.no_grad():
+        emb = model.get_node_embeddings(torch.tensor([[0], [1], [N]]).cuda())[:, 0, :].cpu().numpy()
+    assert float(np.abs(emb[0]).max()) == 0.0 and float(np.abs(emb[1]).max()) > 0 and float(np.abs(emb[2]).max()) > 0
+
+
+def test_trainer_prefetch_and_host_loop_match_plain_steps(golden):
+    """The next-batch prefetch of Trainer.step (negatives sampled on a side stream under the previous step) and the
+    host-fed loop (pinned positives, prefetched H2D, asynchronous loss read-back) train exactly like plain step() calls:
+    same sampler streams, same dropout seeds -> same per-step losses and the same weights after 6 steps."""
+    from matcha_b200.sampler import KmerHashSet, NegativeSampler
+    from matcha_b200.trainer import Trainer
+    rng = np.random.default_rng(33)
+    cr = golden["chrom_range"]
+    kmers = _toy_kmers(rng, cr, 20000)
+    hs = KmerHashSet(len(kmers), width=5).insert(kmers)
+    P, steps = 512, 6
+    pos_host = torch.from_numpy(kmers[rng.choice(len(kmers), P * steps, replace=False)]).pin_memory()
+    w_host = torch.from_numpy(rng.uniform(0.5, 3.0, P * steps).astype(np.float32)).pin_memory()
+    pos_dev, w_dev = pos_host.cuda(), w_host.cuda()
+    results = {}
+    for mode in ("plain", "prefetch", "host", "miss"):
+        model = model_from_golden(golden)
+        tr = Trainer(model, NegativeSampler(hs, cr, neg_num=3, seed=4), alpha=1.0, beta=0.3, seed=9)
+        losses = []
+        if mode == "host":
+            out, h2d, d2h = tr.run_host_batches(pos_host, w_host, P, steps)
+            assert h2d == P * 5 * 8 + P * 4 and d2h == 12
+            losses = [out[i].numpy().copy() for i in range(steps)]
+        else:
+            for i in range(steps):
+                cur = (pos_dev[i * P:(i + 1) * P], w_dev[i * P:(i + 1) * P])
+                nxt = (pos_dev[(i + 1) * P:(i + 2) * P], w_dev[(i + 1) * P:(i + 2) * P]) if i + 1 < steps else (None, None)
+                if mode == "plain":
+                    tr.step(*cur)
+                elif mode == "prefetch":
+                    tr.step(*cur, *nxt)
+                else:     # announce a batch, then pass a different tensor object holding the same rows: falls back, still correct
+                    tr.step(cur[0].clone(), cur[1].clone(), *nxt)
+                losses.append(tr.loss_out.cpu().numpy().copy())
+        torch.cuda.synchronize()
+        results[mode] = (np.stack(losses), tr.e.flat.detach().cpu().numpy().copy())
+    for mode in ("prefetch", "host"):
+        np.testing.assert_allclose(results[mode][0], results["plain"][0], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(results[mode][1], results["plain"][1], rtol=1e-4, atol=2e-6)
+    # a missed prefetch consumes extra sampler steps (different negatives) but must stay finite and trained
+    assert np.isfinite(results["miss"][0]).all() and np.isfinite(results["miss"][1]).all()
