@@ -158,6 +158,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything libraries print while we run (NCCL's version banner goes to fd 1)
+    # is sent to stderr instead; the saved descriptor is restored for the final print
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(obj), flush=True)
     config = {"workload": WORKLOADS[args.workload], "hyperedges_per_gpu_per_step": args.pos_per_step * (1 + NEG_NUM),
               "positives_per_gpu_per_step": args.pos_per_step, "neg_num": NEG_NUM, "padded_width": 5,
               "kmers_per_size": args.kmers_per_size, "parallelism": f"dp{world}",
@@ -178,7 +188,7 @@ def main():
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -402,7 +412,7 @@ def main():
     line["encoder_hbm"] = {k: {"GB/s": alg[k][1] / (prof[k][0] / prof[k][1] * 1e-3) / 1e9, "ms_per_launch": prof[k][0] / prof[k][1],
                                "frac_of_peak": alg[k][1] / (prof[k][0] / prof[k][1] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
                            for k in ("enc0_gather_gemm", "enc0_wgrad") if k in prof}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

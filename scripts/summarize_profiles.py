@@ -48,7 +48,7 @@ def launches(tag):
         a[1] += us
     tot = sum(a[1] for a in agg.values())
     out = [f"# {tag} - ncu launch list (bench.py, fused + row-chain kernels on)\n",
-           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline`",
+           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline [--no-pairs]`",
            "(400 launches after the first 200 = about six training steps; cold-cache, serialised: compare SHARES, not absolutes)\n",
            "| kernel | launches | total us | share |", "|---|---:|---:|---:|"]
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
