@@ -229,6 +229,16 @@ class Engine:
             raise MatchaError("x must be [B, L]")
         x = x.to(self.dev, torch.int64).contiguous()
         B, L = x.shape
+        if B > 0:
+            # nn.Embedding in the reference raises on ids outside [0, N] (Modules.py:243-249); the kernels index the
+            # attribute / feature tables with them, so the public entry point checks (one small reduction + sync)
+            lo, hi = torch.aminmax(x)
+            lo, hi = int(lo), int(hi)
+            if lo < 0 or hi > self.desc.n_nodes:
+                raise MatchaError(f"node ids must lie in [0, {self.desc.n_nodes}] (0 = padding): got [{lo}, {hi}]")
+        if B == 0:      # empty batch: nothing to launch (an empty tensor has no device pointer to hand to the library)
+            return (torch.empty(0, 1, dtype=torch.float32, device=self.dev),
+                    torch.zeros(1, dtype=torch.float32, device=self.dev))
         self.prepare()
         if training and torch.is_grad_enabled():
             anchor = self._model().layer_norm1.weight
@@ -249,8 +259,10 @@ class Engine:
         self.ensure_bound()
         ids = ids.to(self.dev, torch.int64).contiguous().view(-1)
         T = ids.numel()
-        self.prepare()
         out = torch.empty(T, self.d, dtype=torch.float32, device=self.dev)
+        if T == 0:
+            return out
+        self.prepare()
         if training and self.desc.p_feature > 0:
             raise MatchaError("train-mode get_node_embeddings (feature dropout) is only defined inside forward()")
         ws = self._workspace(T, 1, False)

@@ -248,7 +248,7 @@ class Classifier(nn.Module):
         """x [b, L] int64 -> [b, L, d] (eval-mode encoder output; Modules.py:252-259)."""
         sz_b, len_seq = x.shape
         out = self._engine().node_embeddings(x.reshape(-1), training=self.training)
-        out = out.view(sz_b, len_seq, -1)
+        out = out.view(sz_b, len_seq, out.shape[-1])
         if return_recon:
             return out, torch.zeros(1, device=out.device)
         return out

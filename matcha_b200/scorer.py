@@ -76,6 +76,8 @@ class PairScorer:
         eng = self.engine
         if out is None:
             out = torch.empty(p_end - p_begin, dtype=torch.float32, device=eng.dev)
+        if p_end == p_begin:        # empty shard / min_distance beyond the chromosome
+            return out
         if eng.d != 64:
             return self._score_range_generic(lo, hi, min_dis, p_begin, p_end, sigmoid, out)
         if impl == "tc":
