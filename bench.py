@@ -369,6 +369,10 @@ def main():
     real_tokens = P * (1 + NEG_NUM) * float(real.sum()) / len(ds["positives"])
     alg["enc0_gather_gemm"] = ("hbm", real_tokens * (row_bytes + 512.0))
     alg["enc0_wgrad"] = ("hbm", real_tokens * (row_bytes + 512.0))
+    # reconstruction head (fused forward + gradient pass): every eligible token (real, outside the drawn chromosome) reads
+    # its 4 * n_r byte target row, its E row, and adds a dtE row; the chromosome is drawn uniformly (Modules.py:192)
+    n_chrom = len(ds["nums"])
+    alg["recon_pred_gemm"] = ("hbm", real_tokens * (1.0 - 1.0 / n_chrom) * (4.0 * ds["N"] / n_chrom + 512.0))
     top = max(prof.items(), key=lambda kv: kv[1][0])
     tot_ms = sum(v[0] for v in prof.values())
     name, (tms, calls, _) = top
@@ -410,7 +414,7 @@ def main():
     breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
         small = make_dataset(args.workload, kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
         r = cpu_reference_arm(small, args.cpu_baseline_steps, 3)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}

@@ -366,7 +366,7 @@ template <int L>
 __global__ void __launch_bounds__(kBThreads, 1)
 attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict__ wpairs, const float* __restrict__ bq,
                       const float* __restrict__ dd_in, const float* __restrict__ probs, float* __restrict__ dxhat_parts,
-                      float* __restrict__ part, float* __restrict__ dbq, float* __restrict__ db_dyn, int64_t T) {
+                      float* __restrict__ dW, float* __restrict__ dbq, float* __restrict__ db_dyn, int64_t T) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sX = smem + kBWBytes;
@@ -643,10 +643,12 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
       live_prev = live;
     }
     if (my_tiles > 0) drain_dxhat(my_tiles - 1, t_prev, live_prev);
-    // ---------------- weight-gradient slice of this CTA -> split-K partial ----------------
+    // ---------------- weight-gradient slice of this CTA: reduced over the token splits with 128-bit atomics ----------------
+    // (the S = 37 CTAs of a head pair finish within microseconds of each other; their 98 KB slices land in L2's atomic
+    // units instead of a partial buffer + a reduction launch.  dW was zeroed with the rest of the derived gradients.)
     mbar_wait(&done, 0);
     tc_fence_after();
-    {
+    if (my_tiles > 0) {
       const int f = q * 32 + lane;                 // TMEM lane = feature row of the piece pair
       const int hrow = (2 * hp + (f >> 6)) * kD + (f & 63);
 #pragma unroll 1
@@ -655,11 +657,11 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         tmem_ld32_issue(tlane + kColDW + g * 64 + hl * 32, v);
         tmem_ld_wait(v);
         const int row = ((g == 0) ? 2 * kH * kD : (g == 1 ? kH * kD : 0)) + hrow;
-        float* dst = part + ((int64_t)sp * kQKG + row) * kD + hl * 32;
+        float* dst = dW + (int64_t)row * kD + hl * 32;
 #pragma unroll
         for (int c = 0; c < 32; c += 4)
-          *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
-                                                            __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+          atomicAdd(reinterpret_cast<float4*>(dst + c), make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                                                    __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -670,20 +672,6 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
-}
-
-__global__ void attn_wgrad_reduce_kernel(const float* __restrict__ part, int splits, float* __restrict__ dW) {
-  const int64_t total = (int64_t)kQKG * kD / 4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int sp = 0; sp < splits; ++sp) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(part) + (int64_t)sp * total + i);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-    float4* d = reinterpret_cast<float4*>(dW) + i;
-    float4 cur = *d;
-    *d = make_float4(cur.x + s.x, cur.y + s.y, cur.z + s.z, cur.w + s.w);
-  }
 }
 
 template <typename K>
@@ -711,10 +699,9 @@ int launch_bwd_L(const uint8_t* xt, const uint8_t* wpairs, const float* bq, cons
   if (!once) { if (int rc = set_smem_attr_a(attn_fused_bwd_kernel<L>, kBSmem)) return rc; once = true; }
   const int64_t ntiles = num_atiles(T, L);
   const int S = (int)(ntiles < kSMs / 4 ? ntiles : kSMs / 4);
-  attn_fused_bwd_kernel<L><<<4 * S, kBThreads, kBSmem, s>>>(xt, wpairs, bq, dd, probs, dxhat_parts, part, dbq, db_dyn, T);
+  (void)part;       // split-K partial buffer of earlier builds: the slices are reduced with atomics now
+  attn_fused_bwd_kernel<L><<<4 * S, kBThreads, kBSmem, s>>>(xt, wpairs, bq, dd, probs, dxhat_parts, dW, dbq, db_dyn, T);
   MATCHA_CHECK_LAUNCH("attn_fused_bwd");
-  attn_wgrad_reduce_kernel<<<kSMs, 256, 0, s>>>(part, S, dW);
-  MATCHA_CHECK_LAUNCH("attn_wgrad_reduce");
   return MATCHA_OK;
 }
 

@@ -811,7 +811,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     // fused path: recompute + attention backward + data / weight gradients of the QKG projection in one kernel; the
     // per-head-pair dxhat partials live in the (otherwise unused) dQKG area
     dx_parts = 4;
-    if ((rc = PROF(P_ATTN_BWD, 2, launch_attn_fused_bwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wpairs),
+    if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_fused_bwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wpairs),
                                                         m->derived + l.bqkg, x, w.dU, w.probs, w.dQKG, w.tc_scratch,
                                                         DG + l.wqkg, DG + l.bqkg, DG + l.bdyn, B, L, dattn, chain ? 1 : 0, s)))) return rc;
   } else if (use_tiles(m, T)) {
