@@ -221,7 +221,7 @@ __global__ void prep_g_kernel(const matcha_model_desc m) {
     m.derived[l.bdyn_part + h * D + o] = acc;
   }
 }
-__global__ void prep_tables_kernel(const matcha_model_desc m) {
+__global__ void prep_bdyn_kernel(const matcha_model_desc m) {
   const int D = m.d;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {   // b_dyn = fc1.bias + sum_h (fc1_h Wv_h b_v), heads added in a fixed order
     const DerivedLayout l = derived_layout(D);
@@ -230,6 +230,10 @@ __global__ void prep_tables_kernel(const matcha_model_desc m) {
     m.derived[l.bdyn + c] = s;
     for (int h = 0; h < kH; ++h) m.derived[l.bqkg + 2 * kH * D + h * D + c] = 0.f;   // the G part of the folded bias is zero
   }
+}
+// grouped-contraction tables of the node encoder (pointers and leading dimensions only: no dependence on the other folds)
+__global__ void prep_tables_kernel(const matcha_model_desc m) {
+  const int D = m.d;
   const int c = threadIdx.x;
   if (c >= m.n_chrom) return;
   GemmGroup* t0 = const_cast<GemmGroup*>(table_ptr(m.derived, D, TAB_ENC0));
@@ -282,17 +286,25 @@ static int side_stream(SideStream** out) {
 }
 
 // matcha_prepare may be issued on a different stream than the passes that consume the derived weights (it depends on the
-// weights only, so the trainer runs it beside batch assembly): it records this event when its last kernel is queued,
-// and the encoder -- the first consumer in every pass -- waits for it AFTER the token bucketing, which needs no weights.
-static int prepare_event(cudaEvent_t* out) {
-  static cudaEvent_t g[16] = {};
+// weights only, so the trainer runs it beside batch assembly).  It records two events: PREP_ENCODER once everything the
+// node encoder reads is queued (grouped-contraction tables, pre-split encoder weights -- queued first), PREP_ALL at its
+// end.  A pass waits for the first one AFTER its weight-free token bucketing and for the second one only before the
+// attribute mix, so the attention / row-chain folds run beside the encoder and the reconstruction head.
+enum { PREP_ENCODER = 0, PREP_ALL = 1 };
+static int prepare_event(int which, cudaEvent_t* out) {
+  static cudaEvent_t g[16][2] = {};
   int dev = 0;
   if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
   if (dev < 0 || dev >= 16) { set_error("prepare_event: device index %d out of range", dev); return MATCHA_ERR_ARG; }
-  if (g[dev] == nullptr)
-    if (int rc = check_cuda(cudaEventCreateWithFlags(&g[dev], cudaEventDisableTiming), "cudaEventCreate")) return rc;
-  *out = g[dev];
+  if (g[dev][which] == nullptr)
+    if (int rc = check_cuda(cudaEventCreateWithFlags(&g[dev][which], cudaEventDisableTiming), "cudaEventCreate")) return rc;
+  *out = g[dev][which];
   return MATCHA_OK;
+}
+static int wait_prepared(int which, cudaStream_t s) {
+  cudaEvent_t ev;
+  if (int rc = prepare_event(which, &ev)) return rc;
+  return check_cuda(cudaStreamWaitEvent(s, ev, 0), "cudaStreamWaitEvent");
 }
 
 // derived-parameter gradients -> gradients of the reference's own parameters
@@ -404,7 +416,7 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
   };
   w.counts = (int32_t*)take(sizeof(int32_t) * (MATCHA_MAX_CHROM + 2));
   w.group_off = (int32_t*)take(sizeof(int32_t) * (MATCHA_MAX_CHROM + 2));
-  w.cursor = (int32_t*)take(sizeof(int32_t) * (MATCHA_MAX_CHROM + 2));
+  w.cursor = (int32_t*)take(sizeof(int32_t) * (int64_t)bucket_hist_ints());      // per-block histograms of the bucketing kernel
   w.perm = (int32_t*)take(sizeof(int32_t) * (T + 1));
   w.recon = (float*)take(sizeof(float) * 4);
   const int64_t row = sizeof(float) * T * D;
@@ -488,12 +500,8 @@ static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   const int64_t QKGm = 3 * (int64_t)kH * Dm;
   (void)QKGm;
   int rc;
-  if ((rc = PROF(P_BUCKET, 3, launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s)))) return rc;
-  {   // the derived weights of the most recent matcha_prepare (possibly queued on another stream)
-    cudaEvent_t ev;
-    if ((rc = prepare_event(&ev))) return rc;
-    if ((rc = check_cuda(cudaStreamWaitEvent(s, ev, 0), "cudaStreamWaitEvent"))) return rc;
-  }
+  if ((rc = PROF(P_BUCKET, 1, launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s)))) return rc;
+  if ((rc = wait_prepared(PREP_ENCODER, s))) return rc;     // the most recent matcha_prepare (possibly queued on another stream)
   if ((rc = check_cuda(cudaMemsetAsync(w.H0, 0, sizeof(float) * T * Dm, s), "memset H0"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * Dm, s), "memset E"))) return rc;
   if (use_enc_tc(m, T)) {    // both encoder layers in one tcgen05 kernel over the bucketed token list
@@ -525,6 +533,7 @@ static int run_mix_qkg(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   int rc;
   const float* P = m->params;
   const DerivedLayout l = derived_layout(m->d);
+  if ((rc = wait_prepared(PREP_ALL, s))) return rc;          // attention / row-chain folds of the most recent matcha_prepare
   if (fused_L > 0 && use_chain(m, T, fused_L))     // attribute mix + next_w + LayerNorm statistics + tiles in one kernel
     return PROF(P_MIX, 1, launch_chain_mix_fwd(w.E, x, m->attr_table, m->attr_dim, P + m->off_attr_w, P + m->off_attr_b,
                                                m->derived + l.wchain + CW_NEXT_K * (kChainWBytes / 4), P + m->off_next_b, nullptr,
@@ -639,12 +648,21 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   const DerivedLayout l = derived_layout(m->d);
   (void)l;
   prof_begin(P_PREP, s);
+  cudaEvent_t ev;
+  // (1) what the node encoder reads: queued first, so a pass can start its encoder while the rest is still folding
+  prep_tables_kernel<<<1, MATCHA_MAX_CHROM, 0, s>>>(*m);
+  MATCHA_CHECK_LAUNCH("prep_tables");
+  if (model_uses_csr(m) && (rc = launch_csr_prepare(m, l.total, s))) return rc;
+  if (enc_tc_eligible(m) && (rc = launch_enc_tc_prepare(m, l.total, s))) return rc;
+  if ((rc = prepare_event(PREP_ENCODER, &ev))) return rc;
+  if ((rc = check_cuda(cudaEventRecord(ev, s), "cudaEventRecord"))) return rc;
+  // (2) attention and row-chain folds
   prep_qk_kernel<<<3 * kH * m->d, m->d, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_qk");
   prep_g_kernel<<<(kH * m->d * m->d + 255) / 256, 256, 0, s>>>(*m);
   MATCHA_CHECK_LAUNCH("prep_g");
-  prep_tables_kernel<<<1, MATCHA_MAX_CHROM, 0, s>>>(*m);
-  MATCHA_CHECK_LAUNCH("prep_tables");
+  prep_bdyn_kernel<<<1, 128, 0, s>>>(*m);
+  MATCHA_CHECK_LAUNCH("prep_bdyn");
   if (m->d == kD) {      // pre-split bf16 hi | lo operand copies for the tcgen05 kernels (embed_dim 64 only)
     // (the K-major / MN-major copies of the whole W_qkg are only read by the decomposed pipeline: built there, on demand)
     if ((rc = launch_split_w_heads(m->derived + l.wqkg, m->derived + l.wheads, s))) return rc;
@@ -657,11 +675,8 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
                                  wc + CW_PFF1_MN * st, s))) return rc;
     }
   }
-  if (model_uses_csr(m) && (rc = launch_csr_prepare(m, l.total, s))) return rc;
-  if (enc_tc_eligible(m) && (rc = launch_enc_tc_prepare(m, l.total, s))) return rc;
   prof_end(P_PREP, 10, s);
-  cudaEvent_t ev;
-  if ((rc = prepare_event(&ev))) return rc;
+  if ((rc = prepare_event(PREP_ALL, &ev))) return rc;
   return check_cuda(cudaEventRecord(ev, s), "cudaEventRecord");
 }
 

@@ -95,42 +95,88 @@ __device__ __forceinline__ int chrom_of(const ChromMeta& cm, int64_t id) {
     if (id >= cm.start[c] && id < cm.end[c]) return c;
   return cm.n;               // ids outside every range behave like padding (zero encoder output)
 }
-__global__ void bucket_count_kernel(const int64_t* __restrict__ x, int64_t T, const ChromMeta cm, int32_t* counts) {
-  __shared__ int32_t h[MATCHA_MAX_CHROM + 1];
-  for (int i = threadIdx.x; i <= cm.n; i += blockDim.x) h[i] = 0;
-  __syncthreads();
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x)
-    atomicAdd(&h[chrom_of(cm, x[t])], 1);
-  __syncthreads();
-  for (int i = threadIdx.x; i <= cm.n; i += blockDim.x)
-    if (h[i]) atomicAdd(&counts[i], h[i]);
+// count + scan + scatter in ONE launch (was memset + two kernels, ~40 us of latency in front of every encoder pass).
+// Every block histograms its contiguous token slice in shared memory and publishes the histogram; after a grid-wide
+// rendezvous (all blocks are co-resident: grid <= one block per SM) thread c of every block derives, for chromosome c,
+// the group offset (totals of the chromosomes before it) plus the tokens that lower-numbered blocks place in it -- a
+// private, contention-free range -- and the block scatters its tokens with shared-memory atomics.  `arrive` must be zero
+// at launch (the launcher's memset); the spin is bounded: a scheduling surprise traps instead of hanging the GPU.
+// warp-aggregated shared-memory counter increment: lanes with the same bucket elect a leader that adds their count once;
+// returns this lane's slot (old value + rank among its peers), -1 for inactive lanes.  Called by all 32 lanes.
+__device__ __forceinline__ int32_t warp_agg_inc(int32_t* ctr, int c, bool valid, int lane) {
+  const unsigned active = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return -1;
+  const unsigned peers = __match_any_sync(active, c);
+  const int leader = __ffs(peers) - 1;
+  int32_t old = 0;
+  if (lane == leader) old = atomicAdd(&ctr[c], __popc(peers));
+  old = __shfl_sync(peers, old, leader);
+  return old + __popc(peers & ((1u << lane) - 1u));
 }
-// scan + scatter in one launch: every block derives the group offsets from the (complete) counts, histograms its own
-// contiguous token slice in shared memory, reserves one range per chromosome with a single global atomic, and places its
-// tokens with shared-memory atomics (82 k contended global atomics on ~23 cursors -> ~23 per block)
-__global__ void bucket_scatter_kernel(const int64_t* __restrict__ x, int64_t T, const ChromMeta cm, const int32_t* __restrict__ counts,
-                                      int32_t* __restrict__ group_off, int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
-  __shared__ int32_t h[MATCHA_MAX_CHROM + 1], base[MATCHA_MAX_CHROM + 1];
-  for (int i = threadIdx.x; i <= cm.n; i += blockDim.x) h[i] = 0;
+__global__ void __launch_bounds__(256) bucket_fused_kernel(const int64_t* __restrict__ x, int64_t T, const ChromMeta cm,
+                                                           int32_t* __restrict__ counts, int32_t* __restrict__ group_off,
+                                                           int32_t* __restrict__ perm, int32_t* __restrict__ hist,
+                                                           int32_t* __restrict__ arrive) {
+  __shared__ int32_t h[MATCHA_MAX_CHROM + 1], base[MATCHA_MAX_CHROM + 1], tot[MATCHA_MAX_CHROM + 1];
+  const int nb = cm.n + 1;                                   // buckets: chromosomes + the pad bucket
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) { h[i] = 0; tot[i] = 0; base[i] = 0; }
   __syncthreads();
   const int64_t per = (T + gridDim.x - 1) / gridDim.x;
   const int64_t t0 = (int64_t)blockIdx.x * per, t1 = (t0 + per < T) ? t0 + per : T;
-  for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) atomicAdd(&h[chrom_of(cm, x[t])], 1);
+  const int iters = (int)((t1 - t0 + blockDim.x - 1) / blockDim.x);      // block-uniform trip count (warp collectives inside)
+  // the bucket of each of this thread's tokens is kept for the scatter phase (slices are <= 8 tokens per thread except for
+  // very long batches, which recompute)
+  constexpr int kKeep = 8;
+  int8_t mine[kKeep];
+  for (int it = 0; it < iters; ++it) {
+    const int64_t t = t0 + (int64_t)it * blockDim.x + threadIdx.x;
+    const bool valid = t < t1;
+    const int c = valid ? chrom_of(cm, x[t]) : 0;
+    if (it < kKeep) mine[it] = (int8_t)c;
+    warp_agg_inc(h, c, valid, lane);
+  }
   __syncthreads();
-  if (threadIdx.x <= cm.n) {          // one thread per chromosome: the range reservations (global atomics with a return value)
-    const int c = threadIdx.x;        // go out in parallel instead of as a serial chain of ~23 round trips
-    int32_t acc = 0;
-    for (int cc = 0; cc < c; ++cc) acc += counts[cc];
-    if (blockIdx.x == 0) group_off[c] = acc;
-    if (c < cm.n) {
-      base[c] = h[c] ? acc + atomicAdd(&cursor[c], h[c]) : 0;       // cursor holds the per-chromosome fill (zeroed by the launcher)
-      h[c] = 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[(int64_t)blockIdx.x * nb + i] = h[i];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(arrive, 1);
+    unsigned spins = 0;
+    while (atomicAdd(arrive, 0) < (int)gridDim.x) {
+      if (++spins > (1u << 22)) __trap();
+      __nanosleep(100);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // totals per bucket and the tokens that lower-numbered blocks place in each bucket: all threads stream the published
+  // histograms (independent coalesced loads) into shared-memory sums
+  for (int i = threadIdx.x; i < (int)gridDim.x * nb; i += blockDim.x) {
+    const int32_t v = __ldcg(hist + i);
+    if (v != 0) {
+      const int bk = i / nb, c = i - bk * nb;
+      atomicAdd(&tot[c], v);
+      if (bk < (int)blockIdx.x) atomicAdd(&base[c], v);
     }
   }
   __syncthreads();
-  for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-    const int c = chrom_of(cm, x[t]);
-    if (c < cm.n) perm[base[c] + atomicAdd(&h[c], 1)] = (int32_t)t;
+  if (threadIdx.x < nb) {
+    const int c = threadIdx.x;
+    int32_t off = 0;
+    for (int cc = 0; cc < c; ++cc) off += tot[cc];
+    h[c] = base[c] + off;                                   // this block's first slot of bucket c
+    if (blockIdx.x == 0) { counts[c] = tot[c]; group_off[c] = off; }
+  }
+  __syncthreads();
+  for (int it = 0; it < iters; ++it) {
+    const int64_t t = t0 + (int64_t)it * blockDim.x + threadIdx.x;
+    const bool valid = t < t1;
+    int c = 0;
+    if (valid) c = it < kKeep ? (int)mine[it] : chrom_of(cm, x[t]);
+    const bool real = valid && c < cm.n;                    // pads are counted, not listed
+    const int32_t slot = warp_agg_inc(h, c, real, lane);
+    if (real) perm[slot] = (int32_t)t;
   }
 }
 __global__ void active_flags_kernel(const int32_t* counts, int n_chrom, int rchrom, int64_t T, int32_t* active) {
@@ -601,24 +647,18 @@ __global__ void iota_i64_kernel(int64_t* out, int64_t n) {
 // ==========================================================================================
 // launchers
 // ==========================================================================================
+int bucket_hist_ints() { return kSMs * (MATCHA_MAX_CHROM + 1); }
+// counts [n + 1] (+ one spare int at index MATCHA_MAX_CHROM + 1: the rendezvous counter), group_off [n + 1], perm [T],
+// hist: bucket_hist_ints() ints of scratch
 int launch_bucket(const int64_t* x, int64_t T, const ChromMeta& cm, int32_t* counts, int32_t* group_off,
-                  int32_t* cursor, int32_t* perm, cudaStream_t s) {
-  // counts and cursor start at zero; when they sit in one small span of the workspace (group_off between them is rewritten
-  // by the scatter kernel anyway) a single memset covers both
-  const ptrdiff_t span = reinterpret_cast<char*>(cursor + cm.n + 1) - reinterpret_cast<char*>(counts);
-  if (cursor > counts && group_off > counts && group_off < cursor && span <= 4096) {
-    if (int rc = check_cuda(cudaMemsetAsync(counts, 0, (size_t)span, s), "memset counts..cursor")) return rc;
-  } else {
-    if (int rc = check_cuda(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (cm.n + 1), s), "memset counts")) return rc;
-    if (int rc = check_cuda(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (cm.n + 1), s), "memset cursor")) return rc;
-  }
+                  int32_t* hist, int32_t* perm, cudaStream_t s) {
+  int32_t* arrive = counts + MATCHA_MAX_CHROM + 1;
+  if (int rc = check_cuda(cudaMemsetAsync(arrive, 0, sizeof(int32_t), s), "memset bucket rendezvous")) return rc;
   int blocks = (int)((T + 1023) / 1024);
   if (blocks < 1) blocks = 1;
-  if (blocks > kSMs * 4) blocks = kSMs * 4;
-  bucket_count_kernel<<<blocks, 256, 0, s>>>(x, T, cm, counts);
-  MATCHA_CHECK_LAUNCH("bucket_count");
-  bucket_scatter_kernel<<<blocks, 256, 0, s>>>(x, T, cm, counts, group_off, cursor, perm);
-  MATCHA_CHECK_LAUNCH("bucket_scatter");
+  if (blocks > kSMs) blocks = kSMs;            // co-resident by construction: the kernel holds a grid-wide rendezvous
+  bucket_fused_kernel<<<blocks, 256, 0, s>>>(x, T, cm, counts, group_off, perm, hist, arrive);
+  MATCHA_CHECK_LAUNCH("bucket_fused");
   return MATCHA_OK;
 }
 

@@ -36,9 +36,11 @@ struct ChromMeta {
   int64_t end[MATCHA_MAX_CHROM];
 };
 
-// counts[0..C-1] tokens per chromosome, counts[C] = pads; group_off[C+1]; perm lists token indices by chromosome
+// counts[0..C-1] tokens per chromosome, counts[C] = pads (counts holds MATCHA_MAX_CHROM + 2 ints: the last one is the
+// kernel's rendezvous counter); group_off[C+1]; perm lists token indices by chromosome; hist: bucket_hist_ints() ints
+int bucket_hist_ints();
 int launch_bucket(const int64_t* x, int64_t T, const ChromMeta& cm, int32_t* counts, int32_t* group_off,
-                  int32_t* cursor, int32_t* perm, cudaStream_t s);
+                  int32_t* hist, int32_t* perm, cudaStream_t s);
 
 // xhat_tiles (optional): also emit the pre-split tiles (num_token_tiles(T) * kXTileBytes bytes, tail rows zeroed)
 int launch_ln_fwd(int d, const float* X, float* xhat, float* rstd, int64_t T, uint8_t* xhat_tiles, cudaStream_t s);
