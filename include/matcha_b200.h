@@ -163,6 +163,24 @@ int matcha_adamw(float* params, const float* grads, float* exp_avg, float* exp_a
                  float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * k-mer enumeration + counting — generate_kmers.py:8-69 (build_dict) and :86-141: the producer of
+ * all_<k>_counter.npy / all_<k>_freq_counter.npy.
+ *   members / offsets   dev int64 CSR of the clusters (unique ascending node ids per cluster, process.py:72-78)
+ *   work_prefix         dev int64 [n_clusters + 1]: prefix sums of C(n_c, k) over the clusters with
+ *                       k <= n_c <= max_cluster_size (0 work for the others, generate_kmers.py:88-91); total_work = last entry
+ *   table               capacity (power of two) slots of 16 bytes, zero-filled by the caller; counts dev int32 [capacity],
+ *                       zero-filled; status dev int32 [1], zero-filled (1 table full, 2 bad prefix / cluster > 64, 3 id range)
+ * A k-subset is counted iff every adjacent gap of its sorted ids exceeds min_distance (:16-17,:23-32).
+ * matcha_kmer_collect appends the k-mers seen >= min_freq times (:40) in arbitrary order (the reference's own
+ * order is process-pool completion order); n_out may exceed max_out, in which case nothing past max_out was written.
+ * --------------------------------------------------------------------------------------------- */
+int matcha_kmer_count(const int64_t* members, const int64_t* offsets, int64_t n_clusters, const int64_t* work_prefix,
+                      int64_t total_work, int32_t k, int32_t min_distance, void* table, int64_t capacity,
+                      int32_t* counts, int32_t* status, void* stream);
+int matcha_kmer_collect(const void* table, int64_t capacity, const int32_t* counts, int32_t k, int32_t min_freq,
+                        int64_t* rows, int32_t* freq, int64_t max_out, uint64_t* n_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Positive k-mer hash set + negative sampler — main.py:361-459 (generate_negative), :345-346
  * (neighbor_check), utils.py:75-97 (build_hash; exact set instead of a Bloom filter).
  * Table: `capacity` (power of two) slots of 16 bytes PLUS one trailing status slot, i.e.

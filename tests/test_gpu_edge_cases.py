@@ -157,3 +157,46 @@ def test_score_tuples_ragged_batches(golden, model):
             x[i, :len(s)] = s
         want, _ = O.forward(oracle_from_model(model), torch.from_numpy(x))
         np.testing.assert_allclose(o.cpu().numpy(), want.numpy(), rtol=1e-4, atol=5e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# k-mer enumeration + counting (generate_kmers.py) -- bit-exact vs the reference's own output and vs the oracle
+# ------------------------------------------------------------------------------------------
+def test_kmer_counting_matches_reference_output_bit_exact():
+    import os
+    from conftest import GOLDEN
+    from matcha_b200.kmers import count_kmers
+    g = np.load(os.path.join(GOLDEN, "kmer_small.npz"))
+    for ci, (k, min_dis, max_size, min_freq) in enumerate(g["cases"]):
+        rows, freq = count_kmers(g["members"], g["offsets"], int(k), int(min_dis), int(max_size), int(min_freq))
+        want_rows, want_freq = g[f"rows/{ci}"], g[f"freq/{ci}"]
+        assert rows.shape == want_rows.shape, (ci, rows.shape, want_rows.shape)
+        assert (rows == want_rows).all() and (freq == want_freq).all(), ci
+
+
+def test_kmer_counting_matches_oracle_and_edges():
+    from matcha_b200 import MatchaError
+    from matcha_b200.kmers import clusters_to_csr, count_kmers
+    from oracle import kmer_oracle as KO
+    rng = np.random.default_rng(12)
+    clusters = []
+    for _ in range(3000):
+        size = int(min(40, 1 + rng.geometric(0.2)))                      # sizes 2..40: some above max_cluster_size, some of one node
+        a = int(rng.integers(1, 5000))
+        clusters.append(sorted(set(int(np.clip(a + rng.integers(-15, 16), 1, 60000)) for _ in range(size))))
+    members, offsets = clusters_to_csr(clusters)
+    for (k, min_dis, max_size, min_freq) in [(2, 0, 25, 2), (3, 1, 25, 2), (5, 0, 14, 1), (6, 0, 10, 1)]:
+        rows, freq = count_kmers(members, offsets, k, min_dis, max_size, min_freq)
+        want_rows, want_freq = KO.count_kmers(clusters, k, min_dis, max_size, min_freq)
+        assert rows.shape == want_rows.shape and (rows == want_rows).all() and (freq == want_freq).all(), (k, min_dis)
+    # nothing eligible / nothing frequent enough -> empty results of the right shape
+    r, f = count_kmers(*clusters_to_csr([[1, 2], [3, 4]]), 3)
+    assert r.shape == (0, 3) and f.shape == (0,)
+    r, f = count_kmers(*clusters_to_csr([[1, 2, 3], [4, 5, 6]]), 3, min_freq_cutoff=2)
+    assert r.shape == (0, 3)
+    r, f = count_kmers(*clusters_to_csr([[1, 2, 3], [1, 2, 3], [1, 2, 9]]), 2, min_freq_cutoff=2)
+    assert r.tolist() == [[1, 2], [1, 3], [2, 3]] and f.tolist() == [3, 2, 2]
+    with pytest.raises(MatchaError):                                     # a table too small for the distinct k-mers reports it
+        count_kmers(members, offsets, 3, capacity=64)
+    with pytest.raises(MatchaError):
+        count_kmers(*clusters_to_csr([[1, 2, 1 << 21]]), 2, min_freq_cutoff=1)

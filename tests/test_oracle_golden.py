@@ -140,3 +140,28 @@ def test_d128_gradients_match_reference(golden128):
             assert abs(float(g.double().norm()) - ref) <= 2e-4 * ref + 1e-9, k
             checked += 1
     assert checked == len(live_ref)
+
+
+# ------------------------------------------------------------------------------------------
+# k-mer enumeration / counting oracle vs the unmodified reference's build_dict
+# ------------------------------------------------------------------------------------------
+def test_kmer_oracle_matches_reference_build_dict():
+    import os
+
+    import numpy as np
+    from conftest import GOLDEN
+    from oracle import kmer_oracle as KO
+    g = np.load(os.path.join(GOLDEN, "kmer_small.npz"))
+    members, offsets = g["members"], g["offsets"]
+    clusters = [members[offsets[i]:offsets[i + 1]] for i in range(len(offsets) - 1)]
+    assert len(g["cases"]) == 7
+    for ci, (k, min_dis, max_size, min_freq) in enumerate(g["cases"]):
+        rows, freq = KO.count_kmers(clusters, int(k), int(min_dis), int(max_size), int(min_freq))
+        assert rows.shape == g[f"rows/{ci}"].shape and (rows == g[f"rows/{ci}"]).all(), (k, min_dis)
+        assert (freq == g[f"freq/{ci}"]).all()
+        # domain facts: rows ascending with every gap > min_distance; frequencies respect the cutoff
+        assert (np.diff(rows, axis=1) > min_dis).all() and (freq >= min_freq).all()
+    # enumeration work the kernel has to cover
+    sizes = np.diff(offsets)
+    assert KO.n_subsets(sizes, 3, 25).sum() == sum(len(list(__import__("itertools").combinations(range(int(n)), 3)))
+                                                   for n in sizes if 3 <= n <= 25)
