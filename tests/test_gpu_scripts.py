@@ -85,3 +85,29 @@ def test_denoise_and_predict_multiway(workdir):
     with torch.no_grad():
         want = torch.sigmoid(model(torch.from_numpy(x).cuda())).cpu().numpy().reshape(-1)
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_generate_kmers_script_matches_the_oracle(tmp_path):
+    """scripts/generate_kmers.py on an edge_list.npy written as process.py:87 writes it (object array of lists)."""
+    from oracle import kmer_oracle as KO
+    rng = np.random.default_rng(4)
+    clusters = []
+    for _ in range(1500):
+        size = int(min(28, 2 + rng.geometric(0.3)))
+        a = int(rng.integers(1, 600))
+        clusters.append(sorted(set(int(np.clip(a + rng.integers(-10, 11), 1, 700)) for _ in range(size))))
+    code, temp = tmp_path / "Code", tmp_path / "Temp"
+    code.mkdir(); temp.mkdir()
+    arr = np.empty(len(clusters), dtype=object)
+    for i, c in enumerate(clusters):
+        arr[i] = c
+    np.save(temp / "edge_list.npy", arr, allow_pickle=True)
+    cfg = {"temp_dir": "../Temp", "max_cluster_size": 25, "k-mer_size": [2, 3, 4], "min_distance": 1, "min_freq_cutoff": 2}
+    json.dump(cfg, open(code / "config.JSON", "w"))
+    out = _run("generate_kmers.py", str(code))
+    assert "Quick summarize" in out
+    for k in (2, 3, 4):
+        rows = np.load(temp / ("all_%d_counter.npy" % k))
+        freq = np.load(temp / ("all_%d_freq_counter.npy" % k))
+        want_rows, want_freq = KO.count_kmers(clusters, k, 1, 25, 2)
+        assert rows.shape == want_rows.shape and (rows == want_rows).all() and (freq == want_freq).all(), k
