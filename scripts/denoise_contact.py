@@ -19,21 +19,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import Modules  # noqa: F401,E402  (needed by torch.load of the whole-module pickle)
 from utils import get_config  # noqa: E402
 
+from matcha_b200.denoise import denoise_matrix  # noqa: E402
 from matcha_b200.parallel import init_from_env  # noqa: E402
 from matcha_b200.scorer import PairScorer, pair_count, pair_index_to_ij  # noqa: E402
-
-
-def fill_symmetric(n, ii, jj, vals):
-    """proba2matrix (denoise_contact.py:31-61) for pairs: m[i, j] += v; m = m + m.T (the diagonal doubles)."""
-    m = np.zeros((n, n), dtype="float32")
-    np.add.at(m, (ii, jj), vals)
-    return m + m.T
-
-
-def sqrt_coverage_normalise(m):
-    c1 = np.sqrt(np.mean(m, axis=-1, keepdims=True))
-    c2 = np.sqrt(np.mean(m, axis=0, keepdims=True))
-    return m / (c1 + 1e-15) / (c2 + 1e-15)
 
 
 def main():
@@ -58,14 +46,7 @@ def main():
         ii, jj = pair_index_to_ij(np.arange(total), lo, hi, min_dis)
         ii, jj = ii - lo, jj - lo
         weight = origin[ii + lo - 1, jj + lo - 1]                                         # :160
-        my_proba = sqrt_coverage_normalise(fill_symmetric(n, ii, jj, proba))              # :162-166
-        origin_part = fill_symmetric(n, ii, jj, weight)
-        gap1, gap2 = origin_part.sum(-1) == 0, origin_part.sum(0) == 0
-        origin_part = sqrt_coverage_normalise(origin_part)
-        my = sqrt_coverage_normalise(np.maximum(my_proba * origin_part, my_proba))        # :176-181
-        my[gap1, :] = 0.0
-        my[:, gap2] = 0.0
-        my = transformer.fit_transform(my.reshape((-1, 1))).reshape((n, -1))              # :189
+        my = denoise_matrix(n, ii, jj, proba, weight, transformer)                        # :162-189
         np.save("../%s_denoise.npy" % chrom_name[i], my.astype("float32"))
         bin1.append(ii + lo - 1); bin2.append(jj + lo - 1); balanced.append(my[ii, jj])   # :152-153,205
         print("%s: %d pairs scored" % (chrom_name[i], total))

@@ -258,3 +258,31 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["config"]["workload"].startswith("cfg2") and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_denoise_postprocessing_matches_the_reference_script():
+    """matcha_b200.denoise (the numpy tail of denoise_contact.py:31-61,160-189) against matrices and pixel values produced
+    by EXECUTING the reference's own loop (oracle/make_denoise_golden.py): same pair order (generate_pair_wise), same
+    0-based global bin ids, same denoised matrix `my` and `balanced` values, min_distance 0 and 2, chromosomes with gaps."""
+    from sklearn.preprocessing import QuantileTransformer
+    from matcha_b200.denoise import denoise_matrix
+    from matcha_b200.scorer import pair_index_to_ij
+    g = np.load(os.path.join(ROOT, "tests", "golden", "denoise_small.npz"))
+    cr, origin = g["chrom_range"], g["origin"]
+    for ci in range(2):
+        min_dis = int(g[f"min_dis/{ci}"])
+        for c, (lo, hi) in enumerate(cr):
+            lo, hi = int(lo), int(hi)
+            n = hi - lo
+            logits = g[f"logits/{ci}/{c}"]
+            total = len(logits)
+            full = n - min_dis
+            assert total == full * (full + 1) // 2                                    # == matcha_pair_count(lo, hi, min_dis)
+            ii, jj = pair_index_to_ij(np.arange(total), lo, hi, min_dis)
+            assert (ii - 1 == g[f"bin1/{ci}/{c}"]).all() and (jj - 1 == g[f"bin2/{ci}/{c}"]).all()
+            proba = torch.sigmoid(torch.from_numpy(logits)).numpy()                   # denoise_contact.py:155
+            weight = origin[ii - 1, jj - 1]                                           # :160
+            tr = QuantileTransformer(n_quantiles=1000, output_distribution="uniform")
+            my = denoise_matrix(n, ii - lo, jj - lo, proba, weight, tr)
+            np.testing.assert_allclose(my, g[f"my/{ci}/{c}"], rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(my[ii - lo, jj - lo], g[f"balanced/{ci}/{c}"], rtol=1e-6, atol=1e-7)
