@@ -1,12 +1,12 @@
 """Stand-alone timing / agreement check of the fused kernels against the decomposed pipeline (own process):
-    python tests/fused_check.py [B] [L]"""
+    python scripts/dev/fused_check.py [B] [L]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import model_from_golden  # noqa: E402

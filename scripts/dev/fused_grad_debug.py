@@ -1,12 +1,12 @@
 """Per-parameter gradient error of the fused attention kernels vs the decomposed pipeline (debug aid):
-    python tests/fused_grad_debug.py [L] [B] [p_drop_on]"""
+    python scripts/dev/fused_grad_debug.py [L] [B] [p_drop_on]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import model_from_golden  # noqa: E402

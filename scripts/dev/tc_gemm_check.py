@@ -1,11 +1,11 @@
 """Stand-alone check of the tcgen05 contraction kernels against fp64 torch (run in its own process so a
-trap cannot poison other tests):  python tests/tc_gemm_check.py"""
+trap cannot poison other tests):  python scripts/dev/tc_gemm_check.py"""
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from matcha_b200 import _lib as L  # noqa: E402
 
 
