@@ -48,3 +48,29 @@ def oracle_from_model(model):
 def step_seed(eng):
     """The dropout seed the engine used for its most recent forward (see Engine.next_seed)."""
     return (eng.seed_base * 0x9E3779B97F4A7C15 + eng.tape_id * 0xD1B54A32D192ED03) & ((1 << 64) - 1)
+
+
+def tc_gemm_rel_err(form, M, N, K, impl, bias=False, seed=0, v2=True):
+    """matcha_gemm (form 0: A.B^T, 1: A.B, 2: A^T.B) against fp64 torch: max abs error / max |ref|."""
+    from matcha_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    if form == 0:
+        A, B = torch.randn(M, K, device="cuda", generator=g), torch.randn(N, K, device="cuda", generator=g)
+        ref = A.double() @ B.double().t()
+    elif form == 1:
+        A, B = torch.randn(M, K, device="cuda", generator=g), torch.randn(K, N, device="cuda", generator=g)
+        ref = A.double() @ B.double()
+    else:
+        A, B = torch.randn(K, M, device="cuda", generator=g), torch.randn(K, N, device="cuda", generator=g)
+        ref = A.double().t() @ B.double()
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    if b is not None:
+        ref = ref + b.double()
+    Cm = torch.zeros(M, N, device="cuda")
+    ns = lib.matcha_gemm_scratch_floats(M) if form == 2 else (N * 64 if (form == 0 and v2) else 0)
+    scratch = torch.empty(max(ns, 1), device="cuda")
+    L.check(lib.matcha_gemm(form, impl, A.data_ptr(), B.data_ptr(), Cm.data_ptr(), L.ptr(b), M, N, K, A.stride(0),
+                            B.stride(0), N, scratch.data_ptr(), ns, L.stream_ptr()), "matcha_gemm")
+    torch.cuda.synchronize()
+    return (Cm.double() - ref).abs().max().item() / ref.abs().max().item()

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import model_from_golden, oracle_from_model, step_seed
+from helpers import model_from_golden, oracle_from_model, step_seed, tc_gemm_rel_err
 from oracle import hypersagnn_oracle as O
 from oracle import sampler_oracle as SO
 
@@ -60,8 +60,7 @@ def test_gemm_simt_matches_torch(form, M, N, K):
                                         (2, 1536, 64, 3000), (2, 512, 64, 20000)])
 def test_gemm_tcgen05_matches_fp64(form, M, N, K):
     """tcgen05 path (bf16 hi/lo split x3, fp32 TMEM accumulator): ~2^-16 relative error per product."""
-    from tc_gemm_check import run
-    assert run(form, M, N, K, impl=1, bias=(form == 0)) < 3e-5
+    assert tc_gemm_rel_err(form, M, N, K, impl=1, bias=(form == 0)) < 3e-5
 
 
 def test_pipeline_agrees_between_simt_and_tcgen05(golden, model):
