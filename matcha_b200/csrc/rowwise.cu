@@ -2,6 +2,7 @@
 // Layout rule: one HALF-WARP owns one token row (64 floats = 16 lanes x float4, one coalesced 256 B
 // access) or one hyperedge (its L <= 8 rows in turn); row reductions are 4 xor-shuffles.
 #include <cuda_bf16.h>
+#include <cooperative_groups.h>
 
 #include "rowwise.cuh"
 
@@ -97,10 +98,11 @@ __device__ __forceinline__ int chrom_of(const ChromMeta& cm, int64_t id) {
 }
 // count + scan + scatter in ONE launch (was memset + two kernels, ~40 us of latency in front of every encoder pass).
 // Every block histograms its contiguous token slice in shared memory and publishes the histogram; after a grid-wide
-// rendezvous (all blocks are co-resident: grid <= one block per SM) thread c of every block derives, for chromosome c,
-// the group offset (totals of the chromosomes before it) plus the tokens that lower-numbered blocks place in it -- a
-// private, contention-free range -- and the block scatters its tokens with shared-memory atomics.  `arrive` must be zero
-// at launch (the launcher's memset); the spin is bounded: a scheduling surprise traps instead of hanging the GPU.
+// barrier thread c of every block derives, for chromosome c, the group offset (totals of the chromosomes before it) plus
+// the tokens that lower-numbered blocks place in it -- a private, contention-free range -- and the block scatters its
+// tokens with shared-memory atomics.  The barrier is cooperative_groups' grid.sync() under cudaLaunchCooperativeKernel:
+// the runtime guarantees co-residency of the whole grid (or fails the launch with an error code) whatever else runs on
+// other streams, under MPS / MIG, or on a part with fewer SMs -- no hand-rolled spin, no trap.
 // warp-aggregated shared-memory counter increment: lanes with the same bucket elect a leader that adds their count once;
 // returns this lane's slot (old value + rank among its peers), -1 for inactive lanes.  Called by all 32 lanes.
 __device__ __forceinline__ int32_t warp_agg_inc(int32_t* ctr, int c, bool valid, int lane) {
@@ -115,8 +117,7 @@ __device__ __forceinline__ int32_t warp_agg_inc(int32_t* ctr, int c, bool valid,
 }
 __global__ void __launch_bounds__(256) bucket_fused_kernel(const int64_t* __restrict__ x, int64_t T, const ChromMeta cm,
                                                            int32_t* __restrict__ counts, int32_t* __restrict__ group_off,
-                                                           int32_t* __restrict__ perm, int32_t* __restrict__ hist,
-                                                           int32_t* __restrict__ arrive) {
+                                                           int32_t* __restrict__ perm, int32_t* __restrict__ hist) {
   __shared__ int32_t h[MATCHA_MAX_CHROM + 1], base[MATCHA_MAX_CHROM + 1], tot[MATCHA_MAX_CHROM + 1];
   const int nb = cm.n + 1;                                   // buckets: chromosomes + the pad bucket
   const int lane = threadIdx.x & 31;
@@ -138,18 +139,7 @@ __global__ void __launch_bounds__(256) bucket_fused_kernel(const int64_t* __rest
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[(int64_t)blockIdx.x * nb + i] = h[i];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    atomicAdd(arrive, 1);
-    unsigned spins = 0;
-    while (atomicAdd(arrive, 0) < (int)gridDim.x) {
-      if (++spins > (1u << 22)) __trap();
-      __nanosleep(100);
-    }
-    __threadfence();
-  }
-  __syncthreads();
+  cooperative_groups::this_grid().sync();
   // totals per bucket and the tokens that lower-numbered blocks place in each bucket: all threads stream the published
   // histograms (independent coalesced loads) into shared-memory sums
   for (int i = threadIdx.x; i < (int)gridDim.x * nb; i += blockDim.x) {
@@ -648,17 +638,32 @@ __global__ void iota_i64_kernel(int64_t* out, int64_t n) {
 // launchers
 // ==========================================================================================
 int bucket_hist_ints() { return kSMs * (MATCHA_MAX_CHROM + 1); }
-// counts [n + 1] (+ one spare int at index MATCHA_MAX_CHROM + 1: the rendezvous counter), group_off [n + 1], perm [T],
-// hist: bucket_hist_ints() ints of scratch
+// counts [n + 1], group_off [n + 1], perm [T], hist: bucket_hist_ints() ints of scratch
 int launch_bucket(const int64_t* x, int64_t T, const ChromMeta& cm, int32_t* counts, int32_t* group_off,
                   int32_t* hist, int32_t* perm, cudaStream_t s) {
-  int32_t* arrive = counts + MATCHA_MAX_CHROM + 1;
-  if (int rc = check_cuda(cudaMemsetAsync(arrive, 0, sizeof(int32_t), s), "memset bucket rendezvous")) return rc;
+  // grid limit of the cooperative launch: what the device can keep resident at once (queried, not assumed), capped by
+  // the histogram scratch (one row per block)
+  static int max_blocks[16] = {};
+  int dev = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (dev < 0 || dev >= 16) { set_error("launch_bucket: device index %d out of range", dev); return MATCHA_ERR_ARG; }
+  if (max_blocks[dev] == 0) {
+    int per_sm = 0, sms = 0, coop = 0;
+    if (int rc = check_cuda(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev), "cudaDeviceGetAttribute")) return rc;
+    if (!coop) { set_error("launch_bucket: device %d does not support cooperative launches", dev); return MATCHA_ERR_UNSUPPORTED; }
+    if (int rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_fused_kernel, 256, 0), "occupancy")) return rc;
+    if (int rc = check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
+    int lim = per_sm * sms;
+    if (lim < 1) { set_error("launch_bucket: the bucketing kernel does not fit on an SM"); return MATCHA_ERR_CUDA; }
+    max_blocks[dev] = lim < kSMs ? lim : kSMs;
+  }
   int blocks = (int)((T + 1023) / 1024);
   if (blocks < 1) blocks = 1;
-  if (blocks > kSMs) blocks = kSMs;            // co-resident by construction: the kernel holds a grid-wide rendezvous
-  bucket_fused_kernel<<<blocks, 256, 0, s>>>(x, T, cm, counts, group_off, perm, hist, arrive);
-  MATCHA_CHECK_LAUNCH("bucket_fused");
+  if (blocks > max_blocks[dev]) blocks = max_blocks[dev];
+  ChromMeta cm_arg = cm;
+  void* args[] = {(void*)&x, (void*)&T, (void*)&cm_arg, (void*)&counts, (void*)&group_off, (void*)&perm, (void*)&hist};
+  if (int rc = check_cuda(cudaLaunchCooperativeKernel((const void*)bucket_fused_kernel, dim3(blocks), dim3(256), args, 0, s),
+                          "cudaLaunchCooperativeKernel(bucket_fused)")) return rc;
   return MATCHA_OK;
 }
 
