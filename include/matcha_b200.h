@@ -222,6 +222,61 @@ int matcha_pair_tc_score_range(const void* workspace, int64_t lo, int64_t hi, in
                                int32_t apply_sigmoid, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Validation metrics on the device — utils.py:32-72 (roc_auc_cuda: sklearn roc_auc_score / average_precision_score
+ * over all samples and per hyperedge size; accuracy), called from main.py:189-195,246-252.  SURVEY.md section 8f rank 3.
+ *   score, label  dev fp32 [n] (label > 0.5 = positive; accuracy compares score >= 0.5 with label >= 0.5)
+ *   cls           dev int32 [n] class id (hyperedge size) in [0, n_classes), or NULL with n_classes = 0
+ *   out           dev fp64 [(1 + n_classes) * 4]: row 0 = all samples, row 1 + c = class c;
+ *                 columns {AUROC, AUPR, accuracy, count}; AUROC / AUPR are NaN where a row has one label only
+ * Ties share one threshold exactly as sklearn's distinct-value curves do.
+ * --------------------------------------------------------------------------------------------- */
+int64_t matcha_metrics_workspace_bytes(int64_t n);
+int matcha_binary_metrics(const float* score, const float* label, const int32_t* cls, int64_t n, int32_t n_classes,
+                          double* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Denoise post-processing — denoise_contact.py:31-61 (proba2matrix) and :160-192 (per-chromosome tail).  SURVEY 8f rank 2.
+ *   proba      dev fp32 [matcha_pair_count] sigmoid scores of ONE chromosome of n bins, generate_pair_wise order
+ *              (what matcha_pair_tc_score_range(apply_sigmoid = 1) writes)
+ *   origin     dev fp32: observed contacts of the same bins, element (i, j) at origin[i * origin_ld + j]
+ *              (a view into intra_adj.npy; only j >= i + min_dis is read, as :160 does)
+ *   my         dev fp32 [n, n]: the reference's `my` before the quantile transform (:177-185)
+ * matcha_quantile_uniform applies sklearn QuantileTransformer(output_distribution="uniform")._transform_col in place
+ * given the fitted table (quantiles, references: dev fp64 [nq]); matcha_pair_gather reads my at the scored pairs
+ * (the `balanced` pixel column, :205); matcha_gather_f32 fetches the fit's subsample.
+ * --------------------------------------------------------------------------------------------- */
+int64_t matcha_denoise_workspace_bytes(int64_t n);
+int matcha_denoise_matrix(const float* proba, const float* origin, int64_t origin_ld, int64_t n, int32_t min_dis, float* my,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int matcha_quantile_uniform(float* x, int64_t n, const double* quantiles, const double* references, int32_t nq, void* stream);
+int matcha_gather_f32(const float* src, const int64_t* idx, int64_t n, float* out, void* stream);
+int matcha_pair_gather(const float* my, int64_t n, int32_t min_dis, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feature construction — SURVEY.md section 8f rank 4.
+ *   matcha_corrcoef              np.corrcoef(A) with NaN -> 0 of one chromosome's intra-contact block (main.py:572-577):
+ *                                A dev fp32 [n, lda] (rows = variables), out dev fp32 [n, ldo]; centred and contracted in
+ *                                float64 like numpy; workspace matcha_corrcoef_workspace_bytes(n) (an n x n fp64 matrix)
+ *   matcha_zscore_positive_rows  Modules.py:147-152 in place on dev fp32 [nrows, ld]: the positive entries of each row are
+ *                                z-scored among themselves (ddof 0, fp32 like scipy.stats.mstats.zscore), NaN -> 0
+ *   matcha_adj_from_pixels       process.py:148-170: cooler pixels (bin1, bin2 dev int64, count dev fp64, NaN skipped) ->
+ *                                intra / inter dev fp64 [N, N] (zero-filled by the caller); cool2node dev int64
+ *                                [n_cool_bins] holds the 1-based node id of a cooler bin or <= 0; node2chrom dev int32 [N + 1]
+ *   matcha_adj_from_clusters     process.py:90-105: CSR clusters (1-based node ids) -> adj dev fp64 [N, N] += 1 for every
+ *                                ordered pair i != j of a cluster
+ * --------------------------------------------------------------------------------------------- */
+int64_t matcha_corrcoef_workspace_bytes(int64_t n);
+int matcha_corrcoef(const float* A, int64_t lda, int64_t n, float* out, int64_t ldo, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+int matcha_zscore_positive_rows(float* M, int64_t ld, int64_t nrows, int64_t ncols, void* stream);
+int matcha_adj_from_pixels(const int64_t* bin1, const int64_t* bin2, const double* count, int64_t n_pixels,
+                           const int64_t* cool2node, int64_t n_cool_bins, const int32_t* node2chrom, int64_t n_nodes,
+                           double* intra, double* inter, void* stream);
+int matcha_adj_from_clusters(const int64_t* members, const int64_t* offsets, int64_t n_clusters, int64_t n_nodes, double* adj,
+                             void* stream);
+int matcha_f64_to_f32(const double* in, float* out, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Building blocks exposed for tests (dense fp32 contractions used by the passes above).
  *   form 0: C[M,N]  = A[M,K] . B[N,K]^T (+bias)      form 1: C[M,N] = A[M,K] . B[K,N]
  *   form 2: C[M,N] += A[K,M]^T . B[K,N]

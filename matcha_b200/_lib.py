@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmatcha_b200.so")
-SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu", "recon_tc.cu", "enc_tc.cu", "kmers.cu"]
+SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu", "recon_tc.cu", "enc_tc.cu", "kmers.cu", "metrics.cu", "denoise.cu", "features.cu"]
 NVCC_COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                       "-Xcompiler", "-fPIC"]
 NVCC_LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
@@ -133,6 +133,19 @@ SYMBOLS = {
     "matcha_pair_tc_score_range": (C.c_int, [_P, _I64, _I64, _I32, _I64, _I64, _I32, _P, _P]),
     "matcha_kmer_count": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P]),
     "matcha_kmer_collect": (C.c_int, [_P, _I64, _P, _I32, _I32, _P, _P, _I64, _P, _P]),
+    "matcha_metrics_workspace_bytes": (_I64, [_I64]),
+    "matcha_binary_metrics": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _I64, _P]),
+    "matcha_denoise_workspace_bytes": (_I64, [_I64]),
+    "matcha_denoise_matrix": (C.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I64, _P]),
+    "matcha_quantile_uniform": (C.c_int, [_P, _I64, _P, _P, _I32, _P]),
+    "matcha_gather_f32": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "matcha_pair_gather": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "matcha_corrcoef_workspace_bytes": (_I64, [_I64]),
+    "matcha_corrcoef": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _I64, _P]),
+    "matcha_zscore_positive_rows": (C.c_int, [_P, _I64, _I64, _I64, _P]),
+    "matcha_adj_from_pixels": (C.c_int, [_P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P]),
+    "matcha_adj_from_clusters": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
+    "matcha_f64_to_f32": (C.c_int, [_P, _P, _I64, _P]),
     "matcha_gemm": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _I64, _P]),
     "matcha_gemm_scratch_floats": (_I64, [_I64]),
 }

@@ -152,8 +152,14 @@ class Engine:
         self._keep.append(attr)
         desc.attr_dim, desc.attr_table = attr.shape[1], attr.data_ptr()
         inter = getattr(ne, "inter_initial", None)
-        if inter is not None and not getattr(inter, "sparse", False) and inter.embedding.shape[0] == desc.n_nodes \
-                and inter.embedding.shape[1] == desc.n_nodes:
+        self.inter_problem = None            # why no reconstruction target is bound (reported when a caller asks for one)
+        if inter is None:
+            self.inter_problem = "node_embedding.inter_initial is None"
+        elif getattr(inter, "sparse", False):
+            self.inter_problem = "a scipy-sparse inter_initial is not supported (pass the dense [N, N] array of main.py:569)"
+        elif tuple(inter.embedding.shape) != (desc.n_nodes, desc.n_nodes):
+            self.inter_problem = f"inter_initial has shape {tuple(inter.embedding.shape)}, expected [{desc.n_nodes}, {desc.n_nodes}]"
+        else:
             it = inter.embedding.to(dev, torch.float32).contiguous()
             self._keep.append(it)
             desc.inter, desc.inter_ld = it.data_ptr(), it.shape[1]
@@ -202,6 +208,11 @@ class Engine:
     # ------------------------------------------------------------------------------------
     # raw passes (no autograd)
     # ------------------------------------------------------------------------------------
+    def require_inter(self):
+        """Modules.py:192-199 needs the z-scored inter-chromosomal table; without one the loss would silently be 0."""
+        if not self.desc.inter:
+            raise MatchaError("reconstruction loss requested but no inter-chromosomal target is bound: " + str(self.inter_problem))
+
     def run_forward(self, x, training, seed, random_chrom, logits=None, recon=None):
         B, L = x.shape
         ws = self._workspace(B, L, training)
@@ -239,6 +250,8 @@ class Engine:
         if B == 0:      # empty batch: nothing to launch (an empty tensor has no device pointer to hand to the library)
             return (torch.empty(0, 1, dtype=torch.float32, device=self.dev),
                     torch.zeros(1, dtype=torch.float32, device=self.dev))
+        if random_chrom >= 0 and self.C > 1:
+            self.require_inter()              # return_recon=True with no usable target: fail, do not report 0 (Modules.py:192-199)
         self.prepare()
         if training and torch.is_grad_enabled():
             anchor = self._model().layer_norm1.weight

@@ -30,8 +30,15 @@ class Trainer:
         self.e.seed_base = (int(seed) + 0x632BE59BD9B4E019 * int(rank)) & ((1 << 64) - 1)
         self.sampler = sampler
         self.alpha, self.beta = float(alpha), float(beta)
+        if self.beta != 0.0 and self.e.C > 1:
+            self.e.require_inter()            # beta * recon with no target would silently train on 0 (main.py phase 1!)
         self.opt = FlatAdamW(self.e, lr=lr, weight_decay=weight_decay)
         self.world = int(world_size)
+        if self.world > 1:
+            # every replica must start from the SAME weights: rank 0's parameters win (a launcher that forgot to seed the
+            # constructors identically would otherwise all-reduce gradients taken at different points forever)
+            import torch.distributed as dist
+            dist.broadcast(self.e.flat, src=0)
         self.neg_num = sampler.neg_num
         # the per-step chromosome draw of Modules.py:192 -- one shared stream so all ranks draw the same one
         self.recon_rng = recon_rng or np.random.RandomState(seed)

@@ -30,10 +30,14 @@ def main():
     members, offsets = clusters_to_csr([np.asarray(d, dtype=np.int64) for d in data])
     for k in k_list:
         rows, freq = count_kmers(members, offsets, int(k), int(min_dis), int(max_size), int(min_freq_cutoff))
-        print()
-        print(rows.shape)
-        np.save(os.path.join(temp_dir, "all_%d_counter.npy" % k), rows)
-        np.save(os.path.join(temp_dir, "all_%d_freq_counter.npy" % k), freq)
+        if len(rows) > 0:                                           # generate_kmers.py:134-141: nothing is written for an empty set
+            print()
+            print(rows.shape)
+            np.save(os.path.join(temp_dir, "all_%d_counter.npy" % k), rows)
+            np.save(os.path.join(temp_dir, "all_%d_freq_counter.npy" % k), freq)
+        else:
+            print("size %d: no k-mer reaches min_freq_cutoff = %d -- all_%d_counter.npy NOT written (main.py will not find it)"
+                  % (k, min_freq_cutoff, k))
         print("Quick summarize")                                    # generate_kmers.py:142-145
         print("total data", len(freq))
         for c in [2, 3, 4, 5, 6, 7, 8]:

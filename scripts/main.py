@@ -22,6 +22,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from Modules import Classifier, DataGenerator, MultipleEmbedding, device  # noqa: E402
 from utils import accuracy, build_hash, get_config, roc_auc_cuda  # noqa: E402
 
+from matcha_b200.features import corrcoef_features  # noqa: E402
 from matcha_b200.hyper_sagnn import pad_edges  # noqa: E402
 from matcha_b200.parallel import init_from_env, shard_rows  # noqa: E402
 from matcha_b200.sampler import NegativeSampler  # noqa: E402
@@ -78,13 +79,18 @@ def predict(model, samples, batch=int(1e5)):  # main.py:482-494
 
 
 def eval_epoch(model, trainer, sampler, data, weight, batch, rng):
-    """main.py:200-258: 10 000 sampled validation edges + fresh negatives, eval mode, metrics per size."""
+    """main.py:200-258: 10 000 sampled validation edges + fresh negatives, eval mode, metrics per size (on the device).
+    A validation set smaller than one batch is evaluated as one short batch instead of being skipped."""
     model.eval()
     idx = rng.permutation(len(data))[:10000]
+    if len(idx) == 0:
+        model.train()
+        return 0.0, "", 0.0, 0.0
     preds, labels, sizes = [], [], []
     bce_tot, n = 0.0, 0
+    stop = max(len(idx) - batch + 1, 1)
     with torch.no_grad():
-        for i in range(0, len(idx) - batch + 1, batch):
+        for i in range(0, stop, batch):
             pos = torch.from_numpy(data[idx[i:i + batch]]).to(device)
             neg, valid = sampler.sample(pos.contiguous())
             x = torch.cat([pos, neg])
@@ -106,7 +112,7 @@ def train(model, trainer, sampler, training_data, validation_data, epochs, batch
     valid_best = [0.0]
     edges, weights = training_data
     gen = DataGenerator(edges, weights, int(batch), steps_per_epoch // max(1, (max_size - min_size + 1)) or 1,
-                        min_size=min_size, max_size=max_size)
+                        min_size=min_size, max_size=max_size, rng=np.random.RandomState(rng.randint(1 << 30)))
     for epoch_i in range(epochs):
         if rank == 0:
             save_embeddings(model, n_nodes)
@@ -134,11 +140,14 @@ def train(model, trainer, sampler, training_data, validation_data, epochs, batch
         v_bce, v_acc, v_auc1, v_auc2 = eval_epoch(model, trainer, sampler, validation_data[0], validation_data[1], batch, rng)
         print("  - (Validation-hyper) bce: %7.4f,  acc: %s, auc: %s, aupr: %s, elapse: %3.3f s" %
               (v_bce, v_acc, v_auc1, v_auc2, time.time() - start))
-        aupr = float(v_auc2.split(" ")[1])
-        if rank == 0 and aupr >= max(valid_best):
+        # main.py:313-321 parses valid_auc2.split(" ")[-2] -- the SIZE LABEL of the last size class ("... 5 0.871"), a
+        # constant -- so its `>= max(...)` test always holds and the reference saves every epoch and ends on the last one.
+        # Mirrored here (drop-in behaviour), not "fixed" into a best-AUPR selection.
+        key = float(str(v_auc2).split(" ")[-2]) if len(str(v_auc2).split(" ")) >= 2 else 0.0
+        valid_best.append(key)
+        if rank == 0 and key >= max(valid_best):
             torch.save({"model_link": model.state_dict(), "epoch": epoch_i}, os.path.join(temp_dir, "model.chkpt"))
             torch.save(model, os.path.join(temp_dir, "model2load"))
-        valid_best.append(aupr)
 
 
 def main():
@@ -153,7 +162,11 @@ def main():
     steps_per_epoch = int(os.environ.get("MATCHA_STEPS_PER_EPOCH", 4000))
     epochs1, epochs2 = int(os.environ.get("MATCHA_EPOCHS1", 3)), int(os.environ.get("MATCHA_EPOCHS2", 30))
     rank, world, local = init_from_env()
+    # identical host RNG streams on every rank: same initial weights (Trainer also broadcasts rank 0's), same shuffles,
+    # same train / test split -> `rank::world` slices partition ONE global batch
     rng = np.random.RandomState(0)
+    np.random.seed(0)
+    torch.manual_seed(0)
 
     chrom_range = np.load(os.path.join(temp_dir, "chrom_range.npy"))
     num = [int(v[1] - v[0]) for v in chrom_range]
@@ -162,12 +175,9 @@ def main():
 
     inter_initial = np.load(os.path.join(temp_dir, "inter_adj.npy")).astype("float32")
     adj = np.load(os.path.join(temp_dir, "intra_adj.npy")).astype("float32")
-    embeddings_initial = []
-    for v in chrom_range:                                     # main.py:572-577
-        with np.errstate(invalid="ignore", divide="ignore"):
-            temp = np.corrcoef(adj[v[0] - 1:v[1] - 1, v[0] - 1:v[1] - 1]).astype("float32")
-        temp[np.isnan(temp)] = 0.0
-        embeddings_initial.append(temp)
+    # main.py:572-577: np.corrcoef of every chromosome block, NaN -> 0 -- on the device (matcha_b200/features.py: float64
+    # contraction like numpy's); MultipleEmbedding takes numpy arrays, as in the reference
+    embeddings_initial = [t.cpu().numpy() for t in corrcoef_features(adj, chrom_range)]
     attribute_dict = get_attributes(num, len(config["chrom_list"]))
 
     weight /= np.mean(weight)

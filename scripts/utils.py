@@ -22,29 +22,27 @@ def build_hash(data, compress=True, min_size=2, max_size=5, capacity=None):
 
 
 def roc_auc_cuda(y_true, y_pred, size_list, max_size):
-    """utils.py:32-54: 'all <auc> <k> <auc> ...' strings (sklearn on the host, once per epoch)."""
-    from sklearn.metrics import average_precision_score, roc_auc_score
-    y_t = (y_true > 0.5).float().cpu().numpy().reshape(-1)
-    y_p = y_pred.detach().float().cpu().numpy().reshape(-1)
-    s = np.asarray(size_list.cpu() if torch.is_tensor(size_list) else size_list).reshape(-1)
-    roc_str, aupr_str = "all %.3f " % roc_auc_score(y_t, y_p), "all %.3f " % average_precision_score(y_t, y_p)
-    for k in np.unique(s):
-        m = s == k
-        if y_t[m].min() == y_t[m].max():
-            continue
-        roc_str += "%s %.3f " % (str(int(k)), roc_auc_score(y_t[m], y_p[m]))
-        aupr_str += "%s %.3f " % (str(int(k)), average_precision_score(y_t[m], y_p[m]))
-    return roc_str[:-1], aupr_str[:-1]
+    """utils.py:32-54: 'all <auc> <k> <auc> ...' strings.  The curves are computed on the device
+    (matcha_b200/metrics.py: radix sort + fp64 curve areas per size); only the result table is copied back."""
+    from matcha_b200.metrics import metric_strings
+    # (the reference wraps this in `except BaseException: return 0.0, 0.0` because sklearn raises on one-label slices;
+    # the device kernel reports those slices as NaN and they are left out of the strings, so nothing is swallowed here)
+    _, roc_str, aupr_str = metric_strings(_dev(y_true), _dev(y_pred), _dev(size_list), _max_size(size_list, max_size))
+    return roc_str, aupr_str
 
 
 def accuracy(output, target, size_list=None, max_size=None):
     """utils.py:57-72."""
-    out, tgt = output.detach().cpu().reshape(-1), target.detach().cpu().reshape(-1)
+    from matcha_b200.metrics import binary_metrics, metric_strings
     if size_list is None:
-        return "%.3f " % float(((out >= 0.5) == (tgt >= 0.5)).float().mean())
-    s = np.asarray(size_list.cpu() if torch.is_tensor(size_list) else size_list).reshape(-1)
-    acc_str = ""
-    for k in np.unique(s):
-        m = torch.from_numpy(s == k)
-        acc_str += "%s %.3f " % (str(int(k)), float(((out[m] >= 0.5) == (tgt[m] >= 0.5)).float().mean()))
-    return acc_str
+        return "%.3f " % binary_metrics(_dev(target), _dev(output))["all"][2]
+    return metric_strings(_dev(target), _dev(output), _dev(size_list), _max_size(size_list, max_size))[0]
+
+
+def _dev(t):
+    t = t if torch.is_tensor(t) else torch.as_tensor(np.asarray(t))
+    return t if t.is_cuda else t.cuda()
+
+
+def _max_size(size_list, max_size):
+    return int(max_size) if max_size else int(torch.as_tensor(size_list).max())

@@ -261,11 +261,11 @@ def test_bench_reference_arm_prints_one_contract_line():
 
 
 def test_denoise_postprocessing_matches_the_reference_script():
-    """matcha_b200.denoise (the numpy tail of denoise_contact.py:31-61,160-189) against matrices and pixel values produced
+    """oracle.denoise_oracle (the numpy restatement of denoise_contact.py:31-61,160-189) against matrices and pixel values produced
     by EXECUTING the reference's own loop (oracle/make_denoise_golden.py): same pair order (generate_pair_wise), same
     0-based global bin ids, same denoised matrix `my` and `balanced` values, min_distance 0 and 2, chromosomes with gaps."""
     from sklearn.preprocessing import QuantileTransformer
-    from matcha_b200.denoise import denoise_matrix
+    from oracle.denoise_oracle import denoise_matrix
     from matcha_b200.scorer import pair_index_to_ij
     g = np.load(os.path.join(ROOT, "tests", "golden", "denoise_small.npz"))
     cr, origin = g["chrom_range"], g["origin"]
@@ -321,3 +321,18 @@ def test_gpu_suite_collects():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     n = [ln for ln in r.stdout.splitlines() if "::" in ln]
     assert len(n) >= 90, len(n)
+
+
+def test_features_oracle_matches_the_reference_functions():
+    """oracle/features_oracle.py (numpy restatement of process.py:90-105 and :148-170) against arrays written by the
+    UNMODIFIED functions (oracle/make_features_golden.py -> tests/golden/features_small.npz): float64, bit for bit."""
+    from oracle import features_oracle as FO
+    g = np.load(os.path.join(ROOT, "tests", "golden", "features_small.npz"))
+    N = int(g["chrom_range"][-1, 1]) - 1
+    clusters = [g["members"][a:b] for a, b in zip(g["offsets"][:-1], g["offsets"][1:])]
+    np.testing.assert_array_equal(FO.edgelist2adj(clusters, N), g["edge_adj"])
+    c2n = {i: int(v) for i, v in enumerate(g["cool2node"]) if v > 0}
+    n2c = {i: int(g["node2chrom"][i]) for i in range(1, N + 1)}
+    intra, inter = FO.pixels2adj(g["bin1"], g["bin2"], g["count"], c2n, n2c, N)
+    np.testing.assert_array_equal(intra, g["intra"])
+    np.testing.assert_array_equal(inter, g["inter"])
