@@ -9,7 +9,10 @@ GPU negative sampler -> Classifier forward (train mode, dropout on) -> weighted 
 backward -> (NCCL all-reduce) -> AdamW.  `value` is measured with the positives already resident in HBM;
 `e2e` repeats the measurement with HOST (pinned) positives copied in and the loss copied out every step.
 `--impl reference` times the CPU oracle port of the reference path (the reference is pure Python and does
-not travel to the GPU box) on this box's host cores, reference batch (96 positives + 288 negatives).
+not travel to the GPU box) on this box's host cores, on the SAME configuration (same data set, same 4096 positives +
+12288 negatives per step).  The line also carries `cfg3` (the same step on BASELINE configs[2]'s 30,344 bins, with
+HBM rooflines of the node-encoder and reconstruction-head kernels) and `pair_scores` (configs[3]: all-pairs scoring,
+kernel-only and end to end through table build + scoring + on-device denoise post-processing + D2H).
 Prints ONE JSON line.
 """
 import argparse
@@ -95,7 +98,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (sampler + fwd + bwd + AdamW), reference batch size
 # ------------------------------------------------------------------------------------------
-def cpu_reference_arm(ds, steps, warmup, seed=0):
+def cpu_reference_arm(ds, steps, warmup, seed=0, P=96):
     import torch
     from oracle import hypersagnn_oracle as O
     from oracle import sampler_oracle as SO
@@ -113,7 +116,6 @@ def cpu_reference_arm(ds, steps, warmup, seed=0):
     rng = np.random.RandomState(seed)
     m1 = {n: torch.zeros_like(om.params[n]) for n in names}
     m2 = {n: torch.zeros_like(om.params[n]) for n in names}
-    P = 96
     pos_all, w_all = ds["positives"], ds["pos_weight"]
     times = []
     for it in range(warmup + steps):
@@ -135,7 +137,8 @@ def cpu_reference_arm(ds, steps, warmup, seed=0):
             times.append(dt)
     per_step = float(np.mean(times))
     return {"value": P * (1 + NEG_NUM) / per_step, "ms_per_step": per_step * 1e3, "cores": os.cpu_count(),
-            "sample": f"{steps} steps of 96 positives + 288 negatives (reference batch, main.py:527-528) after {warmup} warm-up"}
+            "sample": f"{steps} steps of {P} positives + {P * NEG_NUM} negatives after {warmup} warm-up "
+                      f"(sampler + forward + backward + AdamW of the oracle port, torch CPU ops on {os.cpu_count()} threads)"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -147,7 +150,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kmers-per-size", type=int, default=KMERS_PER_SIZE)
     ap.add_argument("--pos-per-step", type=int, default=POS_PER_STEP)
-    ap.add_argument("--cpu-baseline-steps", type=int, default=40)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=8)
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the configs[2] (30,344 bins) sub-measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-impl", type=int, default=-1, help="-1 library default, 0 SIMT, 1 tcgen05")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -177,14 +181,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ds = make_dataset(args.workload, kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
-        r = cpu_reference_arm(ds, max(1, args.steps), max(1, args.warmup))
-        cfg = dict(config, hyperedges_per_gpu_per_step=384, positives_per_gpu_per_step=96,
-                   note="CPU oracle port of the reference path at the reference's batch size; the unmodified reference is "
-                        "Python that cannot travel to the GPU box")
+        # same configuration as our arm (same data set, same batch); every step is one batch of the workload
+        ds = make_dataset(args.workload, kmers_per_size=args.kmers_per_size, seed=0)
+        r = cpu_reference_arm(ds, max(1, args.steps), max(1, args.warmup), P=args.pos_per_step)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "note": "CPU oracle port of the reference path (oracle/hypersagnn_oracle.py + oracle/sampler_oracle.py, pinned to the "
+                        "unmodified Modules.py by tests/golden); the reference itself is Python that cannot travel to the GPU box",
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -205,135 +209,226 @@ def main():
     lib = _lib.load()
     if args.gemm_impl >= 0:
         lib.matcha_set_gemm_impl(args.gemm_impl)
-
-    ds = make_dataset(args.workload, kmers_per_size=args.kmers_per_size, seed=0)      # same data on every rank
-    model = build_model(ds, seed=1)
-    hs = KmerHashSet(len(ds["dict"]), width=5).insert(ds["dict"])
-    sampler = NegativeSampler(hs, ds["chrom_range"], min_dis=0, neg_num=NEG_NUM, seed=2 + rank)
-    trainer = Trainer(model, sampler, alpha=1.0, beta=0.001, seed=3, world_size=world, rank=rank)
-    P = args.pos_per_step
-    # this rank's positives: rows rank::world of a shuffled global pool
-    g = np.random.RandomState(7)
-    perm = g.permutation(len(ds["positives"]))
-    pos_host = torch.from_numpy(ds["positives"][perm][rank::world].copy()).pin_memory()
-    w_host = torch.from_numpy(ds["pos_weight"][perm][rank::world].copy()).pin_memory()
-    pos_dev, w_dev = pos_host.cuda(), w_host.cuda()
-    nb = len(pos_host) // P
-    assert nb >= 1, "not enough positives for one step"
-    T = P * (1 + NEG_NUM) * 5
+    peaks = load_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(n_steps, host_io, start):
-        if host_io:
-            # the package's own host-fed loop (matcha_b200/trainer.py): per step one H2D copy of the batch from pinned
-            # memory (prefetched one step ahead on a copy stream) and one D2H read of the step's losses (asynchronous,
-            # all n_steps rows are on the host when it returns)
-            losses, _, _ = trainer.run_host_batches(pos_host, w_host, P, n_steps, start)
-            assert bool(torch.isfinite(losses).all())
-            return
-        for i in range(n_steps):
-            b, b2 = (start + i) % nb, (start + i + 1) % nb
-            if i + 1 < n_steps:      # the next batch's positives: its negatives are sampled under this step
-                trainer.step(pos_dev[b * P:(b + 1) * P], w_dev[b * P:(b + 1) * P], pos_dev[b2 * P:(b2 + 1) * P], w_dev[b2 * P:(b2 + 1) * P])
-            else:
-                trainer.step(pos_dev[b * P:(b + 1) * P], w_dev[b * P:(b + 1) * P])
-
-    def timed(n_steps, host_io, start, profile=False):
-        barrier()
-        if profile:
-            lib.matcha_profile_enable(1)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        run(n_steps, host_io, start)
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-        prof = None
-        if profile:
-            lib.matcha_profile_enable(0)
-            n = lib.matcha_profile_labels()
-            tms, calls, kern = (C.c_float * n)(), (C.c_int64 * n)(), (C.c_int64 * n)()
-            _lib.check(lib.matcha_profile_read(tms, calls, kern, n), "profile_read")
-            prof = {lib.matcha_profile_label_name(i).decode(): (tms[i], calls[i], kern[i]) for i in range(n) if calls[i]}
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, prof
+        return ms
+
+    def read_profile():
+        n = lib.matcha_profile_labels()
+        tms, calls, kern = (C.c_float * n)(), (C.c_int64 * n)(), (C.c_int64 * n)()
+        _lib.check(lib.matcha_profile_read(tms, calls, kern, n), "profile_read")
+        return {lib.matcha_profile_label_name(i).decode(): (tms[i], calls[i], kern[i]) for i in range(n) if calls[i]}
+
+    def measure_training(ds, P, steps, warm, want_e2e, want_big, clocks=None):
+        """One training configuration: device-timed steps (inputs resident in HBM), per-call-site profile, optionally the
+        host-fed end-to-end loop and the 4x batch.  Every rank executes exactly the same sequence of steps."""
+        model = build_model(ds, seed=1)
+        hs = KmerHashSet(len(ds["dict"]), width=5).insert(ds["dict"])
+        sampler = NegativeSampler(hs, ds["chrom_range"], min_dis=0, neg_num=NEG_NUM, seed=2 + rank)
+        trainer = Trainer(model, sampler, alpha=1.0, beta=0.001, seed=3, world_size=world, rank=rank)
+        g = np.random.RandomState(7)
+        perm = g.permutation(len(ds["positives"]))
+        pos_host = torch.from_numpy(ds["positives"][perm][rank::world].copy()).pin_memory()     # rows rank::world of a shuffled pool
+        w_host = torch.from_numpy(ds["pos_weight"][perm][rank::world].copy()).pin_memory()
+        pos_dev, w_dev = pos_host.cuda(), w_host.cuda()
+        st = {"P": P, "nb": len(pos_host) // P}
+        assert st["nb"] >= 1, "not enough positives for one step"
+
+        def run(n_steps, host_io, start):
+            P_, nb = st["P"], st["nb"]
+            if host_io:
+                # the package's own host-fed loop (matcha_b200/trainer.py): per step one H2D copy of the batch from pinned
+                # memory (prefetched one step ahead on a copy stream) and one D2H read of the step's losses
+                losses, _, _ = trainer.run_host_batches(pos_host, w_host, P_, n_steps, start)
+                assert bool(torch.isfinite(losses).all())
+                return
+            for i in range(n_steps):
+                b, b2 = (start + i) % nb, (start + i + 1) % nb
+                if i + 1 < n_steps:      # the next batch's positives: its negatives are sampled under this step
+                    trainer.step(pos_dev[b * P_:(b + 1) * P_], w_dev[b * P_:(b + 1) * P_], pos_dev[b2 * P_:(b2 + 1) * P_],
+                                 w_dev[b2 * P_:(b2 + 1) * P_])
+                else:
+                    trainer.step(pos_dev[b * P_:(b + 1) * P_], w_dev[b * P_:(b + 1) * P_])
+
+        def timed(n_steps, host_io, start, profile=False):
+            barrier()
+            if profile:
+                lib.matcha_profile_enable(1)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            run(n_steps, host_io, start)
+            ev1.record()
+            barrier()
+            ms = ev0.elapsed_time(ev1)
+            prof = None
+            if profile:
+                lib.matcha_profile_enable(0)
+                prof = read_profile()
+            return max_over_ranks(ms), prof
+
+        if clocks is not None:
+            clocks.start()                           # started before the warm-up: nvidia-smi takes a while to produce samples
+        run(warm, False, 0)
+        # the extra untimed steps on both sides give nvidia-smi time to sample the clocks under the same load
+        run(max(20, steps), False, 0)
+        ms_dev, _ = timed(steps, False, warm)                        # the reported value: no per-call-site events
+        run(max(20, steps), False, 0)
+        torch.cuda.synchronize()
+        clk = clocks.stop() if clocks is not None else None
+        _, prof = timed(steps, False, warm, profile=True)            # same steps again with CUDA events per call site
+        out = {"ms_dev": ms_dev, "prof": prof, "clk": clk, "P": P}
+        if want_e2e:
+            run(2, True, 0)
+            out["ms_e2e"], _ = timed(steps, True, warm + steps)
+        out["losses"] = trainer.mean_losses()
+        if want_big and len(pos_host) // (4 * P) >= 2:
+            # supplementary: the same step at 4x the batch (a part of a step does not depend on the batch, DESIGN.md section 5)
+            st["P"], st["nb"] = 4 * P, len(pos_host) // (4 * P)
+            run(3, False, 0)
+            k_big = max(5, steps // 3)
+            ms_big, _ = timed(k_big, False, 3)
+            out["big"] = {"hyperedges_per_gpu_per_step": 4 * P * (1 + NEG_NUM), "value": 4 * P * (1 + NEG_NUM) * world * k_big / (ms_big * 1e-3),
+                          "unit": UNIT, "ms_per_step": ms_big / k_big, "steps": k_big}
+        # HBM accounting of the node encoder / reconstruction head (4 * n_c bytes per real token + 512 B; n_c averaged over
+        # the real tokens of the positives pool: negatives stay on their positive's chromosomes)
+        node_nc = np.zeros(ds["N"] + 1, dtype=np.float64)
+        for (cs, ce) in ds["chrom_range"]:
+            node_nc[int(cs):int(ce)] = float(ce - cs)
+        real = ds["positives"] != 0
+        out["row_bytes"] = 4.0 * float(node_nc[ds["positives"][real]].mean())
+        out["real_tokens"] = P * (1 + NEG_NUM) * float(real.sum()) / len(ds["positives"])
+        del trainer, model, hs, sampler, pos_dev, w_dev
+        torch.cuda.empty_cache()
+        return out
+
+    def hbm_kernels(ds, m):
+        """achieved HBM GB/s of the encoder / reconstruction-head call sites of one measured configuration"""
+        n_chrom = len(ds["nums"])
+        alg = {"enc0_gather_gemm": m["real_tokens"] * (m["row_bytes"] + 512.0), "enc0_wgrad": m["real_tokens"] * (m["row_bytes"] + 512.0),
+               # every eligible token (real, outside the uniformly drawn chromosome, Modules.py:192) reads its 4 * n_r byte target
+               # row and its E row and adds a dtE row
+               "recon_pred_gemm": m["real_tokens"] * (1.0 - 1.0 / n_chrom) * (4.0 * ds["N"] / n_chrom + 512.0)}
+        res = {}
+        for k, work in alg.items():
+            if k in m["prof"]:
+                per = m["prof"][k][0] / m["prof"][k][1]
+                res[k] = {"GB/s": work / (per * 1e-3) / 1e9, "ms_per_launch": per, "frac_of_peak": work / (per * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "algorithmic_bytes_per_launch": work}
+        return res
 
     def pair_scorer_bench(iters=5):
         """Second metric of BASELINE.json: pair-scores/s of the denoise all-pairs scorer (denoise_contact.py:67-88) on
         configs[3]'s shape -- chr1 at 10 kb, 24,897 bins, n(n+1)/2 = 3.1e8 pairs generated on the device -- sharded by
-        contiguous pair range across ranks with no communication.  The per-node tables are synthetic (the kernel's cost
-        does not depend on their values); their construction from a model is covered by the parity tests."""
+        contiguous pair range across ranks with no communication.  `value` times the scoring kernel alone on resident
+        tables; `e2e` is the whole denoise path of one chromosome from a trained-shape model: per-node table build
+        (matcha_pair_tables: the encoder over 24,897 rows of 100 KB) + table packing + scoring (sharded) + gather of the
+        packed scores to rank 0 + on-device post-processing (denoise_contact.py:160-192) + D2H of the finished matrix."""
+        from matcha_b200 import hyper_sagnn as M
+        from matcha_b200.denoise import QuantileUniform, denoise_matrix
+        from matcha_b200.scorer import PairScorer
         n, d = 24897, 64
         gen = torch.Generator(device="cuda").manual_seed(5)
-        D = torch.randn(n + 1, d, device="cuda", generator=gen)
-        S = torch.randn(n + 1, d, device="cuda", generator=gen)
-        cw = torch.rand(d, device="cuda", generator=gen)
-        cb = torch.zeros(1, device="cuda")
         total = int(lib.matcha_pair_count(1, n + 1, 0))
         b, e = total * rank // world, total * (rank + 1) // world
+        # a model of the cfg4 shape: ONE chromosome of 24,897 bins; feature values do not change the cost
+        feats = (torch.randn(n, n, device="cuda", generator=gen) * (1.0 / np.sqrt(n))).cpu().numpy()
+        cr = np.asarray([[1, n + 1]], dtype=np.int64)
+        attr = np.concatenate([np.zeros((1, 2), np.float32), np.stack([np.ones(n, np.float32), np.arange(n, dtype=np.float32) / n], 1)], 0)
+        torch.manual_seed(1)
+        ne = M.MultipleEmbedding([feats], d, False, np.asarray([n]), cr, None)
+        model = M.Classifier(n_head=8, d_model=d, d_k=d, d_v=d, node_embedding=ne, diag_mask=True, bottle_neck=d,
+                             attribute_dict=attr).to(M.device)
+        model.eval()
+        del feats
+        sc = PairScorer(model)
         out = torch.empty(e - b, dtype=torch.float32, device="cuda")
-        nbytes = int(lib.matcha_pair_tc_workspace_bytes(1, n + 1))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        _lib.check(lib.matcha_pair_tc_prepare(_lib.ptr(D), _lib.ptr(S), _lib.ptr(cw), _lib.ptr(cb), d, 1, n + 1, _lib.ptr(ws), nbytes,
-                                              _lib.stream_ptr()), "matcha_pair_tc_prepare")
+        origin = (torch.rand(n, n, device="cuda", generator=gen) < 0.02).float()
+        host_my = torch.empty(n, n, dtype=torch.float32).pin_memory() if rank == 0 else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
 
-        def once():
-            _lib.check(lib.matcha_pair_tc_score_range(_lib.ptr(ws), 1, n + 1, 0, b, e, 1, _lib.ptr(out),
-                                                      _lib.stream_ptr()), "matcha_pair_tc_score_range")
+        def kernel_only():
+            sc.score_range(1, n + 1, 0, b, e, sigmoid=True, out=out)
+
+        def whole(record):
+            if record: ev[0].record()
+            sc.refresh()                                   # per-node tables from the model (encoder over every node)
+            sc._pack(1, n + 1)                             # operand blocks of the tensor-core scorer
+            if record: ev[1].record()
+            sc.score_range(1, n + 1, 0, b, e, sigmoid=True, out=out)
+            if record: ev[2].record()
+            if world > 1:
+                width = (total + world - 1) // world + 1
+                send = torch.zeros(width, dtype=torch.float32, device="cuda")
+                send[:e - b] = out
+                bufs = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+                dist.gather(send, bufs, dst=0)
+                if rank == 0:
+                    full = torch.empty(total, dtype=torch.float32, device="cuda")
+                    for r in range(world):
+                        rb, re_ = total * r // world, total * (r + 1) // world
+                        full[rb:re_] = bufs[r][:re_ - rb]
+            else:
+                full = out
+            if record: ev[3].record()
+            if rank == 0:
+                my = denoise_matrix(full, origin, n, 0, QuantileUniform(1000, random_state=0))
+                if record: ev[4].record()
+                host_my.copy_(my, non_blocking=True)
+            elif record:
+                ev[4].record()
+            if record: ev[5].record()
+
         for _ in range(3):
-            once()
+            kernel_only()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(iters):
-            once()
+            kernel_only()
         ev1.record()
         barrier()
-        ms = ev0.elapsed_time(ev1) / iters
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        del out
-        return total, ms
+        ms = max_over_ranks(ev0.elapsed_time(ev1) / iters)
+        whole(False)
+        barrier()
+        t0 = time.perf_counter()
+        whole(True)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        stages = {"tables_ms": ev[0].elapsed_time(ev[1]), "score_ms": ev[1].elapsed_time(ev[2]), "gather_ms": ev[2].elapsed_time(ev[3]),
+                  "postprocess_ms": ev[3].elapsed_time(ev[4]), "d2h_ms": ev[4].elapsed_time(ev[5])}
+        e2e_ms = max_over_ranks(ev[0].elapsed_time(ev[5]))
+        del out, origin, sc, model
+        torch.cuda.empty_cache()
+        return total, ms, e2e_ms, wall_ms, stages
 
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()                               # started before the warm-up: nvidia-smi takes a while to produce samples
-    run(warmup, False, 0)
-    # every rank runs the same steps (the step holds a collective when world > 1); the extra untimed steps on both sides
-    # give nvidia-smi time to sample the clocks while the GPU is under the same load
-    run(max(20, args.steps), False, 0)
-    ms_dev, _ = timed(args.steps, False, warmup)                     # the reported value: no per-call-site events
-    run(max(20, args.steps), False, 0)
-    torch.cuda.synchronize()
-    clk = clocks.stop() if rank == 0 else None
-    _, prof = timed(args.steps, False, warmup, profile=True)        # same steps again with CUDA events per call site
-    run(2, True, 0)
-    ms_e2e, _ = timed(args.steps, True, warmup + args.steps)
-    losses = trainer.mean_losses()
-    # supplementary: the same step at 4x the batch (every rank runs it: the step holds a collective).  About 0.33 ms of a
-    # step does not depend on the batch (DESIGN.md section 5), so throughput keeps rising with it; the headline `value`
-    # stays at the batch the earlier rounds were measured on
-    big = None
-    P_big = 4 * P
-    if len(pos_host) // P_big >= 2:
-        P_saved, nb_saved = P, nb
-        P, nb = P_big, len(pos_host) // P_big
-        run(3, False, 0)
-        k_big = max(5, args.steps // 3)
-        ms_big, _ = timed(k_big, False, 3)
-        big = {"hyperedges_per_gpu_per_step": P_big * (1 + NEG_NUM), "value": P_big * (1 + NEG_NUM) * world * k_big / (ms_big * 1e-3),
-               "unit": UNIT, "ms_per_step": ms_big / k_big, "steps": k_big}
-        P, nb = P_saved, nb_saved
-    pair_total, pair_ms = (0, 1.0) if args.no_pairs else pair_scorer_bench()
+    ds = make_dataset(args.workload, kmers_per_size=args.kmers_per_size, seed=0)      # same data on every rank
+    P = args.pos_per_step
+    T = P * (1 + NEG_NUM) * 5
+    m = measure_training(ds, P, args.steps, warmup, True, True, ClockSampler(local) if rank == 0 else None)
+    ms_dev, prof, clk, ms_e2e, losses, big = m["ms_dev"], m["prof"], m["clk"], m["ms_e2e"], m["losses"], m.get("big")
+    # configs[2] (whole genome at 100 kb, 30,344 bins): the configuration BASELINE names for 8-GPU training, measured at
+    # every N with the same per-GPU batch (weak scaling) -- the encoder and the reconstruction head stream real HBM here
+    cfg3 = None
+    if not args.no_cfg3 and args.workload == "cfg2":
+        ds3 = make_dataset("cfg3", kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
+        k3 = max(5, args.steps // 2)
+        m3 = measure_training(ds3, P, k3, 3, False, False)
+        cfg3 = {"workload": WORKLOADS["cfg3"], "value": P * (1 + NEG_NUM) * world * k3 / (m3["ms_dev"] * 1e-3), "unit": UNIT,
+                "ms_per_step": m3["ms_dev"] / k3, "steps": k3, "n_gpus": world, "hyperedges_per_gpu_per_step": P * (1 + NEG_NUM),
+                "kernel_ms_per_step": {k: round(v[0] / k3, 4) for k, v in sorted(m3["prof"].items(), key=lambda kv: -kv[1][0])},
+                "hbm_kernels": hbm_kernels(ds3, m3), "losses": m3["losses"]}
+        del ds3
+    pair_total, pair_ms, pair_e2e_ms, pair_wall_ms, pair_stages = (0, 1.0, 1.0, 1.0, {}) if args.no_pairs else pair_scorer_bench()
 
     if rank != 0:
         if world > 1:
@@ -342,7 +437,6 @@ def main():
     per_step = P * (1 + NEG_NUM) * world
     value = per_step * args.steps / (ms_dev * 1e-3)
     e2e = per_step * args.steps / (ms_e2e * 1e-3)
-    peaks = load_peaks()
     # dominant call site and its roofline (algorithmic flops / bytes per launch)
     d, qkg = 64, 1536
     impl_env = os.environ.get("MATCHA_GEMM_IMPL", "1") if args.gemm_impl < 0 else str(args.gemm_impl)
@@ -357,22 +451,9 @@ def main():
             "qkg_gemm": ("tensor", 2.0 * T * qkg * d), "qkg_wgrad": ("tensor", 2.0 * T * qkg * d), "qkg_dgrad": ("tensor", 2.0 * T * qkg * d),
             "attn_fwd": ("hbm", T * (qkg + d) * 4.0), "attn_bwd": ("hbm", T * (2 * qkg + d) * 4.0),
         }
-    # node encoder (HBM-bound once the feature tables exceed L2): every real token reads its 4 * n_c byte feature row;
-    # forward also writes H0 and E (512 B), backward reads dE and H0 (512 B).  Re-reads by the backward kernel's column
-    # groups are implementation cost.  n_c is averaged over the real tokens of the positives pool (negatives stay on the
-    # positive's chromosomes)
-    node_nc = np.zeros(ds["N"] + 1, dtype=np.float64)
-    for (cs, ce) in ds["chrom_range"]:
-        node_nc[int(cs):int(ce)] = float(ce - cs)
-    real = ds["positives"] != 0
-    row_bytes = 4.0 * float(node_nc[ds["positives"][real]].mean())
-    real_tokens = P * (1 + NEG_NUM) * float(real.sum()) / len(ds["positives"])
-    alg["enc0_gather_gemm"] = ("hbm", real_tokens * (row_bytes + 512.0))
-    alg["enc0_wgrad"] = ("hbm", real_tokens * (row_bytes + 512.0))
-    # reconstruction head (fused forward + gradient pass): every eligible token (real, outside the drawn chromosome) reads
-    # its 4 * n_r byte target row, its E row, and adds a dtE row; the chromosome is drawn uniformly (Modules.py:192)
-    n_chrom = len(ds["nums"])
-    alg["recon_pred_gemm"] = ("hbm", real_tokens * (1.0 - 1.0 / n_chrom) * (4.0 * ds["N"] / n_chrom + 512.0))
+    enc = hbm_kernels(ds, m)
+    for k, v in enc.items():
+        alg[k] = ("hbm", v["algorithmic_bytes_per_launch"])
     top = max(prof.items(), key=lambda kv: kv[1][0])
     tot_ms = sum(v[0] for v in prof.values())
     name, (tms, calls, _) = top
@@ -409,14 +490,18 @@ def main():
                         "sharded by pair range over the ranks",
             "roofline": {"bound": "hbm", "achieved": pair_rate * 4.0 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": pair_rate * 4.0 / 1e9 / peaks["hbm_gbs"] / world, "peak_source": peaks["src"],
-                         "note": "4 bytes written per pair; tables (12.7 MB) stay in L2"}}
+                         "note": "4 bytes written per pair; tables (12.7 MB) stay in L2"},
+            "e2e": {"value": pair_total / (pair_e2e_ms * 1e-3), "unit": "pair-scores/s", "ms": pair_e2e_ms, "wall_ms": pair_wall_ms,
+                    "stages_ms_rank0": {k: round(v, 3) for k, v in pair_stages.items()}, "d2h_bytes": 24897 * 24897 * 4,
+                    "what": "model -> per-node tables (encoder over 24,897 rows of 100 KB) -> packed operands -> all-pairs scores (sharded) "
+                            "-> gather to rank 0 -> denoise post-processing on the device (denoise_contact.py:160-192, quantile map "
+                            "included) -> finished [n, n] matrix copied to pinned host memory"}}
     launches = int(sum(v[2] for v in prof.values()))
     breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
-        small = make_dataset(args.workload, kmers_per_size=min(args.kmers_per_size, 100_000), seed=0)
-        r = cpu_reference_arm(small, args.cpu_baseline_steps, 3)
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only: a bounded sample (~15 s)
+        r = cpu_reference_arm(ds, args.cpu_baseline_steps, 2, P=args.pos_per_step)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -425,11 +510,12 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(P * 5 * 8 + P * 4), "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "kernel_ms_per_step": breakdown, "losses": losses,
-            "pair_scores": None if args.no_pairs else pair, "large_batch": big}
+            "pair_scores": None if args.no_pairs else pair, "large_batch": big, "cfg3": cfg3,
+            "bloom_agreement": "not measured: the reference's positive set is pybloom_live.BloomFilter (third party, version unpinned, "
+                               "absent from this image); membership here is exact (bit-exact vs a CPU set, tests/test_gpu_parity.py)"}
     # achieved HBM GB/s of the node-encoder kernels (the north star's evidence for the sparse-row encoder)
-    line["encoder_hbm"] = {k: {"GB/s": alg[k][1] / (prof[k][0] / prof[k][1] * 1e-3) / 1e9, "ms_per_launch": prof[k][0] / prof[k][1],
-                               "frac_of_peak": alg[k][1] / (prof[k][0] / prof[k][1] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-                           for k in ("enc0_gather_gemm", "enc0_wgrad") if k in prof}
+    line["encoder_hbm"] = {k: {kk: vv for kk, vv in v.items() if kk != "algorithmic_bytes_per_launch"} for k, v in enc.items()
+                           if k in ("enc0_gather_gemm", "enc0_wgrad")}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
