@@ -56,6 +56,14 @@ void matcha_set_recon_tc(int32_t on);
 /* 1 (default) = both node-encoder layers (Modules.py:104-122) run as one tcgen05 kernel over the chromosome-bucketed
  * token list (dense feature rows, embed_dim 64, >= 1024 tokens), 0 = two grouped SIMT launches; also MATCHA_ENC_TC=0 */
 void matcha_set_enc_tc(int32_t on);
+/* 1 (default) = the fused attention FORWARD runs in "X-form" for widths L <= 5 (csrc/attn_xform.cu: scores and value mixing
+ * re-associated onto the neighbours' input rows, held in registers: no per-head warp shuffles), 0 = the Q/K/G shuffle form
+ * of csrc/attn_fused.cu; also MATCHA_XFORM=0 */
+void matcha_set_xform(int32_t on);
+/* bf16 products per tcgen05 contraction step of the attention block: 3 (default) = hi*hi + hi*lo + lo*hi of the bf16 hi|lo
+ * operand split (fp32-accurate: ~2^-16 relative), 1 = hi*hi only ("bf16 mode", BASELINE's stated-tolerance option:
+ * measured logit / gradient error in DESIGN.md); also MATCHA_BF16=1 */
+void matcha_set_mma_passes(int32_t passes);
 
 /* ---------------------------------------------------------------------------------------------
  * Model description: where every live tensor of Modules.Classifier sits.

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmatcha_b200.so")
-SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu", "recon_tc.cu", "enc_tc.cu", "kmers.cu", "metrics.cu", "denoise.cu", "features.cu"]
+SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "attn_xform.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu", "recon_tc.cu", "enc_tc.cu", "kmers.cu", "metrics.cu", "denoise.cu", "features.cu"]
 NVCC_COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                       "-Xcompiler", "-fPIC"]
 NVCC_LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         path = os.path.join(CSRC, src)
         if (not force) and os.path.exists(obj) and os.path.getmtime(obj) >= max(hdr_mtime, os.path.getmtime(path)):
             return obj, None
-        cmd = [nvcc] + NVCC_COMPILE_FLAGS + ["-c", "-o", obj, path]
+        cmd = [nvcc] + NVCC_COMPILE_FLAGS + os.environ.get("MATCHA_NVCC_EXTRA", "").split() + ["-c", "-o", obj, path]
         if verbose:
             print(" ".join(cmd), flush=True)
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -113,6 +113,8 @@ SYMBOLS = {
     "matcha_set_chain": (None, [_I32]),
     "matcha_set_recon_tc": (None, [_I32]),
     "matcha_set_enc_tc": (None, [_I32]),
+    "matcha_set_xform": (None, [_I32]),
+    "matcha_set_mma_passes": (None, [_I32]),
     "matcha_derived_elems": (_I64, [_MD]),
     "matcha_workspace_bytes": (_I64, [_MD, _I64, _I32, _I32]),
     "matcha_prepare": (C.c_int, [_MD, _P]),

@@ -138,7 +138,7 @@ attn_fused_fwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int ws = 0; uint32_t wp = 0, xp[2] = {0u, 0u};
       for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
         for (int s = 0; s < 2; ++s) {
@@ -160,7 +160,7 @@ attn_fused_fwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(128, 192, false, false);
       int ws = 0; uint32_t wp = 0, xp[2] = {0u, 0u}, ap[2] = {0u, 0u};
       for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
@@ -398,7 +398,7 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&w_full, kBWBytes);
       for (int p = 0; p < 3; ++p)
         bulk_g2s(sW + p * kBWPiece, wpairs + (int64_t)hp * kBWBytes + p * kBWPiece, kBWPiece, &w_full);
@@ -412,7 +412,7 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idescR = make_idesc(128, 128, false, false);
       constexpr uint32_t idescD = make_idesc(128, 64, false, true);
       constexpr uint32_t idescW = make_idesc(128, 64, true, true);

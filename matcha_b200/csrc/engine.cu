@@ -100,6 +100,23 @@ static bool use_fused(const matcha_model_desc* m, int64_t T, int L) {
   return m->d == kD && fused_impl() == 1 && gemm_impl() == 1 && L >= 2 && L <= 6 && T >= kTilePathMinTokens;
 }
 
+static int g_xform = -1;      // X-form fused attention forward (MATCHA_XFORM=0 keeps the Q/K/G shuffle form of attn_fused.cu)
+static bool use_xform(const matcha_model_desc* m, int64_t T, int L) {
+  if (g_xform < 0) {
+    const char* e = getenv("MATCHA_XFORM");
+    g_xform = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_xform == 1 && use_fused(m, T, L) && L <= 5;
+}
+static int g_passes = -1;     // bf16 products per tcgen05 contraction step in the attention block: 3 (default) or 1 (MATCHA_BF16=1)
+static int mma_passes() {
+  if (g_passes < 0) {
+    const char* e = getenv("MATCHA_BF16");
+    g_passes = (e && e[0] == '1') ? 1 : 3;
+  }
+  return g_passes;
+}
+
 static int g_enc_tc = -1;     // tensor-core node encoder forward (MATCHA_ENC_TC=0 keeps the two grouped SIMT launches)
 static bool enc_tc_eligible(const matcha_model_desc* m) { return m->d == kD && !model_uses_csr(m); }
 static bool use_enc_tc(const matcha_model_desc* m, int64_t T) {
@@ -132,7 +149,7 @@ static int run_gemm(const GemmDesc& d, cudaStream_t s, int label, bool allow_tc 
 // derived-parameter layout
 // ------------------------------------------------------------------------------------------
 struct DerivedLayout {
-  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, wheads, wpairs, wchain, tables, total;  // float offsets
+  int64_t wqkg, bqkg, bdyn, bdyn_part, wsplit, wtsplit, wheads, wpairs, wchain, wx, vx, tables, total;  // float offsets
 };
 static __host__ __device__ DerivedLayout derived_layout(int D) {
   DerivedLayout l;
@@ -146,7 +163,9 @@ static __host__ __device__ DerivedLayout derived_layout(int D) {
   l.wheads = l.wtsplit + QKG * D;                        // per-head [Q_h | K_h | G_h] chunks for the fused attention kernels
   l.wpairs = l.wheads + (int64_t)kH * kHeadWBytes / 4;   // per-head-pair G | K | Q piece pairs for the fused backward
   l.wchain = l.wpairs + (int64_t)4 * kPairWBytes / 4;    // next_w, pff_w0, pff_w1: K-major and MN-major pre-split copies
-  l.tables = l.wchain + (int64_t)6 * kChainWBytes / 4;
+  l.wx = l.wchain + (int64_t)6 * kChainWBytes / 4;       // X-form attention forward: per-head N_h | Wg_h blocks, then v_h
+  l.vx = l.wx + (int64_t)kH * kXformWBytes / 4;
+  l.tables = l.vx + kH * D;
   l.tables = (l.tables + 63) / 64 * 64;
   const int64_t table_floats = (int64_t)(sizeof(GemmGroup) * MATCHA_MAX_CHROM + 3) / 4;
   l.total = l.tables + 4 * table_floats;
@@ -619,6 +638,8 @@ void matcha_set_fused(int32_t on) { g_fused = on != 0; }
 void matcha_set_chain(int32_t on) { g_chain = on != 0; }
 void matcha_set_recon_tc(int32_t on) { g_recon_tc = on != 0; }
 void matcha_set_enc_tc(int32_t on) { g_enc_tc = on != 0; }
+void matcha_set_xform(int32_t on) { g_xform = on != 0; }
+void matcha_set_mma_passes(int32_t passes) { g_passes = passes == 1 ? 1 : 3; }
 int matcha_version(void) { return 100; }
 
 // CSR models keep W0T_c [n_c, 64] (and, in derived_grad, its gradient) after the fixed-size part
@@ -666,6 +687,7 @@ int matcha_prepare(const matcha_model_desc* m, void* stream) {
   if (m->d == kD) {      // pre-split bf16 hi | lo operand copies for the tcgen05 kernels (embed_dim 64 only)
     // (the K-major / MN-major copies of the whole W_qkg are only read by the decomposed pipeline: built there, on demand)
     if ((rc = launch_split_w_heads(m->derived + l.wqkg, m->derived + l.wheads, s))) return rc;
+    if ((rc = launch_prep_xform(m->derived + l.wqkg, m->derived + l.bqkg, m->derived + l.wx, m->derived + l.vx, s))) return rc;
     if (m->grads && (rc = launch_split_w_pairs(m->derived + l.wqkg, m->derived + l.wpairs, s))) return rc;
     {
       float* wc = m->derived + l.wchain;
@@ -730,7 +752,12 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
   const bool fused = use_fused(m, T, L);
   if ((rc = run_mix_qkg(m, x, T, w, s, fused ? L : 0, training))) return rc;
   DropCfg dattn = make_drop(seed, SITE_ATTN, m->p_attn, training != 0);
-  if (fused) {
+  if (fused && use_xform(m, T, L)) {
+    if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_xform_fwd(w.xhat_t, w.xhat, reinterpret_cast<const uint8_t*>(m->derived + l.wx),
+                                                        m->derived + l.vx, m->derived + l.bdyn, x, w.U, training ? w.probs : nullptr, B, L,
+                                                        dattn, mma_passes(), s))))
+      return rc;
+  } else if (fused) {
     if ((rc = PROF(P_ATTN_FWD, 1, launch_attn_fused_fwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wheads),
                                                         m->derived + l.bqkg, m->derived + l.bdyn, x, w.U, training ? w.probs : nullptr, B, L,
                                                         dattn, s))))

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
   auto chunk_end = [&](int64_t c) { const int64_t e = chunk_begin(c) + G; return e < a.f_end ? e : a.f_end; };
 
   if (warp == 0) {
-    if (lane == 0 && f0 < f1) {
+    if (f0 < f1 && elect_one()) {
       int64_t ti, tj, cur_ti = -1, na = 0, k = 0;
       for (int64_t c = 0; c < my_chunks; ++c) {
         flat_to_tile(chunk_begin(c), a.nb, a.bmd, ti, tj);
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kPThreads, 1) pair_tc_kernel(const PairArgs a)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && f0 < f1) {
+    if (f0 < f1 && elect_one()) {
       constexpr uint32_t idesc = make_idesc(128, 128, false, false);
       int64_t ti, tj, cur_ti = -1, na = 0, k = 0;
       // descriptors are built once: advancing an operand by one k-step (4096 B) adds 256 to the 16-byte address field

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kFThreads, 1) qkg_fwd_tiles_kernel(const uint8
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int ws = 0, xs = 0; uint32_t wp = 0, xp = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         mbar_wait(&x_empty[xs], xp ^ 1);
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kFThreads, 1) qkg_fwd_tiles_kernel(const uint8
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(128, 128, false, false);
       int ws = 0, as = 0, xs = 0; uint32_t wp = 0, ap = 0, xp = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kDThreads, 1) qkg_dgrad_tiles_kernel(const uin
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0; uint32_t ph = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int fc = 0; fc < kGChunks; ++fc) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kDThreads, 1) qkg_dgrad_tiles_kernel(const uin
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(128, 64, false, true);
       int st = 0, as = 0; uint32_t ph = 0, ap = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kWThreads, 1) qkg_wgrad_tiles_kernel(const uin
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int gs = 0, xs = 0; uint32_t gp = 0, xp = 0;
       for (int64_t tile = t_begin; tile < t_end; ++tile) {
         mbar_wait(&x_empty[xs], xp ^ 1);
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kWThreads, 1) qkg_wgrad_tiles_kernel(const uin
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(128, kWN, true, true);
       int gs = 0, xs = 0; uint32_t gp = 0, xp = 0;
       for (int64_t tile = t_begin; tile < t_end; ++tile) {

@@ -77,6 +77,14 @@ int launch_ln_fwd_atiles(const float* X, float* xhat, float* rstd, int64_t T, in
 int launch_attn_fused_fwd(const uint8_t* xhat_tiles, const uint8_t* wheads, const float* bq, const float* b_dyn,
                           const int64_t* x, float* U, float* probs, int64_t B, int L, DropCfg drop, cudaStream_t s);
 
+// X-form forward (attn_xform.cu, L <= 5): neighbours' xhat rows stay in registers, no per-head shuffles.
+//   wx  8 per-head blocks of kXformWBytes (N_h = Wk_h^T Wq_h | Wg_h, bf16 hi | lo), vx [8, 64] = Wk_h^T bq_h: launch_prep_xform
+//   passes  3 = bf16x3 split contractions (fp32-accurate), 1 = single bf16 pass (stated-tolerance mode)
+constexpr int kXformWBytes = 32768;
+int launch_prep_xform(const float* W, const float* bq, void* wx, float* vx, cudaStream_t s);
+int launch_attn_xform_fwd(const uint8_t* xhat_tiles, const float* xhat, const uint8_t* wx, const float* vx, const float* b_dyn,
+                          const int64_t* x, float* U, float* probs, int64_t B, int L, DropCfg drop, int passes, cudaStream_t s);
+
 // backward of the same block: recompute per head pair, shuffle attention backward, tcgen05 data and weight gradients.
 //   wpairs       launch_split_w_pairs output (4 head pairs x 3 pieces x 32 KB)
 //   dxhat_parts  [4, T, 64] per-head-pair partial data gradients (summed by launch_ln_tanh_bwd)

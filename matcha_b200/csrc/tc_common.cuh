@@ -135,6 +135,23 @@ __device__ __forceinline__ void umma_x3(uint32_t tmem_d, uint32_t a_hi, uint32_t
   umma_bf16(tmem_d, make_smem_desc(a_hi, a_lbo, 128), make_smem_desc(b_hi, b_lbo, 128), idesc, 1u);
 }
 
+// one lane of a converged warp (CUTLASS's elect_one_sync): single-thread roles branch on this instead of `lane == 0`, so
+// ptxas knows the tcgen05.mma / commit sequence runs converged and emits the uniform-datapath instructions directly (a
+// `lane == 0` branch makes it wrap every UTCHMMA in an ELECT / BRA.U.ANY loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor of the same operand layout at another shared-memory address: only the 14-bit address field changes
+__device__ __forceinline__ uint64_t desc_at(uint64_t base_desc, uint32_t byte_offset) { return base_desc + (uint64_t)(byte_offset >> 4); }
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
