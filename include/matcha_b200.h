@@ -171,6 +171,33 @@ int matcha_adamw(float* params, const float* grads, float* exp_avg, float* exp_a
                  float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Data-parallel step boundary over NVLink peer memory (no counterpart in the single-process
+ * reference): cross-GPU barrier -> all-reduce of the flat gradient buffers (P2P loads, summed in rank order so every
+ * replica computes bit-identical values) -> mean -> AdamW on the own replica (same semantics as matcha_adamw, activity flags
+ * OR-ed over ranks) -> barrier -> the own gradient buffer is zeroed for the next step.  One launch instead of
+ * ncclAllReduce + AdamW + memset.
+ *   grad_ptrs / active_ptrs / barrier_ptrs   HOST arrays of `world` device pointers, entry r = rank r's buffer as mapped
+ *                                            into this process (cudaIpcOpenMemHandle); entry `rank` = the own buffer
+ *   barrier buffer                           matcha_dp_barrier_bytes() bytes per rank, zero-filled once at set-up
+ *   epoch                                    1, 2, 3, ... : the same value on every rank for the same step
+ * All ranks must call this once per step with the same arguments (it spins, bounded, until every peer has arrived).
+ * --------------------------------------------------------------------------------------------- */
+int32_t matcha_dp_blocks(void);
+int matcha_enable_peer_access(int32_t peer_device);   /* cudaDeviceEnablePeerAccess from the current device, idempotent */
+/* CUDA IPC: handle (64 bytes) of the cudaMalloc allocation starting at base_ptr; map a peer process's allocation for kernels
+ * of the current device (cudaIpcMemLazyEnablePeerAccess); unmap */
+int matcha_ipc_get_handle(const void* base_ptr, uint8_t* handle64);
+int matcha_ipc_open(const uint8_t* handle64, void** mapped_base);
+int matcha_ipc_close(void* mapped_base);
+int64_t matcha_dp_barrier_bytes(void);
+int matcha_dp_reduce_adamw(int32_t world, int32_t rank, const void* const* grad_ptrs, const void* const* active_ptrs,
+                           void* const* barrier_ptrs, float* params, float* exp_avg, float* exp_avg_sq,
+                           int32_t* active_reduced, int64_t n_always, int64_t n_flat, int32_t n_seg, int32_t n_flags,
+                           const int64_t* seg_begin, const int64_t* seg_end, const int32_t* seg_flag, int32_t* seg_step,
+                           int32_t step, uint32_t epoch, float lr, float beta1, float beta2, float eps, float weight_decay,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * k-mer enumeration + counting — generate_kmers.py:8-69 (build_dict) and :86-141: the producer of
  * all_<k>_counter.npy / all_<k>_freq_counter.npy.
  *   members / offsets   dev int64 CSR of the clusters (unique ascending node ids per cluster, process.py:72-78)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmatcha_b200.so")
-SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "attn_xform.cu", "chain.cu", "rowwise.cu", "optim.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu", "recon_tc.cu", "enc_tc.cu", "kmers.cu", "metrics.cu", "denoise.cu", "features.cu"]
+SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "attn_xform.cu", "chain.cu", "rowwise.cu", "optim.cu", "dp_fused.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu", "recon_tc.cu", "enc_tc.cu", "kmers.cu", "metrics.cu", "denoise.cu", "features.cu"]
 NVCC_COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                       "-Xcompiler", "-fPIC"]
 NVCC_LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
@@ -123,6 +123,14 @@ SYMBOLS = {
     "matcha_backward": (C.c_int, [_MD, _P, _I64, _I32, _U64, _I32, _P, _F, _P, _P, _I64, _P]),
     "matcha_node_embeddings": (C.c_int, [_MD, _P, _I64, _P, _P, _I64, _P]),
     "matcha_adamw": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _P]),
+    "matcha_dp_blocks": (_I32, []),
+    "matcha_enable_peer_access": (C.c_int, [_I32]),
+    "matcha_ipc_get_handle": (C.c_int, [_P, _P]),
+    "matcha_ipc_open": (C.c_int, [_P, _P]),
+    "matcha_ipc_close": (C.c_int, [_P]),
+    "matcha_dp_barrier_bytes": (_I64, []),
+    "matcha_dp_reduce_adamw": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _I32,
+                                         C.c_uint32, _F, _F, _F, _F, _F, _P]),
     "matcha_hashset_insert": (C.c_int, [_P, _I64, _P, _I64, _I32, _P]),
     "matcha_hashset_contains": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _P]),
     "matcha_neg_sample": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _I32,

@@ -34,11 +34,14 @@ class Trainer:
             self.e.require_inter()            # beta * recon with no target would silently train on 0 (main.py phase 1!)
         self.opt = FlatAdamW(self.e, lr=lr, weight_decay=weight_decay)
         self.world = int(world_size)
+        self.rank = int(rank)
+        self._peer = None
         if self.world > 1:
             # every replica must start from the SAME weights: rank 0's parameters win (a launcher that forgot to seed the
             # constructors identically would otherwise all-reduce gradients taken at different points forever)
             import torch.distributed as dist
             dist.broadcast(self.e.flat, src=0)
+            self._setup_peer_step()
         self.neg_num = sampler.neg_num
         # the per-step chromosome draw of Modules.py:192 -- one shared stream so all ranks draw the same one
         self.recon_rng = recon_rng or np.random.RandomState(seed)
@@ -51,6 +54,41 @@ class Trainer:
         self._side = torch.cuda.Stream(device=self.e.dev)
         self._side2 = torch.cuda.Stream(device=self.e.dev)     # assembles the next step's batch (see step())
         self._copy = None
+
+    def _setup_peer_step(self):
+        """Map every rank's gradient buffer / activity flags / barrier flags into this process so the step boundary runs as
+        ONE kernel over NVLink peer memory (csrc/dp_fused.cu).  Falls back to the NCCL all-reduce + AdamW launches when the
+        GPUs cannot map each other (MATCHA_DP_FUSED=0 forces that path).  The decision is made collectively."""
+        import ctypes as C
+        import os
+        import torch.distributed as dist
+        from .parallel import PeerBuffers, peer_access_available
+        e = self.e
+        ok = os.environ.get("MATCHA_DP_FUSED", "1") != "0" and dist.get_backend() == "nccl" and self.world <= 8 \
+            and peer_access_available(self.world) and e.n_flat % 4 == 0 and e.n_always % 4 == 0
+        flag = torch.tensor([1 if ok else 0], device=e.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return
+        bar = torch.zeros(int(e.lib.matcha_dp_barrier_bytes()) // 4, dtype=torch.int32, device=e.dev)
+        self.active_red = torch.zeros_like(e.active)
+        torch.cuda.synchronize()
+        dist.barrier()
+        peers = {"g": PeerBuffers(e.gflat, self.rank, self.world), "a": PeerBuffers(e.active, self.rank, self.world),
+                 "b": PeerBuffers(bar, self.rank, self.world)}
+        arr = lambda pb: (C.c_void_p * self.world)(*pb.ptrs)
+        self._peer = {"bufs": peers, "g": arr(peers["g"]), "a": arr(peers["a"]), "b": arr(peers["b"]), "epoch": 0}
+        dist.barrier()
+
+    def _peer_step(self):
+        """all-reduce + mean + AdamW + gradient-buffer clear in one launch (every rank calls it once per step)."""
+        e, o, pr = self.e, self.opt, self._peer
+        pr["epoch"] += 1
+        o.t += 1
+        check(e.lib.matcha_dp_reduce_adamw(self.world, self.rank, pr["g"], pr["a"], pr["b"], ptr(e.flat), ptr(o.m1), ptr(o.m2),
+                                           ptr(self.active_red), e.n_always, e.n_flat, len(e.segments), e.active.numel(),
+                                           ptr(o.seg_begin), ptr(o.seg_end), ptr(o.seg_flag), ptr(o.seg_step), o.t, pr["epoch"],
+                                           o.lr, o.betas[0], o.betas[1], o.eps, o.wd, stream_ptr()), "matcha_dp_reduce_adamw")
 
     def _buffers(self, P, L):
         if self._buf_P == (P, L):
@@ -122,12 +160,16 @@ class Trainer:
             self._pending = (next_pos.data_ptr(), next_w.data_ptr(), P, L)
         check(lib.matcha_bce_loss(ptr(self.logits), ptr(self.y), ptr(w), n, self.alpha, self.beta, ptr(self.recon),
                                   ptr(self.dlogit), ptr(self.loss_out), stream_ptr()), "matcha_bce_loss")
-        e.gflat.zero_()
+        if self._peer is None or self._peer["epoch"] == 0:
+            e.gflat.zero_()                     # (the fused data-parallel step clears the buffer itself afterwards)
         e.run_backward(x, seed, rchrom, self.dlogit, self.beta)
         self._released[slot].record(main)
-        # one collective per step: gradients + activity flags (no-op when world == 1)
-        scale = allreduce_grads_and_flags(e.gflat, e.n_flat, e.active, self.world)
-        self.opt.step(grad_scale=scale)
+        if self._peer is not None:
+            self._peer_step()                   # barrier + P2P all-reduce + mean + AdamW + clear: one launch over NVLink
+        else:
+            # one collective per step: gradients + activity flags (no-op when world == 1)
+            scale = allreduce_grads_and_flags(e.gflat, e.n_flat, e.active, self.world)
+            self.opt.step(grad_scale=scale)
         self.loss_sum += self.loss_out
         self.steps += 1
         self._slot = slot ^ 1 if self._pending is not None else slot
