@@ -181,6 +181,7 @@ int matcha_adamw(float* params, const float* grads, float* exp_avg, float* exp_a
  *   barrier buffer                           matcha_dp_barrier_bytes() bytes per rank, zero-filled once at set-up
  *   epoch                                    1, 2, 3, ... : the same value on every rank for the same step
  * All ranks must call this once per step with the same arguments (it spins, bounded, until every peer has arrived).
+ * world = 1 (barrier_ptrs may be NULL) is the single-replica form: AdamW + gradient-buffer clear in one launch.
  * --------------------------------------------------------------------------------------------- */
 int32_t matcha_dp_blocks(void);
 int matcha_enable_peer_access(int32_t peer_device);   /* cudaDeviceEnablePeerAccess from the current device, idempotent */

@@ -46,6 +46,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 __device__ __forceinline__ void peer_barrier(const DpArgs& a, int phase, uint32_t epoch) {
+  if (a.world == 1) { __syncthreads(); return; }      // single replica: the same kernel is the fused AdamW + clear
   __syncthreads();
   if ((int)threadIdx.x < a.world) {
     const int peer = threadIdx.x;
@@ -179,17 +180,17 @@ int matcha_dp_reduce_adamw(int32_t world, int32_t rank, const void* const* grad_
                            int64_t n_always, int64_t n_flat, int32_t n_seg, int32_t n_flags, const int64_t* seg_begin,
                            const int64_t* seg_end, const int32_t* seg_flag, int32_t* seg_step, int32_t step, uint32_t epoch, float lr,
                            float beta1, float beta2, float eps, float weight_decay, void* stream) {
-  MATCHA_REQUIRE(world >= 2 && world <= kDpMaxWorld && rank >= 0 && rank < world, "matcha_dp_reduce_adamw: world=%d rank=%d (2..%d ranks)",
+  MATCHA_REQUIRE(world >= 1 && world <= kDpMaxWorld && rank >= 0 && rank < world, "matcha_dp_reduce_adamw: world=%d rank=%d (1..%d ranks)",
                  (int)world, (int)rank, kDpMaxWorld);
-  MATCHA_REQUIRE(grad_ptrs && active_ptrs && barrier_ptrs && params && exp_avg && exp_avg_sq && active_reduced && step >= 1 && epoch >= 1,
+  MATCHA_REQUIRE(grad_ptrs && active_ptrs && (world == 1 || barrier_ptrs) && params && exp_avg && exp_avg_sq && active_reduced && step >= 1 && epoch >= 1,
                  "matcha_dp_reduce_adamw: NULL argument");
   MATCHA_REQUIRE(n_seg >= 0 && n_seg <= kDpMaxSeg && n_flat % 4 == 0 && n_always % 4 == 0, "matcha_dp_reduce_adamw: n_seg=%d (<= %d), buffers 4-float aligned",
                  (int)n_seg, kDpMaxSeg);
   DpArgs a;
   a.world = world; a.rank = rank;
   for (int r = 0; r < world; ++r) {
-    MATCHA_REQUIRE(grad_ptrs[r] && active_ptrs[r] && barrier_ptrs[r], "matcha_dp_reduce_adamw: peer %d pointers missing", r);
-    a.g[r] = (const float*)grad_ptrs[r]; a.act[r] = (const int32_t*)active_ptrs[r]; a.bar[r] = (uint32_t*)barrier_ptrs[r];
+    MATCHA_REQUIRE(grad_ptrs[r] && active_ptrs[r] && (world == 1 || barrier_ptrs[r]), "matcha_dp_reduce_adamw: peer %d pointers missing", r);
+    a.g[r] = (const float*)grad_ptrs[r]; a.act[r] = (const int32_t*)active_ptrs[r]; a.bar[r] = world == 1 ? nullptr : (uint32_t*)barrier_ptrs[r];
   }
   a.p = params; a.m1 = exp_avg; a.m2 = exp_avg_sq; a.g_own = const_cast<float*>(a.g[rank]);
   a.act_red = active_reduced; a.n_always = n_always; a.n_flat = n_flat; a.n_seg = n_seg; a.n_flags = n_flags;

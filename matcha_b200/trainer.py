@@ -21,7 +21,10 @@ from .sampler import NegativeSampler
 
 class Trainer:
     def __init__(self, model, sampler: NegativeSampler, alpha=1.0, beta=0.001, lr=1e-3, weight_decay=0.01,
-                 seed=0, world_size=1, rank=0, recon_rng=None):
+                 seed=0, world_size=1, rank=0, recon_rng=None, fused_boundary=True):
+        """fused_boundary=False keeps the step boundary as separate launches (all-reduce, AdamW) and leaves the step's
+        gradients in the flat buffer afterwards (tests that inspect them); the default clears the buffer inside the fused
+        boundary kernel."""
         model.train()
         self.model = model
         self.e = model._engine()
@@ -36,12 +39,19 @@ class Trainer:
         self.world = int(world_size)
         self.rank = int(rank)
         self._peer = None
+        if self.world == 1 and fused_boundary and self.e.n_flat % 4 == 0 and self.e.n_always % 4 == 0:
+            # single replica: the same kernel without barriers = AdamW + gradient-buffer clear in ONE launch
+            import ctypes as C
+            self.active_red = torch.zeros_like(self.e.active)
+            self._peer = {"g": (C.c_void_p * 1)(self.e.gflat.data_ptr()), "a": (C.c_void_p * 1)(self.e.active.data_ptr()), "b": None,
+                          "epoch": 0}
         if self.world > 1:
             # every replica must start from the SAME weights: rank 0's parameters win (a launcher that forgot to seed the
             # constructors identically would otherwise all-reduce gradients taken at different points forever)
             import torch.distributed as dist
             dist.broadcast(self.e.flat, src=0)
-            self._setup_peer_step()
+            if fused_boundary:
+                self._setup_peer_step()
         self.neg_num = sampler.neg_num
         # the per-step chromosome draw of Modules.py:192 -- one shared stream so all ranks draw the same one
         self.recon_rng = recon_rng or np.random.RandomState(seed)
@@ -85,6 +95,8 @@ class Trainer:
         e, o, pr = self.e, self.opt, self._peer
         pr["epoch"] += 1
         o.t += 1
+        if self.world == 1 and pr["g"][0] != e.gflat.data_ptr():      # the engine re-bound its buffers (model.to(...))
+            pr["g"][0], pr["a"][0] = e.gflat.data_ptr(), e.active.data_ptr()
         check(e.lib.matcha_dp_reduce_adamw(self.world, self.rank, pr["g"], pr["a"], pr["b"], ptr(e.flat), ptr(o.m1), ptr(o.m2),
                                            ptr(self.active_red), e.n_always, e.n_flat, len(e.segments), e.active.numel(),
                                            ptr(o.seg_begin), ptr(o.seg_end), ptr(o.seg_flag), ptr(o.seg_step), o.t, pr["epoch"],
