@@ -362,11 +362,21 @@ __device__ __forceinline__ void store_drow(uint8_t* sD, int p0, int r, const flo
   }
 }
 
+// umma_x3s with a run-time pass count: 3 = fp32-accurate bf16 split, 1 = hi * hi only (bf16 mode)
+__device__ __forceinline__ void umma_xps(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t a_lbo,
+                                         uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, bool first, int passes) {
+  if (passes == 3) {
+    umma_x3s(tmem_d, a_hi, a_lo, b_hi, b_lo, a_lbo, a_sbo, b_lbo, b_sbo, idesc, first);
+  } else {
+    umma_bf16(tmem_d, make_smem_desc(a_hi, a_lbo, a_sbo), make_smem_desc(b_hi, b_lbo, b_sbo), idesc, first ? 0u : 1u);
+  }
+}
+
 template <int L>
 __global__ void __launch_bounds__(kBThreads, 1)
 attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict__ wpairs, const float* __restrict__ bq,
                       const float* __restrict__ dd_in, const float* __restrict__ probs, float* __restrict__ dxhat_parts,
-                      float* __restrict__ dW, float* __restrict__ dbq, float* __restrict__ db_dyn, int64_t T) {
+                      float* __restrict__ dW, float* __restrict__ dbq, float* __restrict__ db_dyn, int64_t T, int passes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sX = smem + kBWBytes;
@@ -429,8 +439,8 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         const uint32_t wh = smem_u32(sW + g * kBWPiece), wl = wh + 16384;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_x3s(tmem_base + kColR + rb * 128, xh + ks * 4096, xl + ks * 4096, wh + ks * 4096, wl + ks * 4096, 2048, 128,
-                   2048, 128, idescR, ks == 0);
+          umma_xps(tmem_base + kColR + rb * 128, xh + ks * 4096, xl + ks * 4096, wh + ks * 4096, wl + ks * 4096, 2048, 128,
+                   2048, 128, idescR, ks == 0, passes);
         umma_commit(&r_full[rb]);
       };
       if (N > 0) recompute(0);
@@ -447,12 +457,12 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         const uint32_t wh = smem_u32(sW + gp * kBWPiece), wl = wh + 16384;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)   // dxhat[128 tok, 64] += d[128 tok, 128 f] . W_piece[128 f, 64]   (B MN-major)
-          umma_x3s(tmem_base + kColDX, dh + ks * 4096, dl + ks * 4096, wh + ks * 256, wl + ks * 256, 2048, 128, 128, 2048,
-                   idescD, g == 0 && ks == 0);
+          umma_xps(tmem_base + kColDX, dh + ks * 4096, dl + ks * 4096, wh + ks * 256, wl + ks * 256, 2048, 128, 128, 2048,
+                   idescD, g == 0 && ks == 0, passes);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)   // dW_piece[128 f, 64] += d^T[128 f, 128 tok] . xhat[128 tok, 64]  (both MN-major)
-          umma_x3s(tmem_base + kColDW + gp * 64, dh + ks * 256, dl + ks * 256, xh + ks * 256, xl + ks * 256, 128, 2048, 128,
-                   2048, idescW, k == 0 && ks == 0);
+          umma_xps(tmem_base + kColDW + gp * 64, dh + ks * 256, dl + ks * 256, xh + ks * 256, xl + ks * 256, 128, 2048, 128,
+                   2048, idescW, k == 0 && ks == 0, passes);
         umma_commit(&d_empty);
         if (g == 2) { umma_commit(&dx_full); umma_commit(&x_empty[xb]); }
       }
@@ -694,13 +704,13 @@ int launch_fwd_L(const uint8_t* xt, const uint8_t* wheads, const float* bq, cons
 template <int L>
 int launch_bwd_L(const uint8_t* xt, const uint8_t* wpairs, const float* bq, const float* dd,
                  const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn, int64_t T,
-                 cudaStream_t s) {
+                 int passes, cudaStream_t s) {
   static bool once = false;
   if (!once) { if (int rc = set_smem_attr_a(attn_fused_bwd_kernel<L>, kBSmem)) return rc; once = true; }
   const int64_t ntiles = num_atiles(T, L);
   const int S = (int)(ntiles < kSMs / 4 ? ntiles : kSMs / 4);
   (void)part;       // split-K partial buffer of earlier builds: the slices are reduced with atomics now
-  attn_fused_bwd_kernel<L><<<4 * S, kBThreads, kBSmem, s>>>(xt, wpairs, bq, dd, probs, dxhat_parts, dW, dbq, db_dyn, T);
+  attn_fused_bwd_kernel<L><<<4 * S, kBThreads, kBSmem, s>>>(xt, wpairs, bq, dd, probs, dxhat_parts, dW, dbq, db_dyn, T, passes);
   MATCHA_CHECK_LAUNCH("attn_fused_bwd");
   return MATCHA_OK;
 }
@@ -730,7 +740,7 @@ __global__ void mask_drop_kernel(float* __restrict__ dU, const int64_t* __restri
 
 int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, float* dU,
                           const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn,
-                          int64_t B, int L, DropCfg drop, int premasked, cudaStream_t s) {
+                          int64_t B, int L, DropCfg drop, int premasked, int passes, cudaStream_t s) {
   if (B <= 0) return MATCHA_OK;
   const int64_t T = B * L;
   if (!premasked) {
@@ -740,11 +750,11 @@ int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, cons
     MATCHA_CHECK_LAUNCH("mask_drop");
   }
   switch (L) {
-    case 2: return launch_bwd_L<2>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
-    case 3: return launch_bwd_L<3>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
-    case 4: return launch_bwd_L<4>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
-    case 5: return launch_bwd_L<5>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
-    case 6: return launch_bwd_L<6>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, s);
+    case 2: return launch_bwd_L<2>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, passes, s);
+    case 3: return launch_bwd_L<3>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, passes, s);
+    case 4: return launch_bwd_L<4>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, passes, s);
+    case 5: return launch_bwd_L<5>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, passes, s);
+    case 6: return launch_bwd_L<6>(xhat_tiles, wpairs, bq, dU, probs, dxhat_parts, part, dW, dbq, db_dyn, T, passes, s);
     default: set_error("attn_fused_bwd: padded width L=%d unsupported (2..6)", L); return MATCHA_ERR_ARG;
   }
 }

@@ -855,7 +855,7 @@ int matcha_backward(const matcha_model_desc* m, const int64_t* x, int64_t B, int
     dx_parts = 4;
     if ((rc = PROF(P_ATTN_BWD, 1, launch_attn_fused_bwd(w.xhat_t, reinterpret_cast<const uint8_t*>(m->derived + l.wpairs),
                                                         m->derived + l.bqkg, x, w.dU, w.probs, w.dQKG, w.tc_scratch,
-                                                        DG + l.wqkg, DG + l.bqkg, DG + l.bdyn, B, L, dattn, chain ? 1 : 0, s)))) return rc;
+                                                        DG + l.wqkg, DG + l.bqkg, DG + l.bdyn, B, L, dattn, chain ? 1 : 0, mma_passes(), s)))) return rc;
   } else if (use_tiles(m, T)) {
     // tile path: the attention backward emits dQKG directly as bf16 hi|lo MMA tiles; rows of the last tile beyond T are zero
     const int64_t nt = num_token_tiles(T);

@@ -94,7 +94,7 @@ int launch_split_w_pairs(const float* W, void* out, cudaStream_t s);
 int64_t attn_fused_bwd_scratch_floats();
 int launch_attn_fused_bwd(const uint8_t* xhat_tiles, const uint8_t* wpairs, const float* bq, const int64_t* x, float* dU,
                           const float* probs, float* dxhat_parts, float* part, float* dW, float* dbq, float* db_dyn,
-                          int64_t B, int L, DropCfg drop, int premasked, cudaStream_t s);
+                          int64_t B, int L, DropCfg drop, int premasked, int passes, cudaStream_t s);
 constexpr int kPairWBytes = 3 * 32768;                 // per head pair: G | K | Q piece pairs, bf16 hi | lo
 
 // row-chain kernels (chain.cu): the 64-wide layers around the attention block on tensor cores, thread = tile row
