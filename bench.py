@@ -39,6 +39,7 @@ WORKLOADS = {
     # the same at any N, so `--workload cfg3 --gpus 1` measures one rank of it): parity cases, selectable here
     "cfg1": "cfg1: synthetic SPRITE-like clusters, chr1+chr2 at 1 Mb (494 bins), k=2..5 mixed, embed_dim 64",
     "cfg3": "cfg3: synthetic SPRITE-like clusters, whole-genome 100 kb (30344 bins, 23 chromosomes), k=2..5 mixed, embed_dim 64",
+    "cfg5": "cfg5: synthetic SPRITE-like clusters, whole-genome 50 kb (60653 bins, 23 chromosomes), k=2..5 mixed, embed_dim 128",
 }
 POS_PER_STEP = 4096          # positives per GPU per step; x3 negatives -> 16384 hyperedges / GPU / step
 NEG_NUM = 3
@@ -152,6 +153,8 @@ def main():
     ap.add_argument("--pos-per-step", type=int, default=POS_PER_STEP)
     ap.add_argument("--cpu-baseline-steps", type=int, default=8)
     ap.add_argument("--no-cfg3", action="store_true", help="skip the configs[2] (30,344 bins) sub-measurement")
+    ap.add_argument("--cfg5", action="store_true", help="also measure configs[4] (60,653 bins, embed_dim 128: fp32 SIMT contractions); "
+                                                        "needs ~60 GB of host memory per rank for the synthetic dense matrices")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-impl", type=int, default=-1, help="-1 library default, 0 SIMT, 1 tcgen05")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -428,6 +431,24 @@ def main():
                 "kernel_ms_per_step": {k: round(v[0] / k3, 4) for k, v in sorted(m3["prof"].items(), key=lambda kv: -kv[1][0])},
                 "hbm_kernels": hbm_kernels(ds3, m3), "losses": m3["losses"]}
         del ds3
+    # configs[4] (whole genome at 50 kb, 60,653 bins, embed_dim 128): every contraction runs on the fp32 SIMT path at this
+    # width; opt-in because the synthetic dense N x N matrices need ~60 GB of host memory per rank
+    cfg5 = None
+    if args.cfg5:
+        import psutil
+        avail = psutil.virtual_memory().available
+        if avail < 70e9 * max(1, world):
+            cfg5 = {"skipped": "host memory: %.0f GB available, ~60 GB per rank needed" % (avail / 1e9)}
+        else:
+            ds5 = make_dataset("cfg5", kmers_per_size=min(args.kmers_per_size, 50_000), seed=0)
+            k5 = max(3, args.steps // 4)
+            m5 = measure_training(ds5, P, k5, 3, False, False)
+            cfg5 = {"workload": WORKLOADS["cfg5"], "value": P * (1 + NEG_NUM) * world * k5 / (m5["ms_dev"] * 1e-3), "unit": UNIT,
+                    "ms_per_step": m5["ms_dev"] / k5, "steps": k5, "n_gpus": world, "hyperedges_per_gpu_per_step": P * (1 + NEG_NUM),
+                    "contractions": "fp32 SIMT (embed_dim 128 has no tcgen05 path yet)",
+                    "kernel_ms_per_step": {k: round(v[0] / k5, 4) for k, v in sorted(m5["prof"].items(), key=lambda kv: -kv[1][0])},
+                    "losses": m5["losses"]}
+            del ds5
     pair_total, pair_ms, pair_e2e_ms, pair_wall_ms, pair_stages = (0, 1.0, 1.0, 1.0, {}) if args.no_pairs else pair_scorer_bench()
 
     if rank != 0:
@@ -496,6 +517,18 @@ def main():
                     "what": "model -> per-node tables (encoder over 24,897 rows of 100 KB) -> packed operands -> all-pairs scores (sharded) "
                             "-> gather to rank 0 -> denoise post-processing on the device (denoise_contact.py:160-192, quantile map "
                             "included) -> finished [n, n] matrix copied to pinned host memory"}}
+    # SURVEY 8f rank 1 (generate_kmers.py): k-mer enumeration + counting on synthetic clusters, the producer of this path's inputs
+    kmers = None
+    if not args.no_pairs:
+        try:
+            import importlib.util
+            import types
+            spec = importlib.util.spec_from_file_location("bench_kmers", os.path.join(ROOT, "scripts", "bench_kmers.py"))
+            bk = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(bk)
+            kmers = bk.measure(types.SimpleNamespace(clusters=500_000, nodes=30344, k=3, min_distance=0, min_freq=2, cpu_sample=5000))
+        except Exception as exc:      # a secondary measurement must not take the headline line down
+            kmers = {"error": repr(exc)}
     launches = int(sum(v[2] for v in prof.values()))
     breakdown = {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
 
@@ -510,7 +543,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(P * 5 * 8 + P * 4), "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "kernel_ms_per_step": breakdown, "losses": losses,
-            "pair_scores": None if args.no_pairs else pair, "large_batch": big, "cfg3": cfg3,
+            "pair_scores": None if args.no_pairs else pair, "large_batch": big, "cfg3": cfg3, "cfg5": cfg5, "kmers": kmers,
             "bloom_agreement": "not measured: the reference's positive set is pybloom_live.BloomFilter (third party, version unpinned, "
                                "absent from this image); membership here is exact (bit-exact vs a CPU set, tests/test_gpu_parity.py)"}
     # achieved HBM GB/s of the node-encoder kernels (the north star's evidence for the sparse-row encoder)

@@ -52,6 +52,15 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
+    line = measure(args)
+    print(json.dumps(line))
+    if args.out:
+        open(args.out, "w").write(json.dumps(line) + "\n")
+
+
+def measure(args):
+    """args: namespace with clusters, nodes, k, min_distance, min_freq, cpu_sample.  Returns the result dict (also used by
+    bench.py for its `kmers` sub-object)."""
     import torch
     from math import comb
     from matcha_b200 import _lib
@@ -69,7 +78,7 @@ def main():
     while cap < 2 * total:
         cap <<= 1
     cap = min(cap, 1 << 27)
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", torch.cuda.current_device())
     md, od, pd = (torch.from_numpy(a).to(dev) for a in (members, offsets, prefix))
     table = torch.zeros(2 * cap, dtype=torch.int64, device=dev)
     counts = torch.zeros(cap, dtype=torch.int32, device=dev)
@@ -117,9 +126,7 @@ def main():
                          "note": "algorithmic bytes per subset: 8k member ids + 16 B slot + 4 B count; random access"},
             "cpu_baseline": {"value": cpu_subsets / cpu_s, "unit": "k-subsets/s", "cores": 1, "kind": "port",
                              "sample": f"first {ns} clusters ({cpu_subsets} subsets), oracle/kmer_oracle.py"}}
-    print(json.dumps(line))
-    if args.out:
-        open(args.out, "w").write(json.dumps(line) + "\n")
+    return line
 
 
 if __name__ == "__main__":
