@@ -53,6 +53,7 @@ void matcha_set_chain(int32_t on);
 /* 1 (default) = the reconstruction head (Modules.py:192-199) and its backward run as one fused tcgen05 kernel per pass
  * (needs the fused path), 0 = four SIMT launches through a [T, n_r] buffer; also MATCHA_RECON_TC=0 */
 void matcha_set_recon_tc(int32_t on);
+void matcha_set_recon_pipe(int32_t on);   /* pipelined gradient pass of the reconstruction head (default on) */
 /* 1 (default) = both node-encoder layers (Modules.py:104-122) run as one tcgen05 kernel over the chromosome-bucketed
  * token list (dense feature rows, embed_dim 64, >= 1024 tokens), 0 = two grouped SIMT launches; also MATCHA_ENC_TC=0 */
 void matcha_set_enc_tc(int32_t on);

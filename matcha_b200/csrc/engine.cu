@@ -134,6 +134,14 @@ static bool use_recon_tc(const matcha_model_desc* m, int64_t T, int L) {
   }
   return g_recon_tc == 1 && use_fused(m, T, L);
 }
+static int g_recon_pipe = -1;   // pipelined gradient pass of that head (MATCHA_RECON_PIPE=0 keeps the unit-serial kernel)
+static bool use_recon_pipe() {
+  if (g_recon_pipe < 0) {
+    const char* e = getenv("MATCHA_RECON_PIPE");
+    g_recon_pipe = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_recon_pipe == 1;
+}
 
 static int run_gemm(const GemmDesc& d, cudaStream_t s, int label, bool allow_tc = true) {
   prof_begin(label, s);
@@ -409,6 +417,7 @@ struct Workspace {
   uint8_t *v0_t, *attr_t, *u_t, *h1_t, *dh2_t, *dh1_t, *dp_t, *dv0_t;   // row-chain tiles kept for the weight-gradient kernel
   float* wpair_scratch;
   float *dlogit, *dH2, *dXs, *dH1pre, *dU, *dQKG, *dxhat, *dP, *dV0, *dtE, *dE, *dH0pre, *tc_scratch;
+  uint8_t* recon_tiles;    // tanh(E) operand tiles of the eligible tokens (recon_pipe.cu)
   float* recon_stash;      // unscaled dRw [n_r, 64] | drb [n_r] left by the training forward of the fused recon head
   int64_t tc_scratch_floats;
   int64_t pred_ld;
@@ -467,6 +476,7 @@ static Workspace carve(const matcha_model_desc* m, int64_t B, int L, int trainin
       w.wpair_scratch = (float*)take(sizeof(float) * wgrad_pair_scratch_floats());
     }
     if (m->inter) w.recon_stash = (float*)take(sizeof(float) * max_chrom_len(m) * (D + 1));
+    if (m->inter && tc) w.recon_tiles = (uint8_t*)take(recon_pipe_tile_bytes(T));
     w.tc_scratch_floats = gemm_tc_scratch_floats(QKG);
     w.tc_scratch = (float*)take(sizeof(float) * w.tc_scratch_floats);
   }
@@ -637,6 +647,7 @@ void matcha_set_gemm_impl(int32_t impl) { g_gemm_impl = impl; }
 void matcha_set_fused(int32_t on) { g_fused = on != 0; }
 void matcha_set_chain(int32_t on) { g_chain = on != 0; }
 void matcha_set_recon_tc(int32_t on) { g_recon_tc = on != 0; }
+void matcha_set_recon_pipe(int32_t on) { g_recon_pipe = on != 0; }
 void matcha_set_enc_tc(int32_t on) { g_enc_tc = on != 0; }
 void matcha_set_xform(int32_t on) { g_xform = on != 0; }
 void matcha_set_mma_passes(int32_t passes) { g_passes = passes == 1 ? 1 : 3; }
@@ -734,7 +745,12 @@ int matcha_forward(const matcha_model_desc* m, const int64_t* x, int64_t B, int3
           if ((rc = check_cuda(cudaMemsetAsync(st, 0, sizeof(float) * (re - rs) * (Dm + 1), s), "memset recon stash"))) return rc;
           if ((rc = check_cuda(cudaMemsetAsync(w.dtE, 0, sizeof(float) * T * Dm, s), "memset dtE"))) return rc;
         }
-        if ((rc = PROF(P_RECON_PRED, 1, launch_recon_tc(w.E, x, T, m->inter, m->inter_ld, rs, re, m->params + m->off_rw[random_chrom],
+        if (training && use_recon_pipe()) {
+          if ((rc = PROF(P_RECON_PRED, 2, launch_recon_pipe(w.E, x, T, m->inter, m->inter_ld, rs, re, m->params + m->off_rw[random_chrom],
+                                                            m->params + m->off_rb[random_chrom], w.counts, random_chrom, m->n_chrom,
+                                                            w.perm, w.group_off, w.recon, st, st + (re - rs) * Dm, w.dtE,
+                                                            w.recon_tiles, s)))) return rc;
+        } else if ((rc = PROF(P_RECON_PRED, 1, launch_recon_tc(w.E, x, T, m->inter, m->inter_ld, rs, re, m->params + m->off_rw[random_chrom],
                                                         m->params + m->off_rb[random_chrom], w.counts, random_chrom, m->n_chrom,
                                                         w.perm, w.group_off, w.recon, st, training ? st + (re - rs) * Dm : nullptr,
                                                         training ? w.dtE : nullptr, 1.f, training ? 1 : 0, s)))) return rc;

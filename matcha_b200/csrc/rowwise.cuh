@@ -137,6 +137,15 @@ int launch_recon_tc(const float* E, const int64_t* x, int64_t T, const float* in
 
 int launch_axpy(const float* in, float scale, float* out, int64_t n, cudaStream_t s);      // out += scale * in
 
+// pipelined gradient pass of the same head (recon_pipe.cu; same outputs as mode 1 with beta = 1): a pre-pass writes tanh(E) of
+// the eligible tokens as operand tiles into `tiles` (recon_pipe_tile_bytes(T) bytes), one persistent CTA per SM walks an equal
+// share of the (token tile x column block) units with the target loads of the next unit in flight
+int64_t recon_pipe_tile_bytes(int64_t T);
+int launch_recon_pipe(const float* E, const int64_t* x, int64_t T, const float* inter, int64_t inter_ld, int64_t rs, int64_t re,
+                      const float* Rw, const float* rb, const int32_t* counts, int rchrom, int n_chrom, const int32_t* perm,
+                      const int32_t* group_off, float* recon_out, float* dRw, float* drb, float* dtE, uint8_t* tiles,
+                      cudaStream_t s);
+
 // node encoder forward on tensor cores (enc_tc.cu): dense feature rows, embed_dim 64.  The pre-split weight chunks live in
 // the derived buffer from float offset split_base (enc_tc_split_floats(m) floats, rebuilt by launch_enc_tc_prepare)
 int64_t enc_tc_split_floats(const matcha_model_desc* m);
