@@ -23,14 +23,13 @@ namespace {
 
 constexpr int kPThreads = 320;                        // warps 0-7 compute, warp 8 producer, warp 9 MMA issuer
 constexpr int kPRec = 32768 + 1024;                   // tile record: hi 16 KB | lo 16 KB | tok[128] | row[128]  (int32)
-constexpr int kPA = 2 * 10 * 2048, kPAHalf = 10 * 2048;   // sA buffer: hi 10 planes | lo 10 planes (planes 8, 9: ones / zero)
+constexpr int kPA = 32768, kPAHalf = 16384;           // sA buffer: hi 8 planes | lo 8 planes
 constexpr int kPW = 32768;                            // sW: 128 target columns x 64 features, hi 16 KB | lo 16 KB
 constexpr int kPG = 65536;                            // sG: gdiff^T, hi 32 KB | lo 32 KB
-constexpr int kPABufs = 3;                            // operand ring: the bulk copies of unit u + 2 start when unit u - 1 retires
-constexpr int kPStageRow = 10;                        // dtE scatter staging: 32 rows x (8 floats + pad) per warp
-constexpr int kPStage = 8 * 32 * kPStageRow * 4;      // 10 240
-constexpr int kPSmem = kPABufs * kPA + kPW + kPG + kPStage;            // 231 424
-constexpr uint32_t kColP = 0, kColDT = 256, kColDW = 384;              // P^T 2 x 128 | dtE 2 x 64 | dRw 80
+constexpr int kPABufs = 3;                            // operand ring: the bulk copies of unit u + 3 start when unit u retires
+constexpr int kPTab = 1024;                           // index words of a tile (ride with the operand buffer)
+constexpr int kPSmem = kPABufs * (kPA + kPTab) + kPW + kPG;            // 199 680
+constexpr uint32_t kColP = 0, kColDT = 256, kColDW = 384;              // P^T 2 x 128 | dtE 2 x 64 | dRw 64
 
 struct PipeArgs {
   const uint8_t* tiles;
@@ -77,12 +76,17 @@ __global__ void __launch_bounds__(256) recon_tiles_kernel(const float* __restric
   }
 }
 
+// 16-byte vector reduction: one instruction adds four consecutive floats of a row
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;                                   // ring of kPABufs operand buffers
   uint8_t* sW = smem + kPABufs * kPA;
   uint8_t* sG = sW + kPW;
-  float* sStage = reinterpret_cast<float*>(sG + kPG);
+  uint8_t* sTabB = sG + kPG;                            // ring of index tables: [tok 128 | row 128] int32
   __shared__ uint64_t a_full[kPABufs], a_free[kPABufs], p_full[2], d_full[2], g_full;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,15 +105,6 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
     mbar_init(&g_full, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < kPABufs * 128; i += kPThreads) {      // ones column (feature 64) / zero plane never change
-    const int r = i & 127;
-    uint8_t* base = sA + (i >> 7) * kPA;
-    sts16(base + 8 * 2048 + r * 16, make_uint4(0x00003F80u, 0u, 0u, 0u));
-    sts16(base + 9 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
-    sts16(base + kPAHalf + 8 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
-    sts16(base + kPAHalf + 9 * 2048 + r * 16, make_uint4(0u, 0u, 0u, 0u));
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -158,17 +153,17 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
           const int64_t kk = k + i;
           const int sb = (int)(kk % kPABufs);
           mbar_wait_backoff(&a_free[sb], (uint32_t)((kk / kPABufs) & 1) ^ 1u);
-          mbar_expect_tx(&a_full[sb], 32768);
+          mbar_expect_tx(&a_full[sb], kPA + kPTab);
           const uint8_t* rec = a.tiles + (tile0 + i) * (int64_t)kPRec;
-          bulk_g2s(sA + sb * kPA, rec, 16384, &a_full[sb]);
-          bulk_g2s(sA + sb * kPA + kPAHalf, rec + 16384, 16384, &a_full[sb]);
+          bulk_g2s(sTabB + sb * kPTab, rec + 32768, kPTab, &a_full[sb]);
+          bulk_g2s(sA + sb * kPA, rec, kPA, &a_full[sb]);
         }
       }
     } else if (warp == 9) {
       if (elect_one()) {
         constexpr uint32_t idescP = make_idesc(128, 128, false, false);
         constexpr uint32_t idescD = make_idesc(128, 64, true, true);
-        constexpr uint32_t idescW = make_idesc(128, 80, false, true);
+        constexpr uint32_t idescW = make_idesc(128, 64, false, true);
         auto mma1 = [&](int64_t i) {          // P^T[128 col, 128 tok] = Rw block . tanh(E)^T   (K = 64)
           const int64_t kk = k + i;
           const int b = (int)(kk & 1), sb = (int)(kk % kPABufs);
@@ -194,7 +189,7 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
             umma_x3s(tmem_base + kColDT + b * 64, gh + ks * 256, gl + ks * 256, wh + ks * 256, wl + ks * 256, 128, 2048, 128, 2048,
                      idescD, ks == 0);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)      // dRw[128 col, 80] += gdiff^T[128 col, 128 tok] . [tanh(E) | 1][128 tok, 80]
+          for (int ks = 0; ks < 8; ++ks)      // dRw[128 col, 64] += gdiff^T[128 col, 128 tok] . tanh(E)[128 tok, 64]
             umma_x3s(tmem_base + kColDW, gh + ks * 4096, gl + ks * 4096, ah + ks * 256, al + ks * 256, 2048, 128, 128, 2048, idescW,
                      i == 0 && ks == 0);
           umma_commit(&d_full[b]);
@@ -208,31 +203,32 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
       const int64_t col = cb * 128 + c;
       const bool col_ok = col < n_r;
       const float rbc = col_ok ? __ldg(a.rb + col) : 0.f;
+      const float cmask = col_ok ? 1.f : 0.f;
       const float* tbase = a.inter + (a.rs - 1) + (col_ok ? col : n_r - 1);      // columns beyond n_r: loaded, masked out
-      float* stage = sStage + warp * (32 * kPStageRow);
       float tv[64];
-      // index words of a tile for this thread: token of tile row c (dtE scatter), target rows of tokens 64 h + lane and
-      // 64 h + 32 + lane (handed round the warp with shuffles when the target loads are issued)
-      struct Idx { int32_t tok, r0, r1; };
-      auto load_idx = [&](int64_t tile) {
-        const int32_t* tab = reinterpret_cast<const int32_t*>(a.tiles + tile * (int64_t)kPRec + 32768);
-        Idx x;
-        x.tok = __ldg(tab + c); x.r0 = __ldg(tab + 128 + h * 64 + lane); x.r1 = __ldg(tab + 128 + h * 64 + 32 + lane);
-        return x;
-      };
+      float bsum = 0.f;                                      // bias gradient of this thread's column over its 64 tokens per unit
+      int32_t t_next = -1;
       // 64 target values of this thread's column: tokens [64 h, 64 h + 64) of a tile; one coalesced 128-byte row segment per
-      // warp instruction, all 64 loads in flight
-      // (unconditional loads: rows past the end of the list read row 0 and are masked when the difference is formed -- a
-      // predicated load would make ptxas select on the result and wait for every load where it is issued)
-      auto load_targets = [&](const Idx& x) {
+      // warp instruction, all 64 loads in flight.  Row indices: broadcast reads of the tile's index table.  (Unconditional
+      // loads: rows past the end of the list read row 0 and are masked when the difference is formed -- a predicated load
+      // makes ptxas select on the result and wait for every load where it is issued.)
+      auto load_targets = [&](int64_t kk) {
+        const int sb = (int)(kk % kPABufs);
+        mbar_wait(&a_full[sb], (uint32_t)((kk / kPABufs) & 1));
+        const int32_t* tab = reinterpret_cast<const int32_t*>(sTabB + sb * kPTab);
+        t_next = tab[c];
+        const int4* rows = reinterpret_cast<const int4*>(tab + 128 + h * 64);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int32_t row = __shfl_sync(0xffffffffu, j < 32 ? x.r0 : x.r1, j & 31);
-          tv[j] = __ldg(tbase + (int64_t)row * a.inter_ld);
+        for (int j = 0; j < 16; ++j) {
+          const int4 r4 = rows[j];
+          tv[4 * j] = __ldg(tbase + (int64_t)r4.x * a.inter_ld);
+          tv[4 * j + 1] = __ldg(tbase + (int64_t)r4.y * a.inter_ld);
+          tv[4 * j + 2] = __ldg(tbase + (int64_t)r4.z * a.inter_ld);
+          tv[4 * j + 3] = __ldg(tbase + (int64_t)r4.w * a.inter_ld);
         }
       };
-      // dtE rows of a finished unit: TMEM lane = token row, this thread: features [32 h, 32 h + 32) -> atomic adds, four
-      // rows x 8 consecutive floats (one 32-byte sector each) per instruction
+      // dtE rows of a finished unit: TMEM lane = token row, this thread: features [32 h, 32 h + 32) -> eight 16-byte
+      // vector reductions into the token's row
       auto scatter_dte = [&](int64_t kk, int32_t t) {
         const int b = (int)(kk & 1);
         mbar_wait(&d_full[b], (uint32_t)((kk >> 1) & 1));
@@ -241,30 +237,22 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
         tmem_ld32_issue(tlane + kColDT + b * 64 + h * 32, d0);
         tmem_ld_wait(d0);
         tc_fence_before();
+        if (t >= 0) {
+          float* dst = a.dtE + (int64_t)t * 64 + h * 32;
 #pragma unroll
-        for (int part = 0; part < 4; ++part) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float2*>(stage + lane * kPStageRow + 2 * j) =
-                make_float2(__uint_as_float(d0[part * 8 + 2 * j]), __uint_as_float(d0[part * 8 + 2 * j + 1]));
-          __syncwarp();
-#pragma unroll
-          for (int r4 = 0; r4 < 8; ++r4) {
-            const int row = r4 * 4 + (lane >> 3);
-            const int32_t tr = __shfl_sync(0xffffffffu, t, row);
-            if (tr >= 0) atomicAdd(a.dtE + (int64_t)tr * 64 + h * 32 + part * 8 + (lane & 7), stage[row * kPStageRow + (lane & 7)]);
-          }
-          __syncwarp();
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(dst + 4 * j, __uint_as_float(d0[4 * j]), __uint_as_float(d0[4 * j + 1]), __uint_as_float(d0[4 * j + 2]),
+                       __uint_as_float(d0[4 * j + 3]));
         }
       };
 
-      Idx cur = load_idx(tile0), nxt = n > 1 ? load_idx(tile0 + 1) : cur;
       int32_t t_prev = -1;
-      load_targets(cur);
+      load_targets(k);
       for (int64_t i = 0; i < n; ++i) {
         const int64_t kk = k + i;
         const int b = (int)(kk & 1);
         const int64_t nvalid = elig - (tile0 + i) * 128;
+        const int32_t t_cur = t_next;
         mbar_wait(&p_full[b], (uint32_t)((kk >> 1) & 1));
         tc_fence_after();
         uint4 ghi[8], glo[8];
@@ -274,12 +262,23 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
           tmem_ld32_issue(tlane + kColP + b * 128 + h * 64 + j2 * 32, pv);
           tmem_ld_wait(pv);
           float g[32];
+          if (nvalid >= 128) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float dv = 0.f;
-            if (col_ok && h * 64 + j2 * 32 + j < nvalid) dv = __uint_as_float(pv[j]) + rbc - tv[j2 * 32 + j];
-            loss = fmaf(dv, dv, loss);
-            g[j] = dv * gscale;
+            for (int j = 0; j < 32; ++j) {
+              const float dv = (__uint_as_float(pv[j]) + rbc - tv[j2 * 32 + j]) * cmask;
+              loss = fmaf(dv, dv, loss);
+              g[j] = dv * gscale;
+              bsum += g[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float dv = 0.f;
+              if (col_ok && h * 64 + j2 * 32 + j < nvalid) dv = __uint_as_float(pv[j]) + rbc - tv[j2 * 32 + j];
+              loss = fmaf(dv, dv, loss);
+              g[j] = dv * gscale;
+              bsum += g[j];
+            }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -296,12 +295,7 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&g_full);
-        const int32_t t_cur = cur.tok;
-        if (i + 1 < n) {      // next unit's target rows: in flight under this unit's second and third contraction
-          load_targets(nxt);
-          cur = nxt;
-          if (i + 2 < n) nxt = load_idx(tile0 + i + 2);
-        }
+        if (i + 1 < n) load_targets(kk + 1);      // next unit's target rows: in flight under this unit's second and third contraction
         if (i > 0) scatter_dte(kk - 1, t_prev);
         t_prev = t_cur;
       }
@@ -314,13 +308,10 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
         tmem_ld_wait(v);
         if (col_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(a.dRw + col * 64 + h * 32 + j, __uint_as_float(v[j]));
-        }
-        if (h == 1) {
-          uint32_t b8[8];
-          tmem_ld8_issue(tlane + kColDW + 64, b8);
-          tmem_ld_wait(b8);
-          if (col_ok) atomicAdd(a.drb + col, __uint_as_float(b8[0]));
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(a.dRw + col * 64 + h * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          atomicAdd(a.drb + col, bsum);
         }
       }
     }
