@@ -6,7 +6,7 @@
 // CTA per SM (profiles/r02_ncu_recon.md: 6.6 us per unit, 7 % of the HBM peak at cfg3) on a (token split x column block)
 // grid whose size is not a multiple of the SM count.  Here:
 //   * a pre-pass writes tanh(E) of the ELIGIBLE tokens once as bf16 hi | lo operand tiles (+ the token / target-row index of
-//     every tile row), so a unit's A operand is three bulk copies instead of a scattered gather + 8192 tanhf per column block;
+//     every tile row), so a unit's A operand is two bulk copies instead of a scattered gather + 8192 tanhf per column block;
 //   * the units (column block major) are cut into 148 equal contiguous ranges: one persistent CTA per SM, dRw resident in
 //     TMEM while the CTA stays inside a column block (a range touches at most two);
 //   * the first contraction is TRANSPOSED:  P^T[col, tok] = Rw_block . tanh(E)^T, so TMEM lane = target column and a warp
@@ -14,11 +14,21 @@
 //     thread has its 64 target loads of the NEXT unit in flight while the tensor cores work on the current one;
 //   * gdiff^T is stored [tok/8][col][8 tok]: K-major for dRw (K = tokens) and, with the strides swapped, MN-major for dtE;
 //   * warp roles: 8 compute warps, one bulk-copy producer, one MMA issuer; P^T and dtE double buffered in TMEM, the operand
-//     tiles in a ring of three (released by the tensor pipe's own commit).
+//     tiles in a ring of three (released by the tensor pipe's own commit); the bias gradient is summed in registers and
+//     dtE leaves as 16-byte vector reductions.
+// Measured (scripts/dev/recon_trace.py, cfg3, chr1 = 20 column blocks): 2.9 us per unit -- the 60 bf16x3 MMAs of a unit
+// take 2.0 us at the sustained tensor rate, the SIMT phase 2.7 us while its target rows miss L2 (1.25 us when they hit).
 #include "rowwise.cuh"
 #include "tc_common.cuh"
 
 namespace matcha {
+#ifdef MATCHA_RECON_TRACE
+__device__ unsigned long long g_rtrace[4096];
+// slot layout: unit i (first 40 of CTA 0's first segment) x 16 events
+#define RTRACE(ev) do { if (blockIdx.x == 0 && k == 0 && i < 40) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_rtrace[i * 16 + (ev)] = _t; } } while (0)
+#else
+#define RTRACE(ev) do { } while (0)
+#endif
 namespace {
 
 constexpr int kPThreads = 320;                        // warps 0-7 compute, warp 8 producer, warp 9 MMA issuer
@@ -112,12 +122,12 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
   const uint32_t wh = smem_u32(sW), wl = wh + 16384;
   const uint32_t gh = smem_u32(sG), gl = gh + 32768;
   float loss = 0.f;
-  int64_t k = 0;                                          // units this CTA has finished (every role counts alike)
+  int k = 0;                                              // units this CTA has finished (every role counts alike)
 
   for (int64_t u0 = u_begin; u0 < u_end;) {
     const int64_t cb = u0 / ntiles;
     const int64_t seg_end = (cb + 1) * ntiles < u_end ? (cb + 1) * ntiles : u_end;
-    const int64_t n = seg_end - u0, tile0 = u0 - cb * ntiles;
+    const int n = (int)(seg_end - u0), tile0 = (int)(u0 - cb * ntiles);
     if (warp < 8) {   // Rw block -> sW (row = target column; this thread: features [32 h, 32 h + 32)), zero rows beyond n_r
       const int r = tid & 127, h = tid >> 7;
       const int64_t col = cb * 128 + r;
@@ -149,12 +159,12 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
 
     if (warp == 8) {
       if (elect_one()) {
-        for (int64_t i = 0; i < n; ++i) {
-          const int64_t kk = k + i;
+        for (int i = 0; i < n; ++i) {
+          const int kk = k + i;
           const int sb = (int)(kk % kPABufs);
           mbar_wait_backoff(&a_free[sb], (uint32_t)((kk / kPABufs) & 1) ^ 1u);
           mbar_expect_tx(&a_full[sb], kPA + kPTab);
-          const uint8_t* rec = a.tiles + (tile0 + i) * (int64_t)kPRec;
+          const uint8_t* rec = a.tiles + (int64_t)(tile0 + i) * kPRec;
           bulk_g2s(sTabB + sb * kPTab, rec + 32768, kPTab, &a_full[sb]);
           bulk_g2s(sA + sb * kPA, rec, kPA, &a_full[sb]);
         }
@@ -164,8 +174,8 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
         constexpr uint32_t idescP = make_idesc(128, 128, false, false);
         constexpr uint32_t idescD = make_idesc(128, 64, true, true);
         constexpr uint32_t idescW = make_idesc(128, 64, false, true);
-        auto mma1 = [&](int64_t i) {          // P^T[128 col, 128 tok] = Rw block . tanh(E)^T   (K = 64)
-          const int64_t kk = k + i;
+        auto mma1 = [&](int i) {          // P^T[128 col, 128 tok] = Rw block . tanh(E)^T   (K = 64)
+          const int kk = k + i;
           const int b = (int)(kk & 1), sb = (int)(kk % kPABufs);
           mbar_wait_backoff(&a_full[sb], (uint32_t)((kk / kPABufs) & 1));
           tc_fence_after();
@@ -177,11 +187,13 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
           umma_commit(&p_full[b]);
         };
         mma1(0);
-        for (int64_t i = 0; i < n; ++i) {
+        for (int i = 0; i < n; ++i) {
           if (i + 1 < n) mma1(i + 1);
-          const int64_t kk = k + i;
+          const int kk = k + i;
           const int b = (int)(kk & 1), sb = (int)(kk % kPABufs);
+          RTRACE(8);
           mbar_wait_backoff(&g_full, (uint32_t)(kk & 1));
+          RTRACE(9);
           tc_fence_after();
           const uint32_t ah = smem_u32(sA + sb * kPA), al = ah + kPAHalf;
 #pragma unroll
@@ -194,6 +206,7 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
                      i == 0 && ks == 0);
           umma_commit(&d_full[b]);
           umma_commit(&a_free[sb]);
+          RTRACE(10);
         }
       }
     } else {
@@ -212,24 +225,24 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
       // warp instruction, all 64 loads in flight.  Row indices: broadcast reads of the tile's index table.  (Unconditional
       // loads: rows past the end of the list read row 0 and are masked when the difference is formed -- a predicated load
       // makes ptxas select on the result and wait for every load where it is issued.)
-      auto load_targets = [&](int64_t kk) {
+      auto load_targets = [&](int kk, int half) {
         const int sb = (int)(kk % kPABufs);
-        mbar_wait(&a_full[sb], (uint32_t)((kk / kPABufs) & 1));
+        if (half == 0) mbar_wait(&a_full[sb], (uint32_t)((kk / kPABufs) & 1));
         const int32_t* tab = reinterpret_cast<const int32_t*>(sTabB + sb * kPTab);
-        t_next = tab[c];
-        const int4* rows = reinterpret_cast<const int4*>(tab + 128 + h * 64);
+        if (half == 0) t_next = tab[c];
+        const int4* rows = reinterpret_cast<const int4*>(tab + 128 + h * 64 + half * 32);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const int4 r4 = rows[j];
-          tv[4 * j] = __ldg(tbase + (int64_t)r4.x * a.inter_ld);
-          tv[4 * j + 1] = __ldg(tbase + (int64_t)r4.y * a.inter_ld);
-          tv[4 * j + 2] = __ldg(tbase + (int64_t)r4.z * a.inter_ld);
-          tv[4 * j + 3] = __ldg(tbase + (int64_t)r4.w * a.inter_ld);
+          tv[half * 32 + 4 * j] = __ldg(tbase + (int64_t)r4.x * a.inter_ld);
+          tv[half * 32 + 4 * j + 1] = __ldg(tbase + (int64_t)r4.y * a.inter_ld);
+          tv[half * 32 + 4 * j + 2] = __ldg(tbase + (int64_t)r4.z * a.inter_ld);
+          tv[half * 32 + 4 * j + 3] = __ldg(tbase + (int64_t)r4.w * a.inter_ld);
         }
       };
       // dtE rows of a finished unit: TMEM lane = token row, this thread: features [32 h, 32 h + 32) -> eight 16-byte
       // vector reductions into the token's row
-      auto scatter_dte = [&](int64_t kk, int32_t t) {
+      auto scatter_dte = [&](int kk, int32_t t) {
         const int b = (int)(kk & 1);
         mbar_wait(&d_full[b], (uint32_t)((kk >> 1) & 1));
         tc_fence_after();
@@ -247,13 +260,16 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
       };
 
       int32_t t_prev = -1;
-      load_targets(k);
-      for (int64_t i = 0; i < n; ++i) {
-        const int64_t kk = k + i;
+      load_targets(k, 0);
+      load_targets(k, 1);
+      for (int i = 0; i < n; ++i) {
+        const int kk = k + i;
         const int b = (int)(kk & 1);
-        const int64_t nvalid = elig - (tile0 + i) * 128;
+        const int nvalid = (int)(elig - (int64_t)(tile0 + i) * 128 < 128 ? elig - (int64_t)(tile0 + i) * 128 : 128);
         const int32_t t_cur = t_next;
+        if (tid == 0) RTRACE(0);
         mbar_wait(&p_full[b], (uint32_t)((kk >> 1) & 1));
+        if (tid == 0) RTRACE(1);
         tc_fence_after();
         uint4 ghi[8], glo[8];
 #pragma unroll
@@ -284,9 +300,13 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
           for (int j = 0; j < 4; ++j)
             split8(make_float4(g[8 * j], g[8 * j + 1], g[8 * j + 2], g[8 * j + 3]),
                    make_float4(g[8 * j + 4], g[8 * j + 5], g[8 * j + 6], g[8 * j + 7]), ghi[j2 * 4 + j], glo[j2 * 4 + j]);
+          // this half's target registers are free: the next unit's loads go out now and fly under the rest of this unit
+          if (i + 1 < n) load_targets(kk + 1, j2);
         }
         tc_fence_before();
+        if (tid == 0) RTRACE(2);
         if (i > 0) mbar_wait(&d_full[b ^ 1], (uint32_t)(((kk - 1) >> 1) & 1));      // previous unit's contractions done: sG is free
+        if (tid == 0) RTRACE(3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           sts16(sG + (h * 8 + j) * 2048 + c * 16, ghi[j]);
@@ -295,8 +315,9 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&g_full);
-        if (i + 1 < n) load_targets(kk + 1);      // next unit's target rows: in flight under this unit's second and third contraction
+        if (tid == 0) RTRACE(4);
         if (i > 0) scatter_dte(kk - 1, t_prev);
+        if (tid == 0) RTRACE(5);
         t_prev = t_cur;
       }
       scatter_dte(k + n - 1, t_prev);
@@ -332,6 +353,12 @@ __global__ void __launch_bounds__(kPThreads, 1) recon_pipe_kernel(const PipeArgs
 }
 
 }  // namespace
+
+#ifdef MATCHA_RECON_TRACE
+extern "C" int matcha_recon_trace(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_rtrace, sizeof(unsigned long long) * 4096) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int64_t recon_pipe_tile_bytes(int64_t T) { return (num_token_tiles(T) + 1) * (int64_t)kPRec; }
 
