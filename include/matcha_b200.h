@@ -54,6 +54,9 @@ void matcha_set_chain(int32_t on);
  * (needs the fused path), 0 = four SIMT launches through a [T, n_r] buffer; also MATCHA_RECON_TC=0 */
 void matcha_set_recon_tc(int32_t on);
 void matcha_set_recon_pipe(int32_t on);   /* pipelined gradient pass of the reconstruction head (default on) */
+/* 1 (default) = embed_dim-128 models run their contractions on the general tcgen05 kernel (csrc/gemm_tcg.cu, bf16x3) from
+ * 1024 token rows on, 0 = fp32 SIMT kernel; also MATCHA_GEMM_TCG=0 */
+void matcha_set_gemm_tcg(int32_t on);
 /* 1 (default) = both node-encoder layers (Modules.py:104-122) run as one tcgen05 kernel over the chromosome-bucketed
  * token list (dense feature rows, embed_dim 64, >= 1024 tokens), 0 = two grouped SIMT launches; also MATCHA_ENC_TC=0 */
 void matcha_set_enc_tc(int32_t on);
@@ -317,7 +320,8 @@ int matcha_f64_to_f32(const double* in, float* out, int64_t n, void* stream);
  * Building blocks exposed for tests (dense fp32 contractions used by the passes above).
  *   form 0: C[M,N]  = A[M,K] . B[N,K]^T (+bias)      form 1: C[M,N] = A[M,K] . B[K,N]
  *   form 2: C[M,N] += A[K,M]^T . B[K,N]
- * impl 0 = SIMT fp32, 1 = tcgen05 (bf16x3 split, fp32 accumulate in TMEM)
+ * impl 0 = SIMT fp32, 1 = tcgen05 (bf16x3 split, fp32 accumulate in TMEM) kernels specialised on the embed_dim-64 shapes,
+ * 2 = general tcgen05 kernel (any shape with >= 1024 token rows and N >= 64; csrc/gemm_tcg.cu)
  * --------------------------------------------------------------------------------------------- */
 int matcha_gemm(int32_t form, int32_t impl, const float* A, const float* B, float* C, const float* bias,
                 int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, float* scratch,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmatcha_b200.so")
-SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "qkg_tiles.cu", "attn_fused.cu", "attn_xform.cu", "chain.cu", "rowwise.cu", "optim.cu", "dp_fused.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu", "recon_tc.cu", "recon_pipe.cu", "enc_tc.cu", "kmers.cu", "metrics.cu", "denoise.cu", "features.cu"]
+SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tcg.cu", "qkg_tiles.cu", "attn_fused.cu", "attn_xform.cu", "chain.cu", "rowwise.cu", "optim.cu", "dp_fused.cu", "sampler.cu", "scorer.cu", "pair_tc.cu", "csr_encoder.cu", "recon_tc.cu", "recon_pipe.cu", "enc_tc.cu", "kmers.cu", "metrics.cu", "denoise.cu", "features.cu"]
 NVCC_COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                       "-Xcompiler", "-fPIC"]
 NVCC_LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
@@ -113,6 +113,7 @@ SYMBOLS = {
     "matcha_set_chain": (None, [_I32]),
     "matcha_set_recon_tc": (None, [_I32]),
     "matcha_set_recon_pipe": (None, [_I32]),
+    "matcha_set_gemm_tcg": (None, [_I32]),
     "matcha_set_enc_tc": (None, [_I32]),
     "matcha_set_xform": (None, [_I32]),
     "matcha_set_mma_passes": (None, [_I32]),

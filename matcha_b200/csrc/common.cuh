@@ -156,5 +156,7 @@ int launch_split_weights_k64(const float* W, int64_t ldw, int64_t N, void* out, 
 
 int launch_gemm_simt(const GemmDesc& d, cudaStream_t stream);
 int launch_gemm_tc(const GemmDesc& d, cudaStream_t stream, bool* handled);
+// general tcgen05 kernel (gemm_tcg.cu): gathered / grouped / ragged problems with >= 1024 token rows
+int launch_gemm_tcg(const GemmDesc& d, cudaStream_t stream, bool* handled);
 
 }  // namespace matcha

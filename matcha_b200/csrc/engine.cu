@@ -143,11 +143,24 @@ static bool use_recon_pipe() {
   return g_recon_pipe == 1;
 }
 
+// general tcgen05 contraction kernel (gemm_tcg.cu) for the models the fused embed_dim-64 kernels do not cover (embed_dim 128):
+// MATCHA_GEMM_TCG=0 keeps the fp32 SIMT kernel.  g_tcg_model is set per call by validate()
+static int g_tcg = -1;
+static bool g_tcg_model = false;
+static bool use_tcg() {
+  if (g_tcg < 0) {
+    const char* e = getenv("MATCHA_GEMM_TCG");
+    g_tcg = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_tcg == 1 && g_tcg_model;
+}
+
 static int run_gemm(const GemmDesc& d, cudaStream_t s, int label, bool allow_tc = true) {
   prof_begin(label, s);
   int rc = MATCHA_OK;
   bool handled = false;
   if (allow_tc && gemm_impl() == 1) rc = launch_gemm_tc(d, s, &handled);
+  if (!rc && !handled && allow_tc && gemm_impl() == 1 && use_tcg()) rc = launch_gemm_tcg(d, s, &handled);
   if (!rc && !handled) rc = launch_gemm_simt(d, s);
   prof_end(label, 1, s);
   return rc;
@@ -492,6 +505,7 @@ static int validate(const matcha_model_desc* m) {
     return MATCHA_ERR_UNSUPPORTED;
   }
   MATCHA_REQUIRE(m->n_chrom >= 1 && m->n_chrom <= MATCHA_MAX_CHROM, "n_chrom=%d out of range", m->n_chrom);
+  g_tcg_model = m->d != kD;
   MATCHA_REQUIRE(m->params && m->derived, "params / derived buffers missing");
   MATCHA_REQUIRE(m->attr_dim >= 1 && m->attr_table, "attribute table missing");
   const bool csr = model_uses_csr(m);
@@ -648,6 +662,7 @@ void matcha_set_fused(int32_t on) { g_fused = on != 0; }
 void matcha_set_chain(int32_t on) { g_chain = on != 0; }
 void matcha_set_recon_tc(int32_t on) { g_recon_tc = on != 0; }
 void matcha_set_recon_pipe(int32_t on) { g_recon_pipe = on != 0; }
+void matcha_set_gemm_tcg(int32_t on) { g_tcg = on != 0; }
 void matcha_set_enc_tc(int32_t on) { g_enc_tc = on != 0; }
 void matcha_set_xform(int32_t on) { g_xform = on != 0; }
 void matcha_set_mma_passes(int32_t passes) { g_passes = passes == 1 ? 1 : 3; }
@@ -1029,6 +1044,13 @@ int matcha_gemm(int32_t form, int32_t impl, const float* A, const float* B, floa
   if (impl == 1 && form == 0 && K == 64 && N % 128 == 0 && scratch && scratch_floats >= N * 64 && ldb % 4 == 0) {
     if (int rc = launch_split_weights_k64(B, ldb, N, scratch, (cudaStream_t)stream)) return rc;   // v2 kernel path
     d.b_split = reinterpret_cast<const uint8_t*>(scratch);
+  }
+  if (impl == 2) {      // general tcgen05 kernel (gemm_tcg.cu)
+    bool handled = false;
+    int rc = launch_gemm_tcg(d, (cudaStream_t)stream, &handled);
+    if (rc) return rc;
+    if (!handled) { set_error("matcha_gemm: problem too small for the general tcgen05 kernel"); return MATCHA_ERR_UNSUPPORTED; }
+    return MATCHA_OK;
   }
   if (impl == 1) {
     bool handled = false;

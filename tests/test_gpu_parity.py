@@ -63,6 +63,15 @@ def test_gemm_tcgen05_matches_fp64(form, M, N, K):
     assert tc_gemm_rel_err(form, M, N, K, impl=1, bias=(form == 0)) < 3e-5
 
 
+@pytest.mark.parametrize("form,M,N,K", [(0, 4099, 3072, 128), (0, 1500, 250, 2491), (0, 1024, 64, 70), (1, 5000, 128, 3072),
+                                        (1, 1100, 2491, 128), (1, 2048, 72, 64), (2, 3072, 128, 5000), (2, 128, 2491, 1500),
+                                        (2, 200, 70, 1024)])
+def test_general_tcgen05_gemm_matches_fp64(form, M, N, K):
+    """General tcgen05 kernel (csrc/gemm_tcg.cu): the embed_dim-128 shapes of cfg5 and ragged M / N / K edges in all three
+    forms, bias epilogue in form 0, split-K atomics in form 2."""
+    assert tc_gemm_rel_err(form, M, N, K, impl=2, bias=(form == 0), v2=False) < 3e-5
+
+
 def test_pipeline_agrees_between_simt_and_tcgen05(golden, model):
     L = _lib()
     lib = L.load()
@@ -689,6 +698,43 @@ def test_d128_train_step_with_dropout_matches_oracle(golden128, L, B, monkeypatc
         scale = float(np.abs(gref).max())
         err = float(np.abs(p.grad.cpu().numpy() - gref).max())
         assert err <= 5e-4 * scale + 2e-7, (k, err, scale)
+
+
+def test_d128_general_tcgen05_step_matches_simt(golden128, monkeypatch):
+    """embed_dim 128 at 10,240 tokens: one training step (dropout ON, reconstruction head on) with every contraction on the
+    general tcgen05 kernel against the same step on the fp32 SIMT kernel -- logits, recon loss, every gradient."""
+    lib = _lib().load()
+    L, B = 5, 2048
+    rng = np.random.default_rng(5)
+    N = int(golden128["embeddings"].shape[0])
+    xs = np.zeros((B, L), dtype=np.int64)
+    for b in range(B):
+        k = L if b % 2 == 0 else int(rng.integers(2, L + 1))
+        xs[b, :k] = np.sort(rng.choice(np.arange(1, N + 1), size=k, replace=False))
+    x = torch.from_numpy(xs).cuda()
+    y = torch.from_numpy((rng.random((B, 1)) < 0.4).astype("float32")).cuda()
+    w = torch.from_numpy(rng.uniform(0.5, 3.0, size=(B, 1)).astype("float32")).cuda()
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([1]))
+    res = {}
+    try:
+        for on in (0, 1):
+            lib.matcha_set_gemm_tcg(on)
+            model = model_from_golden(golden128, d=128)
+            model.train()
+            model._engine().seed_base = 23
+            pred, rl = model(x, return_recon=True)
+            (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.25 * rl.sum()).backward()
+            res[on] = (pred.detach().cpu().numpy(), float(rl.detach().sum()),
+                       {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None})
+    finally:
+        lib.matcha_set_gemm_tcg(1)
+    np.testing.assert_allclose(res[1][0], res[0][0], rtol=2e-4, atol=1e-4)
+    assert abs(res[1][1] - res[0][1]) <= 1e-4 * abs(res[0][1])
+    assert res[0][2].keys() == res[1][2].keys()
+    for k, g0 in res[0][2].items():
+        scale = float(np.abs(g0).max())
+        err = float(np.abs(res[1][2][k] - g0).max())
+        assert err <= 3e-4 * scale + 2e-7, (k, err, scale)
 
 
 # ------------------------------------------------------------------------------------------
