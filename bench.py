@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--pos-per-step", type=int, default=POS_PER_STEP)
     ap.add_argument("--cpu-baseline-steps", type=int, default=8)
     ap.add_argument("--no-cfg3", action="store_true", help="skip the configs[2] (30,344 bins) sub-measurement")
-    ap.add_argument("--cfg5", action="store_true", help="also measure configs[4] (60,653 bins, embed_dim 128: fp32 SIMT contractions); "
+    ap.add_argument("--cfg5", action="store_true", help="also measure configs[4] (60,653 bins, embed_dim 128: general tcgen05 contractions); "
                                                         "needs ~60 GB of host memory per rank for the synthetic dense matrices")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-impl", type=int, default=-1, help="-1 library default, 0 SIMT, 1 tcgen05")
@@ -431,8 +431,8 @@ def main():
                 "kernel_ms_per_step": {k: round(v[0] / k3, 4) for k, v in sorted(m3["prof"].items(), key=lambda kv: -kv[1][0])},
                 "hbm_kernels": hbm_kernels(ds3, m3), "losses": m3["losses"]}
         del ds3
-    # configs[4] (whole genome at 50 kb, 60,653 bins, embed_dim 128): every contraction runs on the fp32 SIMT path at this
-    # width; opt-in because the synthetic dense N x N matrices need ~60 GB of host memory per rank
+    # configs[4] (whole genome at 50 kb, 60,653 bins, embed_dim 128): the contractions run on the general tcgen05 kernel
+    # (csrc/gemm_tcg.cu), the row-wise kernels on their embed_dim-128 SIMT instantiations; opt-in because the synthetic dense N x N matrices need ~60 GB of host memory per rank
     cfg5 = None
     if args.cfg5:
         import psutil
@@ -445,7 +445,7 @@ def main():
             m5 = measure_training(ds5, P, k5, 3, False, False)
             cfg5 = {"workload": WORKLOADS["cfg5"], "value": P * (1 + NEG_NUM) * world * k5 / (m5["ms_dev"] * 1e-3), "unit": UNIT,
                     "ms_per_step": m5["ms_dev"] / k5, "steps": k5, "n_gpus": world, "hyperedges_per_gpu_per_step": P * (1 + NEG_NUM),
-                    "contractions": "fp32 SIMT (embed_dim 128 has no tcgen05 path yet)",
+                    "contractions": "general tcgen05 kernel (csrc/gemm_tcg.cu, bf16x3 split, fp32 accumulate); row-wise kernels fp32 SIMT",
                     "kernel_ms_per_step": {k: round(v[0] / k5, 4) for k, v in sorted(m5["prof"].items(), key=lambda kv: -kv[1][0])},
                     "losses": m5["losses"]}
             del ds5

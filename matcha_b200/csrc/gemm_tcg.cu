@@ -359,7 +359,8 @@ int launch_gemm_tcg(const GemmDesc& d, cudaStream_t stream, bool* handled) {
   const bool tn = d.form == FORM_TN;
   const int64_t rows = d.ngroups > 0 ? d.total_rows : (tn ? d.K : d.M);      // token dimension
   const int64_t maxN = (tn && d.ngroups > 0) ? d.max_group_dim : d.N;
-  if (rows < 1024 || maxN < 64 || d.M <= 0) return MATCHA_OK;
+  if (rows < 1024 || maxN < 64) return MATCHA_OK;
+  if ((tn || d.ngroups == 0) && d.M <= 0) return MATCHA_OK;     // grouped NT / NN launches carry their row counts in group_off
   if (!tn && d.ngroups == 0 && d.K < 32) return MATCHA_OK;
   if (tn && d.M < 64) return MATCHA_OK;
   const int BN = maxN >= 128 ? 128 : 64;
