@@ -5,12 +5,20 @@
 // area) -> dropout from the counter RNG -> bf16 hi | lo A tile -> tcgen05 against the pre-split W0 chunk }, applies
 // tanh to the accumulator row, stores H0 (the backward pass needs it), and chains the 64 x 64 contraction with W1_c.
 // Replaces two grouped SIMT launches and the H0 re-read between them.
+#include <stdlib.h>
 #include <string.h>
 
 #include "rowwise.cuh"
 #include "tc_common.cuh"
 
 namespace matcha {
+#ifdef MATCHA_ENC_TRACE
+__device__ unsigned long long g_etrace[4096];
+// first 250 steps of CTA 0: 16 event slots per step
+#define ETRACE(ev) do { if (blockIdx.x == 0 && sidx < 250u) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_etrace[sidx * 16 + (ev)] = _t; } } while (0)
+#else
+#define ETRACE(ev) do { } while (0)
+#endif
 namespace {
 
 constexpr int kFThreads = 256;                 // forward kernel: two warpgroups split every 64-wide row
@@ -254,6 +262,231 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
 }
 
 // ==========================================================================================
+// Pipelined forward (default; enc_tc_fwd_kernel above stays as the cross-check, MATCHA_ENC_PIPE=0).
+// The unit kernel above runs  gather -> split -> copy weights -> barrier -> MMA  once per 64-column chunk with the global
+// loads of one chunk in flight per CTA (29 % of the HBM copy rate at cfg3).  Here the feature rows of a chunk arrive by
+// asynchronous copies (cp.async, 16-byte pieces, no register staging) issued by a producer warp into a ring of three fp32
+// staging tiles together with one bulk copy of the chunk's pre-split weights -- so two chunks of feature rows are in flight
+// per SM whatever the compute warps do;
+// sixteen compute warps turn a landed stage into the bf16 hi | lo operand tile (dropout from the counter RNG, two tiles so the
+// conversion of chunk k + 1 runs under the MMAs of chunk k; with eight warps this conversion was the critical path: 1.2 us
+// per chunk, scripts/dev/enc_trace.py); one thread issues the MMAs.  One persistent CTA per SM.
+//   step = (tile, chunk kc) for kc < nchunk, then (tile, W1): H0 = tanh(acc) -> A tile -> E = H0 . W1_c^T
+// ==========================================================================================
+constexpr int kPFThreads = 672;                 // warps 0-15 compute, warps 16-19 producers (32 rows each), warp 20 MMA issuer
+constexpr int kPFRow = 272;                     // staging row stride: 64 floats + 16 B (conflict-free 16-byte reads down a column)
+constexpr int kPFStageF = 128 * kPFRow;         // 34 816
+constexpr int kPFStage = kPFStageF + kEChunk;   // + the chunk's pre-split weights: 51 200
+constexpr int kPFStages = 3;
+constexpr int kPFSmem = kPFStages * kPFStage + 2 * kEA;      // 219 136
+constexpr uint32_t kPFColAcc = 0, kPFColE = 64;
+
+__global__ void __launch_bounds__(kPFThreads, 1)
+enc_pipe_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const int64_t* __restrict__ x,
+                    const int32_t* __restrict__ perm, const int32_t* __restrict__ group_off, float* __restrict__ H0,
+                    float* __restrict__ E, const DropCfg drop) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sStage = smem;
+  uint8_t* sA = smem + kPFStages * kPFStage;      // two operand tiles of kEA
+  __shared__ uint64_t f_full[kPFStages], f_free[kPFStages], a_full[2], a_free[2], acc_full, e_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ const float* sRow[128];              // feature-row pointers of the producer's current tile
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+  if (tid == 512) {
+    for (int i = 0; i < kPFStages; ++i) { mbar_init(&f_full[i], 129); mbar_init(&f_free[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 16); mbar_init(&a_free[i], 1); }
+    mbar_init(&acc_full, 1); mbar_init(&e_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // every role walks the same tile list: chromosome c contributes ceil(count_c / 128) tiles of its bucket
+  struct Cursor { int c; int64_t before; };
+  auto next_tile = [&](Cursor& cu, int64_t ti, int& cnt) -> bool {
+    for (; cu.c < em.n; ++cu.c) {
+      cnt = group_off[cu.c + 1] - group_off[cu.c];
+      const int64_t nt = (cnt + 127) / 128;
+      if (ti < cu.before + nt) return true;
+      cu.before += nt;
+    }
+    return false;
+  };
+
+  if (warp >= 16 && warp < 20) {
+    // ---------------- producers: feature rows (32 per warp) + weight chunk of every step ----------------
+    // rows: 16-byte cp.async pieces (an instruction moves two 256-byte row chunks; pieces of dead rows / beyond the row are
+    // zero-filled), weights: one 16 KB bulk copy.  f_full counts the 128 lanes' cp.async arrivals + the bulk copy's expect_tx.
+    // (one producer warp for all 128 rows: 4.0 us per chunk -- a single warp does not issue LDGSTS fast enough)
+    // (one bulk copy per ROW was measured first: ~50 ns per copy, 6.7 us per chunk -- the copy engine is not a gather unit)
+    Cursor cu{0, 0};
+    uint32_t sidx = 0;
+    const int half = lane >> 4, piece = lane & 15, pw = warp - 16;
+    const float** myRow = sRow + pw * 32;
+    for (int64_t ti = blockIdx.x;; ti += gridDim.x) {
+      int cnt = 0;
+      if (!next_tile(cu, ti, cnt)) break;
+      const int c = cu.c;
+      const int off = (int)(ti - cu.before) * 128;
+      const int nrows = cnt - off < 128 ? cnt - off : 128;
+      const int64_t ld = em.ld[c];
+      const int nchunk = (em.nc[c] + 63) / 64;
+      const uint8_t* wbase = wsplit + em.woff[c];
+      __syncwarp();
+      {
+        const int r = pw * 32 + lane;
+        const float* fr = em.feat[c];
+        if (r < nrows) fr += (x[perm[group_off[c] + off + r]] - em.start[c]) * ld;
+        myRow[lane] = fr;
+      }
+      __syncwarp();
+      for (int kc = 0; kc <= nchunk; ++kc, ++sidx) {
+        const int st = (int)(sidx % kPFStages);
+        uint8_t* stage = sStage + st * kPFStage;
+        if (pw == 0 && lane == 0) ETRACE(0);
+        mbar_wait_backoff(&f_free[st], ((sidx / kPFStages) & 1u) ^ 1u);
+        if (pw == 0 && lane == 0) ETRACE(1);
+        if (pw == 0 && lane == 0) {
+          mbar_expect_tx(&f_full[st], kEChunk);
+          bulk_g2s(stage + kPFStageF, wbase + (int64_t)kc * kEChunk, kEChunk, &f_full[st]);     // kc == nchunk: W1_c
+        }
+        if (kc < nchunk) {
+          const int64_t col = (int64_t)kc * 64 + piece * 4;
+          const bool col_ok = col < ld;
+          const uint32_t dst0 = smem_u32(stage) + (pw * 32 + half) * kPFRow + piece * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int r = 2 * j + half;
+            const float* src = myRow[r] + (col_ok ? col : 0);
+            const uint32_t nbytes = (col_ok && pw * 32 + r < nrows) ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 2 * j * kPFRow), "l"(src), "r"(nbytes) : "memory");
+          }
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&f_full[st])) : "memory");
+        if (pw == 0 && lane == 0) ETRACE(2);
+      }
+    }
+  } else if (warp == 20) {
+    // ---------------- MMA issuer ----------------
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(128, 64, false, false);
+      Cursor cu{0, 0};
+      uint32_t sidx = 0;
+      for (int64_t ti = blockIdx.x;; ti += gridDim.x) {
+        int cnt = 0;
+        if (!next_tile(cu, ti, cnt)) break;
+        const int nchunk = (em.nc[cu.c] + 63) / 64;
+        for (int kc = 0; kc <= nchunk; ++kc, ++sidx) {
+          const int st = (int)(sidx % kPFStages), ab = (int)(sidx & 1);
+          mbar_wait_backoff(&f_full[st], (sidx / kPFStages) & 1u);
+          ETRACE(8);
+          mbar_wait_backoff(&a_full[ab], (sidx >> 1) & 1u);
+          ETRACE(9);
+          tc_fence_after();
+          const uint32_t ah = smem_u32(sA + ab * kEA), al = ah + 16384;
+          const uint32_t wh = smem_u32(sStage + st * kPFStage + kPFStageF), wl = wh + 8192;
+          const uint32_t dcol = tmem_base + (kc < nchunk ? kPFColAcc : kPFColE);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_x3s(dcol, ah + ks * 4096, al + ks * 4096, wh + ks * 2048, wl + ks * 2048, 2048, 128, 1024, 128, idesc,
+                     (kc == 0 || kc == nchunk) && ks == 0);
+          umma_commit(&f_free[st]);
+          umma_commit(&a_free[ab]);
+          if (kc == nchunk - 1) umma_commit(&acc_full);
+          if (kc == nchunk) umma_commit(&e_full);
+          ETRACE(10);
+        }
+      }
+    }
+  } else {
+    // ---------------- compute warps: thread (r, q4) = token row r (TMEM lane r), quarter q4 of every 64-wide row ----------------
+    const int r = tid & 127, q4 = tid >> 7, wq = warp & 3;
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    Cursor cu{0, 0};
+    uint32_t sidx = 0, tcount = 0;
+    auto put_tile = [&](uint32_t si, const float (&v)[16]) {      // 16 floats of row r -> planes 2 q4, 2 q4 + 1 of operand tile si & 1
+      const int ab = (int)(si & 1);
+      mbar_wait(&a_free[ab], ((si >> 1) & 1u) ^ 1u);
+      uint8_t* at = sA + ab * kEA;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint4 hi, lo;
+        split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+               make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+        sts16(at + (q4 * 2 + j) * 2048 + r * 16, hi);
+        sts16(at + 16384 + (q4 * 2 + j) * 2048 + r * 16, lo);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[ab]);
+    };
+    for (int64_t ti = blockIdx.x;; ti += gridDim.x, ++tcount) {
+      int cnt = 0;
+      if (!next_tile(cu, ti, cnt)) break;
+      const int c = cu.c;
+      const int off = (int)(ti - cu.before) * 128;
+      const int nrows = cnt - off < 128 ? cnt - off : 128;
+      const bool live = r < nrows;
+      const int64_t t = live ? perm[group_off[c] + off + r] : 0;
+      const int nchunk = (em.nc[c] + 63) / 64;
+      for (int kc = 0; kc < nchunk; ++kc, ++sidx) {
+        const int st = (int)(sidx % kPFStages);
+        if (tid == 0) ETRACE(4);
+        mbar_wait(&f_full[st], (sidx / kPFStages) & 1u);
+        if (tid == 0) ETRACE(5);
+        const float* srow = reinterpret_cast<const float*>(sStage + st * kPFStage + r * kPFRow) + q4 * 16;
+        const int64_t kf = (int64_t)kc * 64 + q4 * 16;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 e = *reinterpret_cast<const float4*>(srow + 4 * j);
+          if (drop.thr != 0u && live) e = drop_apply4(drop, (uint64_t)t, (uint32_t)(kf + 4 * j), e);      // dead rows / columns beyond the row arrive zero-filled
+          v[4 * j] = e.x; v[4 * j + 1] = e.y; v[4 * j + 2] = e.z; v[4 * j + 3] = e.w;
+        }
+        put_tile(sidx, v);
+        if (tid == 0) ETRACE(6);
+      }
+      // ---- H0 = tanh(acc): kept for the backward pass, and the A operand of the W1 step ----
+      {
+        mbar_wait(&acc_full, tcount & 1u);
+        tc_fence_after();
+        float d0[16];
+        tmem_ld16(tlane + kPFColAcc + q4 * 16, d0);
+        tc_fence_before();
+        float hv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hv[i] = live ? tanhf(d0[i]) : 0.f;
+        put_tile(sidx, hv);
+        if (live) {
+          float4* dst = reinterpret_cast<float4*>(H0 + t * 64 + q4 * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(hv[4 * j], hv[4 * j + 1], hv[4 * j + 2], hv[4 * j + 3]);
+        }
+        ++sidx;
+      }
+      {
+        mbar_wait(&e_full, tcount & 1u);
+        tc_fence_after();
+        float d0[16];
+        tmem_ld16(tlane + kPFColE + q4 * 16, d0);
+        tc_fence_before();
+        if (live) {
+          float4* dst = reinterpret_cast<float4*>(E + t * 64 + q4 * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(d0[4 * j], d0[4 * j + 1], d0[4 * j + 2], d0[4 * j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// ==========================================================================================
 // backward:  dH0pre = (dE . W1_c) * (1 - H0^2),   dW1_c += dE^T . H0,   dW0_c += dH0pre^T . dropout(F_c rows)
 // One CTA = 256 threads: thread (r, h) owns token row r (TMEM lane r) and half h of every 64-wide row.  The two weight
 // gradients share ONE M = 128 contraction per operand tile: the stacked tile sS = [dE | dH0pre] (128 feature rows, K =
@@ -459,6 +692,14 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+EncMeta make_meta(const matcha_model_desc* m, int64_t* total_bytes);
+}  // namespace
+#ifdef MATCHA_ENC_TRACE
+extern "C" int matcha_enc_trace(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_etrace, sizeof(unsigned long long) * 4096) == cudaSuccess ? 0 : -2;
+}
+#endif
+namespace {
 EncMeta make_meta(const matcha_model_desc* m, int64_t* total_bytes) {
   EncMeta em;
   memset(&em, 0, sizeof(em));
@@ -509,6 +750,29 @@ int launch_enc_tc_fwd(const matcha_model_desc* m, int64_t split_base, const int6
   }
   const EncMeta em = make_meta(m, nullptr);
   int64_t tiles = (T + 127) / 128 + m->n_chrom;            // upper bound; the kernel stops at the real tile count
+  // pipelined kernel for wide feature rows (cfg3: 1 319 bins per chromosome on average, cfg4: 24 897); at cfg2 (133 bins: at
+  // most four chunks per tile) the per-tile epilogue dominates and two unit CTAs per SM overlap it better (measured: 39 us vs
+  // 50 us at cfg2, 203 us vs 172 us at cfg3).  MATCHA_ENC_PIPE = 0 / 1 forces one of them
+  static int pipe = -1;
+  if (pipe < 0) {
+    const char* e = getenv("MATCHA_ENC_PIPE");
+    pipe = !e ? 2 : (e[0] == '0' ? 0 : 1);
+  }
+  int64_t bins = 0;
+  for (int c = 0; c < m->n_chrom; ++c) bins += m->chrom_end[c] - m->chrom_start[c];
+  if (pipe == 1 || (pipe == 2 && bins >= 512 * (int64_t)m->n_chrom)) {
+    static bool once2 = false;
+    if (!once2) {
+      if (int rc = check_cuda(cudaFuncSetAttribute(enc_pipe_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPFSmem),
+                              "cudaFuncSetAttribute"))
+        return rc;
+      once2 = true;
+    }
+    enc_pipe_fwd_kernel<<<(unsigned)(tiles < kSMs ? tiles : kSMs), kPFThreads, kPFSmem, s>>>(
+        em, reinterpret_cast<const uint8_t*>(m->derived + split_base), x, perm, group_off, H0, E, drop);
+    MATCHA_CHECK_LAUNCH("enc_pipe_fwd");
+    return MATCHA_OK;
+  }
   const unsigned grid = (unsigned)(tiles < 2 * kSMs ? tiles : 2 * kSMs);
   enc_tc_fwd_kernel<<<grid, kFThreads, kESmem, s>>>(em, reinterpret_cast<const uint8_t*>(m->derived + split_base), x, perm,
                                                     group_off, H0, E, drop);
