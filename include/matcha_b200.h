@@ -189,6 +189,10 @@ int matcha_adamw(float* params, const float* grads, float* exp_avg, float* exp_a
  * --------------------------------------------------------------------------------------------- */
 int32_t matcha_dp_blocks(void);
 int matcha_enable_peer_access(int32_t peer_device);   /* cudaDeviceEnablePeerAccess from the current device, idempotent */
+/* Form of the data-parallel step boundary below: 0 = one-shot (every rank reads every peer's whole gradient buffer), 1 =
+ * two-shot (rank r reduces the r-th part of every block's slice and writes the mean into all replicas), 2 = by world size
+ * (default: two-shot from 4 ranks on); also MATCHA_DP_TWO_SHOT=0 / 1.  Both forms give bit-identical weights. */
+void matcha_set_dp_two_shot(int32_t mode);
 /* CUDA IPC: handle (64 bytes) of the cudaMalloc allocation starting at base_ptr; map a peer process's allocation for kernels
  * of the current device (cudaIpcMemLazyEnablePeerAccess); unmap */
 int matcha_ipc_get_handle(const void* base_ptr, uint8_t* handle64);

@@ -4,13 +4,18 @@
 //   ->  cross-GPU barrier  ->  zero the own gradient buffer for the next step.
 // It replaces   copy flags -> ncclAllReduce(gflat) -> copy flags -> 3 AdamW launches -> gflat.zero_()   (7 launches, the
 // collective exposed on the main stream) with one launch whose transfer overlaps its arithmetic chunk by chunk.
-// "One-shot" form: each element is read once from every peer (world x 4 B over NVLink per element); the gradient buffer is
-// 2.5 MB (cfg2) .. 66 MB (cfg5), so at 8 GPUs a rank pulls 17 .. 460 MB per step over 900 GB/s links.
+// Two forms.  "One-shot" (2 ranks): each element is read once from every peer (world x 4 B over NVLink per element).
+// "Two-shot" (4 and 8 ranks; MATCHA_DP_TWO_SHOT=0 / 1 forces one): the gradient buffer is 2.5 MB (cfg2) .. 66 MB (cfg5), so a
+// one-shot rank would pull 17 .. 460 MB per step at 8 GPUs; instead rank r reduces the r-th part of every block's slice
+// (reading it from all peers), writes the mean into ALL replicas' gradient buffers in place (only the owner of a part ever
+// reads it, so the overwrite races with nothing), and after the second barrier every rank runs AdamW on its own buffer and
+// clears it in the same pass: 2 (world - 1) / world x 4 B per element over NVLink -- a quarter of the one-shot traffic at 8.
 //
 // Barriers are per block: block b of every rank signals block b of every peer (a monotonically increasing epoch written
 // into the peer's flag array with release semantics) and waits for theirs; block b of every rank works on the same slice
 // of the buffers, so the second barrier tells a rank that its slice is no longer being read before it zeroes it.
 // Spins are bounded: a dead peer traps this context instead of hanging the GPU.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -37,6 +42,7 @@ struct DpArgs {
   float lr, b1, b2, eps, wd;
   int step;
   uint32_t epoch;
+  int two_shot;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -93,29 +99,19 @@ __global__ void __launch_bounds__(kDpThreads) dp_reduce_adamw_kernel(const DpArg
   const int64_t n4 = (a.n_flat + 3) / 4;
   const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
   const int64_t q0 = (int64_t)blockIdx.x * per, q1 = (q0 + per < n4) ? q0 + per : n4;
-  for (int64_t q = q0 + threadIdx.x; q < q1; q += kDpThreads) {
-    const int64_t i = q * 4;
-    float bc1, bc2s;
-    bool on;
-    if (i < a.n_always) {
-      on = true; bc1 = bc1a; bc2s = bc2sa;
-    } else {
-      int lo = 0, hi = a.n_seg;                    // last segment with begin <= i (segments are sorted, 64-element aligned)
-      while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (s_beg[m] <= i) lo = m; else hi = m; }
-      on = a.n_seg > 0 && i >= s_beg[lo] && i < s_end[lo] && s_on[lo];
-      bc1 = s_bc1[lo]; bc2s = s_bc2s[lo];
-    }
-    if (!on) continue;
-    float4 g = *reinterpret_cast<const float4*>(a.g[0] + i);
-    for (int r = 1; r < a.world; ++r) {            // rank order: identical sums on every replica
-      const float4 v = *reinterpret_cast<const float4*>(a.g[r] + i);
-      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
-    }
+  auto segment = [&](int64_t i, float& bc1, float& bc2s) -> bool {
+    if (i < a.n_always) { bc1 = bc1a; bc2s = bc2sa; return true; }
+    int lo = 0, hi = a.n_seg;                      // last segment with begin <= i (segments are sorted, 64-element aligned)
+    while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (s_beg[m] <= i) lo = m; else hi = m; }
+    bc1 = s_bc1[lo]; bc2s = s_bc2s[lo];
+    return a.n_seg > 0 && i >= s_beg[lo] && i < s_end[lo] && s_on[lo];
+  };
+  auto adamw4 = [&](int64_t i, const float4 g, float scale, float bc1, float bc2s) {
     float4 p = *reinterpret_cast<float4*>(a.p + i), m1 = *reinterpret_cast<float4*>(a.m1 + i), m2 = *reinterpret_cast<float4*>(a.m2 + i);
     float* pp = &p.x; float* pm1 = &m1.x; float* pm2 = &m2.x; const float* pg = &g.x;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float gg = pg[e] * inv_world;
+      const float gg = pg[e] * scale;
       pp[e] *= (1.f - a.lr * a.wd);
       pm1[e] = a.b1 * pm1[e] + (1.f - a.b1) * gg;
       pm2[e] = a.b2 * pm2[e] + (1.f - a.b2) * gg * gg;
@@ -125,6 +121,42 @@ __global__ void __launch_bounds__(kDpThreads) dp_reduce_adamw_kernel(const DpArg
     *reinterpret_cast<float4*>(a.p + i) = p;
     *reinterpret_cast<float4*>(a.m1 + i) = m1;
     *reinterpret_cast<float4*>(a.m2 + i) = m2;
+  };
+  if (a.two_shot && a.world > 1) {
+    // reduce-scatter + all-gather through the peers' buffers: this rank owns part `rank` of the block's slice
+    const int64_t len = q1 > q0 ? q1 - q0 : 0;
+    const int64_t s0 = q0 + len * a.rank / a.world, s1 = q0 + len * (a.rank + 1) / a.world;
+    for (int64_t q = s0 + threadIdx.x; q < s1; q += kDpThreads) {
+      const int64_t i = q * 4;
+      float bc1, bc2s;
+      if (!segment(i, bc1, bc2s)) continue;
+      float4 g = *reinterpret_cast<const float4*>(a.g[0] + i);
+      for (int r = 1; r < a.world; ++r) {          // rank order: one sum, written to every replica
+        const float4 v = *reinterpret_cast<const float4*>(a.g[r] + i);
+        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      }
+      g.x *= inv_world; g.y *= inv_world; g.z *= inv_world; g.w *= inv_world;
+      for (int r = 0; r < a.world; ++r) *reinterpret_cast<float4*>(const_cast<float*>(a.g[r]) + i) = g;
+    }
+    peer_barrier(a, 1, a.epoch);                   // every part of this slice has landed in every replica's buffer
+    for (int64_t q = q0 + threadIdx.x; q < q1; q += kDpThreads) {
+      const int64_t i = q * 4;
+      float bc1, bc2s;
+      if (segment(i, bc1, bc2s)) adamw4(i, *reinterpret_cast<const float4*>(a.g_own + i), 1.f, bc1, bc2s);
+      *reinterpret_cast<float4*>(a.g_own + i) = make_float4(0.f, 0.f, 0.f, 0.f);       // nobody reads it any more this step
+    }
+    return;
+  }
+  for (int64_t q = q0 + threadIdx.x; q < q1; q += kDpThreads) {
+    const int64_t i = q * 4;
+    float bc1, bc2s;
+    if (!segment(i, bc1, bc2s)) continue;
+    float4 g = *reinterpret_cast<const float4*>(a.g[0] + i);
+    for (int r = 1; r < a.world; ++r) {            // rank order: identical sums on every replica
+      const float4 v = *reinterpret_cast<const float4*>(a.g[r] + i);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    adamw4(i, g, inv_world, bc1, bc2s);
   }
   // every rank has finished reading this slice of every buffer: clear the own one for the next step's accumulation
   peer_barrier(a, 1, a.epoch);
@@ -143,6 +175,9 @@ using namespace matcha;
 
 extern "C" {
 
+static int g_two_shot = -1;
+/* form of the data-parallel step boundary: 0 one-shot, 1 two-shot, 2 by world size (default) */
+void matcha_set_dp_two_shot(int32_t mode) { g_two_shot = mode < 0 ? -1 : (mode > 2 ? 2 : mode); }
 int32_t matcha_dp_blocks(void) { return kSMs; }
 /* kernels of the current device may dereference memory of `peer_device` afterwards (idempotent) */
 int matcha_enable_peer_access(int32_t peer_device) {
@@ -196,6 +231,11 @@ int matcha_dp_reduce_adamw(int32_t world, int32_t rank, const void* const* grad_
   a.act_red = active_reduced; a.n_always = n_always; a.n_flat = n_flat; a.n_seg = n_seg; a.n_flags = n_flags;
   a.seg_begin = seg_begin; a.seg_end = seg_end; a.seg_flag = seg_flag; a.seg_step = seg_step;
   a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.step = step; a.epoch = epoch;
+  if (g_two_shot < 0) {            // by world size (two-shot from 4 ranks on) unless MATCHA_DP_TWO_SHOT=0 / 1 forces a form
+    const char* e = getenv("MATCHA_DP_TWO_SHOT");
+    g_two_shot = !e ? 2 : (e[0] == '0' ? 0 : 1);
+  }
+  a.two_shot = g_two_shot == 2 ? (world >= 4) : g_two_shot;
   cudaStream_t s = (cudaStream_t)stream;
   prof_begin(P_ADAMW, s);
   dp_reduce_adamw_kernel<<<kSMs, kDpThreads, 0, s>>>(a);
