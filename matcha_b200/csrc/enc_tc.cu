@@ -16,8 +16,10 @@ namespace matcha {
 __device__ unsigned long long g_etrace[4096];
 // first 250 steps of CTA 0: 16 event slots per step
 #define ETRACE(ev) do { if (blockIdx.x == 0 && sidx < 250u) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_etrace[sidx * 16 + (ev)] = _t; } } while (0)
+#define BTRACE(ev) do { if (blockIdx.x == 0 && iidx < 250u) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_etrace[iidx * 16 + (ev)] = _t; } } while (0)
 #else
 #define ETRACE(ev) do { } while (0)
+#define BTRACE(ev) do { } while (0)
 #endif
 namespace {
 
@@ -692,6 +694,298 @@ enc_tc_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ==========================================================================================
+// Pipelined backward (default; enc_tc_bwd_kernel above stays as the cross-check, MATCHA_ENC_PIPE_BWD=0).  Same products, same
+// work items (chromosome, column group of kBMaxChunks feature chunks, 128-token tile), same TMEM layout; different schedule:
+//   * the feature chunks of an item arrive by cp.async (four producer warps, 16-byte pieces, two fp32 staging tiles) while
+//     sixteen converter warps (thread = quarter row) turn the landed chunk into the bf16 hi | lo operand tile -- two tiles, so
+//     the conversion of chunk k + 1 runs under the 24 MMAs of chunk k -- and one thread issues the MMAs;
+//   * the dW1_c contraction is issued for the first column group of a chromosome only (the unit kernel accumulates it in
+//     every group and publishes the first).
+// ==========================================================================================
+constexpr int kPBThreads = 672;                 // warps 0-15 converters, 16-19 producers (32 rows each), 20 MMA issuer
+constexpr int kPBStages = 3;                    // two chunks of feature rows in flight while one is converted (two stages: 243 us at cfg3)
+constexpr int kPBSmem = kBS + kBB + kPBStages * kPFStageF + kEChunk;          // 65 536 + 32 768 + 104 448 + 16 384 = 219 136
+
+struct BwdItem {            // one work item of the backward list and what changes with it
+  int c, grp, kc0, kc1, off, nrows, nchunk;
+  bool new_group;
+};
+
+__global__ void __launch_bounds__(kPBThreads, 1)
+enc_pipe_bwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const int64_t* __restrict__ x,
+                    const int32_t* __restrict__ perm, const int32_t* __restrict__ group_off, const float* __restrict__ dE,
+                    const float* __restrict__ H0, float* __restrict__ grads, const DropCfg drop) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sS = smem;                                   // [dE | dH0pre] stacked operand tile, hi 32 KB | lo 32 KB
+  uint8_t* sB = smem + kBS;                             // operand tile (H0 / feature chunk), hi 16 KB | lo 16 KB
+  uint8_t* sStage = smem + kBS + kBB;                   // ring of fp32 staging tiles
+  uint8_t* sW1 = sStage + kPBStages * kPFStageF;
+  __shared__ uint64_t st_full[kPBStages], st_free[kPBStages], b_full, b_free, e_full, dh_full, s_full, item_done, flush_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ const float* sRow[128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 512) {
+    for (int i = 0; i < kPBStages; ++i) { mbar_init(&st_full[i], 128); mbar_init(&st_free[i], 16); }
+    mbar_init(&b_full, 16); mbar_init(&b_free, 1);
+    mbar_init(&e_full, 16); mbar_init(&dh_full, 1); mbar_init(&s_full, 16); mbar_init(&item_done, 1); mbar_init(&flush_done, 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // this CTA's contiguous range of the item list (as enc_tc_bwd_kernel)
+  auto n_groups = [&](int cc) { return ((em.nc[cc] + 63) / 64 + kBMaxChunks - 1) / kBMaxChunks; };
+  int64_t total = 0;
+  for (int c = 0; c < em.n; ++c) total += (int64_t)((group_off[c + 1] - group_off[c] + 127) / 128) * n_groups(c);
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t ti0 = (int64_t)blockIdx.x * per, ti1 = (ti0 + per < total) ? ti0 + per : total;
+  struct Walk { int c; int64_t before; int cur_c, cur_kc0; };
+  auto next_item = [&](Walk& w, int64_t ti, BwdItem& it) -> bool {
+    int cnt = 0;
+    int64_t nt = 0;
+    for (; w.c < em.n; ++w.c) {
+      cnt = group_off[w.c + 1] - group_off[w.c];
+      nt = (cnt + 127) / 128;
+      const int64_t ni = nt * n_groups(w.c);
+      if (ti < w.before + ni) break;
+      w.before += ni;
+    }
+    if (w.c >= em.n) return false;
+    it.c = w.c;
+    it.nchunk = (em.nc[w.c] + 63) / 64;
+    it.grp = (int)((ti - w.before) / nt);
+    it.kc0 = it.grp * kBMaxChunks;
+    it.kc1 = it.kc0 + kBMaxChunks < it.nchunk ? it.kc0 + kBMaxChunks : it.nchunk;
+    it.off = (int)((ti - w.before) - (int64_t)it.grp * nt) * 128;
+    it.nrows = cnt - it.off < 128 ? cnt - it.off : 128;
+    it.new_group = it.c != w.cur_c || it.kc0 != w.cur_kc0;
+    w.cur_c = it.c; w.cur_kc0 = it.kc0;
+    return true;
+  };
+
+  if (warp >= 16 && warp < 20) {
+    // ---------------- producers: the feature chunks of every item ----------------
+    const int half = lane >> 4, piece = lane & 15, pw = warp - 16;
+    const float** myRow = sRow + pw * 32;
+    Walk w{0, 0, -1, -1};
+    BwdItem it;
+    uint32_t cidx = 0;
+    for (int64_t ti = ti0; ti < ti1; ++ti) {
+      if (!next_item(w, ti, it)) break;
+      const int64_t ld = em.ld[it.c];
+      __syncwarp();
+      {
+        const int r = pw * 32 + lane;
+        const float* fr = em.feat[it.c];
+        if (r < it.nrows) fr += (x[perm[group_off[it.c] + it.off + r]] - em.start[it.c]) * ld;
+        myRow[lane] = fr;
+      }
+      __syncwarp();
+      for (int kc = it.kc0; kc < it.kc1; ++kc, ++cidx) {
+        const int st = (int)(cidx % kPBStages);
+        mbar_wait_backoff(&st_free[st], ((cidx / kPBStages) & 1u) ^ 1u);
+        const int64_t col = (int64_t)kc * 64 + piece * 4;
+        const bool col_ok = col < ld;
+        const uint32_t dst0 = smem_u32(sStage + st * kPFStageF) + (pw * 32 + half) * kPFRow + piece * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int r = 2 * j + half;
+          const float* src = myRow[r] + (col_ok ? col : 0);
+          const uint32_t nbytes = (col_ok && pw * 32 + r < it.nrows) ? 16u : 0u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 2 * j * kPFRow), "l"(src), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&st_full[st])) : "memory");
+      }
+    }
+  } else if (warp == 20) {
+    // ---------------- MMA issuer ----------------
+    if (elect_one()) {
+      constexpr uint32_t idescD = make_idesc(128, 64, false, true);     // dH0 = dE . W1          (B MN-major)
+      constexpr uint32_t idescW = make_idesc(128, 64, true, true);      // [dE | dH0pre]^T . tile  (both MN-major)
+      const uint32_t sh = smem_u32(sS), sl = sh + 32768;
+      const uint32_t vh = smem_u32(sW1), vl = vh + 8192;
+      Walk w{0, 0, -1, -1};
+      BwdItem it;
+      uint32_t bidx = 0, iidx = 0, nflush = 0;
+      bool fresh = true, first_item = true;
+      for (int64_t ti = ti0; ti < ti1; ++ti, ++iidx) {
+        if (!next_item(w, ti, it)) break;
+        if (it.new_group) {
+          if (!first_item) { mbar_wait_backoff(&flush_done, nflush & 1u); ++nflush; }      // the accumulators were read out
+          fresh = true;
+        }
+        first_item = false;
+        mbar_wait_backoff(&e_full, iidx & 1u);
+        BTRACE(8);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)       // dH0[128 tok, 64] = dE[128 tok, 64 o] . W1[64 o, 64 k]
+          umma_x3s(tmem_base + kColDH, sh + ks * 4096, sl + ks * 4096, vh + ks * 256, vl + ks * 256, 2048, 128, 128, 1024, idescD, ks == 0);
+        umma_commit(&dh_full);
+        mbar_wait_backoff(&s_full, iidx & 1u);
+        BTRACE(9);
+        tc_fence_after();
+        auto wgrad = [&](uint32_t dcol) {    // [dE | dH0pre]^T[128 feat, 128 tok] . operand tile[128 tok, 64]
+          mbar_wait_backoff(&b_full, bidx & 1u);
+          tc_fence_after();
+          const uint32_t bh = smem_u32(sB), bl = bh + 16384;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_x3s(tmem_base + dcol, sh + ks * 256, sl + ks * 256, bh + ks * 256, bl + ks * 256, 128, 2048, 128, 2048, idescW,
+                     fresh && ks == 0);
+          umma_commit(&b_free);
+          ++bidx;
+        };
+        if (it.kc0 == 0) wgrad(kColW1);                                     // lanes 0..63 = dW1_c (first column group only)
+        for (int kc = it.kc0; kc < it.kc1; ++kc) wgrad(kColW0 + (kc - it.kc0) * 64);     // lanes 64..127 = dW0_c[:, chunk kc]
+        umma_commit(&item_done);
+        BTRACE(10);
+        fresh = false;
+      }
+    }
+  } else {
+    // ---------------- converters: thread (r, q4) = token row r (TMEM lane r), quarter q4 of every 64-wide row ----------------
+    const int r = tid & 127, q4 = tid >> 7, wq = warp & 3;
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    Walk w{0, 0, -1, -1};
+    BwdItem it;
+    uint32_t bidx = 0, cidx = 0, iidx = 0;
+    int cur_c = -1, prev_c = -1, prev_kc0 = 0, prev_kc1 = 0;
+    bool have_prev = false;
+    auto put_quarter = [&](uint8_t* tile, int lo_off, int plane0, const float (&v)[16]) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint4 hi, lo;
+        split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+               make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+        sts16(tile + (plane0 + j) * 2048 + r * 16, hi);
+        sts16(tile + lo_off + (plane0 + j) * 2048 + r * 16, lo);
+      }
+    };
+    auto put_b = [&](const float (&v)[16]) {       // next operand tile: stored as soon as the previous one's MMAs have read it
+      mbar_wait(&b_free, (bidx & 1u) ^ 1u);
+      put_quarter(sB, 16384, q4 * 2, v);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_full);
+      ++bidx;
+    };
+    // TMEM -> atomics on the weight gradients of chromosome c, chunks [kc0, kc1): TMEM lane = stacked feature row
+    auto flush = [&](int c, int kc0, int kc1) {
+      tc_fence_after();
+      const int rr = wq * 32 + lane;
+      if (rr < 64) {                         // warps of lane quarters 0, 1: dW1_c[o = rr][k], this thread: k in [16 q4, 16 q4 + 16)
+        if (kc0 == 0) {
+          float v[16];
+          tmem_ld16(tlane + kColW1 + q4 * 16, v);
+          float* dst = grads + em.off_w1[c] + (int64_t)rr * 64 + q4 * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + i, v[i]);
+        }
+      } else {                               // lane quarters 2, 3: dW0_c[f = rr - 64][k]
+        const int nc = em.nc[c];
+        float* dst = grads + em.off_w0[c] + (int64_t)(rr - 64) * nc;
+        for (int kc = kc0; kc < kc1; ++kc) {
+          float v[16];
+          tmem_ld16(tlane + kColW0 + (kc - kc0) * 64 + q4 * 16, v);
+          const int k0 = kc * 64 + q4 * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (k0 + i < nc) atomicAdd(dst + k0 + i, v[i]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&flush_done);
+    };
+    for (int64_t ti = ti0; ti < ti1; ++ti, ++iidx) {
+      if (!next_item(w, ti, it)) break;
+      if (tid == 0) BTRACE(0);
+      if (have_prev) mbar_wait(&item_done, (iidx - 1) & 1u);      // the previous item's MMAs have read sS (and finished its group)
+      if (tid == 0) BTRACE(1);
+      if (it.new_group && have_prev) flush(prev_c, prev_kc0, prev_kc1);
+      if (tid == 0) BTRACE(2);
+      if (it.c != cur_c) {        // W1_c chunk (K-major for the forward; read MN-major here); no MMA is in flight
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const uint4* s4 = reinterpret_cast<const uint4*>(wsplit + em.woff[it.c] + (int64_t)it.nchunk * kEChunk);
+        uint4* d4 = reinterpret_cast<uint4*>(sW1);
+#pragma unroll
+        for (int i = 0; i < kEChunk / 16 / 512; ++i) d4[tid + i * 512] = __ldg(s4 + tid + i * 512);
+        cur_c = it.c;
+      }
+      const bool live = r < it.nrows;
+      const int64_t t = live ? perm[group_off[it.c] + it.off + r] : 0;
+      // ---- dE rows -> planes 0..7 of sS (requesting them before the wait above was measured slower: 244 -> 268 us) ----
+      float hv[16];
+      {
+        float v[16];
+        const float4* src = reinterpret_cast<const float4*>(dE + t * 64 + q4 * 16);
+        const float4* hsrc = reinterpret_cast<const float4*>(H0 + t * 64 + q4 * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 e = live ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 hh = live ? __ldg(hsrc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * j] = e.x; v[4 * j + 1] = e.y; v[4 * j + 2] = e.z; v[4 * j + 3] = e.w;
+          hv[4 * j] = hh.x; hv[4 * j + 1] = hh.y; hv[4 * j + 2] = hh.z; hv[4 * j + 3] = hh.w;
+        }
+        put_quarter(sS, 32768, q4 * 2, v);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&e_full);
+      if (tid == 0) BTRACE(3);
+      if (it.kc0 == 0) put_b(hv);            // H0 tile: the B operand of dW1_c
+      // ---- dH0pre = (dE . W1) * (1 - H0^2) -> planes 8..15 of sS ----
+      {
+        mbar_wait(&dh_full, iidx & 1u);
+        if (tid == 0) BTRACE(4);
+        tc_fence_after();
+        float d0[16];
+        tmem_ld16(tlane + kColDH + q4 * 16, d0);
+        tc_fence_before();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = live ? d0[i] * (1.f - hv[i] * hv[i]) : 0.f;      // tanh'
+        put_quarter(sS, 32768, 8 + q4 * 2, v);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full);
+      if (tid == 0) BTRACE(5);
+      // ---- feature chunks ----
+      for (int kc = it.kc0; kc < it.kc1; ++kc, ++cidx) {
+        const int st = (int)(cidx % kPBStages);
+        mbar_wait(&st_full[st], (cidx / kPBStages) & 1u);
+        const float* srow = reinterpret_cast<const float*>(sStage + st * kPFStageF + r * kPFRow) + q4 * 16;
+        const int64_t kf = (int64_t)kc * 64 + q4 * 16;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 e = *reinterpret_cast<const float4*>(srow + 4 * j);
+          if (drop.thr != 0u && live) e = drop_apply4(drop, (uint64_t)t, (uint32_t)(kf + 4 * j), e);
+          v[4 * j] = e.x; v[4 * j + 1] = e.y; v[4 * j + 2] = e.z; v[4 * j + 3] = e.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_free[st]);      // the staging tile is in registers
+        put_b(v);
+      }
+      if (tid == 0) BTRACE(6);
+      prev_c = it.c; prev_kc0 = it.kc0; prev_kc1 = it.kc1; have_prev = true;
+    }
+    if (have_prev) {
+      mbar_wait(&item_done, (iidx - 1) & 1u);
+      flush(prev_c, prev_kc0, prev_kc1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 EncMeta make_meta(const matcha_model_desc* m, int64_t* total_bytes);
 }  // namespace
 #ifdef MATCHA_ENC_TRACE
@@ -807,6 +1101,24 @@ int launch_enc_tc_bwd(const matcha_model_desc* m, int64_t split_base, const int6
   const EncMeta em = make_meta(m, nullptr);
   const int64_t tiles = ((T + 127) / 128 + m->n_chrom) * max_col_groups(m);     // upper bound of the item count
   const unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
+  static int pipe = -1;
+  if (pipe < 0) {
+    const char* e = getenv("MATCHA_ENC_PIPE_BWD");
+    pipe = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (pipe == 1) {
+    static bool once2 = false;
+    if (!once2) {
+      if (int rc = check_cuda(cudaFuncSetAttribute(enc_pipe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPBSmem),
+                              "cudaFuncSetAttribute"))
+        return rc;
+      once2 = true;
+    }
+    enc_pipe_bwd_kernel<<<grid, kPBThreads, kPBSmem, s>>>(em, reinterpret_cast<const uint8_t*>(m->derived + split_base), x, perm,
+                                                         group_off, dE, H0, m->grads, drop);
+    MATCHA_CHECK_LAUNCH("enc_pipe_bwd");
+    return MATCHA_OK;
+  }
   enc_tc_bwd_kernel<<<grid, kBThreads, kBSmem, s>>>(em, reinterpret_cast<const uint8_t*>(m->derived + split_base), x, perm,
                                                     group_off, dE, H0, m->grads, drop);
   MATCHA_CHECK_LAUNCH("enc_tc_bwd");
