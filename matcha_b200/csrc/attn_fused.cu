@@ -16,6 +16,14 @@
 #include "tc_common.cuh"
 
 namespace matcha {
+#ifdef MATCHA_ATTNB_TRACE
+__device__ unsigned long long g_abtrace[4096];
+// stage index n (first 250 of CTA 0) x 16 event slots
+#define ABTRACE(ev) do { if (blockIdx.x == 0 && n < 250) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_abtrace[n * 16 + (ev)] = _t; } } while (0)
+#else
+#define ABTRACE(ev) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kAThreads = 320;
@@ -448,8 +456,10 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         if (n + 1 < N) recompute(n + 1);
         const int64_t k = n / 3;
         const int g = (int)(n - 3 * k), xb = (int)(k & 1);
+        ABTRACE(8);
         mbar_wait_backoff(&d_full, (uint32_t)(n & 1));
         if (g == 0) mbar_wait_backoff(&dx_empty, (uint32_t)(k & 1) ^ 1u);
+        ABTRACE(9);
         tc_fence_after();
         // stage g recomputes piece g (G, K, Q) but its d-tile holds the gradient of piece gp (dG, dQ, dK)
         const int gp = (g == 0) ? 0 : (g == 1 ? 2 : 1);
@@ -465,6 +475,7 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
                    2048, idescW, k == 0 && ks == 0, passes);
         umma_commit(&d_empty);
         if (g == 2) { umma_commit(&dx_full); umma_commit(&x_empty[xb]); }
+        ABTRACE(10);
       }
       umma_commit(&done);
     }
@@ -537,6 +548,8 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
 #pragma unroll
         for (int s = 1; s < L; ++s) AT[s - 1] = __shfl_sync(0xffffffffu, A[L - s - 1], src[s - 1]);   // weight of row (i+s) on row i
         if (hp == 0 && hl == 0) {          // db_dyn = sum over tokens of the masked, dropout-scaled gradient
+          // (spreading these 64 column sums over all head pairs / heads, 8 columns per warp, was measured slower: 295 -> 320 us
+          // -- every warp then adds 40 shuffles per tile to the shared-memory pipe that already bounds the kernel)
           float s0, s1; int col0;
           warp_colsum64(dd, lane, s0, s1, col0);
           atomicAdd(&sDbd[col0], s0);
@@ -546,7 +559,9 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
 #pragma unroll
         for (int s = 0; s < L - 1; ++s) dA[s] = 0.f;
         const int rb = (int)(n & 1);
+        if (tid == 64) ABTRACE(0);
         mbar_wait(&r_full[rb], (uint32_t)((n >> 1) & 1));
+        if (tid == 64) ABTRACE(1);
         tc_fence_after();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -574,19 +589,25 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         for (int s = 0; s < L - 1; ++s) dot = fmaf(A[s], dA[s], dot);
 #pragma unroll
         for (int s = 0; s < L - 1; ++s) dS[s] = A[s] * (dA[s] - dot);
-        if (k + 1 < my_tiles) fetch_rows(k + 1);
-        if (k > 0) drain_dxhat(k - 1, t_prev, live_prev);
+        if (tid == 64) ABTRACE(2);
+        if (k + 1 < my_tiles) fetch_rows(k + 1);                // (fetching at the top of the next tile instead: 294 -> 309 us)
+        if (k > 0) drain_dxhat(k - 1, t_prev, live_prev);      // (draining first: 320 -> 330 us)
+        if (tid == 64) ABTRACE(3);
         mbar_wait(&d_empty, (uint32_t)(n & 1) ^ 1u);
+        if (tid == 64) ABTRACE(4);
         store_drow(sD, hl * 8, r, o);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d_full);
+        if (tid == 64) ABTRACE(5);
         ++n;
       }
       // ---------------- stage K: dQ_i = sum_j dS_ij K_j ----------------
       {
         const int rb = (int)(n & 1);
+        if (tid == 64) ABTRACE(0);
         mbar_wait(&r_full[rb], (uint32_t)((n >> 1) & 1));
+        if (tid == 64) ABTRACE(1);
         tc_fence_after();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -610,11 +631,14 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
           atomicAdd(&sDbq[hl * kD + col0], s0);
           atomicAdd(&sDbq[hl * kD + col0 + 1], s1);
         }
+        if (tid == 64) ABTRACE(3);
         mbar_wait(&d_empty, (uint32_t)(n & 1) ^ 1u);
+        if (tid == 64) ABTRACE(4);
         store_drow(sD, hl * 8, r, o);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d_full);
+        if (tid == 64) ABTRACE(5);
         ++n;
       }
       // ---------------- stage Q: dK_i = sum_j dS_ji Q_j ----------------
@@ -623,7 +647,9 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
 #pragma unroll
         for (int s = 1; s < L; ++s) dST[s - 1] = __shfl_sync(0xffffffffu, dS[L - s - 1], src[s - 1]);
         const int rb = (int)(n & 1);
+        if (tid == 64) ABTRACE(0);
         mbar_wait(&r_full[rb], (uint32_t)((n >> 1) & 1));
+        if (tid == 64) ABTRACE(1);
         tc_fence_after();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -642,11 +668,14 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&r_empty[rb]);
+        if (tid == 64) ABTRACE(3);
         mbar_wait(&d_empty, (uint32_t)(n & 1) ^ 1u);
+        if (tid == 64) ABTRACE(4);
         store_drow(sD, hl * 8, r, o);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d_full);
+        if (tid == 64) ABTRACE(5);
         ++n;
       }
       t_prev = t;
@@ -716,6 +745,12 @@ int launch_bwd_L(const uint8_t* xt, const uint8_t* wpairs, const float* bq, cons
 }
 
 }  // namespace
+
+#ifdef MATCHA_ATTNB_TRACE
+extern "C" int matcha_attnb_trace(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_abtrace, sizeof(unsigned long long) * 4096) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int launch_split_w_pairs(const float* W, void* out, cudaStream_t s) {
   split_w_pairs_kernel<<<(4 * 3 * 128 * 8 + 255) / 256, 256, 0, s>>>(W, reinterpret_cast<uint8_t*>(out));
