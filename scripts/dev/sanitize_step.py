@@ -1,7 +1,9 @@
 """Small end-to-end workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): every kernel family
 once -- 2 training steps (tensor-core path, 1,280 hyperedges = 6,400 tokens, recon on), eval forward, pair tables + all-pairs
-scoring of one chromosome, denoise post-processing, metrics, feature construction, k-mer counting, negative sampling.
-    compute-sanitizer --tool memcheck python scripts/dev/sanitize_step.py"""
+scoring of one chromosome, denoise post-processing, metrics, feature construction, k-mer counting, negative sampling, and one
+embed_dim-128 training step (general tcgen05 contraction kernel).  MATCHA_ENC_PIPE=1 puts the pipelined encoder forward on
+this small data set too (it is the default only for wide feature rows).
+    MATCHA_ENC_PIPE=1 compute-sanitizer --tool memcheck python scripts/dev/sanitize_step.py"""
 import os
 import sys
 
@@ -47,5 +49,13 @@ adj = adjacency_from_clusters(mem, off, ds["N"])
 feats = corrcoef_features(adj.float(), ds["chrom_range"])
 zscore_positive_rows_(adj.float().contiguous())
 rows, freq = count_kmers(mem, off, 3, 0, 25, 1)
+# embed_dim 128: one training step with every contraction on the general tcgen05 kernel (csrc/gemm_tcg.cu)
+ds128 = dict(ds)
+ds128["d"] = 128
+model128 = build_model(ds128, seed=1)
+model128.train()
+x128 = torch.from_numpy(ds["positives"][:600]).cuda()
+pred, rl = model128(x128, return_recon=True)
+(torch.nn.functional.binary_cross_entropy_with_logits(pred, torch.ones_like(pred)) + 0.5 * rl.sum()).backward()
 torch.cuda.synchronize()
-print("ok", float(lg.mean()), float(my.mean()), m["all"][:2], len(rows))
+print("ok", float(lg.mean()), float(my.mean()), m["all"][:2], len(rows), float(pred.mean()))
