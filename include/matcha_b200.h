@@ -54,6 +54,10 @@ void matcha_set_chain(int32_t on);
  * (needs the fused path), 0 = four SIMT launches through a [T, n_r] buffer; also MATCHA_RECON_TC=0 */
 void matcha_set_recon_tc(int32_t on);
 void matcha_set_recon_pipe(int32_t on);   /* pipelined gradient pass of the reconstruction head (default on) */
+/* pipelined node-encoder kernels (csrc/enc_tc.cu): forward 0 = unit kernel, 1 = pipelined, 2 = by feature-row width (default:
+ * pipelined from 512 bins per chromosome on average); backward 0 = unit, 1 = pipelined (default); also MATCHA_ENC_PIPE,
+ * MATCHA_ENC_PIPE_BWD */
+void matcha_set_enc_pipe(int32_t fwd, int32_t bwd);
 /* 1 (default) = embed_dim-128 models run their contractions on the general tcgen05 kernel (csrc/gemm_tcg.cu, bf16x3) from
  * 1024 token rows on, 0 = fp32 SIMT kernel; also MATCHA_GEMM_TCG=0 */
 void matcha_set_gemm_tcg(int32_t on);

@@ -114,6 +114,7 @@ SYMBOLS = {
     "matcha_set_recon_tc": (None, [_I32]),
     "matcha_set_recon_pipe": (None, [_I32]),
     "matcha_set_gemm_tcg": (None, [_I32]),
+    "matcha_set_enc_pipe": (None, [_I32, _I32]),
     "matcha_set_dp_two_shot": (None, [_I32]),
     "matcha_set_enc_tc": (None, [_I32]),
     "matcha_set_xform": (None, [_I32]),

@@ -590,7 +590,8 @@ attn_fused_bwd_kernel(const uint8_t* __restrict__ xt, const uint8_t* __restrict_
 #pragma unroll
         for (int s = 0; s < L - 1; ++s) dS[s] = A[s] * (dA[s] - dot);
         if (tid == 64) ABTRACE(2);
-        if (k + 1 < my_tiles) fetch_rows(k + 1);                // (fetching at the top of the next tile instead: 294 -> 309 us)
+        if (k + 1 < my_tiles) fetch_rows(k + 1);                // (fetching at the top of the next tile instead: 294 -> 309 us;
+                                                                //  second half of the row only at the end of stage Q: -> 319 us)
         if (k > 0) drain_dxhat(k - 1, t_prev, live_prev);      // (draining first: 320 -> 330 us)
         if (tid == 64) ABTRACE(3);
         mbar_wait(&d_empty, (uint32_t)(n & 1) ^ 1u);

@@ -1015,6 +1015,10 @@ EncMeta make_meta(const matcha_model_desc* m, int64_t* total_bytes) {
 
 }  // namespace
 
+// forward: 0 unit kernel, 1 pipelined, 2 by feature-row width (default); backward: 0 unit, 1 pipelined (default); -1 = environment
+static int g_enc_pipe_fwd = -1, g_enc_pipe_bwd = -1;
+void set_enc_pipe(int fwd, int bwd) { g_enc_pipe_fwd = fwd; g_enc_pipe_bwd = bwd; }
+
 // floats of the derived buffer taken by the pre-split encoder weights (dense feature rows, embed_dim 64)
 int64_t enc_tc_split_floats(const matcha_model_desc* m) {
   int64_t bytes = 0;
@@ -1047,7 +1051,7 @@ int launch_enc_tc_fwd(const matcha_model_desc* m, int64_t split_base, const int6
   // pipelined kernel for wide feature rows (cfg3: 1 319 bins per chromosome on average, cfg4: 24 897); at cfg2 (133 bins: at
   // most four chunks per tile) the per-tile epilogue dominates and two unit CTAs per SM overlap it better (measured: 39 us vs
   // 50 us at cfg2, 203 us vs 172 us at cfg3).  MATCHA_ENC_PIPE = 0 / 1 forces one of them
-  static int pipe = -1;
+  int& pipe = g_enc_pipe_fwd;
   if (pipe < 0) {
     const char* e = getenv("MATCHA_ENC_PIPE");
     pipe = !e ? 2 : (e[0] == '0' ? 0 : 1);
@@ -1101,7 +1105,7 @@ int launch_enc_tc_bwd(const matcha_model_desc* m, int64_t split_base, const int6
   const EncMeta em = make_meta(m, nullptr);
   const int64_t tiles = ((T + 127) / 128 + m->n_chrom) * max_col_groups(m);     // upper bound of the item count
   const unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
-  static int pipe = -1;
+  int& pipe = g_enc_pipe_bwd;
   if (pipe < 0) {
     const char* e = getenv("MATCHA_ENC_PIPE_BWD");
     pipe = (e && e[0] == '0') ? 0 : 1;

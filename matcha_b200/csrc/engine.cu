@@ -663,6 +663,7 @@ void matcha_set_chain(int32_t on) { g_chain = on != 0; }
 void matcha_set_recon_tc(int32_t on) { g_recon_tc = on != 0; }
 void matcha_set_recon_pipe(int32_t on) { g_recon_pipe = on != 0; }
 void matcha_set_gemm_tcg(int32_t on) { g_tcg = on != 0; }
+void matcha_set_enc_pipe(int32_t fwd, int32_t bwd) { set_enc_pipe(fwd, bwd); }
 void matcha_set_enc_tc(int32_t on) { g_enc_tc = on != 0; }
 void matcha_set_xform(int32_t on) { g_xform = on != 0; }
 void matcha_set_mma_passes(int32_t passes) { g_passes = passes == 1 ? 1 : 3; }

@@ -156,6 +156,7 @@ int launch_enc_tc_fwd(const matcha_model_desc* m, int64_t split_base, const int6
 // backward of the same two layers: dW1_c and dW0_c accumulated into m->grads (chromosomes up to 384 bins: 6 feature
 // chunks resident in TMEM; enc_tc_bwd_fits says whether the model qualifies)
 bool enc_tc_bwd_fits(const matcha_model_desc* m);
+void set_enc_pipe(int fwd, int bwd);     // pipelined encoder kernels: fwd 0 / 1 / 2 (by row width), bwd 0 / 1; -1 = environment
 int launch_enc_tc_bwd(const matcha_model_desc* m, int64_t split_base, const int64_t* x, int64_t T, const int32_t* perm,
                       const int32_t* group_off, const float* dE, const float* H0, DropCfg drop, cudaStream_t s);
 

@@ -790,6 +790,48 @@ def test_recon_head_tensor_core_matches_simt(monkeypatch, L, B, rchrom):
 WIDE = (["chr21", "chr22"], 50_000, 64)
 
 
+@pytest.mark.parametrize("cfg,L,B", [("cfg1", 5, 900), (WIDE, 5, 700), (WIDE, 3, 1100)])
+def test_pipelined_kernels_match_unit_kernels(monkeypatch, cfg, L, B):
+    """The pipelined reconstruction head / encoder forward / encoder backward (warp-specialised, cp.async / bulk-copy rings)
+    against the unit kernels they replace: one training step with dropout on -- same arithmetic, different schedule, so
+    logits, recon loss and every gradient agree to the order of the atomic accumulations."""
+    from matcha_b200.synthetic import build_model, make_dataset
+    lib = _lib().load()
+    ds = make_dataset(cfg, kmers_per_size=3000, seed=3)
+    N = int(ds["chrom_range"][-1][1]) - 1
+    monkeypatch.setattr(np.random, "choice", lambda a, size=None: np.asarray([0]))
+    rng = np.random.default_rng(300 + B)
+    xs = np.zeros((B, L), dtype=np.int64)
+    for b in range(B):
+        k = L if b % 3 else int(rng.integers(2, L + 1))
+        xs[b, :k] = np.sort(rng.choice(np.arange(1, N + 1), size=k, replace=False))
+    x = torch.from_numpy(xs).cuda()
+    y = torch.from_numpy((rng.random((B, 1)) < 0.3).astype("float32")).cuda()
+    w = torch.from_numpy(rng.uniform(0.5, 3, (B, 1)).astype("float32")).cuda()
+    res = {}
+    try:
+        for pipe in (0, 1):
+            lib.matcha_set_recon_pipe(pipe)
+            lib.matcha_set_enc_pipe(pipe, pipe)
+            model = build_model(ds, seed=1)
+            model._engine().seed_base = 29
+            model.train()
+            pred, rl = model(x, return_recon=True)
+            (torch.nn.functional.binary_cross_entropy_with_logits(pred, y, weight=w) + 0.7 * rl.sum()).backward()
+            res[pipe] = ({k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None},
+                         pred.detach().cpu().numpy(), float(rl.detach().sum()))
+    finally:
+        lib.matcha_set_recon_pipe(1)
+        lib.matcha_set_enc_pipe(2, 1)
+    np.testing.assert_allclose(res[1][1], res[0][1], rtol=2e-5, atol=2e-6)
+    assert abs(res[1][2] - res[0][2]) <= 2e-5 * abs(res[0][2])
+    assert res[0][0].keys() == res[1][0].keys()
+    for k, g0 in res[0][0].items():
+        scale = float(np.abs(g0).max())
+        err = float(np.abs(res[1][0][k] - g0).max())
+        assert err <= 5e-5 * scale + 1e-7, (k, err, scale)
+
+
 @pytest.mark.parametrize("cfg,L,B,train", [("cfg1", 5, 700, True), ("cfg1", 3, 450, False), ("cfg1", 4, 1031, True),
                                            (WIDE, 5, 700, True), (WIDE, 3, 900, True)])
 def test_encoder_tensor_core_matches_simt(monkeypatch, cfg, L, B, train):
