@@ -267,20 +267,38 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
 // Pipelined forward (default; enc_tc_fwd_kernel above stays as the cross-check, MATCHA_ENC_PIPE=0).
 // The unit kernel above runs  gather -> split -> copy weights -> barrier -> MMA  once per 64-column chunk with the global
 // loads of one chunk in flight per CTA (29 % of the HBM copy rate at cfg3).  Here the feature rows of a chunk arrive by
-// asynchronous copies (cp.async, 16-byte pieces, no register staging) issued by a producer warp into a ring of three fp32
-// staging tiles together with one bulk copy of the chunk's pre-split weights -- so two chunks of feature rows are in flight
-// per SM whatever the compute warps do;
-// sixteen compute warps turn a landed stage into the bf16 hi | lo operand tile (dropout from the counter RNG, two tiles so the
+// asynchronous copies (cp.async, 16-byte pieces, no register staging) issued by four producer warps into a ring of four fp32
+// staging tiles together with one bulk copy of the chunk's pre-split weights -- so up to three chunks of feature rows are in
+// flight per SM whatever the compute warps do;
+// sixteen compute warps turn a landed stage into the bf16 hi | lo A operand IN TENSOR MEMORY (thread = TMEM lane = token row:
+// tcgen05.st of the packed bf16 pairs, column c = k elements 2c, 2c + 1; A-from-TMEM MMAs -- no operand tile in shared memory,
+// no operand reads on the shared-memory pipe: 172 -> 157 us at cfg3; dropout from the counter RNG; two buffers so the
 // conversion of chunk k + 1 runs under the MMAs of chunk k; with eight warps this conversion was the critical path: 1.2 us
 // per chunk, scripts/dev/enc_trace.py); one thread issues the MMAs.  One persistent CTA per SM.
 //   step = (tile, chunk kc) for kc < nchunk, then (tile, W1): H0 = tanh(acc) -> A tile -> E = H0 . W1_c^T
 // ==========================================================================================
+// the converted A operand lives in TMEM (tcgen05.st by the converter threads, A-from-TMEM MMAs), not in shared memory
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+      : "memory");
+}
+constexpr uint32_t kPFColA = 128;               // two operand buffers of 64 columns: hi 32 | lo 32 (bf16 pairs)
 constexpr int kPFThreads = 672;                 // warps 0-15 compute, warps 16-19 producers (32 rows each), warp 20 MMA issuer
 constexpr int kPFRow = 272;                     // staging row stride: 64 floats + 16 B (conflict-free 16-byte reads down a column)
 constexpr int kPFStageF = 128 * kPFRow;         // 34 816
 constexpr int kPFStage = kPFStageF + kEChunk;   // + the chunk's pre-split weights: 51 200
-constexpr int kPFStages = 3;
-constexpr int kPFSmem = kPFStages * kPFStage + 2 * kEA;      // 219 136
+constexpr int kPFStages = 4;
+constexpr int kPFSmem = kPFStages * kPFStage;                // 204 800 (the operand tiles are in TMEM)
 constexpr uint32_t kPFColAcc = 0, kPFColE = 64;
 
 __global__ void __launch_bounds__(kPFThreads, 1)
@@ -289,12 +307,11 @@ enc_pipe_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const 
                     float* __restrict__ E, const DropCfg drop) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sStage = smem;
-  uint8_t* sA = smem + kPFStages * kPFStage;      // two operand tiles of kEA
   __shared__ uint64_t f_full[kPFStages], f_free[kPFStages], a_full[2], a_free[2], acc_full, e_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ const float* sRow[128];              // feature-row pointers of the producer's current tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
   if (tid == 512) {
     for (int i = 0; i < kPFStages; ++i) { mbar_init(&f_full[i], 129); mbar_init(&f_free[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 16); mbar_init(&a_free[i], 1); }
@@ -388,13 +405,16 @@ enc_pipe_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const 
           mbar_wait_backoff(&a_full[ab], (sidx >> 1) & 1u);
           ETRACE(9);
           tc_fence_after();
-          const uint32_t ah = smem_u32(sA + ab * kEA), al = ah + 16384;
           const uint32_t wh = smem_u32(sStage + st * kPFStage + kPFStageF), wl = wh + 8192;
           const uint32_t dcol = tmem_base + (kc < nchunk ? kPFColAcc : kPFColE);
+          const uint32_t ta_hi = tmem_base + kPFColA + ab * 64, ta_lo = ta_hi + 32;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_x3s(dcol, ah + ks * 4096, al + ks * 4096, wh + ks * 2048, wl + ks * 2048, 2048, 128, 1024, 128, idesc,
-                     (kc == 0 || kc == nchunk) && ks == 0);
+          for (int ks = 0; ks < 4; ++ks) {
+            const bool fresh = (kc == 0 || kc == nchunk) && ks == 0;
+            umma_ts_bf16(dcol, ta_lo + ks * 8, make_smem_desc(wh + ks * 2048, 1024, 128), idesc, fresh ? 0u : 1u);
+            umma_ts_bf16(dcol, ta_hi + ks * 8, make_smem_desc(wl + ks * 2048, 1024, 128), idesc, 1u);
+            umma_ts_bf16(dcol, ta_hi + ks * 8, make_smem_desc(wh + ks * 2048, 1024, 128), idesc, 1u);
+          }
           umma_commit(&f_free[st]);
           umma_commit(&a_free[ab]);
           if (kc == nchunk - 1) umma_commit(&acc_full);
@@ -412,16 +432,14 @@ enc_pipe_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const 
     auto put_tile = [&](uint32_t si, const float (&v)[16]) {      // 16 floats of row r -> planes 2 q4, 2 q4 + 1 of operand tile si & 1
       const int ab = (int)(si & 1);
       mbar_wait(&a_free[ab], ((si >> 1) & 1u) ^ 1u);
-      uint8_t* at = sA + ab * kEA;
+      uint32_t ph[8], pl[8];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint4 hi, lo;
-        split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
-               make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
-        sts16(at + (q4 * 2 + j) * 2048 + r * 16, hi);
-        sts16(at + 16384 + (q4 * 2 + j) * 2048 + r * 16, lo);
-      }
-      fence_async_smem();
+      for (int j = 0; j < 8; ++j) split2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+      tc_fence_after();
+      tmem_st8(tlane + kPFColA + ab * 64 + q4 * 8, ph);
+      tmem_st8(tlane + kPFColA + ab * 64 + 32 + q4 * 8, pl);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[ab]);
     };
@@ -485,7 +503,7 @@ enc_pipe_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // ==========================================================================================
