@@ -277,21 +277,7 @@ enc_tc_fwd_kernel(const EncMeta em, const uint8_t* __restrict__ wsplit, const in
 // per chunk, scripts/dev/enc_trace.py); one thread issues the MMAs.  One persistent CTA per SM.
 //   step = (tile, chunk kc) for kc < nchunk, then (tile, W1): H0 = tanh(acc) -> A tile -> E = H0 . W1_c^T
 // ==========================================================================================
-// the converted A operand lives in TMEM (tcgen05.st by the converter threads, A-from-TMEM MMAs), not in shared memory
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
-               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
-      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-      : "memory");
-}
+// the converted A operand lives in TMEM (tcgen05.st by the converter threads, A-from-TMEM MMAs: tc_common.cuh), not in shared memory
 constexpr uint32_t kPFColA = 128;               // two operand buffers of 64 columns: hi 32 | lo 32 (bf16 pairs)
 constexpr int kPFThreads = 672;                 // warps 0-15 compute, warps 16-19 producers (32 rows each), warp 20 MMA issuer
 constexpr int kPFRow = 272;                     // staging row stride: 64 floats + 16 B (conflict-free 16-byte reads down a column)

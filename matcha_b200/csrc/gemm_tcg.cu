@@ -9,8 +9,10 @@
 //   NT  C[M, N]  = A[M, K] . B[N, K]^T     A, B K-major operand tiles
 //   NN  C[M, N]  = A[M, K] . B[K, N]       B MN-major
 //   TN  C[M, N] += A[K, M]^T . B[K, N]     both MN-major, split over K (tokens) with atomic accumulation
-// 256 threads stage fp32 -> bf16 hi | lo tiles through registers (the next K step's loads are in flight while the tensor
-// pipe works), one thread issues the MMAs, thread (r, h) reads TMEM lane r and half h of the BN accumulator columns.
+// 256 threads stage fp32 -> bf16 hi | lo operands through registers (the next K step's loads are in flight while the tensor
+// pipe works): B tiles (and the transposed A tile of the TN form) into shared memory, the A rows of the NT / NN forms straight
+// into TENSOR MEMORY (thread = row = TMEM lane; A-from-TMEM MMAs: no A tile in shared memory).  One thread issues the MMAs,
+// thread (r, h) reads TMEM lane r and half h of the BN accumulator columns.
 #include "tc_common.cuh"
 
 namespace matcha {
@@ -87,7 +89,9 @@ __global__ void __launch_bounds__(kGT, 2) gemm_tcg_kernel(const GemmDesc d, cons
   }
   if (dead) return;                                // uniform per CTA, before any barrier / allocation
 
-  if (warp == 0) tmem_alloc(&tmem_base_s, BN);
+  constexpr uint32_t kTmemCols = tn ? BN : (BN == 128 ? 256 : 128);     // NT / NN: + 64 columns of A operand (power of two)
+  constexpr uint32_t kColA = BN;                                        // A operand in tensor memory: hi 32 columns | lo 32
+  if (warp == 0) tmem_alloc(&tmem_base_s, kTmemCols);
   if (tid == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -188,14 +192,22 @@ __global__ void __launch_bounds__(kGT, 2) gemm_tcg_kernel(const GemmDesc d, cons
     }
   };
   auto store_tiles = [&]() {
-    if (!tn) {                                     // K-major [k/8][row][8]
+    if (!tn) {                                     // A operand straight into tensor memory: thread = row = TMEM lane, this
+                                                   // thread's 32 k elements = 16 columns of packed bf16 pairs (hi and lo)
+      const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kColA + kh * 16;
 #pragma unroll
-      for (int j = 0; j < kARegs / 2; ++j) {
-        uint4 hi, lo;
-        split8(ra[2 * j], ra[2 * j + 1], hi, lo);
-        sts16(sA + (kh * 4 + j) * 2048 + lr * 16, hi);
-        sts16(sA + kAHalf + (kh * 4 + j) * 2048 + lr * 16, lo);
+      for (int g8 = 0; g8 < 2; ++g8) {
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = ra[g8 * 4 + j];
+          split2(v.x, v.y, ph[2 * j], pl[2 * j]);
+          split2(v.z, v.w, ph[2 * j + 1], pl[2 * j + 1]);
+        }
+        tmem_st8(ta + g8 * 8, ph);
+        tmem_st8(ta + 32 + g8 * 8, pl);
       }
+      tmem_st_wait();
     } else {                                       // MN-major [k/8][m/8][k%8][8 m]
       const int mg = tid & 15, kk = tid >> 4;
 #pragma unroll
@@ -249,10 +261,21 @@ __global__ void __launch_bounds__(kGT, 2) gemm_tcg_kernel(const GemmDesc d, cons
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
+      if (tn) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_x3s(tmem_base, ah + ks * 2 * a_lbo, al + ks * 2 * a_lbo, bh + ks * 2 * b_lbo, bl + ks * 2 * b_lbo, a_lbo, 128, b_lbo, 128,
-                 idesc, k0 == k_begin && ks == 0);
+        for (int ks = 0; ks < 4; ++ks)
+          umma_x3s(tmem_base, ah + ks * 2 * a_lbo, al + ks * 2 * a_lbo, bh + ks * 2 * b_lbo, bl + ks * 2 * b_lbo, a_lbo, 128, b_lbo, 128,
+                   idesc, k0 == k_begin && ks == 0);
+      } else {                                     // A from tensor memory (8 columns per K = 16 step), B from shared memory
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t a_hi = tmem_base + kColA + ks * 8, a_lo = a_hi + 32;
+          const uint64_t b_hi = make_smem_desc(bh + ks * 2 * b_lbo, b_lbo, 128), b_lo = make_smem_desc(bl + ks * 2 * b_lbo, b_lbo, 128);
+          umma_ts_bf16(tmem_base, a_lo, b_hi, idesc, (k0 == k_begin && ks == 0) ? 0u : 1u);
+          umma_ts_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+          umma_ts_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+        }
+      }
       umma_commit(&bar);
     }
     if (k0 + kGBK < k_end) load_tiles(k0 + kGBK);
@@ -333,7 +356,7 @@ __global__ void __launch_bounds__(kGT, 2) gemm_tcg_kernel(const GemmDesc d, cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, BN);
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 template <int FORM, int BN>
