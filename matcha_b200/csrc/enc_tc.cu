@@ -1054,7 +1054,7 @@ int launch_enc_tc_fwd(const matcha_model_desc* m, int64_t split_base, const int6
   int64_t tiles = (T + 127) / 128 + m->n_chrom;            // upper bound; the kernel stops at the real tile count
   // pipelined kernel for wide feature rows (cfg3: 1 319 bins per chromosome on average, cfg4: 24 897); at cfg2 (133 bins: at
   // most four chunks per tile) the per-tile epilogue dominates and two unit CTAs per SM overlap it better (measured: 39 us vs
-  // 50 us at cfg2, 203 us vs 172 us at cfg3).  MATCHA_ENC_PIPE = 0 / 1 forces one of them
+  // 46 us at cfg2, 203 us vs 155 us at cfg3).  MATCHA_ENC_PIPE = 0 / 1 forces one of them
   int& pipe = g_enc_pipe_fwd;
   if (pipe < 0) {
     const char* e = getenv("MATCHA_ENC_PIPE");
