@@ -695,15 +695,17 @@ __global__ void __launch_bounds__(kWThreadsP, 1) wgrad_pair_kernel(const WgradPa
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nbp = 8 + a.b2_planes + 2;                 // B planes per half: B1 | B2 | ones | zeros
   const int b_half = nbp * 2048;
-  uint8_t* sAp = smem;                                  // hi: A1 planes 0-7, A2 planes 8-15 (32 KB) | lo (32 KB)
-  uint8_t* sB = smem + 65536;                           // hi [nbp planes] | lo [nbp planes]
-  __shared__ uint64_t full, empty, done;
+  uint8_t* sAp = smem;                                  // two buffers of: hi A1 planes 0-7, A2 planes 8-15 (32 KB) | lo (32 KB)
+  uint8_t* sB = smem + 2 * 65536;                       // hi [nbp planes] | lo [nbp planes]
+  // the A tiles are double buffered (the next tile's 64 KB land under this tile's MMAs); the B tiles do not fit twice
+  __shared__ uint64_t a_full[2], a_empty[2], full, empty, done;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = nbp * 8;
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
   if (tid == 32) {
     mbar_init(&full, 1); mbar_init(&empty, 1); mbar_init(&done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // constant planes: ones column (bf16 1.0 in column 0 of the plane, hi half only) and zeros
@@ -724,14 +726,18 @@ __global__ void __launch_bounds__(kWThreadsP, 1) wgrad_pair_kernel(const WgradPa
     if (lane == 0) {
       for (int64_t k = 0; k < my_tiles; ++k) {
         const int64_t tile = blockIdx.x + k * gridDim.x;
-        mbar_wait_backoff(&empty, (uint32_t)(k & 1) ^ 1u);
-        mbar_expect_tx(&full, 4 * 16384 + 2 * 16384 + 2 * b2_half);
+        const int ab = (int)(k & 1);
+        uint8_t* sa = sAp + ab * 65536;
+        mbar_wait_backoff(&a_empty[ab], (uint32_t)((k >> 1) & 1) ^ 1u);
+        mbar_expect_tx(&a_full[ab], 4 * 16384);
         const uint8_t* s1 = a.a1 + tile * (int64_t)kCTile;
         const uint8_t* s2 = a.a2 + tile * (int64_t)kCTile;
-        bulk_g2s(sAp, s1, 16384, &full);
-        bulk_g2s(sAp + 16384, s2, 16384, &full);
-        bulk_g2s(sAp + 32768, s1 + 16384, 16384, &full);
-        bulk_g2s(sAp + 49152, s2 + 16384, 16384, &full);
+        bulk_g2s(sa, s1, 16384, &a_full[ab]);
+        bulk_g2s(sa + 16384, s2, 16384, &a_full[ab]);
+        bulk_g2s(sa + 32768, s1 + 16384, 16384, &a_full[ab]);
+        bulk_g2s(sa + 49152, s2 + 16384, 16384, &a_full[ab]);
+        mbar_wait_backoff(&empty, (uint32_t)(k & 1) ^ 1u);
+        mbar_expect_tx(&full, 2 * 16384 + 2 * b2_half);
         const uint8_t* t1 = a.b1 + tile * (int64_t)kCTile;
         const uint8_t* t2 = a.b2 + tile * (int64_t)a.b2_tile_bytes;
         bulk_g2s(sB, t1, 16384, &full);
@@ -743,14 +749,18 @@ __global__ void __launch_bounds__(kWThreadsP, 1) wgrad_pair_kernel(const WgradPa
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, N, true, true);
-      const uint32_t ah = smem_u32(sAp), al = ah + 32768, bh = smem_u32(sB), bl = bh + b_half;
+      const uint32_t bh = smem_u32(sB), bl = bh + b_half;
       for (int64_t k = 0; k < my_tiles; ++k) {
+        const int ab = (int)(k & 1);
+        const uint32_t ah = smem_u32(sAp + ab * 65536), al = ah + 32768;
+        mbar_wait_backoff(&a_full[ab], (uint32_t)((k >> 1) & 1));
         mbar_wait_backoff(&full, (uint32_t)(k & 1));
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)      // K = 16 tokens per step; both operands MN-major (LBO 128: next 8 tokens, SBO 2048: next plane)
           umma_x3s(tmem_base, ah + ks * 256, al + ks * 256, bh + ks * 256, bl + ks * 256, 128, 2048, 128, 2048, idesc,
                    k == 0 && ks == 0);
+        umma_commit(&a_empty[ab]);
         umma_commit(&empty);
       }
       umma_commit(&done);
@@ -869,7 +879,7 @@ int launch_wgrad_pair(const uint8_t* a1, const uint8_t* a2, const uint8_t* b1, c
                       cudaStream_t s) {
   if (ntiles <= 0) return MATCHA_OK;
   const int nbp = 8 + b2_planes + 2, N = nbp * 8;
-  const int smem = 65536 + 2 * nbp * 2048;
+  const int smem = 2 * 65536 + 2 * nbp * 2048;
   static int set_for = 0;
   if (set_for < smem) { if (int rc = set_smem_attr_c(wgrad_pair_kernel, smem)) return rc; set_for = smem; }
   const unsigned grid = (unsigned)(ntiles < kSMs ? ntiles : kSMs);
