@@ -545,7 +545,8 @@ static int run_encoder(const matcha_model_desc* m, const int64_t* x, int64_t T, 
   int rc;
   if ((rc = PROF(P_BUCKET, 1, launch_bucket(x, T, chrom_meta(m), w.counts, w.group_off, w.cursor, w.perm, s)))) return rc;
   if ((rc = wait_prepared(PREP_ENCODER, s))) return rc;     // the most recent matcha_prepare (possibly queued on another stream)
-  if ((rc = check_cuda(cudaMemsetAsync(w.H0, 0, sizeof(float) * T * Dm, s), "memset H0"))) return rc;
+  // E rows of pad tokens are read (the attribute mix walks every token): zero them.  H0 is only ever read through the
+  // chromosome-bucketed token lists (real tokens), so its pad rows need no fill.
   if ((rc = check_cuda(cudaMemsetAsync(E_out, 0, sizeof(float) * T * Dm, s), "memset E"))) return rc;
   if (use_enc_tc(m, T)) {    // both encoder layers in one tcgen05 kernel over the bucketed token list
     const DropCfg fd = make_drop(seed, SITE_FEATURE, m->p_feature, training != 0);
